@@ -1,0 +1,154 @@
+"""BGGE(): Gibbs sampler for genomic G x E models -- host mirror of R/BGGE.R:84-444.
+
+The eigendecompositions (setDEC, R/BGGE.R:119-182), every sweep (R/BGGE.R:274-403) and the
+posterior summaries (R/BGGE.R:408-433) run in libbgge_b200 on the GPU; this module only
+validates arguments, drives the handle and assembles the returned object with the
+reference's field names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+
+
+class BGGEFit(OrderedDict):
+    """The "BGGE" S3 object: yHat, varE, varE.sd, K, chain, ite, burn, thin, y."""
+
+    def __str__(self):   # print.BGGE, R/utils.R:9-18
+        head = "  ".join(f"{v:.3g}" for v in np.asarray(self["yHat"]).ravel()[:10])
+        return ("Model Fitted with: \n " + f"{self['ite']}  Iterations, burning the first  {self['burn']}  and thining every  "
+                f"{self['thin']} \n\n Some predicted Values: \n{head}\n\n Use str() function to found more datailed information.\n")
+
+
+def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
+    """setDEC() of R/BGGE.R:119-182 on the device: per kernel a list of blocks
+    {"s", "U", "pos"} (pos = (start, stop) 0-based half-open, None for type D)."""
+    types = [k["Type"] for k in K.values()]
+    if not all(t in ("BD", "D") for t in types):
+        raise ValueError("Matrix should be of types BD or D")
+    if ne is None:
+        if "BD" in types:
+            raise ValueError("For type BD, number of subjects in each sub matrices should be provided")
+    elif np.size(ne) <= 1 and "BD" in types:
+        raise ValueError("ne invalid. For type BD, number of subjects in each sub matrices should be provided")
+    out = []
+    for k in K.values():
+        Km = _lib.f64(k["Kernel"])
+        n = Km.shape[0]
+        spans = [(0, n)] if k["Type"] == "D" else list(zip(np.cumsum(ne) - np.asarray(ne), np.cumsum(ne)))
+        blocks = []
+        for a, b in spans:
+            a, b = int(a), int(b)
+            m = b - a
+            sub = _lib.f64(Km[a:b, a:b])
+            s = np.empty(m)
+            U = np.empty((m, m), order="F")
+            nr = C.c_int64(0)
+            _lib.call("bgge_eig", _lib.ptr(sub), m, m, float(tol), int(canonical_sign), _lib.ptr(s), _lib.ptr(U),
+                      C.byref(nr))
+            if nr.value > 0:
+                blocks.append({"s": s[:nr.value].copy(), "U": np.asfortranarray(U[:, :nr.value]),
+                               "pos": None if k["Type"] == "D" else (a, b)})
+        if not blocks:
+            raise IndexError("subscript out of bounds")   # tmp[[1]] at R/BGGE.R:177
+        out.append(blocks)
+    return out
+
+
+def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=1e-10, R2=0.5, *, seed=0, chain=0,
+         draws=None, eig=None, device=None):
+    """Fit the G x E model by Gibbs sampling (signature of R/BGGE.R:84 plus keyword-only extras).
+
+    draws : optional (normals, chisq) tapes -> injected-draw mode.
+    eig   : optional precomputed setDEC() result (shared eigenbasis).
+    """
+    y = np.array(y, dtype=np.float64).ravel()
+    n = y.shape[0]
+    if not hasattr(K, "items"):
+        K = OrderedDict((f"K{i + 1}", k) for i, k in enumerate(K))          # R/BGGE.R:203-205
+    names = list(K.keys())
+    nk = len(names)
+    types = [k["Type"] for k in K.values()]
+    if not all(t in ("BD", "D") for t in types):
+        raise ValueError("Matrix should be of types BD or D")                # R/BGGE.R:220
+    if ne is None and "BD" in types:
+        raise ValueError("For type BD, number of subjects in each sub matrices should be provided")
+    if ne is not None and np.size(ne) == 1 and "BD" in types:
+        raise ValueError("Type BD should be used only for block diagonal matrices")   # R/BGGE.R:223
+    ne_arr = None if ne is None else np.ascontiguousarray(np.atleast_1d(ne), dtype=np.int64)
+    q = 0
+    if XF is not None:
+        XF = _lib.f64(np.asarray(XF, dtype=np.float64).reshape(n, -1))
+        q = XF.shape[1]
+    if device is not None:
+        _lib.call("bgge_set_device", int(device))
+
+    h = C.c_void_p()
+    _lib.call("bgge_gibbs_create", n, nk, q, None, C.byref(h))
+    try:
+        _lib.call("bgge_gibbs_set_y", h, _lib.ptr(y), None)
+        if q:
+            _lib.call("bgge_gibbs_set_xf", h, _lib.ptr(XF))
+        for j, k in enumerate(K.values()):
+            tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
+            Km = _lib.f64(k["Kernel"])
+            if Km.shape != (n, n):
+                raise ValueError(f"kernel {names[j]} is {Km.shape}, expected {(n, n)}")
+            if eig is None:
+                _lib.call("bgge_gibbs_add_kernel_matrix", h, j, tcode, _lib.ptr(Km), n, 0,
+                          None if ne_arr is None else _lib.ptr(ne_arr), 0 if ne_arr is None else ne_arr.shape[0],
+                          float(tol), 1)
+            else:
+                _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(np.mean(np.diag(Km))))
+                for blk in eig[j]:
+                    U = _lib.f64(blk["U"])
+                    s = np.ascontiguousarray(blk["s"], dtype=np.float64)
+                    pos0 = 0 if blk["pos"] is None else int(blk["pos"][0])
+                    _lib.call("bgge_gibbs_add_block", h, j, pos0, U.shape[0], U.shape[1], _lib.ptr(s), _lib.ptr(U),
+                              U.shape[0], 0)
+        mode = _lib.RNG_PHILOX
+        if draws is not None:
+            z = np.ascontiguousarray(draws[0], dtype=np.float64)
+            c = np.ascontiguousarray(draws[1], dtype=np.float64)
+            _lib.call("bgge_gibbs_set_tape", h, _lib.ptr(z), z.shape[0], _lib.ptr(c), c.shape[0])
+            mode = _lib.RNG_TAPE
+        _lib.call("bgge_gibbs_init", h, int(ite), int(burn), int(thin), float(R2), mode, int(seed), int(chain))
+        step = int(verbose) if int(verbose) != 0 else int(ite)
+        done = 0
+        while done < ite:                                                    # R/BGGE.R:274, 398-401
+            t0 = time.perf_counter()
+            k = min(step, ite - done)
+            _lib.call("bgge_gibbs_run", h, k)
+            _lib.call("bgge_gibbs_sync", h)
+            done += k
+            if int(verbose) != 0 and done % int(verbose) == 0:
+                print("Iter: ", done, "time: ", round((time.perf_counter() - t0) / k, 3))
+
+        ncum = ite // thin
+        yHat, u, usd, yout = np.empty(n), np.empty((nk, n)), np.empty((nk, n)), np.empty(n)
+        varu, varusd = np.empty(nk), np.empty(nk)
+        varE, varEsd = C.c_double(), C.c_double()
+        _lib.call("bgge_gibbs_summary", h, _lib.ptr(yHat), C.byref(varE), C.byref(varEsd), _lib.ptr(u), _lib.ptr(usd),
+                  _lib.ptr(varu), _lib.ptr(varusd), _lib.ptr(yout))
+        cmu, cve, cvu = np.empty(ncum), np.empty(ncum), np.empty((nk, ncum))
+        cbet = np.empty((ncum, max(q, 1)))
+        _lib.call("bgge_gibbs_chain", h, _lib.ptr(cmu), _lib.ptr(cve), _lib.ptr(cvu), _lib.ptr(cbet))
+    finally:
+        _lib.load().bgge_gibbs_destroy(h)
+
+    out = BGGEFit()
+    out["yHat"] = yHat.reshape(n, 1) if q else yHat                           # R/BGGE.R:411-419
+    out["varE"] = varE.value
+    out["varE.sd"] = varEsd.value
+    out["K"] = OrderedDict((nm, {"u": u[j].copy(), "u.sd": usd[j].copy(), "varu": float(varu[j]),
+                                 "varu.sd": float(varusd[j])}) for j, nm in enumerate(names))
+    out["chain"] = {"mu": cmu, "varE": cve,
+                    "K": OrderedDict((nm, {"varU": cvu[j].copy()}) for j, nm in enumerate(names))}
+    out["ite"], out["burn"], out["thin"] = ite, burn, thin
+    out["y"] = yout
+    return out

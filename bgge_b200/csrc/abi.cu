@@ -1,0 +1,780 @@
+// extern "C" surface of libbgge_b200 (declared in include/bgge_b200.h) and the host-side
+// orchestration behind the host-buffer entry points.
+#include "../../include/bgge_b200.h"
+#include "common.cuh"
+#include "gibbs.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace bgge {
+
+// ------------------------------------------------------------------ error / device plumbing
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static int g_sm_count[64] = {0};
+
+int ensure_device() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libbgge_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return ERR_NODEVICE;
+  }
+  int dev = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) return OK;
+  cudaDeviceProp prop;
+  BGGE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d (%s) is sm_%d%d; libbgge_b200 is built for sm_100a only", dev, prop.name, prop.major,
+              prop.minor);
+    return ERR_NODEVICE;
+  }
+  if (dev >= 0 && dev < 64) g_sm_count[dev] = prop.multiProcessorCount;
+  return OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) ? g_sm_count[dev] : 148;
+}
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// lower-triangular tile list for tile rows [tr0, tr1)
+int build_tiles(int64_t tr0, int64_t tr1, DevBuf<int2>& out, int* ntiles, cudaStream_t st) {
+  std::vector<int2> t;
+  // walk anti-diagonal-ish: longest rows first so the tail of the persistent loop is short
+  for (int64_t ti = tr1 - 1; ti >= tr0; --ti)
+    for (int64_t tj = 0; tj <= ti; ++tj) t.push_back(make_int2((int)ti, (int)tj));
+  *ntiles = (int)t.size();
+  BGGE_CUDA(out.alloc(t.size()));
+  if (!t.empty()) {
+    BGGE_CUDA(cudaMemcpyAsync(out.p, t.data(), t.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    BGGE_CUDA(cudaStreamSynchronize(st));   // t goes out of scope
+  }
+  return OK;
+}
+
+// host X (L x p) -> padded device copy
+int upload_markers(const double* X, int64_t L, int64_t p, DevBuf<double>& dX, int64_t* ldx, int64_t* p_pad) {
+  *ldx = round_up(L, 128);
+  *p_pad = round_up(p, 16);
+  BGGE_CUDA(dX.alloc((size_t)(*ldx) * (size_t)(*p_pad)));
+  BGGE_CUDA(cudaMemset(dX.p, 0, (size_t)(*ldx) * (size_t)(*p_pad) * sizeof(double)));
+  BGGE_CUDA(cudaMemcpy2D(dX.p, (size_t)(*ldx) * sizeof(double), X, (size_t)L * sizeof(double),
+                         (size_t)L * sizeof(double), (size_t)p, cudaMemcpyHostToDevice));
+  return OK;
+}
+
+// device base kernels: K0[b] (L x L, ld L) for each bandwidth
+int base_kernels_device(const double* dX, int64_t ldx, int64_t L, int64_t p, int64_t p_pad, int kind,
+                        const double* bandwidth, int nb, double quantil, std::vector<DevBuf<double>>& K0,
+                        double* out_q, cudaStream_t st) {
+  BGGE_REQUIRE(kind == BGGE_KERNEL_GB || kind == BGGE_KERNEL_GK,
+               "kernel selected is not available. Please choose one method available or make available other "
+               "kernel through argument K");
+  DevBuf<int2> tiles;
+  int ntiles = 0;
+  const int64_t T = (L + 127) / 128;
+  BGGE_TRY(build_tiles(0, T, tiles, &ntiles, st));
+  if (kind == BGGE_KERNEL_GB) {
+    K0.resize(1);
+    BGGE_CUDA(K0[0].alloc((size_t)L * L));
+    BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, K0[0].p, L, 0, (double)p, 1, st));
+    BGGE_CUDA(cudaStreamSynchronize(st));
+    return OK;
+  }
+  BGGE_REQUIRE(nb >= 1 && bandwidth != nullptr, "GK kernel needs at least one bandwidth");
+  DevBuf<double> D, diag, q;
+  DevBuf<unsigned char> scratch;
+  BGGE_CUDA(D.alloc((size_t)L * L));
+  BGGE_CUDA(diag.alloc((size_t)L));
+  BGGE_CUDA(q.alloc(1));
+  BGGE_CUDA(scratch.alloc(quantile_scratch_bytes()));
+  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, D.p, L, 0, 1.0, 1, st));
+  BGGE_TRY(gk_distance_launch(D.p, L, L, diag.p, st));
+  BGGE_TRY(quantile7_launch(D.p, L, L, quantil, scratch.p, q.p, st));
+  K0.resize((size_t)nb);
+  for (int b = 0; b < nb; ++b) {
+    BGGE_CUDA(K0[(size_t)b].alloc((size_t)L * L));
+    BGGE_TRY(gk_exp_launch(D.p, L, L, bandwidth[b], q.p, K0[(size_t)b].p, L, st));
+  }
+  if (out_q) BGGE_CUDA(cudaMemcpyAsync(out_q, q.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BGGE_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+__global__ void philox_test_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  philox4x32_10(c, key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+__global__ void draws_test_kernel(DrawCfg dc, long long n, double* z, double df, double* c) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (z) z[i] = draw_normal(dc, 1, 0u, (unsigned long long)i, 0);
+  if (c) c[i] = draw_chisq(dc, i + 1, STREAM_CHI_E, df, 0);
+}
+
+double mean_sd(const std::vector<double>& v, double* sd) {
+  const size_t k = v.size();
+  long double m = 0.0L;
+  for (double x : v) m += x;
+  m = k ? m / (long double)k : 0.0L;
+  if (sd) {
+    long double ss = 0.0L;
+    for (double x : v) ss += ((long double)x - m) * ((long double)x - m);
+    *sd = k > 1 ? (double)sqrtl(ss / (long double)(k - 1)) : NAN;
+  }
+  return k ? (double)m : NAN;
+}
+
+}  // namespace
+}  // namespace bgge
+
+using namespace bgge;
+
+struct bgge_gibbs {
+  Gibbs g;
+};
+
+extern "C" {
+
+int bgge_version(void) { return 100; }
+const char* bgge_last_error(void) { return last_error(); }
+
+int bgge_device_count(int* count) {
+  BGGE_REQUIRE(count != nullptr, "device_count: NULL output");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    c = 0;
+  }
+  *count = c;
+  return OK;
+}
+
+int bgge_set_device(int device) {
+  BGGE_CUDA(cudaSetDevice(device));
+  return ensure_device();
+}
+
+int bgge_device_memory(uint64_t* free_bytes, uint64_t* total_bytes) {
+  BGGE_TRY(ensure_device());
+  size_t f = 0, t = 0;
+  BGGE_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return OK;
+}
+
+// ====================================================================== getK
+int bgge_marker_ld(int64_t L, int64_t* ldx) {
+  BGGE_REQUIRE(L > 0 && ldx, "marker_ld: bad arguments");
+  *ldx = round_up(L, 128);
+  return OK;
+}
+int bgge_marker_cols(int64_t p, int64_t* p_pad) {
+  BGGE_REQUIRE(p > 0 && p_pad, "marker_cols: bad arguments");
+  *p_pad = round_up(p, 16);
+  return OK;
+}
+
+int bgge_dev_gram(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tile_row0, int64_t tile_row1,
+                  double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, void* stream) {
+  BGGE_TRY(ensure_device());
+  const int64_t T = (L + 127) / 128;
+  BGGE_REQUIRE(dX && dS && L > 0, "dev_gram: NULL pointer or empty matrix");
+  BGGE_REQUIRE(0 <= tile_row0 && tile_row0 <= tile_row1 && tile_row1 <= T, "dev_gram: tile rows [%lld,%lld) outside [0,%lld)",
+               (long long)tile_row0, (long long)tile_row1, (long long)T);
+  BGGE_REQUIRE(divisor != 0.0, "dev_gram: zero divisor");
+  DevBuf<int2> tiles;
+  int ntiles = 0;
+  BGGE_TRY(build_tiles(tile_row0, tile_row1, tiles, &ntiles, as_stream(stream)));
+  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, dS, lds, row_off, divisor, mirror, as_stream(stream)));
+  BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));   // the tile list is freed on return
+  return OK;
+}
+
+int bgge_dev_symmetrize(double* dS, int64_t lds, int64_t L, void* stream) {
+  BGGE_TRY(ensure_device());
+  return symmetrize_launch(dS, lds, L, as_stream(stream));
+}
+
+int bgge_dev_gk_distance(double* dS, int64_t lds, int64_t L, void* stream) {
+  BGGE_TRY(ensure_device());
+  DevBuf<double> diag;
+  BGGE_CUDA(diag.alloc((size_t)L));
+  BGGE_TRY(gk_distance_launch(dS, lds, L, diag.p, as_stream(stream)));
+  BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return OK;
+}
+
+int bgge_dev_quantile7(const double* dD, int64_t ldd, int64_t L, double prob, double* d_q, double* h_q, void* stream) {
+  BGGE_TRY(ensure_device());
+  DevBuf<unsigned char> scratch;
+  DevBuf<double> qtmp;
+  BGGE_CUDA(scratch.alloc(quantile_scratch_bytes()));
+  if (!d_q) {
+    BGGE_CUDA(qtmp.alloc(1));
+    d_q = qtmp.p;
+  }
+  BGGE_TRY(quantile7_launch(dD, ldd, L, prob, scratch.p, d_q, as_stream(stream)));
+  if (h_q) BGGE_CUDA(cudaMemcpyAsync(h_q, d_q, sizeof(double), cudaMemcpyDeviceToHost, as_stream(stream)));
+  BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return OK;
+}
+
+int bgge_dev_gk_exp(const double* dD, int64_t ldd, int64_t L, double bw, const double* d_q, double* dK0, int64_t ldk,
+                    void* stream) {
+  BGGE_TRY(ensure_device());
+  return gk_exp_launch(dD, ldd, L, bw, d_q, dK0, ldk, as_stream(stream));
+}
+
+int bgge_dev_expand(const double* dK0, int64_t ldk, int64_t L, const int32_t* d_gid, const int32_t* d_env, int64_t n,
+                    int mode, int env_k, double* dOut, int64_t ldo, void* stream) {
+  BGGE_TRY(ensure_device());
+  (void)L;
+  return expand_launch(dK0, ldk, d_gid, d_env, n, mode, env_k, dOut, ldo, as_stream(stream));
+}
+
+int bgge_getk_base(const double* X, int64_t L, int64_t p, int kind, const double* bandwidth, int nb, double quantil,
+                   double* out_K0, double* out_q) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(X && out_K0 && L > 0 && p > 0, "getk_base: NULL pointer or empty matrix");
+  DevBuf<double> dX;
+  int64_t ldx, p_pad;
+  BGGE_TRY(upload_markers(X, L, p, dX, &ldx, &p_pad));
+  std::vector<DevBuf<double>> K0;
+  BGGE_TRY(base_kernels_device(dX.p, ldx, L, p, p_pad, kind, bandwidth, nb, quantil, K0, out_q, nullptr));
+  for (size_t b = 0; b < K0.size(); ++b)
+    BGGE_CUDA(cudaMemcpy(out_K0 + b * (size_t)L * L, K0[b].p, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+static int check_codes(const int32_t* v, int64_t n, int64_t levels, const char* what) {
+  for (int64_t i = 0; i < n; ++i)
+    BGGE_REQUIRE(v[i] >= 0 && v[i] < levels, "%s[%lld]=%d outside [0,%lld)", what, (long long)i, v[i], (long long)levels);
+  return OK;
+}
+
+int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int32_t* env, int64_t n, int mode,
+                     int env_k, double* out) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(gid && out && L > 0 && n > 0, "getk_expand: NULL pointer or empty input");
+  BGGE_REQUIRE(mode == BGGE_EXPAND_GI || K0 != nullptr, "getk_expand: K0 is NULL");
+  BGGE_REQUIRE((mode != BGGE_EXPAND_GE && mode != BGGE_EXPAND_ENV) || env != nullptr, "getk_expand: env is NULL");
+  BGGE_TRY(check_codes(gid, n, L, "gid"));
+  DevBuf<double> dK0, dOut;
+  DevBuf<int> dgid, denv;
+  if (K0) {
+    BGGE_CUDA(dK0.alloc((size_t)L * L));
+    BGGE_CUDA(cudaMemcpy(dK0.p, K0, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  BGGE_CUDA(dgid.alloc((size_t)n));
+  BGGE_CUDA(cudaMemcpy(dgid.p, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  if (env) {
+    BGGE_CUDA(denv.alloc((size_t)n));
+    BGGE_CUDA(cudaMemcpy(denv.p, env, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  BGGE_CUDA(dOut.alloc((size_t)n * n));
+  BGGE_TRY(expand_launch(dK0.p, L, dgid.p, denv.p, n, mode, env_k, dOut.p, n, nullptr));
+  BGGE_CUDA(cudaMemcpy(out, dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+int bgge_getk(const double* X, int64_t L, int64_t p, int kind, const double* bandwidth, int nb, double quantil,
+              const int32_t* gid, const int32_t* env, int64_t n, int n_env, int model, int intercept_random,
+              double* const* out, int n_out, double* out_q) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(X && gid && out && L > 0 && p > 0 && n > 0, "getk: NULL pointer or empty input");
+  BGGE_REQUIRE(model >= 0 && model <= 2, "Model selected is not available ");
+  BGGE_REQUIRE(model == 0 || (env != nullptr && n_env >= 1), "getk: env codes needed for MDs/MDe");
+  BGGE_TRY(check_codes(gid, n, L, "gid"));
+  if (env) BGGE_TRY(check_codes(env, n, n_env, "env"));
+  const int nbase = kind == BGGE_KERNEL_GB ? 1 : nb;
+  const int expect = nbase * (model == 0 ? 1 : model == 1 ? 2 : 1 + n_env) + (intercept_random ? 1 : 0);
+  BGGE_REQUIRE(n_out == expect, "getk: %d output matrices supplied, model needs %d", n_out, expect);
+
+  std::vector<DevBuf<double>> K0;
+  {
+    DevBuf<double> dX;
+    int64_t ldx, p_pad;
+    BGGE_TRY(upload_markers(X, L, p, dX, &ldx, &p_pad));
+    BGGE_TRY(base_kernels_device(dX.p, ldx, L, p, p_pad, kind, bandwidth, nb, quantil, K0, out_q, nullptr));
+  }   // markers released before the n x n expansions are allocated
+  DevBuf<int> dgid, denv;
+  DevBuf<double> dOut;
+  BGGE_CUDA(dgid.alloc((size_t)n));
+  BGGE_CUDA(cudaMemcpy(dgid.p, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  if (env) {
+    BGGE_CUDA(denv.alloc((size_t)n));
+    BGGE_CUDA(cudaMemcpy(denv.p, env, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  BGGE_CUDA(dOut.alloc((size_t)n * n));
+  int o = 0;
+  auto emit = [&](const double* k0, int mode, int k) -> int {
+    BGGE_TRY(expand_launch(k0, L, dgid.p, denv.p, n, mode, k, dOut.p, n, nullptr));
+    BGGE_CUDA(cudaMemcpy(out[o++], dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return OK;
+  };
+  for (int b = 0; b < nbase; ++b) BGGE_TRY(emit(K0[(size_t)b].p, BGGE_EXPAND_G, 0));
+  if (model == 1)
+    for (int b = 0; b < nbase; ++b) BGGE_TRY(emit(K0[(size_t)b].p, BGGE_EXPAND_GE, 0));
+  if (model == 2)
+    for (int b = 0; b < nbase; ++b)
+      for (int k = 0; k < n_env; ++k) BGGE_TRY(emit(K0[(size_t)b].p, BGGE_EXPAND_ENV, k));
+  if (intercept_random) BGGE_TRY(emit(nullptr, BGGE_EXPAND_GI, 0));
+  return OK;
+}
+
+// ====================================================================== eigen
+int bgge_dev_eig(double* dA, int64_t m, int64_t lda, double tol, int canonical_sign, double* d_s, double* dU,
+                 int64_t ldu, int64_t max_cols, int64_t* out_nr, void* stream) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(dA && d_s && out_nr, "dev_eig: NULL pointer");
+  DevBuf<double> W;
+  BGGE_CUDA(W.alloc((size_t)m));
+  int64_t nr = 0;
+  BGGE_TRY(eig_decompose(dA, m, lda, tol, W.p, &nr, as_stream(stream)));
+  *out_nr = nr;
+  if (dU) {
+    BGGE_REQUIRE(nr <= max_cols, "dev_eig: %lld eigenvalues exceed tol but output holds %lld columns", (long long)nr,
+                 (long long)max_cols);
+    BGGE_TRY(eig_compact(dA, lda, W.p, m, nr, canonical_sign, d_s, dU, ldu, as_stream(stream)));
+  } else if (nr > 0) {
+    DevBuf<double> tmp;   // eigenvalues only: compact into a 1-row dummy is wasteful; reverse on host
+    std::vector<double> hW((size_t)m), desc((size_t)nr);
+    BGGE_CUDA(cudaMemcpyAsync(hW.data(), W.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, as_stream(stream)));
+    BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    for (int64_t c = 0; c < nr; ++c) desc[(size_t)c] = hW[(size_t)(m - 1 - c)];
+    BGGE_CUDA(cudaMemcpy(d_s, desc.data(), (size_t)nr * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return OK;
+}
+
+int bgge_eig(const double* K, int64_t m, int64_t ldk, double tol, int canonical_sign, double* out_s, double* out_U,
+             int64_t* out_nr) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(K && out_nr && m > 0 && ldk >= m, "eig: NULL pointer or bad dimensions");
+  DevBuf<double> dA, dS, dU;
+  BGGE_CUDA(dA.alloc((size_t)m * m));
+  BGGE_CUDA(dS.alloc((size_t)m));
+  BGGE_CUDA(cudaMemcpy2D(dA.p, (size_t)m * sizeof(double), K, (size_t)ldk * sizeof(double), (size_t)m * sizeof(double),
+                         (size_t)m, cudaMemcpyHostToDevice));
+  if (out_U) BGGE_CUDA(dU.alloc((size_t)m * m));
+  int64_t nr = 0;
+  BGGE_TRY(bgge_dev_eig(dA.p, m, m, tol, canonical_sign, dS.p, dU.p, m, m, &nr, nullptr));
+  *out_nr = nr;
+  if (out_s && nr > 0) BGGE_CUDA(cudaMemcpy(out_s, dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_U && nr > 0) BGGE_CUDA(cudaMemcpy(out_U, dU.p, (size_t)m * nr * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+// ====================================================================== Gibbs handle
+int bgge_gibbs_create(int64_t n, int nk, int q, void* stream, bgge_gibbs** out) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(out != nullptr, "gibbs_create: NULL output");
+  BGGE_REQUIRE(n > 1 && nk >= 1 && nk <= MAXK && q >= 0 && q <= 1024, "gibbs_create: bad sizes n=%lld nk=%d q=%d",
+               (long long)n, nk, q);
+  std::unique_ptr<bgge_gibbs> h(new (std::nothrow) bgge_gibbs());
+  BGGE_REQUIRE(h != nullptr, "gibbs_create: out of host memory");
+  Gibbs& g = h->g;
+  g.n = n;
+  g.nk = nk;
+  g.q = q;
+  g.kernels.resize((size_t)nk);
+  BGGE_CUDA(cudaGetDevice(&g.device));
+  if (stream) {
+    g.stream = as_stream(stream);
+  } else {
+    BGGE_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.own_stream = true;
+  }
+  *out = h.release();
+  return OK;
+}
+
+void bgge_gibbs_destroy(bgge_gibbs* h) { delete h; }
+
+#define BGGE_HANDLE(h)                                                    \
+  BGGE_REQUIRE((h) != nullptr, "NULL gibbs handle");                     \
+  BGGE_CUDA(cudaSetDevice((h)->g.device))
+
+int bgge_gibbs_set_y(bgge_gibbs* h, const double* y, const uint8_t* na_mask) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(y != nullptr, "gibbs_set_y: NULL y");
+  Gibbs& g = h->g;
+  g.y_host.assign(y, y + g.n);
+  if (na_mask) g.na_host.assign(na_mask, na_mask + g.n); else g.na_host.clear();
+  return OK;
+}
+
+int bgge_gibbs_set_xf(bgge_gibbs* h, const double* XF) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.q > 0 && XF != nullptr, "gibbs_set_xf: handle was created with q=0 or XF is NULL");
+  g.xf_host.assign(XF, XF + g.n * g.q);
+  return OK;
+}
+
+int bgge_gibbs_set_kernel(bgge_gibbs* h, int j, int type, double mean_diag) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(j >= 0 && j < g.nk, "gibbs_set_kernel: kernel index %d outside [0,%d)", j, g.nk);
+  BGGE_REQUIRE(type == BGGE_TYPE_D || type == BGGE_TYPE_BD, "Matrix should be of types BD or D");
+  BGGE_REQUIRE(mean_diag > 0.0 && std::isfinite(mean_diag), "gibbs_set_kernel: mean(diag(K)) must be positive");
+  g.kernels[(size_t)j].mean_diag = mean_diag;
+  return OK;
+}
+
+int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64_t nr, const double* s, const double* U,
+                         int64_t ldu, int on_device) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "gibbs_add_block: handle already initialised");
+  BGGE_REQUIRE(j >= 0 && j < g.nk, "gibbs_add_block: kernel index %d outside [0,%d)", j, g.nk);
+  BGGE_REQUIRE(s && U && rows > 0 && nr > 0 && pos0 >= 0 && pos0 + rows <= g.n && ldu >= rows,
+               "gibbs_add_block: bad block pos0=%lld rows=%lld nr=%lld ldu=%lld", (long long)pos0, (long long)rows,
+               (long long)nr, (long long)ldu);
+  for (int64_t c = 0; c < nr; ++c) BGGE_REQUIRE(s[c] > 0.0, "gibbs_add_block: eigenvalue %lld is not positive", (long long)c);
+  HostKernel& hk = g.kernels[(size_t)j];
+  HostBlock bl;
+  bl.pos0 = pos0;
+  bl.rows = rows;
+  bl.nr = nr;
+  if (on_device) {
+    BGGE_REQUIRE(ldu % 2 == 0 && (reinterpret_cast<uintptr_t>(U) & 15u) == 0,
+                 "gibbs_add_block: device U needs an even leading dimension and a 16-byte aligned base");
+    bl.dU = const_cast<double*>(U);
+    bl.ldu = ldu;
+    bl.owns = false;
+  } else {
+    bl.ldu = round_up(rows, 16);
+    BGGE_CUDA(cudaMalloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+    bl.owns = true;
+    hk.blocks.push_back(bl);   // owned from here on (freed by the handle even on failure below)
+    BGGE_CUDA(cudaMemset(bl.dU, 0, (size_t)bl.ldu * nr * sizeof(double)));
+    BGGE_CUDA(cudaMemcpy2D(bl.dU, (size_t)bl.ldu * sizeof(double), U, (size_t)ldu * sizeof(double),
+                           (size_t)rows * sizeof(double), (size_t)nr, cudaMemcpyHostToDevice));
+    hk.s_host.insert(hk.s_host.end(), s, s + nr);
+    return OK;
+  }
+  hk.blocks.push_back(bl);
+  hk.s_host.insert(hk.s_host.end(), s, s + nr);
+  return OK;
+}
+
+int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K, int64_t ldk, int on_device,
+                                 const int64_t* ne, int n_ne, double tol, int canonical_sign) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "gibbs_add_kernel_matrix: handle already initialised");
+  BGGE_REQUIRE(j >= 0 && j < g.nk && K != nullptr && ldk >= g.n, "gibbs_add_kernel_matrix: bad arguments");
+  BGGE_REQUIRE(type == BGGE_TYPE_D || type == BGGE_TYPE_BD, "Matrix should be of types BD or D");
+  const int64_t n = g.n;
+  // mean(diag(K))  (R/BGGE.R:249)
+  std::vector<double> diag((size_t)n);
+  BGGE_CUDA(cudaMemcpy2D(diag.data(), sizeof(double), K, (size_t)(ldk + 1) * sizeof(double), sizeof(double), (size_t)n,
+                         on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+  long double tr = 0.0L;
+  for (double d : diag) tr += d;
+  BGGE_TRY(bgge_gibbs_set_kernel(h, j, type, (double)(tr / (long double)n)));
+
+  std::vector<std::pair<int64_t, int64_t>> spans;   // (pos0, rows)
+  if (type == BGGE_TYPE_D) {
+    spans.push_back({0, n});
+  } else {
+    BGGE_REQUIRE(ne != nullptr && n_ne > 1, "ne invalid. For type BD, number of subjects in each sub matrices should be provided");
+    int64_t pos = 0;
+    for (int k = 0; k < n_ne; ++k) {
+      BGGE_REQUIRE(ne[k] > 0 && pos + ne[k] <= n, "gibbs_add_kernel_matrix: ne does not partition the rows of y");
+      spans.push_back({pos, ne[k]});
+      pos += ne[k];
+    }
+  }
+  HostKernel& hk = g.kernels[(size_t)j];
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (auto& sp : spans) {
+    const int64_t m = sp.second;
+    DevBuf<double> dA, dW, dS;
+    BGGE_CUDA(dA.alloc((size_t)m * m));
+    BGGE_CUDA(dW.alloc((size_t)m));
+    BGGE_CUDA(cudaMemcpy2D(dA.p, (size_t)m * sizeof(double), K + sp.first + sp.first * ldk, (size_t)ldk * sizeof(double),
+                           (size_t)m * sizeof(double), (size_t)m, kind));
+    int64_t nr = 0;
+    BGGE_TRY(eig_decompose(dA.p, m, m, tol, dW.p, &nr, g.stream));
+    if (nr == 0) continue;                                          // R/BGGE.R:162
+    HostBlock bl;
+    bl.pos0 = sp.first;
+    bl.rows = m;
+    bl.nr = nr;
+    bl.ldu = round_up(m, 16);
+    BGGE_CUDA(cudaMalloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+    bl.owns = true;
+    hk.blocks.push_back(bl);
+    BGGE_CUDA(dS.alloc((size_t)nr));
+    BGGE_TRY(eig_compact(dA.p, m, dW.p, m, nr, canonical_sign, dS.p, bl.dU, bl.ldu, g.stream));
+    std::vector<double> s((size_t)nr);
+    BGGE_CUDA(cudaMemcpyAsync(s.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    BGGE_CUDA(cudaStreamSynchronize(g.stream));
+    hk.s_host.insert(hk.s_host.end(), s.begin(), s.end());
+  }
+  BGGE_REQUIRE(!hk.blocks.empty(), "kernel %d: no eigenvalue exceeds tol in any block", j);
+  return OK;
+}
+
+int bgge_gibbs_set_tape(bgge_gibbs* h, const double* normals, int64_t n_normals, const double* chisq, int64_t n_chisq) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(normals && chisq && n_normals > 0 && n_chisq > 0, "gibbs_set_tape: empty tape");
+  // one spare slot: the intercept of iteration ite+1 is drawn ahead and never used
+  BGGE_CUDA(g.ztape.alloc((size_t)n_normals + 1));
+  BGGE_CUDA(g.ctape.alloc((size_t)n_chisq + 1));
+  BGGE_CUDA(cudaMemset(g.ztape.p + n_normals, 0, sizeof(double)));
+  BGGE_CUDA(cudaMemset(g.ctape.p + n_chisq, 0, sizeof(double)));
+  BGGE_CUDA(cudaMemcpy(g.ztape.p, normals, (size_t)n_normals * sizeof(double), cudaMemcpyHostToDevice));
+  BGGE_CUDA(cudaMemcpy(g.ctape.p, chisq, (size_t)n_chisq * sizeof(double), cudaMemcpyHostToDevice));
+  g.zt_len = n_normals;
+  g.ct_len = n_chisq;
+  return OK;
+}
+
+int bgge_gibbs_init(bgge_gibbs* h, int64_t ite, int64_t burn, int64_t thin, double R2, int rng_mode, uint64_t seed,
+                    uint32_t chain) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "gibbs_init: handle already initialised");
+  BGGE_REQUIRE(rng_mode == BGGE_RNG_PHILOX || rng_mode == BGGE_RNG_TAPE, "gibbs_init: unknown rng mode %d", rng_mode);
+  BGGE_REQUIRE(rng_mode != BGGE_RNG_TAPE || g.zt_len > 0, "gibbs_init: tape mode without a tape");
+  g.ite = ite;
+  g.burn = burn;
+  g.thin = thin;
+  g.R2 = R2;
+  g.draw.mode = rng_mode;
+  g.draw.seed = seed;
+  g.draw.chain = chain;
+  return gibbs_init(&g);
+}
+
+int bgge_gibbs_run(bgge_gibbs* h, int64_t iters) {
+  BGGE_HANDLE(h);
+  return gibbs_run(&h->g, iters);
+}
+
+int bgge_gibbs_sync(bgge_gibbs* h) {
+  BGGE_HANDLE(h);
+  BGGE_CUDA(cudaStreamSynchronize(h->g.stream));
+  return OK;
+}
+
+int bgge_gibbs_sizes(bgge_gibbs* h, int64_t* nr, int64_t* n_cum, int64_t* n_na, int64_t* tape_normals,
+                     int64_t* tape_chisq) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  int64_t sum_nr = 0;
+  for (int j = 0; j < g.nk; ++j) {
+    int64_t t = 0;
+    for (auto& b : g.kernels[(size_t)j].blocks) t += b.nr;
+    if (nr) nr[j] = t;
+    sum_nr += t;
+  }
+  int64_t nna = g.n_na;
+  if (!g.initialised) {
+    nna = 0;
+    for (int64_t i = 0; i < (int64_t)g.y_host.size(); ++i)
+      nna += g.na_host.size() == g.y_host.size() ? (g.na_host[(size_t)i] != 0) : std::isnan(g.y_host[(size_t)i]);
+  }
+  if (n_cum) *n_cum = g.initialised ? g.ncum : 0;
+  if (n_na) *n_na = nna;
+  const int64_t ite = g.ite;
+  if (tape_normals) *tape_normals = (int64_t)g.nk * g.n + ite * (1 + g.q + sum_nr + nna);
+  if (tape_chisq) *tape_chisq = ite * (g.nk + 1);
+  return OK;
+}
+
+int bgge_gibbs_state(bgge_gibbs* h, double* mu, double* sigsq, double* sigb, double* u, double* e, double* bet) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised, "gibbs_state: handle not initialised");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  Scal sc;
+  BGGE_CUDA(cudaMemcpy(&sc, g.scal.p, sizeof(Scal), cudaMemcpyDeviceToHost));
+  // The scalar step has already drawn the intercept of iteration done+1 (sc.mu / sc.shift); what R
+  // holds after iteration `done` is mu_done and temp = r - (mu_done - mu0).
+  if (sigsq) *sigsq = sc.sigsq;
+  if (sigb) std::memcpy(sigb, sc.sigb, sizeof(double) * (size_t)g.nk);
+  if (mu) *mu = sc.mu_done;
+  if (u) BGGE_CUDA(cudaMemcpy(u, g.u.p, (size_t)g.n * g.nk * sizeof(double), cudaMemcpyDeviceToHost));
+  if (e) {
+    BGGE_CUDA(cudaMemcpy(e, g.r.p, (size_t)g.n * sizeof(double), cudaMemcpyDeviceToHost));
+    const double sh = sc.mu_done - sc.mu0;
+    for (int64_t i = 0; i < g.n; ++i) e[i] -= sh;
+  }
+  if (bet && g.q > 0) BGGE_CUDA(cudaMemcpy(bet, g.bet.p, (size_t)g.q * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+int bgge_gibbs_chain(bgge_gibbs* h, double* mu, double* varE, double* varU, double* bet) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised, "gibbs_chain: handle not initialised");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  const size_t nc = (size_t)g.ncum;
+  if (nc == 0) return OK;
+  if (mu) BGGE_CUDA(cudaMemcpy(mu, g.chain_mu.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (varE) BGGE_CUDA(cudaMemcpy(varE, g.chain_varE.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (varU) BGGE_CUDA(cudaMemcpy(varU, g.chain_varU.p, nc * g.nk * sizeof(double), cudaMemcpyDeviceToHost));
+  if (bet && g.q > 0) BGGE_CUDA(cudaMemcpy(bet, g.chain_bet.p, nc * g.q * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+int bgge_gibbs_summary(bgge_gibbs* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd,
+                       double* varu, double* varu_sd, double* y) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised, "gibbs_summary: handle not initialised");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  const int64_t n = g.n;
+  const size_t nc = (size_t)g.ncum;
+  std::vector<double> cmu(nc), cve(nc), cvu(nc * g.nk), cbet(nc * std::max(1, g.q));
+  BGGE_TRY(bgge_gibbs_chain(h, cmu.data(), cve.data(), cvu.data(), cbet.data()));
+  // draw <- seq(ite)[seq(ite) %% thin == 0] > burn   (R/BGGE.R:408), limited to what has been run
+  std::vector<size_t> kept;
+  for (size_t slot = 0; slot < nc; ++slot) {
+    const int64_t it = (int64_t)(slot + 1) * g.thin;
+    if (it > g.burn && it <= g.done) kept.push_back(slot);
+  }
+  auto pick = [&](const double* src) {
+    std::vector<double> v;
+    v.reserve(kept.size());
+    for (size_t s : kept) v.push_back(src[s]);
+    return v;
+  };
+  const size_t k = kept.size();
+  const double mu_est = mean_sd(pick(cmu.data()), nullptr);
+  double sd = NAN;
+  const double ve = mean_sd(pick(cve.data()), &sd);
+  if (varE) *varE = ve;
+  if (varE_sd) *varE_sd = sd;
+  for (int j = 0; j < g.nk; ++j) {
+    double sdj = NAN;
+    const double m = mean_sd(pick(cvu.data() + (size_t)j * nc), &sdj);
+    if (varu) varu[j] = m;
+    if (varu_sd) varu_sd[j] = sdj;
+  }
+  std::vector<double> um, m2;
+  if (yHat || u || u_sd) {
+    um.resize((size_t)n * g.nk);
+    BGGE_CUDA(cudaMemcpy(um.data(), g.umean.p, um.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (k == 0) std::fill(um.begin(), um.end(), NAN);
+    if (u) std::memcpy(u, um.data(), um.size() * sizeof(double));
+  }
+  if (u_sd) {
+    m2.resize((size_t)n * g.nk);
+    BGGE_CUDA(cudaMemcpy(m2.data(), g.um2.p, m2.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m2.size(); ++i) u_sd[i] = k > 1 ? std::sqrt(m2[i] / (double)(k - 1)) : NAN;
+  }
+  if (yHat) {
+    std::vector<double> bmean((size_t)std::max(1, g.q), 0.0);
+    for (int c = 0; c < g.q; ++c) {
+      long double a = 0.0L;
+      for (size_t s : kept) a += cbet[s * (size_t)g.q + (size_t)c];
+      bmean[(size_t)c] = k ? (double)(a / (long double)k) : NAN;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+      double v = mu_est;                                            // R/BGGE.R:410-411
+      if (g.q > 0) {
+        double xb = 0.0;
+        for (int c = 0; c < g.q; ++c) xb += g.xf_host[(size_t)(i + (int64_t)c * n)] * bmean[(size_t)c];
+        v += xb;                                                    // R/BGGE.R:414-415
+      }
+      double us = 0.0;
+      for (int j = 0; j < g.nk; ++j) us += um[(size_t)j * n + (size_t)i];
+      yHat[i] = v + us;                                             // R/BGGE.R:418-419
+    }
+  }
+  if (y) BGGE_CUDA(cudaMemcpy(y, g.y.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+// ====================================================================== one-shot BGGE()
+int bgge_fit(const double* y, const uint8_t* na_mask, int64_t n, const double* const* K, const int* types, int nk,
+             const double* XF, int q, const int64_t* ne, int n_ne, int64_t ite, int64_t burn, int64_t thin, double tol,
+             double R2, int rng_mode, uint64_t seed, const double* normals, int64_t n_normals, const double* chisq,
+             int64_t n_chisq, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd, double* varu,
+             double* varu_sd, double* y_out, double* chain_mu, double* chain_varE, double* chain_varU) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(y && K && types && nk >= 1, "fit: NULL pointer");
+  bool any_bd = false;
+  for (int j = 0; j < nk; ++j) {
+    BGGE_REQUIRE(types[j] == BGGE_TYPE_D || types[j] == BGGE_TYPE_BD, "Matrix should be of types BD or D");   // R/BGGE.R:220
+    any_bd |= types[j] == BGGE_TYPE_BD;
+  }
+  BGGE_REQUIRE(!(any_bd && n_ne <= 1), "Type BD should be used only for block diagonal matrices");            // R/BGGE.R:223
+  bgge_gibbs* h = nullptr;
+  BGGE_TRY(bgge_gibbs_create(n, nk, q, nullptr, &h));
+  std::unique_ptr<bgge_gibbs, void (*)(bgge_gibbs*)> guard(h, bgge_gibbs_destroy);
+  BGGE_TRY(bgge_gibbs_set_y(h, y, na_mask));
+  if (q > 0) BGGE_TRY(bgge_gibbs_set_xf(h, XF));
+  for (int j = 0; j < nk; ++j)
+    BGGE_TRY(bgge_gibbs_add_kernel_matrix(h, j, types[j], K[j], n, 0, ne, n_ne, tol, 1));
+  if (rng_mode == BGGE_RNG_TAPE) BGGE_TRY(bgge_gibbs_set_tape(h, normals, n_normals, chisq, n_chisq));
+  BGGE_TRY(bgge_gibbs_init(h, ite, burn, thin, R2, rng_mode, seed, 0));
+  BGGE_TRY(bgge_gibbs_run(h, ite));
+  BGGE_TRY(bgge_gibbs_summary(h, yHat, varE, varE_sd, u, u_sd, varu, varu_sd, y_out));
+  BGGE_TRY(bgge_gibbs_chain(h, chain_mu, chain_varE, chain_varU, nullptr));
+  return OK;
+}
+
+// ====================================================================== test hooks
+int bgge_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  BGGE_TRY(ensure_device());
+  DevBuf<uint32_t> d;
+  BGGE_CUDA(d.alloc(10));
+  BGGE_CUDA(cudaMemcpy(d.p, ctr, 4 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  BGGE_CUDA(cudaMemcpy(d.p + 4, key, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  philox_test_kernel<<<1, 1>>>(d.p, d.p + 4, d.p + 6);
+  BGGE_CUDA(cudaGetLastError());
+  BGGE_CUDA(cudaMemcpy(out, d.p + 6, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+int bgge_test_draws(uint64_t seed, uint32_t chain, int64_t n, double* normals, double df, double* chisq) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(n > 0, "test_draws: n must be positive");
+  DrawCfg dc{};
+  dc.mode = 0;
+  dc.seed = seed;
+  dc.chain = chain;
+  DevBuf<double> z, c;
+  if (normals) BGGE_CUDA(z.alloc((size_t)n));
+  if (chisq) BGGE_CUDA(c.alloc((size_t)n));
+  draws_test_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dc, n, z.p, df, c.p);
+  BGGE_CUDA(cudaGetLastError());
+  if (normals) BGGE_CUDA(cudaMemcpy(normals, z.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (chisq) BGGE_CUDA(cudaMemcpy(chisq, c.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+}  // extern "C"

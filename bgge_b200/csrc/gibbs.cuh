@@ -1,0 +1,113 @@
+// Device-resident Gibbs sampler state for BGGE() (R/BGGE.R:229-403).  Internal header.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace bgge {
+
+constexpr int MAXK = 64;   // max number of kernels (random effects) in one model
+constexpr double NU = 3.0; // R/BGGE.R:245
+
+// RNG stream ids (Philox counter word 3); kernel j's coefficient draws use stream j.
+enum : uint32_t {
+  STREAM_MU = 0xFFFF0001u,
+  STREAM_XF = 0xFFFF0002u,
+  STREAM_NA = 0xFFFF0003u,
+  STREAM_CHI_E = 0xFFFF0004u,
+  STREAM_INIT_U = 0xFFFF0005u,
+  STREAM_CHI_K = 0xFFFE0000u   // + kernel index
+};
+
+struct DrawCfg {
+  int mode;                      // 0 = device Philox, 1 = injected tapes
+  unsigned long long seed;
+  unsigned int chain;
+  const double* zt;              // normals tape (device)
+  const double* ct;              // chi-square tape (device)
+  long long z_init;              // nk * n  (init normals precede the loop)
+  long long z_per_it;            // 1 + q + sum nr + nNa
+  long long z_off_xf;            // 1
+  long long z_off_na;            // 1 + q + sum nr
+  int c_per_it;                  // nk + 1
+};
+
+// chain scalars living in device memory
+struct Scal {
+  double mu, mu0, shift, sigsq, tau, Sce;
+  double mu_done;                // intercept of the last finished iteration (mu is one draw ahead)
+  double sigb[MAXK];
+  double Sc[MAXK];
+  long long it;                  // iteration currently being computed (1-based); 0 before init
+};
+
+struct ATask {                   // CT eigen-columns of one block, all of its rows
+  const double* U;
+  long long ldu;
+  int rows, pos0, ncols, col_off;
+};
+
+struct BTask {                   // one row tile of one block (or of a gap: nr == 0)
+  const double* U;
+  long long ldu;
+  int rows;                      // valid rows in this tile
+  int row0;                      // global row of the tile's first row
+  int urow0;                     // row offset inside the block
+  int nr, col_off;
+};
+
+struct HostBlock {
+  int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, col_off = 0;
+  double* dU = nullptr;
+  bool owns = false;
+};
+
+struct HostKernel {
+  std::vector<HostBlock> blocks;
+  int64_t nr_total = 0;
+  double mean_diag = 1.0;
+  DevBuf<double> s;              // concatenated eigenvalues
+  DevBuf<double> b;              // concatenated coefficients
+  DevBuf<double> bpart;          // per A-task partial sums of b^2/s
+  DevBuf<ATask> atasks;
+  DevBuf<BTask> btasks;
+  int n_atasks = 0, n_btasks = 0, ct = 8, cs = 1;
+  std::vector<double> s_host;
+  long long z_off = 0;           // offset of this kernel's normals inside an iteration
+};
+
+struct Gibbs {
+  int64_t n = 0;
+  int nk = 0, q = 0, n_chains = 1;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<HostKernel> kernels;
+  // data
+  std::vector<double> y_host;
+  std::vector<unsigned char> na_host;
+  std::vector<double> xf_host;
+  int64_t n_na = 0;
+  // device state
+  DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean;
+  DevBuf<int> na_idx;
+  DevBuf<Scal> scal;
+  DevBuf<double> chain_mu, chain_varE, chain_varU, chain_bet;
+  DevBuf<double> ztape, ctape;
+  int64_t zt_len = 0, ct_len = 0;
+  // run config
+  int64_t ite = 0, burn = 0, thin = 1, ncum = 0, done = 0;
+  double R2 = 0.5;
+  DrawCfg draw{};
+  bool initialised = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
+  int xf_blocks = 0;
+
+  ~Gibbs();
+};
+
+int gibbs_init(Gibbs* g);
+int gibbs_run(Gibbs* g, int64_t iters);
+
+}  // namespace bgge

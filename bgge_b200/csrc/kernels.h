@@ -1,0 +1,28 @@
+// Internal (non-ABI) launch interfaces between the translation units of libbgge_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace bgge {
+
+// gram.cu
+int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, const int2* d_tiles, int ntiles,
+                double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st);
+
+// getk.cu
+int symmetrize_launch(double* dS, int64_t lds, int64_t L, cudaStream_t st);
+int gk_distance_launch(double* dS, int64_t lds, int64_t L, double* d_diag_scratch, cudaStream_t st);
+size_t quantile_scratch_bytes();
+int quantile7_launch(const double* dD, int64_t ldd, int64_t L, double prob, void* d_scratch, double* d_q,
+                     cudaStream_t st);
+int gk_exp_launch(const double* dD, int64_t ldd, int64_t L, double bw, const double* d_q, double* dK0, int64_t ldk,
+                  cudaStream_t st);
+int expand_launch(const double* dK0, int64_t ldk, const int* d_gid, const int* d_env, int64_t n, int mode, int kenv,
+                  double* dOut, int64_t ldo, cudaStream_t st);
+
+// eig.cu
+int eig_decompose(double* dA, int64_t m, int64_t lda, double tol, double* d_W, int64_t* nr_out, cudaStream_t st);
+int eig_compact(const double* dV, int64_t ldv, const double* d_W, int64_t m, int64_t nr, int canonical, double* d_s,
+                double* dU, int64_t ldu, cudaStream_t st);
+
+}  // namespace bgge

@@ -1,0 +1,159 @@
+"""getK(): kernel construction for G x E models -- host mirror of R/getK.R:95-237.
+
+Signature, argument meaning, returned structure, names and error behaviour follow the
+reference; all numeric work (R/getK.R:136-149, 138/148/173, 199-201, 207-218, 232) runs
+in libbgge_b200 on the GPU.  What stays here is what stays in R: factor coding,
+validation, naming.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+
+_MODELS = {"SM": 0, "MM": 0, "MDs": 1, "MDe": 2}
+
+
+def _factor(col):
+    """factor(): sorted unique levels, 0-based codes (R/getK.R:101-104)."""
+    col = np.asarray(col)
+    if col.dtype == object:
+        col = np.array([str(v) for v in col])
+    levels, codes = np.unique(col, return_inverse=True)
+    return [v.item() if hasattr(v, "item") else v for v in levels], np.ascontiguousarray(codes, dtype=np.int32)
+
+
+def _columns(Y):
+    if hasattr(Y, "iloc"):
+        return np.asarray(Y.iloc[:, 0]), np.asarray(Y.iloc[:, 1])
+    Ya = np.asarray(Y, dtype=object)
+    if Ya.ndim != 2 or Ya.shape[1] < 2:
+        raise ValueError("Y must have at least two columns (environment, genotype)")
+    return Ya[:, 0], Ya[:, 1]
+
+
+def _named_matrix(km):
+    if isinstance(km, tuple):
+        mat, names = km
+        return np.asarray(mat, dtype=np.float64), [str(v) for v in names]
+    if hasattr(km, "index") and hasattr(km, "to_numpy"):
+        return km.to_numpy(dtype=np.float64), [str(v) for v in km.index]
+    return None, None
+
+
+def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM", "MM", "MDs", "MDe"), quantil=0.5,
+         intercept_random=False, rownames=None):
+    """Create kernels for the genomic G x E models of BGGE().
+
+    Y        : rows of (environment, genotype, ...) -- DataFrame, 2-D array or list of tuples.
+    X        : L x p marker matrix (pre-scaled by the user); row names via ``rownames`` or a
+               DataFrame index.  Not used when ``setKernel`` is given.
+    kernel   : "GB" (X X'/p) or "GK" (Gaussian, exp(-bandwidth * D / quantile(D, quantil))).
+    setKernel: dict/list of user kernels, each a (matrix, names) tuple or a DataFrame.
+    model    : "SM", "MM", "MDs" or "MDe".
+    Returns an OrderedDict name -> {"Kernel": n x n float64 (Fortran order), "Type": "D"|"BD"}.
+    """
+    if not isinstance(kernel, str) or not isinstance(model, str):
+        # the reference has no match.arg: switch() on a length-2 vector errors
+        raise ValueError("EXPR must be a length 1 vector: pass `kernel` and `model` explicitly")
+    ecol, gcol = _columns(Y)
+    env_levels, env = _factor(ecol)
+    subjects, gid = _factor(gcol)
+    n_env, L, n = len(env_levels), len(subjects), gid.shape[0]
+
+    # check for repeated genotypes (R/getK.R:108-109)
+    cell = env.astype(np.int64) * L + gid
+    if np.unique(cell).shape[0] != n:
+        warnings.warn("There are repeated genotypes in some environment. They were kept")
+
+    if model == "SM":
+        if n_env > 1:
+            raise ValueError("Single model choosen, but more than one environment is in the phenotype file")
+    elif model in ("MM", "MDs", "MDe"):
+        if n_env < 2:   # model.matrix() on a one-level factor (R/getK.R:120; tests/testthat/test.R:16-17)
+            raise ValueError("contrasts can be applied only to factors with 2 or more levels")
+    else:
+        raise ValueError("Model selected is not available ")
+    model_code = _MODELS[model]
+
+    n_per_base = 1 if model_code == 0 else (2 if model_code == 1 else 1 + n_env)
+    if setKernel is None:
+        if hasattr(X, "index") and hasattr(X, "to_numpy") and rownames is None:
+            rownames = list(X.index)
+            X = X.to_numpy()
+        if rownames is None:
+            raise ValueError("Genotype names are missing")
+        pos = {str(r): i for i, r in enumerate(rownames)}
+        if not all(str(s) in pos for s in subjects):
+            raise ValueError("Not all genotypes presents in the phenotypic file are in marker matrix")
+        Xs = _lib.f64(np.asarray(X, dtype=np.float64)[[pos[str(s)] for s in subjects], :])   # X[subjects,]
+        p = Xs.shape[1]
+        if kernel == "GB":
+            kind, bw = _lib.GB, np.ones(1)
+        elif kernel == "GK":
+            kind, bw = _lib.GK, np.ascontiguousarray(np.atleast_1d(bandwidth), dtype=np.float64)
+        else:
+            raise ValueError("kernel selected is not available. Please choose one method available or make "
+                             "available other kernel through argument K")
+        nbase = 1 if kind == _lib.GB else bw.shape[0]
+        n_out = nbase * n_per_base + (1 if intercept_random else 0)
+        outs = [np.empty((n, n), dtype=np.float64, order="F") for _ in range(n_out)]
+        arr = (C.c_void_p * n_out)(*[o.ctypes.data for o in outs])
+        q = C.c_double(0.0)
+        _lib.call("bgge_getk", _lib.ptr(Xs), L, p, kind, _lib.ptr(bw), nbase, float(quantil), _lib.ptr(gid),
+                  _lib.ptr(env), n, n_env, model_code, int(bool(intercept_random)), arr, n_out, C.byref(q))
+        tmp_names = [str(i + 1) for i in range(nbase)]
+    else:
+        items = list(setKernel.items()) if hasattr(setKernel, "items") else [(None, k) for k in setKernel]
+        base = []
+        for _nm, km in items:
+            mat, names = _named_matrix(km)
+            if mat is None:
+                raise ValueError("Genotype names are missing in some kernel")
+            pos = {r: i for i, r in enumerate(names)}
+            if not all(str(s) in pos for s in subjects):
+                raise ValueError("Not all genotypes presents in phenotypic file are in the kernel matrix.\n"
+                                 "             Please check dimnames")
+            idx = [pos[str(s)] for s in subjects]
+            base.append(_lib.f64(mat[np.ix_(idx, idx)]))
+        tmp_names = [str(k) for k, _ in items] if hasattr(setKernel, "items") else [str(i + 1) for i in range(len(base))]
+        nbase = len(base)
+        outs = []
+
+        def emit(k0, mode, k=0):
+            o = np.empty((n, n), dtype=np.float64, order="F")
+            _lib.call("bgge_getk_expand", _lib.ptr(k0), L, _lib.ptr(gid), _lib.ptr(env), n, mode, k, _lib.ptr(o))
+            outs.append(o)
+
+        for k0 in base:
+            emit(k0, _lib.EXPAND_G)
+        if model_code == 1:
+            for k0 in base:
+                emit(k0, _lib.EXPAND_GE)
+        if model_code == 2:
+            for k0 in base:
+                for k in range(n_env):
+                    emit(k0, _lib.EXPAND_ENV, k)
+        if intercept_random:
+            emit(None, _lib.EXPAND_GI)
+
+    # names (R/getK.R:184-185, 202, 220-224, 233)
+    out = OrderedDict()
+    it = iter(outs)
+    multi = nbase > 1
+    for t in tmp_names:
+        out["G_" + t if multi else "G"] = {"Kernel": next(it), "Type": "D"}
+    if model_code == 1:
+        for t in tmp_names:
+            out["GE_" + t if multi else "GE"] = {"Kernel": next(it), "Type": "BD"}
+    if model_code == 2:
+        for t in tmp_names:
+            for lev in env_levels:
+                out[f"{lev}_{t}" if multi else str(lev)] = {"Kernel": next(it), "Type": "BD"}
+    if intercept_random:
+        out["Gi"] = {"Kernel": next(it), "Type": "D"}
+    return out

@@ -1,0 +1,206 @@
+/*
+ * libbgge_b200 -- C ABI of the B200-native getK / BGGE hot paths.
+ *
+ * The reference (italo-granato/BGGE v0.6.6) is pure R and has no FFI of its own: its boundary is
+ * the two exported closures getK() (R/getK.R:95-96) and BGGE() (R/BGGE.R:84).  These entry points
+ * are what a `.Call` shim under those two closures binds (INTEGRATION.md shows the shim); the same
+ * symbols are driven from Python/ctypes by bgge_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, otherwise a bgge_status code; bgge_last_error() gives
+ *     the message of the last failure on the calling thread.  Nothing throws, nothing exits.
+ *   - matrices are column-major IEEE doubles (R's layout); index vectors are 0-based int32.
+ *   - `bgge_*`      take HOST buffers and move data themselves.
+ *   - `bgge_dev_*`  take DEVICE pointers on the current CUDA device plus a cudaStream_t (as
+ *                   void*; NULL = default stream) and move nothing; callers own the memory.
+ *   - there is no CPU fallback: without an sm_100 device every compute call fails with
+ *     BGGE_ERR_NODEVICE.
+ */
+#ifndef BGGE_B200_H
+#define BGGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+enum bgge_status {
+  BGGE_OK = 0,
+  BGGE_ERR_INVALID = 1,
+  BGGE_ERR_CUDA = 2,
+  BGGE_ERR_SOLVER = 3,
+  BGGE_ERR_STATE = 4,
+  BGGE_ERR_NODEVICE = 5,
+  BGGE_ERR_TAPE = 6,
+  BGGE_ERR_UNSUPPORTED = 7
+};
+
+/* kernel = switch(kernel) of R/getK.R:133-153 */
+enum bgge_kernel_kind { BGGE_KERNEL_GB = 0, BGGE_KERNEL_GK = 1 };
+/* expansion modes: R/getK.R:138,148,173 (G) / :199-201 (MDs GE) / :207-218 (MDe env k) / :232 (Gi) */
+enum bgge_expand_mode { BGGE_EXPAND_G = 0, BGGE_EXPAND_GE = 1, BGGE_EXPAND_ENV = 2, BGGE_EXPAND_GI = 3 };
+/* K[[i]]$Type of R/BGGE.R:122,144,156 */
+enum bgge_kernel_type { BGGE_TYPE_D = 0, BGGE_TYPE_BD = 1 };
+enum bgge_rng_mode { BGGE_RNG_PHILOX = 0, BGGE_RNG_TAPE = 1 };
+
+/* ------------------------------------------------------------------ library / device */
+int bgge_version(void);
+const char* bgge_last_error(void);
+int bgge_device_count(int* count);
+int bgge_set_device(int device);
+/* free bytes / total bytes of the current device */
+int bgge_device_memory(uint64_t* free_bytes, uint64_t* total_bytes);
+
+/* ------------------------------------------------------------------ getK, host buffers */
+/*
+ * Base kernels over the L genotypes (R/getK.R:131-149).
+ *   X          L x p, X[subjects,] already subset/reordered by the caller (R/getK.R:131)
+ *   kind       GB: K0 = X X' / p (R/getK.R:136).  GK: D = dist(X)^2, q = quantile(D, quantil),
+ *              K0_i = exp(-bandwidth[i] * D / q) (R/getK.R:142-146)
+ *   out_K0     nb matrices L x L, back to back (nb = 1 for GB)
+ *   out_q      optional (may be NULL): the GK quantile
+ */
+int bgge_getk_base(const double* X, int64_t L, int64_t p, int kind, const double* bandwidth, int nb,
+                   double quantil, double* out_K0, double* out_q);
+
+/*
+ * Genotype / environment expansion of one L x L base kernel to n x n (R/getK.R:138,148,173,
+ * 199-201, 207-218, 232).  gid[i] / env[i] = 0-based level codes of Y[,2] / Y[,1] (R/getK.R:101-104).
+ */
+int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int32_t* env, int64_t n,
+                     int mode, int env_k, double* out);
+
+/*
+ * Whole getK numeric body in one call: one upload of X, every requested kernel built on the
+ * device and copied to out[k] (n x n each), in the order getK() returns them:
+ *   G_1..G_nb, then for MDs GE_1..GE_nb, for MDe env_0..env_{E-1} per base kernel, then Gi.
+ * model: 0 = SM/MM, 1 = MDs, 2 = MDe (R/getK.R:188-229).  n_out must equal the kernel count.
+ */
+int bgge_getk(const double* X, int64_t L, int64_t p, int kind, const double* bandwidth, int nb,
+              double quantil, const int32_t* gid, const int32_t* env, int64_t n, int n_env, int model,
+              int intercept_random, double* const* out, int n_out, double* out_q);
+
+/* ------------------------------------------------------------------ getK, device pointers */
+/* Required layout of the device marker matrix: leading dimension ldx = multiple of 128 >= L with
+ * rows L..ldx-1 zero, p_pad = multiple of 16 >= p with columns p..p_pad-1 zero. */
+int bgge_marker_ld(int64_t L, int64_t* ldx);
+int bgge_marker_cols(int64_t p, int64_t* p_pad);
+/*
+ * Gram panel: tile rows [tile_row0, tile_row1) (128 rows each) of the LOWER triangle of
+ * S = X X' / divisor, written to dS[(i - row_off) + j*lds].  mirror != 0 also writes the
+ * transposed entries (needs row_off == 0 and a full L x L dS).
+ */
+int bgge_dev_gram(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tile_row0,
+                  int64_t tile_row1, double* dS, int64_t lds, int64_t row_off, double divisor, int mirror,
+                  void* stream);
+int bgge_dev_symmetrize(double* dS, int64_t lds, int64_t L, void* stream);
+/* in place: Gram matrix -> squared Euclidean distances with exact-zero diagonal (R/getK.R:142) */
+int bgge_dev_gk_distance(double* dS, int64_t lds, int64_t L, void* stream);
+/* exact stats::quantile(type = 7) over all L*L entries; result to device scalar d_q and, if
+ * non-NULL, host scalar h_q (synchronises the stream) */
+int bgge_dev_quantile7(const double* dD, int64_t ldd, int64_t L, double prob, double* d_q, double* h_q,
+                       void* stream);
+int bgge_dev_gk_exp(const double* dD, int64_t ldd, int64_t L, double bw, const double* d_q, double* dK0,
+                    int64_t ldk, void* stream);
+int bgge_dev_expand(const double* dK0, int64_t ldk, int64_t L, const int32_t* d_gid, const int32_t* d_env,
+                    int64_t n, int mode, int env_k, double* dOut, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------ eigen (eig(), R/BGGE.R:112-116) */
+/*
+ * Symmetric eigendecomposition of K (m x m, leading dimension ldk, lower triangle read), values
+ * descending, keep values > tol.  out_s: m doubles; out_U: m x m doubles (first nr columns valid,
+ * leading dimension m); either may be NULL.  canonical_sign != 0 flips each vector so that its
+ * largest-|.| entry is positive (R leaves the sign to LAPACK).
+ */
+int bgge_eig(const double* K, int64_t m, int64_t ldk, double tol, int canonical_sign, double* out_s,
+             double* out_U, int64_t* out_nr);
+/* dA (m x m, lda) is destroyed.  d_s: m doubles.  dU: ldu x max_cols, ldu >= m (rows m..ldu-1 are
+ * zero-filled).  Synchronises the stream (the kept count comes back to the host). */
+int bgge_dev_eig(double* dA, int64_t m, int64_t lda, double tol, int canonical_sign, double* d_s, double* dU,
+                 int64_t ldu, int64_t max_cols, int64_t* out_nr, void* stream);
+
+/* ------------------------------------------------------------------ Gibbs sampler (R/BGGE.R:189-443) */
+typedef struct bgge_gibbs bgge_gibbs;
+
+/* n = length(y), nk = length(K), q = ncol(XF) or 0.  stream NULL: the handle creates its own. */
+int bgge_gibbs_create(int64_t n, int nk, int q, void* stream, bgge_gibbs** out);
+void bgge_gibbs_destroy(bgge_gibbs* h);
+/* y with NA flagged either by na_mask[i] != 0 or, when na_mask is NULL, by NaN (R/BGGE.R:191-200) */
+int bgge_gibbs_set_y(bgge_gibbs* h, const double* y, const uint8_t* na_mask);
+/* XF n x q column-major (R/BGGE.R:208-212) */
+int bgge_gibbs_set_xf(bgge_gibbs* h, const double* XF);
+/* mean(diag(K[[j]]$Kernel)) for the prior scale Sc[j] (R/BGGE.R:249) */
+int bgge_gibbs_set_kernel(bgge_gibbs* h, int j, int type, double mean_diag);
+/*
+ * One eigen block of kernel j (setDEC(), R/BGGE.R:144-154 / 156-171): rows [pos0, pos0+rows) of y,
+ * nr kept eigenpairs, s descending.  on_device == 0: s/U are host pointers (U rows x nr, leading
+ * dimension ldu) and are copied.  on_device != 0: U is a device pointer that the handle borrows
+ * (ldu even, base 16-byte aligned; caller keeps it alive); s is still a host pointer.
+ */
+int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64_t nr, const double* s,
+                         const double* U, int64_t ldu, int on_device);
+/*
+ * Convenience: decompose a kernel matrix on the device exactly as setDEC() does and add its blocks.
+ * K n x n host (on_device == 0) or device pointer (on_device != 0, left intact); type D: one block
+ * over all rows; type BD: one block per ne[] entry, blocks without an eigenvalue > tol are skipped
+ * (R/BGGE.R:162).  Also sets mean(diag(K)).
+ */
+int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K, int64_t ldk, int on_device,
+                                 const int64_t* ne, int n_ne, double tol, int canonical_sign);
+/* injected draws in the reference's call order; copied to the device */
+int bgge_gibbs_set_tape(bgge_gibbs* h, const double* normals, int64_t n_normals, const double* chisq,
+                        int64_t n_chisq);
+/* ite/burn/thin/R2 of R/BGGE.R:84; rng_mode PHILOX uses (seed, chain) */
+int bgge_gibbs_init(bgge_gibbs* h, int64_t ite, int64_t burn, int64_t thin, double R2, int rng_mode,
+                    uint64_t seed, uint32_t chain);
+/* run the next `iters` sweeps (asynchronous on the handle's stream) */
+int bgge_gibbs_run(bgge_gibbs* h, int64_t iters);
+int bgge_gibbs_sync(bgge_gibbs* h);
+/* sizes: nr[j] = total kept eigenvalues of kernel j; n_cum = floor(ite/thin); normals / chisq per call */
+int bgge_gibbs_sizes(bgge_gibbs* h, int64_t* nr, int64_t* n_cum, int64_t* n_na, int64_t* tape_normals,
+                     int64_t* tape_chisq);
+/* current state after the iterations run so far (any pointer may be NULL):
+ * mu, sigsq scalars; sigb[nk]; u[nk*n] kernel-major; e[n] = R's `temp`; bet[q] */
+int bgge_gibbs_state(bgge_gibbs* h, double* mu, double* sigsq, double* sigb, double* u, double* e, double* bet);
+/* thinned chains (all n_cum recorded values, burn-in included, as in out$chain, R/BGGE.R:435):
+ * mu[n_cum], varE[n_cum], varU[nk*n_cum] kernel-major, bet[n_cum*q] row-major by draw */
+int bgge_gibbs_chain(bgge_gibbs* h, double* mu, double* varE, double* varU, double* bet);
+/*
+ * Posterior summaries over the kept draws (R/BGGE.R:408-433): yHat[n], varE, varE_sd, per kernel
+ * u[nk*n], u_sd[nk*n], varu[nk], varu_sd[nk], y[n] with the last imputations (R/BGGE.R:441).
+ * Any pointer may be NULL.
+ */
+int bgge_gibbs_summary(bgge_gibbs* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd,
+                       double* varu, double* varu_sd, double* y);
+
+/* ------------------------------------------------------------------ one-shot BGGE() */
+/*
+ * What the .Call shim under BGGE() invokes: eigen of every kernel (setDEC), `ite` sweeps and the
+ * summaries, in one call.  K[j]: n x n host matrices; types[j]; ne/n_ne as in BGGE(ne=).  XF NULL
+ * when q == 0.  normals/chisq NULL unless rng_mode == BGGE_RNG_TAPE.  Outputs as in
+ * bgge_gibbs_summary + bgge_gibbs_chain (any may be NULL).
+ */
+int bgge_fit(const double* y, const uint8_t* na_mask, int64_t n, const double* const* K, const int* types, int nk,
+             const double* XF, int q, const int64_t* ne, int n_ne, int64_t ite, int64_t burn, int64_t thin,
+             double tol, double R2, int rng_mode, uint64_t seed, const double* normals, int64_t n_normals,
+             const double* chisq, int64_t n_chisq, double* yHat, double* varE, double* varE_sd, double* u,
+             double* u_sd, double* varu, double* varu_sd, double* y_out, double* chain_mu, double* chain_varE,
+             double* chain_varU);
+
+/* ------------------------------------------------------------------ test hooks */
+/* Philox4x32-10 block function on the device (known-answer tests) */
+int bgge_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* n standard normals / chi-squares from the device generator: stream = kernel index semantics */
+int bgge_test_draws(uint64_t seed, uint32_t chain, int64_t n, double* normals, double df, double* chisq);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGGE_B200_H */

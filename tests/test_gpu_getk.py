@@ -1,0 +1,151 @@
+"""GPU parity: getK through the C ABI vs the CPU oracle (bit-exact expansions, <=1e-12 kernels)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import design, markers, relmax
+
+pytestmark = pytest.mark.gpu
+
+TOL_K = 1e-12   # north_star: K matches the reference to <= 1e-12 relative (max|dK| / max|K|)
+
+
+@pytest.mark.parametrize("L,p", [(5, 7), (37, 50), (128, 16), (129, 333), (300, 1279)])
+def test_gb_base_kernel(lib, L, p):
+    X = markers(L, p, 11)
+    out = np.empty((L, L), order="F")
+    lib.call("bgge_getk_base", lib.ptr(lib.f64(X)), L, p, lib.GB, None, 1, 0.5, lib.ptr(out), None)
+    ref = oracle.gb_kernel(X)
+    assert relmax(out, ref) <= TOL_K
+    assert np.array_equal(out, out.T)          # tcrossprod is exactly symmetric
+
+
+@pytest.mark.parametrize("L,p,quantil", [(6, 9, 0.5), (37, 50, 0.5), (130, 257, 0.25), (200, 64, 0.9), (64, 40, 0.0),
+                                         (64, 40, 1.0)])
+def test_gk_base_kernel(lib, L, p, quantil):
+    X = markers(L, p, 5)
+    bw = np.array([1.0, 0.2, 5.0])
+    out = np.empty((3, L, L))
+    outs = np.empty(3 * L * L)
+    q = C.c_double()
+    lib.call("bgge_getk_base", lib.ptr(lib.f64(X)), L, p, lib.GK, lib.ptr(bw), 3, quantil, lib.ptr(outs), C.byref(q))
+    D = oracle.gk_distance(X)
+    qref = oracle.quantile7(D, quantil)
+    if qref > 0:
+        assert abs(q.value - qref) <= 1e-12 * qref
+    for b in range(3):
+        got = outs[b * L * L:(b + 1) * L * L].reshape(L, L, order="F")
+        if qref == 0:
+            continue
+        ref = oracle.gk_kernel(D, bw[b], qref)
+        assert relmax(got, ref) <= TOL_K
+        assert np.all(np.diag(got) == 1.0)     # exact-zero distance on the diagonal
+        assert np.array_equal(got, got.T)
+
+
+def test_quantile_exact_selection(lib):
+    """The device quantile is an exact order statistic: feed a matrix, compare to sort."""
+    import torch
+    rng = np.random.default_rng(3)
+    for L, prob in [(33, 0.5), (100, 0.123), (257, 0.75), (64, 0.5)]:
+        A = rng.gamma(2.0, 50.0, size=(L, L))
+        A = (A + A.T) / 2
+        np.fill_diagonal(A, 0.0)
+        A[3, 5] = A[5, 3] = A[7, 9] = A[9, 7]      # ties
+        d = torch.from_numpy(np.asfortranarray(A).T.copy()).cuda()   # column-major bytes
+        hq = C.c_double()
+        lib.call("bgge_dev_quantile7", C.c_void_p(d.data_ptr()), L, L, prob, None, C.byref(hq), None)
+        assert hq.value == oracle.quantile7(A, prob)
+
+
+MODELS = [("SM", 1), ("MM", 3), ("MDs", 3), ("MDe", 3)]
+
+
+@pytest.mark.parametrize("kernel", ["GB", "GK"])
+@pytest.mark.parametrize("model,E", MODELS)
+def test_getk_models_match_oracle(kernel, model, E):
+    import bgge_b200
+    L, p = 41, 60
+    X = markers(L, p, 2)
+    Y, names = design(L, E, seed=4, shuffle=(model != "SM"), drop=(5 if E > 1 else 0))
+    bw = [1.0, 0.5] if kernel == "GK" else 1
+    got = bgge_b200.getK(Y, X, kernel=kernel, model=model, bandwidth=bw, rownames=names, intercept_random=True)
+    ref = oracle.getK(Y, X, kernel=kernel, model=model, bandwidth=bw, rownames=names, intercept_random=True)
+    assert list(got.keys()) == list(ref.keys())
+    for nm in ref:
+        assert got[nm]["Type"] == ref[nm]["Type"]
+        assert got[nm]["Kernel"].shape == ref[nm]["Kernel"].shape
+        assert relmax(got[nm]["Kernel"], ref[nm]["Kernel"]) <= TOL_K, nm
+        # structural zeros / ones of the expansions are exact
+        assert np.array_equal(got[nm]["Kernel"] == 0, ref[nm]["Kernel"] == 0), nm
+
+
+def test_expansion_is_bit_exact_gather(lib):
+    rng = np.random.default_rng(0)
+    L, n, E = 23, 101, 4
+    K0 = rng.standard_normal((L, L))
+    gid = rng.integers(0, L, size=n).astype(np.int32)
+    env = np.sort(rng.integers(0, E, size=n)).astype(np.int32)
+    for mode, k in [(lib.EXPAND_G, 0), (lib.EXPAND_GE, 0), (lib.EXPAND_ENV, 2), (lib.EXPAND_GI, 0)]:
+        out = np.empty((n, n), order="F")
+        lib.call("bgge_getk_expand", lib.ptr(lib.f64(K0)), L, lib.ptr(gid), lib.ptr(env), n, mode, k, lib.ptr(out))
+        G = K0[np.ix_(gid, gid)]
+        if mode == lib.EXPAND_GE:
+            G = G * (env[:, None] == env[None, :])
+        elif mode == lib.EXPAND_ENV:
+            G = G * ((env == k)[:, None] & (env == k)[None, :])
+        elif mode == lib.EXPAND_GI:
+            G = (gid[:, None] == gid[None, :]).astype(np.float64)
+        assert np.array_equal(out, G)
+
+
+def test_setkernel_path_and_errors():
+    import bgge_b200
+    L, E = 12, 2
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((L, L))
+    A = A @ A.T
+    Y, names = design(L, E)
+    perm = rng.permutation(L)
+    user = {"A": (A[np.ix_(perm, perm)], [names[i] for i in perm])}
+    got = bgge_b200.getK(Y, setKernel=user, model="MDs")
+    ref = oracle.getK(Y, setKernel=user, model="MDs")
+    assert list(got.keys()) == ["G", "GE"] == list(ref.keys())
+    for nm in ref:
+        assert np.array_equal(got[nm]["Kernel"], ref[nm]["Kernel"])
+    with pytest.raises(ValueError):
+        bgge_b200.getK(Y, np.ones((L, 3)), kernel="GB", model="SM", rownames=names)      # >1 env under SM
+    Y1, _ = design(L, 1)
+    with pytest.raises(ValueError):
+        bgge_b200.getK(Y1, np.ones((L, 3)), kernel="GK", model="MM", rownames=names)     # 1 env under MM
+    with pytest.raises(ValueError):
+        bgge_b200.getK(Y, np.ones((L, 3)), kernel="GB", model="MM")                      # no rownames
+    with pytest.raises(ValueError):
+        bgge_b200.getK(Y, np.ones((L, 3)), kernel="XX", model="MM", rownames=names)
+
+
+def test_gram_row_panels_and_symmetrize(lib):
+    """Row-panel build (the multi-GPU decomposition) == one-shot build."""
+    import torch
+    L, p = 300, 160
+    X = markers(L, p, 9)
+    ldx, pp = C.c_int64(), C.c_int64()
+    lib.call("bgge_marker_ld", L, C.byref(ldx))
+    lib.call("bgge_marker_cols", p, C.byref(pp))
+    Xp = torch.zeros((pp.value, ldx.value), dtype=torch.float64, device="cuda")
+    Xp[:p, :L] = torch.from_numpy(X.T.copy()).cuda()
+    S = torch.zeros((L, L), dtype=torch.float64, device="cuda")
+    T = (L + 127) // 128
+    for tr in range(T):   # one tile row per "rank", lower triangle only
+        lib.call("bgge_dev_gram", C.c_void_p(Xp.data_ptr()), ldx.value, L, pp.value, tr, tr + 1,
+                 C.c_void_p(S.data_ptr()), L, 0, float(p), 0, None)
+    lib.call("bgge_dev_symmetrize", C.c_void_p(S.data_ptr()), L, L, None)
+    torch.cuda.synchronize()
+    full = torch.zeros((L, L), dtype=torch.float64, device="cuda")
+    lib.call("bgge_dev_gram", C.c_void_p(Xp.data_ptr()), ldx.value, L, pp.value, 0, T, C.c_void_p(full.data_ptr()), L,
+             0, float(p), 1, None)
+    torch.cuda.synchronize()
+    assert torch.equal(S, full)
+    assert relmax(full.cpu().numpy().T, oracle.gb_kernel(X)) <= TOL_K

@@ -1,0 +1,190 @@
+"""GPU parity: the device Gibbs sweep vs the CPU oracle with an injected draw tape and a shared
+eigenbasis.  Tolerance: per-iteration samples <= 1e-9 relative (north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import design, markers, phenotype, relmax
+
+pytestmark = pytest.mark.gpu
+
+TOL_IT = 1e-9
+
+
+def _problem(L, E, p, model, kernel="GB", seed=0, n_na=0, q=0):
+    X = markers(L, p, seed)
+    Y, names = design(L, E)
+    K = oracle.getK(Y, X, kernel=kernel, model=model, rownames=names)
+    K0 = oracle.gb_kernel(X)
+    y = phenotype(K0, L, E, seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    if n_na:
+        y[rng.choice(y.shape[0], size=n_na, replace=False)] = np.nan
+    XF = None
+    if q:
+        XF = np.c_[np.ones(y.shape[0]), rng.standard_normal((y.shape[0], q - 1))] if q > 1 else rng.standard_normal((y.shape[0], 1))
+    return K, y, XF, [L] * E
+
+
+def _tape(n, nrs, ite, q, n_na, seed):
+    nz, nc = oracle.tape_sizes(n, nrs, ite, q=q, n_na=n_na)
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal(nz)
+    dfs = np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=np.float64), ite)
+    c = rng.chisquare(dfs)
+    return z, c
+
+
+CASES = [
+    # L, E, p, model, kernel, n_na, q
+    (30, 1, 40, "SM", "GB", 0, 0),
+    (25, 3, 40, "MM", "GB", 0, 0),
+    (25, 3, 40, "MDs", "GK", 0, 0),
+    (17, 4, 30, "MDe", "GB", 0, 0),
+    (25, 3, 40, "MDs", "GB", 11, 0),
+    (25, 3, 40, "MM", "GK", 0, 2),
+    (23, 3, 40, "MDs", "GK", 9, 3),
+    (301, 2, 100, "MDs", "GB", 20, 0),     # rows not a multiple of the 256-row tile, odd block starts
+]
+
+
+@pytest.mark.parametrize("L,E,p,model,kernel,n_na,q", CASES)
+def test_per_iteration_parity(L, E, p, model, kernel, n_na, q):
+    import bgge_b200
+    K, y, XF, ne = _problem(L, E, p, model, kernel=kernel, n_na=n_na, q=q)
+    n = y.shape[0]
+    ite = 25
+    Ei = bgge_b200.setDEC(K, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in blocks) for blocks in Ei]
+    z, c = _tape(n, nrs, ite, q, n_na, 7)
+    tr = {"keep_u": True}
+    ref = oracle.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei, trace=tr)
+    got = bgge_b200.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), eig=Ei)
+    # every iteration's scalar samples (thin=1 records all of them)
+    assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= TOL_IT
+    assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= TOL_IT
+    for nm in ref["K"]:
+        assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= TOL_IT, nm
+        assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= TOL_IT, nm
+        assert relmax(got["K"][nm]["u.sd"], ref["K"][nm]["u.sd"]) <= 1e-7, nm
+        assert abs(got["K"][nm]["varu"] - ref["K"][nm]["varu"]) <= TOL_IT * abs(ref["K"][nm]["varu"])
+    assert relmax(np.asarray(got["yHat"]).ravel(), ref["yHat"]) <= TOL_IT
+    assert abs(got["varE"] - ref["varE"]) <= TOL_IT * ref["varE"]
+    assert abs(got["varE.sd"] - ref["varE.sd"]) <= 1e-7 * ref["varE.sd"]
+    assert relmax(got["y"], ref["y"]) <= TOL_IT
+    assert list(got.keys()) == ["yHat", "varE", "varE.sd", "K", "chain", "ite", "burn", "thin", "y"]
+
+
+def test_state_after_each_iteration(lib):
+    """Step the handle one sweep at a time and compare u, e (R's temp), sigb, sigsq, mu."""
+    import bgge_b200
+    K, y, XF, ne = _problem(20, 3, 30, "MDs", n_na=5)
+    n, nk, ite = y.shape[0], len(K), 6
+    Ei = bgge_b200.setDEC(K, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in blocks) for blocks in Ei]
+    z, c = _tape(n, nrs, ite, 0, 5, 3)
+    h = C.c_void_p()
+    lib.call("bgge_gibbs_create", n, nk, 0, None, C.byref(h))
+    lib.call("bgge_gibbs_set_y", h, lib.ptr(y), None)
+    for j, k in enumerate(K.values()):
+        lib.call("bgge_gibbs_set_kernel", h, j, 0 if k["Type"] == "D" else 1, float(np.mean(np.diag(k["Kernel"]))))
+        for blk in Ei[j]:
+            U = lib.f64(blk["U"])
+            lib.call("bgge_gibbs_add_block", h, j, 0 if blk["pos"] is None else blk["pos"][0], U.shape[0], U.shape[1],
+                     lib.ptr(blk["s"]), lib.ptr(U), U.shape[0], 0)
+    lib.call("bgge_gibbs_set_tape", h, lib.ptr(z), z.shape[0], lib.ptr(c), c.shape[0])
+    lib.call("bgge_gibbs_init", h, ite, 0, 1, 0.5, lib.RNG_TAPE, 0, 0)
+    for it in range(1, ite + 1):
+        tr = {"keep_u": True}
+        oracle.BGGE(y, K, ne=ne, ite=it, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei, trace=tr)
+        lib.call("bgge_gibbs_run", h, 1)
+        mu, s2 = C.c_double(), C.c_double()
+        sigb, u, e = np.empty(nk), np.empty((nk, n)), np.empty(n)
+        lib.call("bgge_gibbs_state", h, C.byref(mu), C.byref(s2), lib.ptr(sigb), lib.ptr(u), lib.ptr(e), None)
+        assert abs(mu.value - tr["mu"][-1]) <= TOL_IT * abs(tr["mu"][-1])
+        assert abs(s2.value - tr["varE"][-1]) <= TOL_IT * tr["varE"][-1]
+        assert relmax(sigb, tr["varU"][-1]) <= TOL_IT
+        assert relmax(u, tr["u"][-1]) <= TOL_IT
+        assert relmax(e, tr["e"]) <= TOL_IT
+    lib.load().bgge_gibbs_destroy(h)
+
+
+def test_default_thinning_counts():
+    """ite=1000, burn=200, thin=3 -> 333 recorded, 267 kept."""
+    import bgge_b200
+    K, y, XF, ne = _problem(15, 2, 20, "MM")
+    fit = bgge_b200.BGGE(y, K, ne=ne, seed=1)
+    assert fit["chain"]["mu"].shape == (333,)
+    assert np.all(fit["chain"]["varE"] > 0)
+    assert np.isfinite(fit["yHat"]).all() and fit["yHat"].shape == y.shape
+    assert str(fit).startswith("Model Fitted with")
+
+
+def test_eig_matches_lapack(lib):
+    rng = np.random.default_rng(5)
+    m = 150
+    A = rng.standard_normal((m, 40))
+    K = A @ A.T / 40                      # rank 40 -> tol truncation matters
+    s, U = np.empty(m), np.empty((m, m), order="F")
+    nr = C.c_int64()
+    lib.call("bgge_eig", lib.ptr(lib.f64(K)), m, m, 1e-10, 1, lib.ptr(s), lib.ptr(U), C.byref(nr))
+    sr, Ur = oracle.eig_block(K, 1e-10)
+    assert nr.value == sr.shape[0] == 40
+    assert relmax(s[:40], sr) <= 1e-12
+    U = U[:, :40]
+    assert np.max(np.abs(U.T @ U - np.eye(40))) <= 1e-12
+    assert relmax((U * s[:40]) @ U.T, K) <= 1e-12
+    # canonical sign: largest-|.| entry of every vector is positive
+    assert np.all(U[np.argmax(np.abs(U), axis=0), np.arange(40)] > 0)
+
+
+def test_philox_known_answers(lib):
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kats:
+        c = np.array(ctr, dtype=np.uint32)
+        k = np.array(key, dtype=np.uint32)
+        o = np.zeros(4, dtype=np.uint32)
+        lib.call("bgge_test_philox", lib.ptr(c), lib.ptr(k), lib.ptr(o))
+        assert tuple(int(v) for v in o) == exp
+
+
+def test_device_draw_distributions(lib):
+    from scipy import stats
+    n = 200000
+    z, c = np.empty(n), np.empty(n)
+    lib.call("bgge_test_draws", 123, 4, n, lib.ptr(z), 37.0, lib.ptr(c))
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert stats.kstest(c, "chi2", args=(37.0,)).pvalue > 1e-3
+    z2 = np.empty(n)
+    lib.call("bgge_test_draws", 123, 5, n, lib.ptr(z2), 37.0, None)
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 0.01          # chains are independent streams
+
+
+def test_statistical_agreement_with_oracle():
+    """Device RNG: posterior means within Monte-Carlo error of the oracle's own chains."""
+    import bgge_b200
+    K, y, XF, ne = _problem(60, 3, 200, "MDs", seed=4)
+    kw = dict(ne=ne, ite=3000, burn=500, thin=2)
+    dev = [bgge_b200.BGGE(y, K, seed=s, **kw) for s in (1, 2)]
+    ref = [oracle.BGGE(y, K, draws=oracle.RandomDraws(s), **kw) for s in (11, 12)]
+
+    def mcse(fit, getter):
+        x = getter(fit["chain"])[250:]
+        nb = 25
+        bm = x[:len(x) // nb * nb].reshape(nb, -1).mean(axis=1)
+        return bm.std(ddof=1) / np.sqrt(nb)
+
+    for getter, key in [(lambda ch: ch["varE"], "varE"), (lambda ch: ch["K"]["G"]["varU"], None),
+                        (lambda ch: ch["K"]["GE"]["varU"], None), (lambda ch: ch["mu"], None)]:
+        dm = np.mean([getter(f["chain"])[250:].mean() for f in dev])
+        rm = np.mean([getter(f["chain"])[250:].mean() for f in ref])
+        se = np.sqrt(np.mean([mcse(f, getter) ** 2 for f in dev + ref]))
+        assert abs(dm - rm) <= 6 * se + 1e-3 * abs(rm), (dm, rm, se)
+    yd = np.mean([f["yHat"] for f in dev], axis=0)
+    yr = np.mean([f["yHat"] for f in ref], axis=0)
+    assert np.corrcoef(yd, yr)[0, 1] > 0.995
