@@ -57,8 +57,9 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
     model    : "SM", "MM", "MDs" or "MDe".
     Returns an OrderedDict name -> {"Kernel": n x n float64 (Fortran order), "Type": "D"|"BD"}.
     """
-    if not isinstance(kernel, str) or not isinstance(model, str):
-        # the reference has no match.arg: switch() on a length-2 vector errors (SURVEY.md A.4)
+    if not isinstance(model, str) or (setKernel is None and not isinstance(kernel, str)):
+        # the reference has no match.arg: switch() on a length-2 vector errors (SURVEY.md A.4);
+        # `kernel` is only looked at when setKernel is NULL (R/getK.R:124,133)
         raise ValueError("EXPR must be a length 1 vector: pass `kernel` and `model` explicitly")
     ecol, gcol = _columns(Y)
     env_levels, env = _factor(ecol)
