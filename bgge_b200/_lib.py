@@ -76,6 +76,7 @@ SIGNATURES = {
                                   C.c_uint32]),
     "bgge_gibbs_run": (C.c_int, [C.c_void_p, C.c_int64]),
     "bgge_gibbs_sync": (C.c_int, [C.c_void_p]),
+    "bgge_gibbs_profile": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "bgge_gibbs_sizes": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     "bgge_gibbs_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),

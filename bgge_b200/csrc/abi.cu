@@ -582,6 +582,12 @@ int bgge_gibbs_run(bgge_gibbs* h, int64_t iters) {
   return gibbs_run(&h->g, iters);
 }
 
+int bgge_gibbs_profile(bgge_gibbs* h, int64_t iters, double* ms) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(ms != nullptr, "gibbs_profile: NULL output");
+  return gibbs_profile(&h->g, iters, ms);
+}
+
 int bgge_gibbs_sync(bgge_gibbs* h) {
   BGGE_HANDLE(h);
   BGGE_CUDA(cudaStreamSynchronize(h->g.stream));

@@ -490,7 +490,12 @@ int launch_scalar(Gibbs* g) {
   return OK;
 }
 
-int launch_iteration(Gibbs* g) {
+int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
+  int ne = 0;
+  auto mark = [&]() {
+    if (ev) cudaEventRecord(ev[ne++], g->stream);
+  };
+  mark();
   if (g->q > 0) {
     xf_reduce_kernel<<<g->xf_blocks, 256, 0, g->stream>>>(g->n, g->q, g->xf.p, g->r.p, g->bet.p, g->scal.p,
                                                           g->xf_part.p);
@@ -500,13 +505,18 @@ int launch_iteration(Gibbs* g) {
     xf_apply_kernel<<<(unsigned)((g->n + 255) / 256), 256, 0, g->stream>>>(g->n, g->q, g->xf.p, g->r.p, g->bet.p,
                                                                            g->bet.p + g->q);
     BGGE_CUDA(cudaGetLastError());
+    mark();
   }
   for (int j = 0; j < g->nk; ++j) {
     HostKernel& hk = g->kernels[j];
     if (hk.n_atasks > 0) BGGE_TRY(launch_proj(g, hk, j));
+    mark();
     BGGE_TRY(launch_back(g, hk));
+    mark();
   }
-  return launch_scalar(g);
+  BGGE_TRY(launch_scalar(g));
+  mark();
+  return OK;
 }
 
 }  // namespace
@@ -755,6 +765,52 @@ int gibbs_run(Gibbs* g, int64_t iters) {
   }
   g->done += iters;
   return OK;
+}
+
+// Instrumented (non-graph) sweeps: CUDA events around every launch.  ms layout:
+// [proj_0, back_0, proj_1, back_1, ..., scalar, xf]; each entry is the summed device time.
+int gibbs_profile(Gibbs* g, int64_t iters, double* ms) {
+  if (!g->initialised) {
+    set_error("gibbs: profile before init");
+    return ERR_STATE;
+  }
+  BGGE_REQUIRE(iters >= 0 && g->done + iters <= g->ite, "gibbs: asked for %lld iterations, %lld of %lld already done",
+               (long long)iters, (long long)g->done, (long long)g->ite);
+  const int nslots = 2 * g->nk + 2;
+  for (int i = 0; i < nslots; ++i) ms[i] = 0.0;
+  const int nev = 2 * g->nk + 3 + (g->q > 0 ? 1 : 0);
+  std::vector<cudaEvent_t> ev((size_t)nev);
+  for (auto& e : ev) BGGE_CUDA(cudaEventCreate(&e));
+  int status = OK;
+  for (int64_t i = 0; i < iters && status == OK; ++i) {
+    status = launch_iteration(g, ev.data());
+    if (status != OK) break;
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) {
+      set_error("gibbs_profile: stream synchronize failed");
+      status = ERR_CUDA;
+      break;
+    }
+    int k = 0;
+    float t = 0.f;
+    if (g->q > 0) {
+      cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+      ms[2 * g->nk + 1] += t;
+      ++k;
+    }
+    for (int j = 0; j < g->nk; ++j) {
+      cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+      ms[2 * j] += t;
+      ++k;
+      cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+      ms[2 * j + 1] += t;
+      ++k;
+    }
+    cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+    ms[2 * g->nk] += t;
+    g->done += 1;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return status;
 }
 
 }  // namespace bgge

@@ -109,5 +109,6 @@ struct Gibbs {
 
 int gibbs_init(Gibbs* g);
 int gibbs_run(Gibbs* g, int64_t iters);
+int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
 
 }  // namespace bgge

@@ -160,6 +160,9 @@ int bgge_gibbs_init(bgge_gibbs* h, int64_t ite, int64_t burn, int64_t thin, doub
 /* run the next `iters` sweeps (asynchronous on the handle's stream) */
 int bgge_gibbs_run(bgge_gibbs* h, int64_t iters);
 int bgge_gibbs_sync(bgge_gibbs* h);
+/* run `iters` sweeps without the CUDA graph, CUDA events around every launch; ms[2*nk + 2] receives
+ * summed device milliseconds: proj_0, back_0, ..., proj_{nk-1}, back_{nk-1}, scalar step, XF step */
+int bgge_gibbs_profile(bgge_gibbs* h, int64_t iters, double* ms);
 /* sizes: nr[j] = total kept eigenvalues of kernel j; n_cum = floor(ite/thin); normals / chisq per call */
 int bgge_gibbs_sizes(bgge_gibbs* h, int64_t* nr, int64_t* n_cum, int64_t* n_na, int64_t* tape_normals,
                      int64_t* tape_chisq);
