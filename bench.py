@@ -226,22 +226,17 @@ def gram_build(torch, dist, lib, Xp, ldx, L, pp, divisor, world, rank, stream):
     if world == 1:
         lib.call("bgge_dev_gram", vp(Xp), ldx, L, pp, 0, T, vp(S), L, 0, float(divisor), 1, stream)
         return S
-    ch = (T + 2 * world - 1) // (2 * world)
-    R = ch * 128
+    from bgge_b200 import multigpu
+    ch, R, owners = multigpu.panel_plan(L, world)
     mine = torch.zeros((2, L, R), dtype=torch.float64, device=Xp.device)    # [panel][col j][local row]
-    for k, c in enumerate((rank, 2 * world - 1 - rank)):
-        t0, t1 = min(T, c * ch), min(T, (c + 1) * ch)
+    for k, c in enumerate(owners[rank]):
+        t0, t1 = multigpu.chunk_tile_rows(L, world, c)
         if t1 > t0:
             lib.call("bgge_dev_gram", vp(Xp), ldx, L, pp, t0, t1, vp(mine[k]), R, t0 * 128, float(divisor), 0, stream)
     allp = torch.empty((world, 2, L, R), dtype=torch.float64, device=Xp.device)
     dist.all_gather_into_tensor(allp, mine)
     S.zero_()
-    for r in range(world):
-        for k, c in enumerate((r, 2 * world - 1 - r)):
-            r0 = c * R
-            r1 = min(L, r0 + R)
-            if r1 > r0:
-                S[:, r0:r1] = allp[r, k, :, :r1 - r0]
+    multigpu.assemble_panels(S, allp, L, world)
     lib.call("bgge_dev_symmetrize", vp(S), L, L, stream)
     return S
 
