@@ -6,8 +6,10 @@
 // Work unit: one 128x128 tile of the lower triangle of S, full depth p.  Persistent CTAs walk
 // a host-built tile list.  Per CTA: 16-marker slabs of the two row panels are streamed into a
 // 4-stage shared-memory ring by the TMA unit (cp.async.bulk + mbarrier complete_tx; SASS
-// UBLKCP; warp 0 issues them three blocks ahead), 8 warps each own a 64x32 sub-tile and issue
-// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind).  Shared rows are padded to
+// UBLKCP) issued by a dedicated producer warp whose warpgroup gives its registers to the consumers
+// (setmaxnreg 40 / 232); 8 consumer warps each own a 64x32 sub-tile and issue mma.sync.m8n8k4.f64
+// (SASS DMMA.8x8x4; tcgen05 has no f64 kind).  [r01: a consumer warp doubling as producer spent
+// ~40 % of its time in the 32-copy issue loop and stalled the whole CTA -- profiles/r01_gram_*.]  Shared rows are padded to
 // 132 doubles so the (k = lane%4, m = lane/4) fragment pattern hits 16 distinct 8-byte banks
 // per half-warp.
 #include "common.cuh"
@@ -22,11 +24,12 @@ constexpr int BK = 16;           // markers per stage
 constexpr int SLD = 132;         // padded smem leading dimension (doubles); 132 % 16 == 4
 constexpr int STAGES = 4;
 constexpr int NCONS = 8;         // consumer warps (2 along M x 4 along N)
+constexpr int NTHREADS = 384;    // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg needs groups of 4 warps)
 constexpr int STAGE_DOUBLES = 2 * BK * SLD;
 constexpr uint32_t STAGE_TX_BYTES = 2u * BK * TM * sizeof(double);
 constexpr size_t GRAM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 
-__global__ void __launch_bounds__(NCONS * 32, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const int2* __restrict__ tiles,
                  int ntiles, double* __restrict__ S, int64_t lds, int64_t L, int64_t row_off,
                  double divisor, int mirror) {
@@ -47,31 +50,32 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
   }
   __syncthreads();
 
-  // This CTA's tiles are t = blockIdx.x + m * gridDim.x; its k-blocks form one global sequence
-  // g = m * kblocks + kb that the shared-memory ring is indexed by.
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t total = (uint32_t)my_tiles * (uint32_t)kblocks;
-
-  // Warp 0 doubles as the producer: lane l copies marker row (l & 15) of panel (l >> 4).
-  const int prow = lane & 15;
-  const int pop = lane >> 4;
-  auto produce = [&](uint32_t g) {
-    const int m = g / (uint32_t)kblocks;
-    const int kb = g - (uint32_t)m * (uint32_t)kblocks;
-    const int2 tc = tiles[blockIdx.x + m * gridDim.x];
-    const int stage = g % STAGES;
-    const uint32_t use = g / STAGES;
-    if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1u);
-    if (lane == 0) mbar_expect_tx(&full[stage], STAGE_TX_BYTES);
-    __syncwarp();
-    const double* src = X + (int64_t)(pop ? tc.y : tc.x) * TM + ((int64_t)kb * BK + prow) * ldx;
-    double* dst = sm + (size_t)stage * STAGE_DOUBLES + (size_t)pop * BK * SLD + (size_t)prow * SLD;
-    bulk_g2s(dst, src, TM * sizeof(double), &full[stage]);
-  };
-  if (warp == 0) {
-    for (uint32_t g = 0; g < (uint32_t)(STAGES - 1) && g < total; ++g) produce(g);
+  if (warp >= NCONS) {
+    // ------------------------------------------------------------ producer warpgroup (warps 8..11)
+    // Hands its registers to the consumers; only warp 8 works: lane l streams marker row (l & 15)
+    // of panel (l >> 4) for every k-block of every tile of this CTA, STAGES blocks ahead.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp != NCONS) return;
+    const int row = lane & 15;
+    const int op = lane >> 4;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int2 tc = tiles[t];
+      const double* src = X + (int64_t)(op ? tc.y : tc.x) * TM + (int64_t)row * ldx;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(&empty[stage], ((it / STAGES) & 1u) ^ 1u);
+        if (lane == 0) mbar_expect_tx(&full[stage], STAGE_TX_BYTES);
+        __syncwarp();
+        double* dst = sm + (size_t)stage * STAGE_DOUBLES + (size_t)op * BK * SLD + (size_t)row * SLD;
+        bulk_g2s(dst, src + (int64_t)kb * BK * ldx, TM * sizeof(double), &full[stage]);
+      }
+    }
+    return;
   }
 
+  // -------------------------------------------------------------- consumer warps 0..7
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int wm = warp & 1;     // 64-row half
   const int wn = warp >> 1;    // 32-col quarter
   const int fr = lane >> 2;    // fragment row (m or n) 0..7
@@ -86,8 +90,6 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int kb = 0; kb < kblocks; ++kb, ++it) {
-      // refill the slot drained in the previous iteration with the block STAGES-1 ahead
-      if (warp == 0 && it + STAGES - 1 < total) produce(it + STAGES - 1);
       const int stage = it % STAGES;
       mbar_wait(&full[stage], (it / STAGES) & 1u);
       const double* As = sm + (size_t)stage * STAGE_DOUBLES + wm * 64 + fr;
@@ -146,7 +148,7 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, const i
     attr_set = true;
   }
   int grid = ntiles < sm_count() ? ntiles : sm_count();
-  gram_dmma_kernel<<<grid, NCONS * 32, GRAM_SMEM, st>>>(dX, ldx, (int)(p_pad / BK), d_tiles, ntiles, dS, lds, L,
+  gram_dmma_kernel<<<grid, NTHREADS, GRAM_SMEM, st>>>(dX, ldx, (int)(p_pad / BK), d_tiles, ntiles, dS, lds, L,
                                                              row_off, divisor, mirror);
   BGGE_CUDA(cudaGetLastError());
   return OK;
