@@ -102,10 +102,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's sweep on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_sweep_sample(L, E, model, kernel, iters, seed=0):
-    """Time `iters` iterations of the reference algorithm's sweep (numpy/OpenBLAS restatement,
-    R not installed) with eigen blocks of the true shape (values do not affect timing)."""
-    import oracle
+def cpu_problem(L, E, model, kernel, seed=0):
+    """Inputs of the reference algorithm's sweep with eigen blocks of the true shape.  The values are
+    random (they do not affect timing); building them is not part of any timed region."""
     rng = np.random.default_rng(seed)
     n = L * E
     nr_d = L if kernel == "GK" else L - 1
@@ -116,21 +115,32 @@ def cpu_sweep_sample(L, E, model, kernel, iters, seed=0):
         return {"s": np.sort(rng.random(nr) + 0.01)[::-1].copy(), "U": U, "pos": pos}
 
     eig, K = [], {}
-    eye = {"Kernel": np.broadcast_to(np.ones(1), (n, n)), "Type": "D"}     # only diag() is read (mean(diag(K)))
     eig.append([block(n, nr_d, None)])
-    K["G"] = {"Kernel": eye["Kernel"], "Type": "D"}
+    K["G"] = {"Type": "D", "mean_diag": 1.0}
     if model == "MDs":
         eig.append([block(L, nr_d, (e * L, (e + 1) * L)) for e in range(E)])
-        K["GE"] = {"Kernel": eye["Kernel"], "Type": "BD"}
+        K["GE"] = {"Type": "BD", "mean_diag": 1.0}
     elif model == "MDe":
         for e in range(E):
             eig.append([block(L, nr_d, (e * L, (e + 1) * L))])
-            K[f"E{e}"] = {"Kernel": eye["Kernel"], "Type": "BD"}
-    y = rng.standard_normal(n)
+            K[f"E{e}"] = {"Type": "BD", "mean_diag": 1.0 / E}
+    return {"y": rng.standard_normal(n), "K": K, "eig": eig, "ne": [L] * E}
+
+
+def cpu_sweep_time(prob, iters):
+    """Seconds for `iters` iterations of the reference algorithm's sweep: numpy/OpenBLAS restatement
+    (R is not installed), two dgemv per eigen block per iteration as crossprod() does in R/BGGE.R."""
+    import oracle
     t0 = time.perf_counter()
-    oracle.BGGE(y, K, ne=[L] * E, ite=iters, burn=0, thin=max(1, iters), draws=oracle.RandomDraws(1), eig=eig)
-    dt = time.perf_counter() - t0
-    return iters / dt, dt
+    oracle.BGGE(prob["y"], prob["K"], ne=prob["ne"], ite=iters, burn=0, thin=max(1, iters), draws=oracle.RandomDraws(1),
+                eig=prob["eig"])
+    return time.perf_counter() - t0
+
+
+def default_ref_iters(L, step):
+    # sized so that one step is a few seconds (reference arm) / the baseline sample ~10-20 s of CPU work
+    base = 40 if L >= 5000 else 300 if L >= 2000 else 3000
+    return base if step else 4 * base
 
 
 def run_reference(args):
@@ -138,17 +148,17 @@ def run_reference(args):
     if rank != 0:
         return
     L, p, E, kernel, model, desc = WORKLOADS[args.workload]
-    iters = args.ref_iters or (3 if L >= 5000 else 20 if L >= 2000 else 200)
+    iters = args.ref_iters or default_ref_iters(L, True)
     cores = os.cpu_count()
+    prob = cpu_problem(L, E, model, kernel)
     for _ in range(args.warmup):
-        cpu_sweep_sample(L, E, model, kernel, 1)
-    t_tot, it_tot = 0.0, 0
+        cpu_sweep_time(prob, max(1, iters // 10))
+    t_tot = 0.0
     for _ in range(args.steps):
-        rate, dt = cpu_sweep_sample(L, E, model, kernel, iters)
-        t_tot += dt
-        it_tot += iters
-    val = it_tot / t_tot
-    sample = f"{iters} sweep iterations per step with random eigen blocks of the true shape (values do not affect timing)"
+        t_tot += cpu_sweep_time(prob, iters)
+    val = args.steps * iters / t_tot
+    sample = (f"{iters} sweep iterations per step, numpy/OpenBLAS restatement of R/BGGE.R:274-403 on all host cores, "
+              "eigen blocks of the true shape with random values")
     line = {
         "impl": "reference", "metric": METRIC if args.workload == "c5" else f"Gibbs iterations/sec ({args.workload})",
         "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -252,6 +262,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=0)
     ap.add_argument("--prof-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--two-pass", action="store_true", help="force the two-pass proj/back kernels (no fused sweep)")
     ap.add_argument("--full-eigen", action="store_true", help="decompose the expanded n x n kernels directly")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -274,7 +285,7 @@ def main():
     stream_t = torch.cuda.Stream(device=device)
     L, p, E, kernel, model, desc = WORKLOADS[args.workload]
     n = L * E
-    iters = args.iters or (20 if n >= 30000 else 50 if n >= 10000 else 500)
+    iters = args.iters or (200 if n >= 30000 else 500 if n >= 10000 else 2000)
     pk, pk_src = peaks()
 
     with torch.cuda.stream(stream_t):
@@ -381,6 +392,8 @@ def main():
                 lib.call("bgge_gibbs_set_kernel", h, j, types[j], mean_diags[j])
                 for (pos0, rows, U, ldu, sv) in blocks[j]:
                     lib.call("bgge_gibbs_add_block", h, j, pos0, rows, U.shape[0], lib.ptr(sv), vp(U), ldu, 1)
+            if args.two_pass:
+                lib.call("bgge_gibbs_set_mode", h, 0)
             lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + rank, rank)
             return h
 
@@ -417,6 +430,11 @@ def main():
         prof_ms = prof / max(1, args.prof_iters)
         mu_c, s2_c = C.c_double(), C.c_double()
         lib.call("bgge_gibbs_state", h, C.byref(mu_c), C.byref(s2_c), None, None, None, None)
+        kinfo = []
+        for j in range(nk):
+            f_, cs_, ncl_, nl_ = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            lib.call("bgge_gibbs_kernel_info", h, j, C.byref(f_), C.byref(cs_), C.byref(ncl_), C.byref(nl_))
+            kinfo.append({"fused": bool(f_.value), "cluster_size": cs_.value, "clusters": ncl_.value})
         lib.load().bgge_gibbs_destroy(h)
 
         # ------------------------------------------------------------- e2e: host-buffer BGGE() call per step
@@ -427,20 +445,31 @@ def main():
         cm, cv, cu = np.empty(max(1, ncum)), np.empty(max(1, ncum)), np.empty((nk, max(1, ncum)))
         ve, vesd = C.c_double(), C.c_double()
 
+        e2e_phase = []
+
         def e2e_step():
+            t = [time.perf_counter()]
             hh = make_handle(iters)                       # uploads y from pinned host memory, initialises the chain
+            t.append(time.perf_counter())
             lib.call("bgge_gibbs_run", hh, iters)
+            t.append(time.perf_counter())
             lib.call("bgge_gibbs_summary", hh, lib.ptr(yHat), C.byref(ve), C.byref(vesd), lib.ptr(u_m), lib.ptr(u_sd),
                      lib.ptr(vu), lib.ptr(vusd), lib.ptr(yout))
             lib.call("bgge_gibbs_chain", hh, lib.ptr(cm), lib.ptr(cv), lib.ptr(cu), None)
+            t.append(time.perf_counter())
             lib.load().bgge_gibbs_destroy(hh)
+            t.append(time.perf_counter())
+            e2e_phase.append([round(t[i + 1] - t[i], 4) for i in range(4)])
         e2e_step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        e2e_steps = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             e2e_step()
+            e2e_steps.append(time.perf_counter() - ts)
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         if world > 1:
@@ -451,17 +480,26 @@ def main():
         d2h = 8 * (n * (2 + 2 * nk) + 2 * nk + 2 + max(1, ncum) * (2 + nk))
 
     # ----------------------------------------------------------------- roofline bookkeeping
-    sum_rn = sum(rows * U.shape[0] for blk in blocks for (_p, rows, U, _l, _s) in blk)
+    # fused kernel steps read U once per iteration, two-pass steps twice; the accounting follows the path used
     sum_nr = sum(U.shape[0] for blk in blocks for (_p, rows, U, _l, _s) in blk)
-    bytes_iter = 16 * sum_rn + 8 * n * (4 * nk + 3) + 40 * sum_nr
-    sweep_gbs = bytes_iter * (world * args.steps * iters) / (ms_total * 1e-3) / 1e9 / world
     kern = []
+    u_bytes = 0
     for j in range(nk):
         rn = sum(rows * U.shape[0] for (_p, rows, U, _l, _s) in blocks[j])
         cov = sum(rows for (_p, rows, U, _l, _s) in blocks[j])
         nrj = sum(U.shape[0] for (_p, rows, U, _l, _s) in blocks[j])
-        kern.append({"name": f"proj_kernel[{j}]", "ms": prof_ms[2 * j], "bytes": 8 * rn + 16 * cov + 24 * nrj})
-        kern.append({"name": f"back_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * rn + 32 * n + 8 * nrj})
+        if kinfo[j]["fused"]:
+            ncl = kinfo[j]["clusters"]
+            u_bytes += 8 * rn
+            kern.append({"name": f"sweep_fused_kernel[{j}]", "ms": prof_ms[2 * j],
+                         "bytes": 8 * rn + 16 * cov + 8 * nrj + 8 * cov * 1})
+            kern.append({"name": f"fused_finalize_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * cov * ncl + 32 * n})
+        else:
+            u_bytes += 16 * rn
+            kern.append({"name": f"proj_kernel[{j}]", "ms": prof_ms[2 * j], "bytes": 8 * rn + 16 * cov + 24 * nrj})
+            kern.append({"name": f"back_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * rn + 32 * n + 8 * nrj})
+    bytes_iter = u_bytes + 8 * n * (4 * nk + 3) + 40 * sum_nr
+    sweep_gbs = bytes_iter * (world * args.steps * iters) / (ms_total * 1e-3) / 1e9 / world
     kern.append({"name": "scalar_kernel", "ms": prof_ms[2 * nk], "bytes": 16 * n})
     for k in kern:
         k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
@@ -479,12 +517,14 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref_it = args.ref_iters or (3 if L >= 5000 else 20 if L >= 2000 else 200)
-        cpu_sweep_sample(L, E, model, kernel, 1)
-        rate, dt = cpu_sweep_sample(L, E, model, kernel, ref_it)
-        cpu_base = {"value": rate, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
-                    "sample": f"{ref_it} sweep iterations of the numpy/OpenBLAS restatement (R not installed), eigen "
-                              f"blocks of the true shape with random values, {dt:.1f} s"}
+        ref_it = args.ref_iters or default_ref_iters(L, False)
+        prob = cpu_problem(L, E, model, kernel)
+        cpu_sweep_time(prob, max(1, ref_it // 20))
+        dt = cpu_sweep_time(prob, ref_it)
+        cpu_base = {"value": ref_it / dt, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"{ref_it} sweep iterations of the numpy/OpenBLAS restatement of R/BGGE.R:274-403 (R not "
+                              f"installed), eigen blocks of the true shape with random values, {dt:.1f} s"}
+        del prob
 
     if rank == 0:
         line = {
@@ -494,18 +534,25 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "iters_per_step": iters, "kernels": nk, "n": n, "L": L, "p": p, "E": E,
                        "parallelism": f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain",
-                       "l2": "inputs larger than L2 (U streamed twice per iteration)" if 16 * sum_rn > 256e6
+                       "l2": "inputs larger than L2 (U streamed from HBM every iteration)" if u_bytes > 256e6
                              else "working set fits in L2; latency-bound, HBM roofline not binding",
                        "eigen": "one L x L syevd, blocks derived (balanced design)"},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "step_s": e2e_steps, "phase_s_create_run_fetch_destroy": e2e_phase[1:],
                     "covers": "bgge_gibbs_create + set_y (pinned host) + add_block (device-resident eigen) + init + "
                               f"{iters} sweeps + summary/chain download; eigen and getK are one-off setup below"},
             "gpu_launches": args.steps * iters * (2 * nk + 1),
             "roofline": roofline,
             "cpu_baseline": cpu_base,
             "sweep": {"algorithmic_bytes_per_iter": bytes_iter, "achieved_gbs_per_gpu": sweep_gbs,
-                      "frac_of_hbm_peak": sweep_gbs / pk["hbm_gbs"], "accounting": "2-pass (U read for U'e and for U b)",
+                      "frac_of_hbm_peak": sweep_gbs / pk["hbm_gbs"], "accounting": ("1-pass: U read from HBM once per kernel step (fused proj+draw+back kernel)"
+                                     if all(k["fused"] for k in kinfo) else
+                                     "2-pass (U read for U'e and for U b)" if not any(k["fused"] for k in kinfo)
+                                     else "mixed: fused kernels 1-pass, others 2-pass"),
+                      "two_pass_equivalent_gbs_per_gpu": (16 * sum(rows * U.shape[0] for blk in blocks for (_p, rows, U, _l, _s) in blk)
+                                                          + 8 * n * (4 * nk + 3) + 40 * sum_nr)
+                                                         * (args.steps * iters) / (ms_total * 1e-3) / 1e9,
+                      "kernel_paths": kinfo,
                       "kernels": kern, "last_mu": mu_c.value, "last_varE": s2_c.value},
             "getk": {"contraction_s": t_contr, "contraction_s_all": t_contr_all, "contraction_tflops": flops / t_contr / 1e12,
                      "dgemm_peak_tflops_burst": dg_burst, "dgemm_peak_tflops_sustained": dg_sust,

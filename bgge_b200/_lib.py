@@ -40,6 +40,7 @@ SIGNATURES = {
     "bgge_last_error": (C.c_char_p, []),
     "bgge_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "bgge_set_device": (C.c_int, [C.c_int]),
+    "bgge_release_cache": (C.c_int, []),
     "bgge_device_memory": (C.c_int, [c_uint64_p, c_uint64_p]),
     "bgge_getk_base": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                  C.c_void_p, c_double_p]),
@@ -71,6 +72,9 @@ SIGNATURES = {
                                        C.c_int64, C.c_int]),
     "bgge_gibbs_add_kernel_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                                C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "bgge_gibbs_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgge_gibbs_set_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "bgge_gibbs_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_uint64,
                                   C.c_uint32]),

@@ -61,11 +61,13 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
 
 
 def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=1e-10, R2=0.5, *, seed=0, chain=0,
-         draws=None, eig=None, device=None):
+         draws=None, eig=None, device=None, mode=None):
     """Fit the G x E model by Gibbs sampling (signature of R/BGGE.R:84 plus keyword-only extras).
 
     draws : optional (normals, chisq) tapes -> injected-draw mode.
-    eig   : optional precomputed setDEC() result (shared eigenbasis).
+    eig   : optional precomputed setDEC() result (shared eigenbasis); kernel entries may then carry
+            "mean_diag" instead of the n x n "Kernel".
+    mode  : None/1 = fused single-pass sweep kernels where the shapes fit, 0 = two-pass kernels only.
     """
     y = np.array(y, dtype=np.float64).ravel()
     n = y.shape[0]
@@ -94,17 +96,24 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
         _lib.call("bgge_gibbs_set_y", h, _lib.ptr(y), None)
         if q:
             _lib.call("bgge_gibbs_set_xf", h, _lib.ptr(XF))
+        if mode is not None:
+            _lib.call("bgge_gibbs_set_mode", h, int(mode))
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
-            Km = _lib.f64(k["Kernel"])
-            if Km.shape != (n, n):
-                raise ValueError(f"kernel {names[j]} is {Km.shape}, expected {(n, n)}")
+            if eig is not None and "mean_diag" in k:
+                _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(k["mean_diag"]))
+                Km = None
+            else:
+                Km = _lib.f64(k["Kernel"])
+                if Km.shape != (n, n):
+                    raise ValueError(f"kernel {names[j]} is {Km.shape}, expected {(n, n)}")
             if eig is None:
                 _lib.call("bgge_gibbs_add_kernel_matrix", h, j, tcode, _lib.ptr(Km), n, 0,
                           None if ne_arr is None else _lib.ptr(ne_arr), 0 if ne_arr is None else ne_arr.shape[0],
                           float(tol), 1)
             else:
-                _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(np.mean(np.diag(Km))))
+                if Km is not None:
+                    _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(np.mean(np.diag(Km))))
                 for blk in eig[j]:
                     U = _lib.f64(blk["U"])
                     s = np.ascontiguousarray(blk["s"], dtype=np.float64)

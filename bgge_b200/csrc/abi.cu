@@ -7,7 +7,9 @@
 #include "rng.cuh"
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 namespace bgge {
@@ -24,6 +26,95 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 static int g_sm_count[64] = {0};
+
+// ------------------------------------------------------------------ caching device allocator
+namespace {
+struct PoolBlock {
+  size_t bytes;
+  int device;
+};
+std::mutex g_pool_mu;
+std::map<void*, PoolBlock> g_pool_live;                          // blocks handed out
+std::multimap<std::pair<int, size_t>, void*> g_pool_free;        // (device, bytes) -> cached block
+size_t g_pool_cached = 0;
+constexpr size_t POOL_MAX_BLOCK = 512ull << 20;                  // larger blocks go straight back to the driver
+constexpr size_t POOL_MAX_CACHED = 2048ull << 20;
+
+size_t pool_round(size_t b) {
+  if (b <= (1u << 20)) {
+    size_t r = 512;
+    while (r < b) r <<= 1;
+    return r;
+  }
+  return (b + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+}
+}  // namespace
+
+cudaError_t pool_alloc(void** p, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const size_t rb = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_free.find({dev, rb});
+    if (it != g_pool_free.end()) {
+      *p = it->second;
+      g_pool_free.erase(it);
+      g_pool_cached -= rb;
+      g_pool_live[*p] = {rb, dev};
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, rb);
+  if (e != cudaSuccess) {   // give cached memory back and retry once
+    cudaGetLastError();
+    pool_release_all();
+    e = cudaMalloc(p, rb);
+    if (e != cudaSuccess) return e;
+  }
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_live[*p] = {rb, dev};
+  return cudaSuccess;
+}
+
+void pool_free(void* p) {
+  if (!p) return;
+  PoolBlock b{0, 0};
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_live.find(p);
+    if (it == g_pool_live.end()) {
+      cudaFree(p);
+      return;
+    }
+    b = it->second;
+    g_pool_live.erase(it);
+    if (b.bytes <= POOL_MAX_BLOCK && g_pool_cached + b.bytes <= POOL_MAX_CACHED) {
+      g_pool_free.insert({{b.device, b.bytes}, p});
+      g_pool_cached += b.bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
+void pool_release_all() {
+  std::vector<std::pair<int, void*>> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& kv : g_pool_free) blocks.push_back({kv.first.first, kv.second});
+    g_pool_free.clear();
+    g_pool_cached = 0;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& b : blocks) {
+    cudaSetDevice(b.first);
+    cudaFree(b.second);
+  }
+  cudaSetDevice(cur);
+}
 
 int ensure_device() {
   int count = 0;
@@ -176,6 +267,11 @@ int bgge_device_count(int* count) {
 int bgge_set_device(int device) {
   BGGE_CUDA(cudaSetDevice(device));
   return ensure_device();
+}
+
+int bgge_release_cache(void) {
+  pool_release_all();
+  return OK;
 }
 
 int bgge_device_memory(uint64_t* free_bytes, uint64_t* total_bytes) {
@@ -471,7 +567,7 @@ int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64
     bl.owns = false;
   } else {
     bl.ldu = round_up(rows, 16);
-    BGGE_CUDA(cudaMalloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+    BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
     bl.owns = true;
     hk.blocks.push_back(bl);   // owned from here on (freed by the handle even on failure below)
     BGGE_CUDA(cudaMemset(bl.dU, 0, (size_t)bl.ldu * nr * sizeof(double)));
@@ -530,7 +626,7 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
     bl.rows = m;
     bl.nr = nr;
     bl.ldu = round_up(m, 16);
-    BGGE_CUDA(cudaMalloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+    BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
     bl.owns = true;
     hk.blocks.push_back(bl);
     BGGE_CUDA(dS.alloc((size_t)nr));
@@ -580,6 +676,26 @@ int bgge_gibbs_init(bgge_gibbs* h, int64_t ite, int64_t burn, int64_t thin, doub
 int bgge_gibbs_run(bgge_gibbs* h, int64_t iters) {
   BGGE_HANDLE(h);
   return gibbs_run(&h->g, iters);
+}
+
+int bgge_gibbs_set_mode(bgge_gibbs* h, int mode) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(!h->g.initialised, "gibbs_set_mode: handle already initialised");
+  BGGE_REQUIRE(mode == 0 || mode == 1, "gibbs_set_mode: mode must be 0 (two-pass) or 1 (fused)");
+  h->g.mode = mode;
+  return OK;
+}
+
+int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && j >= 0 && j < g.nk, "gibbs_kernel_info: bad kernel index or handle not initialised");
+  HostKernel& hk = g.kernels[(size_t)j];
+  if (fused) *fused = hk.fused ? 1 : 0;
+  if (cluster_size) *cluster_size = hk.fused ? hk.fused_cs : hk.cs;
+  if (clusters) *clusters = hk.fused ? hk.fused_clusters : hk.n_btasks;
+  if (launches) *launches = 2;
+  return OK;
 }
 
 int bgge_gibbs_profile(bgge_gibbs* h, int64_t iters, double* ms) {

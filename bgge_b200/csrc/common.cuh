@@ -52,7 +52,14 @@ int sm_count();
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// simple RAII device buffer (host side)
+// Device memory comes from a small per-device caching pool (abi.cu): repeated BGGE()/getK() calls
+// reuse their scratch blocks instead of paying cudaMalloc/cudaFree (cudaFree alone cost up to 180 ms
+// per handle teardown in a process that also holds tens of GB of other allocations).
+cudaError_t pool_alloc(void** p, size_t bytes);
+void pool_free(void* p);
+void pool_release_all();
+
+// RAII device buffer (host side).  Callers synchronise the stream that used it before it dies.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -76,7 +83,7 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     n = 0;
   }
@@ -84,7 +91,7 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc((void**)&p, count * sizeof(T));
+    return pool_alloc((void**)&p, count * sizeof(T));
   }
 };
 

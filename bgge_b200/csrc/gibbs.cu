@@ -482,7 +482,7 @@ int launch_scalar(Gibbs* g) {
   a.chain_bet = g->chain_bet.p;
   for (int j = 0; j < g->nk; ++j) {
     a.bpart[j] = g->kernels[j].bpart.p;
-    a.n_bpart[j] = g->kernels[j].n_atasks;
+    a.n_bpart[j] = g->kernels[j].fused ? g->kernels[j].fused_clusters : g->kernels[j].n_atasks;
     a.nr[j] = g->kernels[j].nr_total;
   }
   scalar_kernel<<<1, S_THREADS, 0, g->stream>>>(a, g->draw);
@@ -509,10 +509,17 @@ int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
   }
   for (int j = 0; j < g->nk; ++j) {
     HostKernel& hk = g->kernels[j];
-    if (hk.n_atasks > 0) BGGE_TRY(launch_proj(g, hk, j));
-    mark();
-    BGGE_TRY(launch_back(g, hk));
-    mark();
+    if (hk.fused) {
+      BGGE_TRY(launch_fused(g, hk, j));   // proj + back in one pass over U (sweep_fused.cu)
+      mark();
+      BGGE_TRY(launch_fused_finalize(g, hk, j));
+      mark();
+    } else {
+      if (hk.n_atasks > 0) BGGE_TRY(launch_proj(g, hk, j));
+      mark();
+      BGGE_TRY(launch_back(g, hk));
+      mark();
+    }
   }
   BGGE_TRY(launch_scalar(g));
   mark();
@@ -523,11 +530,12 @@ int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
 
 Gibbs::~Gibbs() {
   cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);   // pooled blocks may be reused as soon as they are released
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (graph) cudaGraphDestroy(graph);
   for (auto& k : kernels)
     for (auto& bl : k.blocks)
-      if (bl.owns && bl.dU) cudaFree(bl.dU);
+      if (bl.owns && bl.dU) pool_free(bl.dU);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -602,6 +610,7 @@ int gibbs_init(Gibbs* g) {
   // ---- per-kernel task lists
   long long z_off = 1 + q;
   long long sum_nr = 0;
+  int max_clusters = 0;
   for (int j = 0; j < g->nk; ++j) {
     HostKernel& hk = g->kernels[j];
     BGGE_REQUIRE(!hk.blocks.empty(), "gibbs: kernel %d has no eigen blocks (all eigenvalues <= tol)", j);
@@ -664,7 +673,9 @@ int gibbs_init(Gibbs* g) {
     BGGE_TRY(upload(hk.btasks, bt, st));
     BGGE_TRY(upload(hk.s, hk.s_host, st));
     BGGE_CUDA(hk.b.alloc((size_t)hk.nr_total));
-    BGGE_CUDA(hk.bpart.alloc((size_t)std::max(1, hk.n_atasks)));
+    if (g->mode == 1) BGGE_TRY(plan_fused(g, hk, st));
+    max_clusters = std::max(max_clusters, hk.fused ? hk.fused_clusters : 0);
+    BGGE_CUDA(hk.bpart.alloc((size_t)std::max(std::max(1, hk.n_atasks), hk.fused_clusters)));
     hk.z_off = z_off;
     z_off += hk.nr_total;
     sum_nr += hk.nr_total;
@@ -692,6 +703,7 @@ int gibbs_init(Gibbs* g) {
   // ---- device state
   g->ncum = g->ite / g->thin;                                       // R/BGGE.R:229
   BGGE_CUDA(g->r.alloc((size_t)n));
+  if (max_clusters > 0) BGGE_CUDA(g->upart.alloc((size_t)n * max_clusters));
   BGGE_CUDA(g->u.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->umean.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->um2.alloc((size_t)n * g->nk));

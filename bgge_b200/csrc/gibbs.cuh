@@ -55,6 +55,18 @@ struct BTask {                   // one row tile of one block (or of a gap: nr =
   int nr, col_off;
 };
 
+struct FPanel {                  // fused path: columns [c0, c1) of one block, handled by one cluster
+  const double* U;
+  long long ldu;
+  int rows, pos0, c0, c1, col_off;
+  int rs;                        // rows per CTA of the cluster (multiple of 16)
+  int slot;                      // upart slot (= cluster index)
+};
+
+struct FTile {                   // fused finalize: 256 rows, clusters [qlo, qhi] contributed (qlo > qhi: none)
+  int row0, rows, qlo, qhi;
+};
+
 struct HostBlock {
   int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, col_off = 0;
   double* dU = nullptr;
@@ -73,6 +85,13 @@ struct HostKernel {
   int n_atasks = 0, n_btasks = 0, ct = 8, cs = 1;
   std::vector<double> s_host;
   long long z_off = 0;           // offset of this kernel's normals inside an iteration
+  // fused single-pass path (sweep_fused.cu)
+  bool fused = false, fused_attr_set = false;
+  int fused_cs = 1, fused_rpt = 1, fused_g = 1, fused_ns = 0, fused_clusters = 0, n_ftiles = 0;
+  size_t fused_smem = 0;
+  DevBuf<FPanel> fpanels;
+  DevBuf<int2> fcluster;
+  DevBuf<FTile> ftiles;
 };
 
 struct Gibbs {
@@ -88,7 +107,8 @@ struct Gibbs {
   std::vector<double> xf_host;
   int64_t n_na = 0;
   // device state
-  DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean;
+  DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart;
+  int mode = 1;                  // 0: two-pass kernels only, 1: fused single-pass where the shape fits
   DevBuf<int> na_idx;
   DevBuf<Scal> scal;
   DevBuf<double> chain_mu, chain_varE, chain_varU, chain_bet;
@@ -110,5 +130,8 @@ struct Gibbs {
 int gibbs_init(Gibbs* g);
 int gibbs_run(Gibbs* g, int64_t iters);
 int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
+int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st);
+int launch_fused(Gibbs* g, HostKernel& hk, int j);
+int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j);
 
 }  // namespace bgge

@@ -1,0 +1,498 @@
+// Single-pass kernel step of the Gibbs sweep: for one random effect j it computes
+//     d = U'(e + u_j),   b ~ N(tau v d, v),   u_j = U b                       (R/BGGE.R:297-306 / 314-338)
+// while reading U from HBM ONCE.  (proj_kernel + back_kernel in gibbs.cu read it twice.)
+//
+// A thread-block cluster of CS CTAs owns a panel of eigen-columns of one block; CTA `rank` owns the
+// row slice [rank*Rs, rank*Rs + Rs).  Per group of G columns:
+//   1. the TMA unit (cp.async.bulk + mbarrier, SASS UBLKCP) lands the CTA's G column slices in a
+//      shared-memory ring (NS groups deep, issued by thread 0);
+//   2. every thread moves its rows of the group to registers (the ring slot is refilled at once),
+//      forms its part of the G dot products against the register-resident residual slice, block-reduces;
+//   3. the G partial dots go to every CTA of the cluster with st.async over distributed shared memory,
+//      completing a transaction barrier on the receiver (no cluster-wide barrier in the loop);
+//   4. one group later (software pipelined, so the exchange latency hides behind step 2 of the next
+//      group) each CTA sums the CS partials in rank order, draws the same b (counter-based Philox or
+//      the injected tape -> identical in all CTAs) and applies u_slice += U_slice b from registers.
+// Partial u per cluster goes to upart[cluster][n]; fused_finalize_kernel sums the clusters in fixed
+// order (deterministic) and does the residual / Welford update of back_kernel.
+#include "gibbs.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+namespace bgge {
+namespace {
+
+constexpr int F_ROLE = 256;                      // threads per compute role (dot warps / axpy warps)
+constexpr int F_THREADS = 2 * F_ROLE + 32;       // + one producer warp (one elected lane issues TMA)
+constexpr int F_ROWS_PER_STEP = 2 * F_ROLE;      // each role thread owns row pairs (16-byte shared loads)
+constexpr int F_MAX_NS = 10;                     // data ring depth limit
+constexpr int NPX = 32;                          // partial-exchange ring depth (see protocol note)
+
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void role_barrier(int id) {   // named barrier over one 256-thread role
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(F_ROLE) : "memory");
+}
+
+// Warp-specialised CTA:
+//   producer (warp 16, one lane)  waits empty[slot], issues the bulk copies of the next group
+//   dot warps 0..7                wait full[slot]; partial dots against the register-resident residual
+//                                 slice; role-local reduction; lanes 0..CS-1 of warp 0 push the partials
+//                                 to every CTA of the cluster (st.async + remote mbarrier complete_tx).
+//                                 They never wait for the exchange and run ahead as far as the ring allows.
+//   axpy warps 8..15              wait pbar[group] (all CS partials), every thread forms d and b itself
+//                                 (partials summed in rank order; draw terms precomputed per 256-column
+//                                 batch), u_slice += U_slice b from the same shared-memory copy, then
+//                                 release the slot (empty[slot]).
+// Protocol note: a remote CTA can send group h only after its axpy finished h - ns (slot reuse), which
+// needs my partials of h - ns; my axpy can lag my dots by ns groups, so up to 2 ns + 1 partial entries
+// are live; NPX = 32 >= 2 * F_MAX_NS + 2 leaves a margin of several microseconds for in-flight stores.
+template <int RPT, int G>
+__global__ void __launch_bounds__(F_THREADS, 1)
+sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cluster_panels,
+                   const double* __restrict__ r, const double* __restrict__ u_old, const double* __restrict__ s,
+                   double* __restrict__ upart, double* __restrict__ bpart, long long n,
+                   const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const uint32_t cs = cluster.num_blocks();
+  const int cid = blockIdx.x / cs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ZB = G * (F_ROLE / G);           // columns per draw batch
+
+  extern __shared__ __align__(128) unsigned char fsm[];
+  // carve: ring[ns] | parts[NPX][8][G] | red[2][8][G] | tvb,zsb,isb[2][ZB] | full[F_MAX_NS] | empty[F_MAX_NS] | pbar[NPX]
+  const int2 cp = cluster_panels[cid];
+  int max_rs = 0;
+  for (int pi = 0; pi < cp.y; ++pi) max_rs = max(max_rs, panels[cp.x + pi].rs);
+  const size_t slot_doubles = (size_t)G * max_rs;
+  double* ring = reinterpret_cast<double*>(fsm);
+  double* parts = ring + (size_t)ns * slot_doubles;
+  double* red = parts + (size_t)NPX * 8 * G;
+  double* tvb = red + 2 * 8 * G;                 // tau * v       per column of a draw batch
+  double* zsb = tvb + 2 * ZB;                    // sqrt(v) * z
+  double* isb = zsb + 2 * ZB;                    // 1 / s
+  uint64_t* full = reinterpret_cast<uint64_t*>(isb + 2 * ZB);
+  uint64_t* empty = full + F_MAX_NS;
+  uint64_t* pbar = empty + F_MAX_NS;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < ns; ++k) {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], F_ROLE / 32);
+    }
+    for (int k = 0; k < NPX; ++k) mbar_init(&pbar[k], 1);
+    mbar_fence_init();
+  }
+  cluster.sync();   // barriers of every CTA exist before anybody sends
+
+  const double shift = sc->shift;
+  const double lam = sc->sigb[j];
+  const double tau = sc->tau;
+  const long long it = sc->it;
+
+  if (warp == 2 * (F_ROLE / 32)) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t lc = 0;
+      for (int pi = 0; pi < cp.y; ++pi) {
+        const FPanel pn = panels[cp.x + pi];
+        const int row0 = (int)rank * pn.rs;
+        const int my_rows = max(0, min(pn.rs, pn.rows - row0));
+        const uint32_t slice_bytes = (uint32_t)((my_rows + 1) & ~1) * (uint32_t)sizeof(double);
+        const double* Ubase = pn.U + row0;
+        for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++lc) {
+          const int slot = lc % ns;
+          const int gc = min(G, pn.c1 - c0);
+          mbar_wait(&empty[slot], ((lc / ns) & 1u) ^ 1u);
+          mbar_expect_tx(&full[slot], slice_bytes * (uint32_t)gc);
+          if (slice_bytes > 0) {
+            double* dst = ring + (size_t)slot * slot_doubles;
+            for (int g = 0; g < gc; ++g)
+              bulk_g2s(dst + (size_t)g * max_rs, Ubase + (long long)(c0 + g) * pn.ldu, slice_bytes, &full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp < F_ROLE / 32) {
+    // ------------------------------------------------------------------ dot warps
+    const int tid = threadIdx.x;
+    uint32_t cc = 0;
+    for (int pi = 0; pi < cp.y; ++pi) {
+      const FPanel pn = panels[cp.x + pi];
+      const int row0 = (int)rank * pn.rs;
+      const int my_rows = max(0, min(pn.rs, pn.rows - row0));
+      double2 e[RPT];   // residual slice e = (r - shift) + u_old, register resident for the whole panel
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int row = k * F_ROWS_PER_STEP + 2 * tid;
+        const long long gi = (long long)pn.pos0 + row0 + row;
+        e[k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
+        e[k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
+      }
+      for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
+        const int slot = cc % ns;
+        const int gc = min(G, pn.c1 - c0);
+        mbar_wait(&full[slot], (cc / ns) & 1u);
+        const double* src = ring + (size_t)slot * slot_doubles + 2 * tid;
+        double* rd = red + (cc & 1u) * 8 * G;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          double a = 0.0;
+          if (g < gc) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+              if (k * F_ROWS_PER_STEP + 2 * tid < my_rows) {
+                const double2 x = *reinterpret_cast<const double2*>(src + (size_t)g * max_rs + k * F_ROWS_PER_STEP);
+                a = fma(x.x, e[k].x, a);
+                a = fma(x.y, e[k].y, a);
+              }
+            }
+          }
+          a = warp_sum(a);
+          if (lane == 0) rd[warp * G + g] = a;
+        }
+        role_barrier(1);
+        if (warp == 0) {
+          const uint32_t pg = cc % NPX;
+          if (lane == 0) mbar_expect_tx(&pbar[pg], cs * (uint32_t)gc * (uint32_t)sizeof(double));
+          __syncwarp();
+          const uint32_t bar_addr = smem_u32(&pbar[pg]);
+          for (int g = 0; g < gc; ++g) {
+            double p = lane < 8 ? rd[lane * G + g] : 0.0;   // fixed tree: deterministic
+            p += __shfl_xor_sync(0xffffffffu, p, 4);
+            p += __shfl_xor_sync(0xffffffffu, p, 2);
+            p += __shfl_xor_sync(0xffffffffu, p, 1);
+            if (lane < (int)cs) {
+              const uint32_t dst = smem_u32(parts + (size_t)pg * 8 * G + (size_t)rank * G + g);
+              st_async_f64(map_to_rank(dst, (uint32_t)lane), p, map_to_rank(bar_addr, (uint32_t)lane));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ axpy warps
+    const int tid = threadIdx.x - F_ROLE;
+    uint32_t cc = 0;
+    double zq = 0.0;   // thread 0 of the role: sum of b^2 / s (R/BGGE.R:96)
+    for (int pi = 0; pi < cp.y; ++pi) {
+      const FPanel pn = panels[cp.x + pi];
+      const int row0 = (int)rank * pn.rs;
+      const int my_rows = max(0, min(pn.rs, pn.rows - row0));
+      const int ncols = pn.c1 - pn.c0;
+      double2 uacc[RPT];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) uacc[k] = make_double2(0.0, 0.0);
+      for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
+        const int slot = cc % ns;
+        const int gc = min(G, pn.c1 - c0);
+        const int rel0 = c0 - pn.c0;
+        if (rel0 % ZB == 0) {
+          // draw batch for panel columns [rel0, rel0 + ZB): the normal draw does not depend on d
+          const int rel = rel0 + tid;
+          if (tid < ZB && rel < ncols) {
+            const long long col = (long long)pn.col_off + pn.c0 + rel;
+            const double sv = s[col];
+            const double vari = sv * lam / (1.0 + sv * lam * tau);                 // R/BGGE.R:302
+            const double z = draw_normal(dc, it, (uint32_t)j, (unsigned long long)col,
+                                         dc.z_init + (it - 1) * dc.z_per_it + z_off + col);
+            const int zb = ((rel0 / ZB) & 1) * ZB + tid;
+            tvb[zb] = tau * vari;
+            zsb[zb] = sqrt(vari) * z;
+            isb[zb] = 1.0 / sv;
+          }
+          role_barrier(2);
+        }
+        const uint32_t pg = cc % NPX;
+        mbar_wait(&pbar[pg], (cc / NPX) & 1u);
+        double bv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          bv[g] = 0.0;
+          if (g < gc) {
+            const double* pp = parts + (size_t)pg * 8 * G + g;
+            double d = 0.0;
+            for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * G];             // rank order
+            const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
+            const double media = tvb[zb] * d;                                       // (tau vari) d   R/BGGE.R:303
+            bv[g] = media + zsb[zb];                                                // + sqrt(vari) z R/BGGE.R:89-92
+            if (tid == 0) zq += bv[g] * bv[g] * isb[zb];
+          }
+        }
+        mbar_wait(&full[slot], (cc / ns) & 1u);   // acquire the TMA-written slot for this role too
+        const double* src = ring + (size_t)slot * slot_doubles + 2 * tid;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          if (k * F_ROWS_PER_STEP + 2 * tid < my_rows) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (g < gc) {
+                const double2 x = *reinterpret_cast<const double2*>(src + (size_t)g * max_rs + k * F_ROWS_PER_STEP);
+                uacc[k].x = fma(x.x, bv[g], uacc[k].x);
+                uacc[k].y = fma(x.y, bv[g], uacc[k].y);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+      // this cluster's contribution to u over the block's rows
+      double* up = upart + (size_t)pn.slot * n + pn.pos0 + row0;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int row = k * F_ROWS_PER_STEP + 2 * tid;
+        if (row < my_rows) up[row] = uacc[k].x;
+        if (row + 1 < my_rows) up[row + 1] = uacc[k].y;
+      }
+      role_barrier(2);   // batch buffers are reused by the next panel
+    }
+    if (rank == 0 && tid == 0) bpart[cid] = zq;
+  }
+  cluster.sync();      // nobody leaves while a peer may still write into its shared memory
+}
+
+// u_j = sum over clusters of upart (fixed order); e <- (e + u_old) - u_new; Welford  (R/BGGE.R:306-307, 392)
+__global__ void __launch_bounds__(256)
+fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict__ upart, long long n,
+                      double* __restrict__ r, double* __restrict__ u, double* __restrict__ umean,
+                      double* __restrict__ um2, const Scal* __restrict__ sc, long long thin, long long burn) {
+  const FTile t = tiles[blockIdx.x];
+  const int row = threadIdx.x;
+  if (row >= t.rows) return;
+  const long long g = (long long)t.row0 + row;
+  double un = 0.0;
+  for (int q = t.qlo; q <= t.qhi; ++q) un += upart[(size_t)q * n + g];
+  const long long it = sc->it;
+  r[g] = (r[g] + u[g]) - un;
+  u[g] = un;
+  if ((it % thin == 0) && (it > burn)) {
+    const double kcount = (double)(it / thin - burn / thin);
+    const double m = umean[g];
+    const double dlt = un - m;
+    const double mn = m + dlt / kcount;
+    umean[g] = mn;
+    um2[g] += dlt * (un - mn);
+  }
+}
+
+template <int RPT, int G>
+int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
+  auto kfn = sweep_fused_kernel<RPT, G>;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(hk.fused_clusters * hk.fused_cs), 1, 1);
+  cfg.blockDim = dim3(F_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = hk.fused_smem;
+  cfg.stream = g->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)hk.fused_cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, kfn, (const FPanel*)hk.fpanels.p, (const int2*)hk.fcluster.p,
+                               (const double*)g->r.p, (const double*)(g->u.p + (size_t)j * g->n),
+                               (const double*)hk.s.p, g->upart.p, hk.bpart.p, (long long)g->n,
+                               (const Scal*)g->scal.p, j, g->draw, hk.z_off, hk.fused_ns));
+  return OK;
+}
+
+struct Combo { int rpt, gcols; };
+constexpr Combo kCombos[] = {{1, 8}, {2, 6}, {3, 4}, {4, 3}, {6, 2}, {8, 1}, {10, 1}, {12, 1}};   // slot <= 48 KB
+
+template <int RPT, int G>
+int occupancy_t(int cs, size_t smem, int* nclusters) {
+  auto kfn = sweep_fused_kernel<RPT, G>;
+  // one template instantiation serves several model kernels with different ring sizes: opt in to the
+  // device maximum once instead of per launch
+  int dev = 0, optin = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  (void)dev;
+  BGGE_REQUIRE((size_t)optin >= smem, "fused plan: %zu bytes of shared memory exceed the device limit %d", smem, optin);
+  BGGE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+  cfg.blockDim = dim3(F_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BGGE_CUDA(cudaOccupancyMaxActiveClusters(nclusters, kfn, &cfg));
+  return OK;
+}
+
+#define BGGE_FUSED_DISPATCH(FN, ...)                       \
+  switch (hk.fused_rpt) {                                  \
+    case 1: return FN<1, 8>(__VA_ARGS__);                  \
+    case 2: return FN<2, 6>(__VA_ARGS__);                  \
+    case 3: return FN<3, 4>(__VA_ARGS__);                  \
+    case 4: return FN<4, 3>(__VA_ARGS__);                  \
+    case 6: return FN<6, 2>(__VA_ARGS__);                  \
+    case 8: return FN<8, 1>(__VA_ARGS__);                  \
+    case 10: return FN<10, 1>(__VA_ARGS__);                \
+    default: return FN<12, 1>(__VA_ARGS__);                \
+  }
+
+int occupancy_dispatch(HostKernel& hk, int cs, size_t smem, int* ncl) { BGGE_FUSED_DISPATCH(occupancy_t, cs, smem, ncl) }
+
+}  // namespace
+
+int launch_fused(Gibbs* g, HostKernel& hk, int j) {
+  auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
+  return run();
+}
+
+int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
+  fused_finalize_kernel<<<hk.n_ftiles, 256, 0, g->stream>>>(hk.ftiles.p, g->upart.p, (long long)g->n, g->r.p,
+                                                            g->u.p + (size_t)j * g->n, g->umean.p + (size_t)j * g->n,
+                                                            g->um2.p + (size_t)j * g->n, g->scal.p,
+                                                            (long long)g->thin, (long long)g->burn);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// Decide whether kernel j can use the fused path and build its panel / tile tables.
+// Returns OK with hk.fused == false when the shape does not fit (caller keeps the two-pass kernels).
+int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
+  hk.fused = false;
+  int64_t max_rows = 0;
+  for (auto& bl : hk.blocks) max_rows = std::max(max_rows, bl.rows);
+  if (max_rows <= 0) return OK;
+  // smallest cluster whose row slice fits the register budget (<= 12 row pairs per thread): long
+  // contiguous column slices (~40 KB) stream best and small clusters leave no SM idle
+  int cs = 1;
+  while (cs < 8 && max_rows > (int64_t)cs * 12 * F_ROWS_PER_STEP) cs *= 2;
+  if (const char* ev = getenv("BGGE_FUSED_CS")) {   // tuning hook
+    const int v = atoi(ev);
+    if (v == 1 || v == 2 || v == 4 || v == 8) cs = std::max(cs, v);
+  }
+  const int64_t rs_max = round_up((max_rows + cs - 1) / cs, 16);
+  const int rpt_need = (int)((rs_max + F_ROWS_PER_STEP - 1) / F_ROWS_PER_STEP);
+  const Combo* combo = nullptr;
+  for (const Combo& c : kCombos)
+    if (c.rpt >= rpt_need) { combo = &c; break; }
+  if (!combo) return OK;   // slices too long for the register budget: two-pass path
+  hk.fused_cs = cs;
+  hk.fused_rpt = combo->rpt;
+  hk.fused_g = combo->gcols;
+  const size_t slot_bytes = (size_t)combo->gcols * rs_max * sizeof(double);
+  const size_t zb = (size_t)combo->gcols * (F_ROLE / combo->gcols);
+  const size_t fixed = ((size_t)NPX * 8 * combo->gcols + 2 * 8 * combo->gcols + 6 * zb) * sizeof(double) +
+                       (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
+  int dev = 0, optin = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t budget = (size_t)optin > fixed + 2048 ? (size_t)optin - fixed - 1024 : 0;
+  int ns = (int)std::min<size_t>(F_MAX_NS, budget / std::max<size_t>(slot_bytes, 16));
+  if (ns < 3) return OK;
+  hk.fused_ns = ns;
+  hk.fused_smem = ns * slot_bytes + fixed;
+  int ncl = 0;
+  BGGE_TRY(occupancy_dispatch(hk, cs, hk.fused_smem, &ncl));
+  if (ncl < 1) return OK;
+  // work-balanced contiguous split of the (block, column) space over the clusters
+  double total = 0.0;
+  for (auto& bl : hk.blocks) total += (double)bl.rows * (double)bl.nr;
+  int64_t total_cols = 0;
+  for (auto& bl : hk.blocks) total_cols += bl.nr;
+  ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, combo->gcols)));
+  std::vector<FPanel> panels;
+  std::vector<int2> cpan((size_t)ncl, make_int2(0, 0));
+  std::vector<std::pair<int, int>> block_q(hk.blocks.size(), {1 << 30, -1});
+  {
+    const double quota = total / (double)ncl;
+    size_t bi = 0;
+    int64_t col = 0;   // next unassigned column of block bi
+    for (int q = 0; q < ncl; ++q) {
+      const bool last = q == ncl - 1;
+      double need = quota;
+      cpan[(size_t)q].x = (int)panels.size();
+      while (bi < hk.blocks.size() && (last || need > 0.02 * quota)) {
+        HostBlock& bl = hk.blocks[bi];
+        const int64_t avail = bl.nr - col;
+        int64_t take = avail;
+        if (!last) {
+          const int64_t want = (int64_t)std::ceil(need / (double)bl.rows);
+          take = std::min<int64_t>(avail, (want + combo->gcols - 1) / combo->gcols * combo->gcols);
+        }
+        if (take <= 0) break;
+        FPanel p{};
+        p.U = bl.dU;
+        p.ldu = bl.ldu;
+        p.rows = (int)bl.rows;
+        p.pos0 = (int)bl.pos0;
+        p.c0 = (int)col;
+        p.c1 = (int)(col + take);
+        p.col_off = (int)bl.col_off;
+        p.rs = (int)round_up((bl.rows + cs - 1) / cs, 16);
+        p.slot = q;
+        panels.push_back(p);
+        block_q[bi].first = std::min(block_q[bi].first, q);
+        block_q[bi].second = std::max(block_q[bi].second, q);
+        need -= (double)bl.rows * (double)take;
+        col += take;
+        if (col >= bl.nr) {
+          ++bi;
+          col = 0;
+        }
+      }
+      cpan[(size_t)q].y = (int)panels.size() - cpan[(size_t)q].x;
+    }
+    BGGE_REQUIRE(bi == hk.blocks.size(), "fused plan: internal error (columns left unassigned)");
+  }
+  // finalize tiles: every row of y, gaps included (qlo > qhi -> zero)
+  std::vector<FTile> tiles;
+  int64_t cursor = 0;
+  auto add_rows = [&](int64_t pos0, int64_t rows, int qlo, int qhi) {
+    for (int64_t r0 = 0; r0 < rows; r0 += 256) {
+      FTile t{};
+      t.row0 = (int)(pos0 + r0);
+      t.rows = (int)std::min<int64_t>(256, rows - r0);
+      t.qlo = qlo;
+      t.qhi = qhi;
+      tiles.push_back(t);
+    }
+  };
+  for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
+    HostBlock& bl = hk.blocks[bi];
+    if (bl.pos0 > cursor) add_rows(cursor, bl.pos0 - cursor, 1, 0);
+    add_rows(bl.pos0, bl.rows, block_q[bi].first, block_q[bi].second);
+    cursor = bl.pos0 + bl.rows;
+  }
+  if (cursor < g->n) add_rows(cursor, g->n - cursor, 1, 0);
+  hk.fused_clusters = ncl;
+  hk.n_ftiles = (int)tiles.size();
+  BGGE_CUDA(hk.fpanels.alloc(panels.size()));
+  BGGE_CUDA(cudaMemcpyAsync(hk.fpanels.p, panels.data(), panels.size() * sizeof(FPanel), cudaMemcpyHostToDevice, st));
+  BGGE_CUDA(hk.fcluster.alloc(cpan.size()));
+  BGGE_CUDA(cudaMemcpyAsync(hk.fcluster.p, cpan.data(), cpan.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  BGGE_CUDA(hk.ftiles.alloc(tiles.size()));
+  BGGE_CUDA(cudaMemcpyAsync(hk.ftiles.p, tiles.data(), tiles.size() * sizeof(FTile), cudaMemcpyHostToDevice, st));
+  BGGE_CUDA(cudaStreamSynchronize(st));
+  hk.fused = true;
+  return OK;
+}
+
+}  // namespace bgge

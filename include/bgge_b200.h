@@ -52,6 +52,8 @@ int bgge_version(void);
 const char* bgge_last_error(void);
 int bgge_device_count(int* count);
 int bgge_set_device(int device);
+/* the library keeps freed device scratch blocks (<= 2 GB in total) for reuse; this returns them to the driver */
+int bgge_release_cache(void);
 /* free bytes / total bytes of the current device */
 int bgge_device_memory(uint64_t* free_bytes, uint64_t* total_bytes);
 
@@ -151,6 +153,11 @@ int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64
  */
 int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K, int64_t ldk, int on_device,
                                  const int64_t* ne, int n_ne, double tol, int canonical_sign);
+/* sweep implementation: 1 (default) = fused single-pass kernel step where the block shapes fit (U read
+ * once per kernel per iteration), 0 = two-pass proj/back kernels only.  Call before bgge_gibbs_init. */
+int bgge_gibbs_set_mode(bgge_gibbs* h, int mode);
+/* after init: which path kernel j uses, its cluster size / cluster (or tile) count, launches per step */
+int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches);
 /* injected draws in the reference's call order; copied to the device */
 int bgge_gibbs_set_tape(bgge_gibbs* h, const double* normals, int64_t n_normals, const double* chisq,
                         int64_t n_chisq);

@@ -324,7 +324,9 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     nu = 3.0                                                                    # :245
     vy = _var(y)
     Sce = (nu + 2) * (1 - R2) * vy                                              # :246
-    Sc = np.array([(nu + 2) * R2 * vy / float(np.mean(np.diag(k["Kernel"]))) for k in K.values()])  # :249
+    # :249 -- a kernel entry may carry "mean_diag" instead of the n x n matrix (tests with supplied eigen blocks)
+    Sc = np.array([(nu + 2) * R2 * vy / float(k["mean_diag"] if "mean_diag" in k else np.mean(np.diag(k["Kernel"])))
+                   for k in K.values()])
     tau = 0.01                                                                  # :251
     u = [draws.normals(n) * (1.0 / (2 * n)) for _ in range(nk)]                 # :254
     sigsq = vy                                                                  # :256

@@ -50,8 +50,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", [1, 0])
 @pytest.mark.parametrize("L,E,p,model,kernel,n_na,q", CASES)
-def test_per_iteration_parity(L, E, p, model, kernel, n_na, q):
+def test_per_iteration_parity(L, E, p, model, kernel, n_na, q, mode):
     import bgge_b200
     K, y, XF, ne = _problem(L, E, p, model, kernel=kernel, n_na=n_na, q=q)
     n = y.shape[0]
@@ -61,7 +62,7 @@ def test_per_iteration_parity(L, E, p, model, kernel, n_na, q):
     z, c = _tape(n, nrs, ite, q, n_na, 7)
     tr = {"keep_u": True}
     ref = oracle.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei, trace=tr)
-    got = bgge_b200.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), eig=Ei)
+    got = bgge_b200.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), eig=Ei, mode=mode)
     # every iteration's scalar samples (thin=1 records all of them)
     assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= TOL_IT
     assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= TOL_IT
@@ -188,3 +189,60 @@ def test_statistical_agreement_with_oracle():
     yd = np.mean([f["yHat"] for f in dev], axis=0)
     yr = np.mean([f["yHat"] for f in ref], axis=0)
     assert np.corrcoef(yd, yr)[0, 1] > 0.995
+
+
+def _synthetic_blocks(spec, seed):
+    """Eigen blocks without a kernel matrix: spec = [(type, [(pos0, rows, nr), ...]), ...]."""
+    rng = np.random.default_rng(seed)
+    eig, K = [], {}
+    for j, (typ, blocks) in enumerate(spec):
+        bl = []
+        for pos0, rows, nr in blocks:
+            Q, _ = np.linalg.qr(rng.standard_normal((rows, nr)))
+            bl.append({"s": np.sort(rng.gamma(2.0, 1.0, nr) + 0.05)[::-1].copy(), "U": np.asfortranarray(Q),
+                       "pos": None if typ == "D" else (pos0, pos0 + rows)})
+        eig.append(bl)
+        K[f"K{j}"] = {"Type": typ, "mean_diag": 0.7 + 0.1 * j}
+    return K, eig
+
+
+BIG = [
+    # n, spec  -- shapes that exercise the cluster paths (rows per block > 4096 -> CS 2/4/8), gaps, ragged slices
+    (9001, [("D", [(0, 9001, 37)])]),                                               # CS=4, odd rows
+    (12000, [("D", [(0, 12000, 19)]), ("BD", [(0, 5000, 23), (7000, 5000, 9)])]),   # CS=2 blocks + gap rows
+    (40000, [("D", [(0, 40000, 21)]), ("BD", [(k * 10000, 10000, 14) for k in range(4)])]),   # the C5 shapes: CS=8 / CS=4
+    (4500, [("BD", [(0, 1500, 300), (1500, 1500, 280), (3000, 1500, 310)])]),       # many columns, small slices (G=4)
+]
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("n,spec", BIG)
+def test_parity_on_large_blocks(n, spec, mode):
+    import bgge_b200
+    K, Ei = _synthetic_blocks(spec, 11)
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(n) * 1.3 + 0.4
+    na = rng.choice(n, size=25, replace=False)
+    y[na] = np.nan
+    ite = 8
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    z, c = _tape(n, nrs, ite, 0, 25, 9)
+    ne = [1, 1]     # only consulted by the validation of BD kernels
+    ref = oracle.BGGE(y, K, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
+    got = bgge_b200.BGGE(y, K, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), eig=Ei, mode=mode)
+    assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= TOL_IT
+    assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= TOL_IT
+    for nm in ref["K"]:
+        assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= TOL_IT, nm
+        assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= TOL_IT, nm
+    assert relmax(got["yHat"], ref["yHat"]) <= TOL_IT
+
+
+def test_fused_and_two_pass_agree_with_device_rng():
+    """Same seed, both sweep implementations: identical draws, results equal to rounding."""
+    import bgge_b200
+    K, y, XF, ne = _problem(40, 3, 60, "MDs", seed=8, n_na=7)
+    a = bgge_b200.BGGE(y, K, ne=ne, ite=200, burn=50, thin=2, seed=5, mode=1)
+    b = bgge_b200.BGGE(y, K, ne=ne, ite=200, burn=50, thin=2, seed=5, mode=0)
+    assert relmax(a["chain"]["varE"], b["chain"]["varE"]) <= 1e-8
+    assert relmax(a["yHat"], b["yHat"]) <= 1e-8
