@@ -27,7 +27,13 @@ import tempfile
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1; the CPU arms are entitled to every host core, and OpenBLAS only
+# honours that if it is set before numpy is imported (threadpoolctl cannot grow the pool afterwards)
+if "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -131,10 +137,13 @@ def cpu_sweep_time(prob, iters):
     """Seconds for `iters` iterations of the reference algorithm's sweep: numpy/OpenBLAS restatement
     (R is not installed), two dgemv per eigen block per iteration as crossprod() does in R/BGGE.R."""
     import oracle
-    t0 = time.perf_counter()
-    oracle.BGGE(prob["y"], prob["K"], ne=prob["ne"], ite=iters, burn=0, thin=max(1, iters), draws=oracle.RandomDraws(1),
-                eig=prob["eig"])
-    return time.perf_counter() - t0
+    from threadpoolctl import threadpool_limits
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is entitled to every host core
+    with threadpool_limits(limits=os.cpu_count()):
+        t0 = time.perf_counter()
+        oracle.BGGE(prob["y"], prob["K"], ne=prob["ne"], ite=iters, burn=0, thin=max(1, iters),
+                    draws=oracle.RandomDraws(1), eig=prob["eig"])
+        return time.perf_counter() - t0
 
 
 def default_ref_iters(L, step):
