@@ -343,53 +343,69 @@ def main():
         mean_diag0 = float(torch.diagonal(K0).mean().item())
 
         # ------------------------------------------------------------- eigen (setup, timed separately)
-        # K0 = V diag(s) V'.  Balanced env-major design: G = Zg K0 Zg' has eigenpairs (E*s, Zg V / sqrt(E)) and
-        # every diagonal block of GE is K0, so one L x L decomposition yields every block of the model.
-        # --full-eigen instead runs setDEC() on the n x n matrices as the reference does.
-        ldu_v = (L + 15) // 16 * 16
-        nr = C.c_int64()
-        A = K0.clone()
-        s_d = torch.empty(L, dtype=torch.float64, device=device)
-        V = torch.empty((L, ldu_v), dtype=torch.float64, device=device)
+        # setDEC() through the library's factorised route (bgge_gibbs_add_expanded_kernel): every block is
+        # decomposed through the L x L problem C^(1/2) K0[T,T] C^(1/2); the n x n kernels are never needed.
+        # The setup handle owns the blocks; the chains below borrow them (one decomposition, many chains).
+        del Kbuf
+        gid_h = gid.cpu().numpy().astype(np.int32)
+        env_h = env.cpu().numpy().astype(np.int32)
+        ne_h = np.full(E, L, dtype=np.int64)
+        kspec = [(0, 0, 0)]                                                   # (type, expand mode, env_k)
+        if model == "MDs":
+            kspec.append((1, 1, 0))
+        elif model == "MDe":
+            kspec += [(1, 2, k) for k in range(E)]
+        nk = len(kspec)
+        h0 = C.c_void_p()
+        lib.call("bgge_gibbs_create", n, nk, 0, stream, C.byref(h0))
+        torch.cuda.synchronize()
         t_eig = time.perf_counter()
-        lib.call("bgge_dev_eig", vp(A), L, L, 1e-10, 1, vp(s_d), vp(V), ldu_v, L, C.byref(nr), stream)
+        for j, (tp, mode, k) in enumerate(kspec):
+            lib.call("bgge_gibbs_add_expanded_kernel", h0, j, tp, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), mode, k,
+                     lib.ptr(ne_h), E, 1e-10, 1)
         torch.cuda.synchronize()
         t_eig = time.perf_counter() - t_eig
-        nr = nr.value
-        del A
-        s_host = s_d[:nr].cpu().numpy().copy()
-        Vn = V[:nr]
-        del Kbuf
-        ldu_g = (n + 15) // 16 * 16
-        UG = torch.zeros((nr, ldu_g), dtype=torch.float64, device=device)
-        for e in range(E):
-            UG[:, e * L:(e + 1) * L] = Vn[:, :L] / math.sqrt(E)
-        sG = (E * s_host).copy()
-        blocks = [[(0, n, UG, ldu_g, sG)]]                                   # per kernel: (pos0, rows, U, ldu, s)
-        types = [0]
-        if model == "MDs":
-            blocks.append([(e * L, L, Vn.clone(), ldu_v, s_host) for e in range(E)])
-            types.append(1)
-        elif model == "MDe":
-            for e in range(E):
-                blocks.append([(e * L, L, Vn.clone(), ldu_v, s_host)])
-                types.append(1)
-        mean_diags = [mean_diag0] + [mean_diag0 if model == "MDs" else mean_diag0 / E] * (n_kernels - 1)
-        nk = len(blocks)
+        blocks, types, mean_diags = [], [], []       # per kernel: list of (pos0, rows, dU ptr, ldu, nr, s)
+        n_eig_problems = 0
+        for j, (tp, mode, k) in enumerate(kspec):
+            nb = C.c_int()
+            lib.call("bgge_gibbs_block_count", h0, j, C.byref(nb))
+            bl = []
+            for b in range(nb.value):
+                pos0, rows, nr_b, ldu_b = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+                lib.call("bgge_gibbs_fetch_block", h0, j, b, C.byref(pos0), C.byref(rows), C.byref(nr_b), None, None, 0)
+                sv = np.empty(nr_b.value)
+                lib.call("bgge_gibbs_fetch_block", h0, j, b, None, None, None, lib.ptr(sv), None, 0)
+                dptr = C.c_void_p()
+                lib.call("bgge_gibbs_block_device", h0, j, b, C.byref(dptr), C.byref(ldu_b))
+                bl.append((pos0.value, rows.value, dptr.value, ldu_b.value, nr_b.value, sv))
+                n_eig_problems += 1
+            blocks.append(bl)
+            types.append(tp)
+            mean_diags.append(mean_diag0 if mode != 2 else mean_diag0 / E)
+        nr = blocks[0][0][4]
 
         # phenotypes: y = mu_env + g + ge + eps, h2 ~ 0.5; one chain per rank (chain id = rank)
+        class _Dev:   # torch view of a library-owned device block
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                                 "strides": None}
+        bpos, brows, bptr, bld, bnr, bs = blocks[-1][0]                       # an L-row block: U (L x nr), s
+        Ub = torch.as_tensor(_Dev(bptr, (bnr, bld)), device=device)[:, :brows]
+        root = Ub * torch.sqrt(torch.from_numpy(bs).to(device)).unsqueeze(1)  # (nr, L): K0 = root' root
         gen = torch.Generator(device=device)
         gen.manual_seed(20260000 + 40)
-        root = (Vn[:, :L] * torch.sqrt(torch.clamp(s_d[:nr], min=0)).unsqueeze(1))   # (nr, L)
-        gvec = torch.randn(nr, generator=gen, device=device, dtype=torch.float64) @ root
+        scale_g = 1.0 if model != "MDe" else math.sqrt(1.0)
+        gvec = scale_g * (torch.randn(bnr, generator=gen, device=device, dtype=torch.float64) @ root)
         yv = torch.empty(n, dtype=torch.float64, device=device)
         for e in range(E):
-            ge = math.sqrt(0.5) * (torch.randn(nr, generator=gen, device=device, dtype=torch.float64) @ root)
+            ge = math.sqrt(0.5) * (torch.randn(bnr, generator=gen, device=device, dtype=torch.float64) @ root)
             yv[e * L:(e + 1) * L] = 0.3 * (e - E / 2) + gvec + ge
         yv += torch.randn(n, generator=gen, device=device, dtype=torch.float64) * yv.std()
         y_pinned = torch.empty(n, dtype=torch.float64).pin_memory()
         y_pinned.copy_(yv.cpu())
         y_np = y_pinned.numpy()
+        del Ub, root
 
         total_iters = (args.warmup + args.steps) * iters + args.prof_iters + 8
 
@@ -399,8 +415,8 @@ def main():
             lib.call("bgge_gibbs_set_y", h, lib.ptr(y_np), None)
             for j in range(nk):
                 lib.call("bgge_gibbs_set_kernel", h, j, types[j], mean_diags[j])
-                for (pos0, rows, U, ldu, sv) in blocks[j]:
-                    lib.call("bgge_gibbs_add_block", h, j, pos0, rows, U.shape[0], lib.ptr(sv), vp(U), ldu, 1)
+                for (pos0, rows, dptr, ldu, nr_b, sv) in blocks[j]:
+                    lib.call("bgge_gibbs_add_block", h, j, pos0, rows, nr_b, lib.ptr(sv), C.c_void_p(dptr), ldu, 1)
             if args.two_pass:
                 lib.call("bgge_gibbs_set_mode", h, 0)
             lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + rank, rank)
@@ -485,18 +501,19 @@ def main():
             dist.barrier()
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_val = world * args.steps * iters / float(te.item())
+        lib.load().bgge_gibbs_destroy(h0)
         h2d = 8 * n
         d2h = 8 * (n * (2 + 2 * nk) + 2 * nk + 2 + max(1, ncum) * (2 + nk))
 
     # ----------------------------------------------------------------- roofline bookkeeping
     # fused kernel steps read U once per iteration, two-pass steps twice; the accounting follows the path used
-    sum_nr = sum(U.shape[0] for blk in blocks for (_p, rows, U, _l, _s) in blk)
+    sum_nr = sum(b[4] for blk in blocks for b in blk)
     kern = []
     u_bytes = 0
     for j in range(nk):
-        rn = sum(rows * U.shape[0] for (_p, rows, U, _l, _s) in blocks[j])
-        cov = sum(rows for (_p, rows, U, _l, _s) in blocks[j])
-        nrj = sum(U.shape[0] for (_p, rows, U, _l, _s) in blocks[j])
+        rn = sum(b[1] * b[4] for b in blocks[j])
+        cov = sum(b[1] for b in blocks[j])
+        nrj = sum(b[4] for b in blocks[j])
         if kinfo[j]["fused"]:
             ncl = kinfo[j]["clusters"]
             u_bytes += 8 * rn
@@ -545,7 +562,7 @@ def main():
                        "parallelism": f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain",
                        "l2": "inputs larger than L2 (U streamed from HBM every iteration)" if u_bytes > 256e6
                              else "working set fits in L2; latency-bound, HBM roofline not binding",
-                       "eigen": "one L x L syevd, blocks derived (balanced design)"},
+                       "eigen": "factorised setDEC in the library: L x L syevd per block, n x n kernels never built"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "step_s": e2e_steps, "phase_s_create_run_fetch_destroy": e2e_phase[1:],
                     "covers": "bgge_gibbs_create + set_y (pinned host) + add_block (device-resident eigen) + init + "
@@ -558,7 +575,7 @@ def main():
                                      if all(k["fused"] for k in kinfo) else
                                      "2-pass (U read for U'e and for U b)" if not any(k["fused"] for k in kinfo)
                                      else "mixed: fused kernels 1-pass, others 2-pass"),
-                      "two_pass_equivalent_gbs_per_gpu": (16 * sum(rows * U.shape[0] for blk in blocks for (_p, rows, U, _l, _s) in blk)
+                      "two_pass_equivalent_gbs_per_gpu": (16 * sum(b[1] * b[4] for blk in blocks for b in blk)
                                                           + 8 * n * (4 * nk + 3) + 40 * sum_nr)
                                                          * (args.steps * iters) / (ms_total * 1e-3) / 1e9,
                       "kernel_paths": kinfo,
@@ -569,7 +586,8 @@ def main():
                      "frac_of_dgemm_sustained": flops / t_contr / 1e12 / dg_sust,
                      "quantile_exp_s": t_q, "expansion_s": t_exp, "expansion_gbs": 8.0 * n * n * len(modes) / t_exp / 1e9,
                      "n_gpus_in_contraction": world, "marker_gen_s": t_gen},
-            "eigen": {"syevd_L_s": t_eig, "L": L, "kept": nr},
+            "eigen": {"setdec_s": t_eig, "problems": n_eig_problems, "L": L, "kept_per_block": nr,
+                      "route": "bgge_gibbs_add_expanded_kernel: one L x L syevd per block (factorised, SURVEY 8f-1)"},
         }
         print(json.dumps(line))
     if world > 1:

@@ -72,6 +72,13 @@ SIGNATURES = {
                                        C.c_int64, C.c_int]),
     "bgge_gibbs_add_kernel_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                                C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "bgge_gibbs_add_expanded_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_double, C.c_int]),
+    "bgge_gibbs_block_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "bgge_gibbs_block_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_int64_p]),
+    "bgge_gibbs_fetch_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int64_p, c_int64_p, c_int64_p, C.c_void_p,
+                                         C.c_void_p, C.c_int64]),
     "bgge_gibbs_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),

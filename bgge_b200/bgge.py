@@ -25,9 +25,29 @@ class BGGEFit(OrderedDict):
                 f"{self['thin']} \n\n Some predicted Values: \n{head}\n\n Use str() function to found more datailed information.\n")
 
 
+def _factor_mean_diag(f):
+    """mean(diag(K)) of an expanded kernel from its factored description (R/BGGE.R:249)."""
+    gid, env = f["gid"], f["env"]
+    d = np.ones(f["L"]) if f["K0"] is None else np.diag(f["K0"])
+    v = d[gid].astype(np.float64)
+    if f["mode"] == _lib.EXPAND_ENV:
+        v = v * (env == f["env_k"])
+    return float(v.mean())
+
+
+def _add_factored(h, j, k, ne_arr, tol, canonical_sign):
+    f = k["factor"]
+    tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
+    K0 = None if f["K0"] is None else _lib.f64(f["K0"])
+    _lib.call("bgge_gibbs_add_expanded_kernel", h, j, tcode, _lib.ptr(K0), f["L"], f["L"], 0, _lib.ptr(f["gid"]),
+              _lib.ptr(f["env"]), f["mode"], f["env_k"], None if ne_arr is None else _lib.ptr(ne_arr),
+              0 if ne_arr is None else ne_arr.shape[0], float(tol), int(canonical_sign))
+
+
 def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
     """setDEC() of R/BGGE.R:119-182 on the device: per kernel a list of blocks
-    {"s", "U", "pos"} (pos = (start, stop) 0-based half-open, None for type D)."""
+    {"s", "U", "pos"} (pos = (start, stop) 0-based half-open, None for type D).  Dense entries go through
+    bgge_eig per block; factored entries (getK(..., factored=True)) through the L x L route."""
     types = [k["Type"] for k in K.values()]
     if not all(t in ("BD", "D") for t in types):
         raise ValueError("Matrix should be of types BD or D")
@@ -36,8 +56,29 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
             raise ValueError("For type BD, number of subjects in each sub matrices should be provided")
     elif np.size(ne) <= 1 and "BD" in types:
         raise ValueError("ne invalid. For type BD, number of subjects in each sub matrices should be provided")
+    ne_arr = None if ne is None else np.ascontiguousarray(np.atleast_1d(ne), dtype=np.int64)
     out = []
     for k in K.values():
+        if "factor" in k:
+            n = k["factor"]["gid"].shape[0]
+            h = C.c_void_p()
+            _lib.call("bgge_gibbs_create", n, 1, 0, None, C.byref(h))
+            try:
+                _add_factored(h, 0, k, ne_arr, tol, canonical_sign)
+                nb = C.c_int()
+                _lib.call("bgge_gibbs_block_count", h, 0, C.byref(nb))
+                blocks = []
+                for b in range(nb.value):
+                    pos0, rows, nr = C.c_int64(), C.c_int64(), C.c_int64()
+                    _lib.call("bgge_gibbs_fetch_block", h, 0, b, C.byref(pos0), C.byref(rows), C.byref(nr), None, None, 0)
+                    s = np.empty(nr.value)
+                    U = np.empty((rows.value, nr.value), order="F")
+                    _lib.call("bgge_gibbs_fetch_block", h, 0, b, None, None, None, _lib.ptr(s), _lib.ptr(U), rows.value)
+                    blocks.append({"s": s, "U": U, "pos": None if k["Type"] == "D" else (pos0.value, pos0.value + rows.value)})
+            finally:
+                _lib.load().bgge_gibbs_destroy(h)
+            out.append(blocks)
+            continue
         Km = _lib.f64(k["Kernel"])
         n = Km.shape[0]
         spans = [(0, n)] if k["Type"] == "D" else list(zip(np.cumsum(ne) - np.asarray(ne), np.cumsum(ne)))
@@ -100,8 +141,12 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
             _lib.call("bgge_gibbs_set_mode", h, int(mode))
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
-            if eig is not None and "mean_diag" in k:
-                _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(k["mean_diag"]))
+            if eig is None and "factor" in k:
+                _add_factored(h, j, k, ne_arr, tol, True)
+                continue
+            if eig is not None and ("mean_diag" in k or "factor" in k):
+                md = k["mean_diag"] if "mean_diag" in k else _factor_mean_diag(k["factor"])
+                _lib.call("bgge_gibbs_set_kernel", h, j, tcode, float(md))
                 Km = None
             else:
                 Km = _lib.f64(k["Kernel"])

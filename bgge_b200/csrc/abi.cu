@@ -640,6 +640,213 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
   return OK;
 }
 
+// setDEC() of an *expanded* kernel without materialising it.  For a block of rows S with
+// genotype codes g(i) and an all-ones mask, K_S = Z K0[T,T] Z' with Z the |S| x |T| incidence matrix and
+// C = Z'Z = diag(counts).  If C^{1/2} K0[T,T] C^{1/2} = W diag(s) W' then K_S = U diag(s) U' with
+// U = Z C^{-1/2} W (orthonormal columns), so the |T| x |T| problem gives the same eigenpairs (> tol) as
+// eigen(K_S) (R/BGGE.R:112-116, 144-171).  Blocks whose mask is not constant fall back to the direct route.
+int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double* K0, int64_t L, int64_t ldk,
+                                   int on_device, const int32_t* gid, const int32_t* env, int mode, int env_k,
+                                   const int64_t* ne, int n_ne, double tol, int canonical_sign) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "gibbs_add_expanded_kernel: handle already initialised");
+  BGGE_REQUIRE(j >= 0 && j < g.nk && gid != nullptr && L > 0, "gibbs_add_expanded_kernel: bad arguments");
+  BGGE_REQUIRE(type == BGGE_TYPE_D || type == BGGE_TYPE_BD, "Matrix should be of types BD or D");
+  BGGE_REQUIRE(mode >= BGGE_EXPAND_G && mode <= BGGE_EXPAND_GI, "gibbs_add_expanded_kernel: unknown expansion mode %d", mode);
+  BGGE_REQUIRE(mode == BGGE_EXPAND_GI || (K0 != nullptr && ldk >= L), "gibbs_add_expanded_kernel: K0 missing");
+  BGGE_REQUIRE((mode != BGGE_EXPAND_GE && mode != BGGE_EXPAND_ENV) || env != nullptr, "gibbs_add_expanded_kernel: env codes missing");
+  const int64_t n = g.n;
+  BGGE_TRY(check_codes(gid, n, L, "gid"));
+  cudaStream_t st = g.stream;
+
+  // base kernel on the device + its diagonal on the host
+  DevBuf<double> k0buf;
+  const double* dK0 = nullptr;
+  int64_t ld0 = L;
+  std::vector<double> diag((size_t)L, 1.0);
+  if (mode != BGGE_EXPAND_GI) {
+    if (on_device) {
+      dK0 = K0;
+      ld0 = ldk;
+    } else {
+      BGGE_CUDA(k0buf.alloc((size_t)L * L));
+      BGGE_CUDA(cudaMemcpy2D(k0buf.p, (size_t)L * sizeof(double), K0, (size_t)ldk * sizeof(double), (size_t)L * sizeof(double),
+                             (size_t)L, cudaMemcpyHostToDevice));
+      dK0 = k0buf.p;
+    }
+    BGGE_CUDA(cudaMemcpy2D(diag.data(), sizeof(double), dK0, (size_t)(ld0 + 1) * sizeof(double), sizeof(double), (size_t)L,
+                           cudaMemcpyDeviceToHost));
+  }
+  auto mask = [&](int64_t a, int64_t b) -> bool {
+    if (mode == BGGE_EXPAND_GE) return env[a] == env[b];
+    if (mode == BGGE_EXPAND_ENV) return env[a] == env_k && env[b] == env_k;
+    return true;
+  };
+  long double tr = 0.0L;   // mean(diag(K)) over all n rows (R/BGGE.R:249)
+  for (int64_t i = 0; i < n; ++i) tr += mask(i, i) ? (long double)diag[(size_t)gid[i]] : 0.0L;
+  BGGE_REQUIRE(tr > 0.0L, "gibbs_add_expanded_kernel: kernel %d has an all-zero diagonal", j);
+  BGGE_TRY(bgge_gibbs_set_kernel(h, j, type, (double)(tr / (long double)n)));
+
+  std::vector<std::pair<int64_t, int64_t>> spans;
+  if (type == BGGE_TYPE_D) {
+    spans.push_back({0, n});
+  } else {
+    BGGE_REQUIRE(ne != nullptr && n_ne > 1, "ne invalid. For type BD, number of subjects in each sub matrices should be provided");
+    int64_t pos = 0;
+    for (int k = 0; k < n_ne; ++k) {
+      BGGE_REQUIRE(ne[k] > 0 && pos + ne[k] <= n, "gibbs_add_expanded_kernel: ne does not partition the rows of y");
+      spans.push_back({pos, ne[k]});
+      pos += ne[k];
+    }
+  }
+  HostKernel& hk = g.kernels[(size_t)j];
+  DevBuf<int> dgid_all, denv_all;   // only for the fallback route
+  for (auto& sp : spans) {
+    const int64_t pos = sp.first, m = sp.second;
+    // is the mask constant on this block?  (first row decides; every pair is checked through the row classes)
+    bool uniform = true, ones = true;
+    if (mode == BGGE_EXPAND_GE) {
+      for (int64_t i = 1; i < m && uniform; ++i) uniform = env[pos + i] == env[pos];
+    } else if (mode == BGGE_EXPAND_ENV) {
+      int64_t in = 0;
+      for (int64_t i = 0; i < m; ++i) in += env[pos + i] == env_k;
+      uniform = in == 0 || in == m;
+      ones = in == m;
+    }
+    if (uniform && !ones) continue;   // all-zero block: no eigenvalue exceeds tol (R/BGGE.R:162)
+    HostBlock bl;
+    bl.pos0 = pos;
+    bl.rows = m;
+    bl.ldu = round_up(m, 16);
+    std::vector<double> s_host;
+    if (uniform) {
+      // ---- factorised route
+      std::vector<int> cnt((size_t)L, 0), slot((size_t)L, -1), T, loc((size_t)m);
+      for (int64_t i = 0; i < m; ++i) ++cnt[(size_t)gid[pos + i]];
+      for (int64_t gidx = 0; gidx < L; ++gidx)
+        if (cnt[(size_t)gidx] > 0) {
+          slot[(size_t)gidx] = (int)T.size();
+          T.push_back((int)gidx);
+        }
+      const int64_t t = (int64_t)T.size();
+      std::vector<double> sqc((size_t)t), isq((size_t)m);
+      for (int64_t a = 0; a < t; ++a) sqc[(size_t)a] = std::sqrt((double)cnt[(size_t)T[(size_t)a]]);
+      for (int64_t i = 0; i < m; ++i) {
+        loc[(size_t)i] = slot[(size_t)gid[pos + i]];
+        isq[(size_t)i] = 1.0 / sqc[(size_t)loc[(size_t)i]];
+      }
+      DevBuf<int> dT, dloc;
+      DevBuf<double> dsqc, disq, dM, dW, dS, dWc;
+      BGGE_CUDA(dT.alloc((size_t)t));
+      BGGE_CUDA(dloc.alloc((size_t)m));
+      BGGE_CUDA(dsqc.alloc((size_t)t));
+      BGGE_CUDA(disq.alloc((size_t)m));
+      BGGE_CUDA(dM.alloc((size_t)t * t));
+      BGGE_CUDA(dW.alloc((size_t)t));
+      BGGE_CUDA(cudaMemcpyAsync(dT.p, T.data(), (size_t)t * sizeof(int), cudaMemcpyHostToDevice, st));
+      BGGE_CUDA(cudaMemcpyAsync(dloc.p, loc.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+      BGGE_CUDA(cudaMemcpyAsync(dsqc.p, sqc.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
+      BGGE_CUDA(cudaMemcpyAsync(disq.p, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+      BGGE_TRY(gather_scale_launch(dK0, ld0, dT.p, dsqc.p, t, dM.p, st));
+      int64_t nr = 0;
+      BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
+      if (nr == 0) continue;                                        // R/BGGE.R:162
+      bl.nr = nr;
+      BGGE_CUDA(dS.alloc((size_t)nr));
+      BGGE_CUDA(dWc.alloc((size_t)t * nr));
+      BGGE_TRY(eig_compact(dM.p, t, dW.p, t, nr, 0, dS.p, dWc.p, t, st));
+      BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+      bl.owns = true;
+      hk.blocks.push_back(bl);
+      BGGE_TRY(expand_rows_launch(dWc.p, t, dloc.p, disq.p, m, nr, bl.dU, bl.ldu, st));
+      if (canonical_sign) {   // same convention as the direct route: largest-|.| entry of each U column positive
+        DevBuf<double> tmpS, tmpU;
+        BGGE_CUDA(tmpS.alloc((size_t)nr));
+        BGGE_CUDA(tmpU.alloc((size_t)bl.ldu * nr));
+        BGGE_CUDA(cudaMemcpyAsync(tmpU.p, bl.dU, (size_t)bl.ldu * nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        BGGE_TRY(sign_fix_launch(tmpU.p, bl.ldu, m, nr, bl.dU, st));
+        BGGE_CUDA(cudaStreamSynchronize(st));
+      }
+      s_host.resize((size_t)nr);
+      BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+      BGGE_CUDA(cudaStreamSynchronize(st));
+    } else {
+      // ---- mixed mask inside the block: materialise the m x m block and decompose it directly
+      if (!dgid_all.p) {
+        BGGE_CUDA(dgid_all.alloc((size_t)n));
+        BGGE_CUDA(cudaMemcpy(dgid_all.p, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        BGGE_CUDA(denv_all.alloc((size_t)n));
+        BGGE_CUDA(cudaMemcpy(denv_all.p, env, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      DevBuf<double> dA, dW, dS;
+      BGGE_CUDA(dA.alloc((size_t)m * m));
+      BGGE_CUDA(dW.alloc((size_t)m));
+      BGGE_TRY(expand_launch(dK0, ld0, dgid_all.p + pos, denv_all.p + pos, m, mode, env_k, dA.p, m, st));
+      int64_t nr = 0;
+      BGGE_TRY(eig_decompose(dA.p, m, m, tol, dW.p, &nr, st));
+      if (nr == 0) continue;
+      bl.nr = nr;
+      BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+      bl.owns = true;
+      hk.blocks.push_back(bl);
+      BGGE_CUDA(dS.alloc((size_t)nr));
+      BGGE_TRY(eig_compact(dA.p, m, dW.p, m, nr, canonical_sign, dS.p, bl.dU, bl.ldu, st));
+      s_host.resize((size_t)nr);
+      BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+      BGGE_CUDA(cudaStreamSynchronize(st));
+    }
+    hk.s_host.insert(hk.s_host.end(), s_host.begin(), s_host.end());
+  }
+  BGGE_REQUIRE(!hk.blocks.empty(), "kernel %d: no eigenvalue exceeds tol in any block", j);
+  return OK;
+}
+
+// eigen blocks held by the handle (tests, reuse of a decomposition)
+int bgge_gibbs_block_count(bgge_gibbs* h, int j, int* n_blocks) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(j >= 0 && j < h->g.nk && n_blocks, "gibbs_block_count: bad arguments");
+  *n_blocks = (int)h->g.kernels[(size_t)j].blocks.size();
+  return OK;
+}
+
+int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int64_t* ldu) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(j >= 0 && j < g.nk && dU && ldu, "gibbs_block_device: bad arguments");
+  HostKernel& hk = g.kernels[(size_t)j];
+  BGGE_REQUIRE(b >= 0 && b < (int)hk.blocks.size(), "gibbs_block_device: bad block index");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  *dU = hk.blocks[(size_t)b].dU;
+  *ldu = hk.blocks[(size_t)b].ldu;
+  return OK;
+}
+
+int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* rows, int64_t* nr, double* s, double* U,
+                           int64_t ldu) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(j >= 0 && j < g.nk, "gibbs_fetch_block: bad kernel index");
+  HostKernel& hk = g.kernels[(size_t)j];
+  BGGE_REQUIRE(b >= 0 && b < (int)hk.blocks.size(), "gibbs_fetch_block: bad block index");
+  const HostBlock& bl = hk.blocks[(size_t)b];
+  if (pos0) *pos0 = bl.pos0;
+  if (rows) *rows = bl.rows;
+  if (nr) *nr = bl.nr;
+  if (s) {
+    int64_t off = 0;   // blocks are appended to s_host in insertion order until init sorts them
+    for (int k = 0; k < b; ++k) off += hk.blocks[(size_t)k].nr;
+    std::memcpy(s, hk.s_host.data() + off, (size_t)bl.nr * sizeof(double));
+  }
+  if (U) {
+    BGGE_REQUIRE(ldu >= bl.rows, "gibbs_fetch_block: ldu too small");
+    BGGE_CUDA(cudaStreamSynchronize(g.stream));
+    BGGE_CUDA(cudaMemcpy2D(U, (size_t)ldu * sizeof(double), bl.dU, (size_t)bl.ldu * sizeof(double),
+                           (size_t)bl.rows * sizeof(double), (size_t)bl.nr, cudaMemcpyDeviceToHost));
+  }
+  return OK;
+}
+
 int bgge_gibbs_set_tape(bgge_gibbs* h, const double* normals, int64_t n_normals, const double* chisq, int64_t n_chisq) {
   BGGE_HANDLE(h);
   Gibbs& g = h->g;

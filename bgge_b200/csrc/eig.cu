@@ -76,7 +76,96 @@ __global__ void compact_desc_kernel(const double* __restrict__ V, int64_t ldv, c
   if (threadIdx.x == 0) sout[c] = W[m - 1 - c];
 }
 
+// M[a,b] = sqrt(c_a c_b) * K0[T_a, T_b]  (t x t), or sqrt(c_a c_b) * [a == b] when K0 == nullptr (Gi)
+__global__ void gather_scale_kernel(const double* __restrict__ K0, int64_t ldk, const int* __restrict__ T,
+                                    const double* __restrict__ sqc, int64_t t, double* __restrict__ M) {
+  const int64_t b = blockIdx.y;
+  const int64_t gb = T[b];
+  const double sb = sqc[b];
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < t; a += (int64_t)gridDim.x * blockDim.x) {
+    const double k = K0 ? K0[T[a] + gb * ldk] : (a == b ? 1.0 : 0.0);
+    M[a + b * t] = sqc[a] * sb * k;
+  }
+}
+
+// U[i, c] = W[loc[i], c] * isq[i]   (rows x nr into the padded layout, pad rows zero)
+__global__ void expand_rows_kernel(const double* __restrict__ W, int64_t ldw, const int* __restrict__ loc,
+                                   const double* __restrict__ isq, int64_t rows, int64_t nr, double* __restrict__ U,
+                                   int64_t ldu) {
+  const int64_t c = blockIdx.y;
+  if (c >= nr) return;
+  const double* w = W + c * ldw;
+  double* u = U + c * ldu;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ldu; i += (int64_t)gridDim.x * blockDim.x)
+    u[i] = i < rows ? w[loc[i]] * isq[i] : 0.0;
+}
+
+// dst[:, c] = +-src[:, c] so that the largest-|.| entry (first on ties) is positive; pad rows zeroed
+__global__ void sign_fix_kernel(const double* __restrict__ src, int64_t ld, int64_t rows, double* __restrict__ dst) {
+  const int64_t c = blockIdx.x;
+  const double* v = src + c * ld;
+  __shared__ double sa[32];
+  __shared__ long long si[32];
+  double best = -1.0;
+  long long bi = 0;
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
+    const double a = fabs(v[i]);
+    if (a > best) { best = a; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    best = threadIdx.x < nw ? sa[threadIdx.x] : -1.0;
+    bi = threadIdx.x < nw ? si[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (threadIdx.x == 0) si[0] = bi;
+  }
+  __syncthreads();
+  const double sgn = v[si[0]] < 0.0 ? -1.0 : 1.0;
+  double* d = dst + c * ld;
+  for (int64_t i = threadIdx.x; i < ld; i += blockDim.x) d[i] = i < rows ? sgn * v[i] : 0.0;
+}
+
 }  // namespace
+
+int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, double* dDst, cudaStream_t st) {
+  if (nr <= 0) return OK;
+  sign_fix_kernel<<<(unsigned)nr, 256, 0, st>>>(dSrc, ld, rows, dDst);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int gather_scale_launch(const double* dK0, int64_t ldk, const int* dT, const double* d_sqc, int64_t t, double* dM,
+                        cudaStream_t st) {
+  if (t <= 0) return OK;
+  unsigned gx = (unsigned)((t + 255) / 256);
+  if (gx > 32) gx = 32;
+  BGGE_REQUIRE(t <= 65535, "expanded eigen: %lld distinct genotypes in one block exceed 65535", (long long)t);
+  gather_scale_kernel<<<dim3(gx, (unsigned)t), 256, 0, st>>>(dK0, ldk, dT, d_sqc, t, dM);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int expand_rows_launch(const double* dW, int64_t ldw, const int* d_loc, const double* d_isq, int64_t rows, int64_t nr,
+                       double* dU, int64_t ldu, cudaStream_t st) {
+  if (nr <= 0) return OK;
+  unsigned gx = (unsigned)((ldu + 255) / 256);
+  if (gx > 64) gx = 64;
+  BGGE_REQUIRE(nr <= 65535, "expanded eigen: %lld eigenpairs in one block exceed 65535", (long long)nr);
+  expand_rows_kernel<<<dim3(gx, (unsigned)nr), 256, 0, st>>>(dW, ldw, d_loc, d_isq, rows, nr, dU, ldu);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
 
 // Step 1: syevd in place (dA lower triangle -> eigenvectors, ascending), eigenvalues to d_W,
 // number of values > tol to *nr_out (which(values > tol), R/BGGE.R:114).  Synchronises.

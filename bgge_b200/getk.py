@@ -45,8 +45,20 @@ def _named_matrix(km):
     return None, None
 
 
+def materialize(entry):
+    """Dense n x n matrix of a factored kernel entry (see getK(..., factored=True))."""
+    if "Kernel" in entry and entry["Kernel"] is not None:
+        return entry["Kernel"]
+    f = entry["factor"]
+    n, L = f["gid"].shape[0], f["L"]
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.call("bgge_getk_expand", _lib.ptr(f["K0"]), L, _lib.ptr(f["gid"]), _lib.ptr(f["env"]), n, f["mode"], f["env_k"],
+              _lib.ptr(out))
+    return out
+
+
 def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM", "MM", "MDs", "MDe"), quantil=0.5,
-         intercept_random=False, rownames=None):
+         intercept_random=False, rownames=None, factored=False):
     """Create kernels for the genomic G x E models of BGGE().
 
     Y        : rows of (environment, genotype, ...) -- DataFrame, 2-D array or list of tuples.
@@ -56,6 +68,11 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
     setKernel: dict/list of user kernels, each a (matrix, names) tuple or a DataFrame.
     model    : "SM", "MM", "MDs" or "MDe".
     Returns an OrderedDict name -> {"Kernel": n x n float64 (Fortran order), "Type": "D"|"BD"}.
+
+    factored=True (extension): the n x n matrices are not built; each entry carries
+    {"Type", "factor": {"K0": L x L base kernel, "gid", "env", "mode", "env_k", "L"}} instead, which BGGE()
+    decomposes through the L x L problem (bgge_gibbs_add_expanded_kernel).  materialize(entry) gives the
+    dense matrix on demand.
     """
     if not isinstance(model, str) or (setKernel is None and not isinstance(kernel, str)):
         # the reference has no match.arg: switch() on a length-2 vector errors (SURVEY.md A.4);
@@ -102,6 +119,12 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
                              "available other kernel through argument K")
         nbase = 1 if kind == _lib.GB else bw.shape[0]
         n_out = nbase * n_per_base + (1 if intercept_random else 0)
+        if factored:
+            K0s = np.empty((nbase, L, L), dtype=np.float64)
+            _lib.call("bgge_getk_base", _lib.ptr(Xs), L, p, kind, _lib.ptr(bw), nbase, float(quantil), _lib.ptr(K0s), None)
+            base_f = [np.asfortranarray(K0s[b].T) for b in range(nbase)]   # symmetric: layout only
+            return _factored_result(base_f, [str(i + 1) for i in range(nbase)], gid, env, env_levels, L, model_code,
+                                    intercept_random)
         outs = [np.empty((n, n), dtype=np.float64, order="F") for _ in range(n_out)]
         arr = (C.c_void_p * n_out)(*[o.ctypes.data for o in outs])
         q = C.c_double(0.0)
@@ -123,6 +146,8 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
             base.append(_lib.f64(mat[np.ix_(idx, idx)]))
         tmp_names = [str(k) for k, _ in items] if hasattr(setKernel, "items") else [str(i + 1) for i in range(len(base))]
         nbase = len(base)
+        if factored:
+            return _factored_result(base, tmp_names, gid, env, env_levels, L, model_code, intercept_random)
         outs = []
 
         def emit(k0, mode, k=0):
@@ -157,4 +182,24 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
                 out[f"{lev}_{t}" if multi else str(lev)] = {"Kernel": next(it), "Type": "BD"}
     if intercept_random:
         out["Gi"] = {"Kernel": next(it), "Type": "D"}
+    return out
+
+
+def _factored_result(base, tmp_names, gid, env, env_levels, L, model_code, intercept_random):
+    """Entries in getK()'s order and with its names (R/getK.R:184-185, 202, 220-224, 233), factored form."""
+    def entry(k0, typ, mode, k=0):
+        return {"Type": typ, "factor": {"K0": k0, "gid": gid, "env": env, "mode": mode, "env_k": k, "L": L}}
+    multi = len(base) > 1
+    out = OrderedDict()
+    for t, k0 in zip(tmp_names, base):
+        out["G_" + t if multi else "G"] = entry(k0, "D", _lib.EXPAND_G)
+    if model_code == 1:
+        for t, k0 in zip(tmp_names, base):
+            out["GE_" + t if multi else "GE"] = entry(k0, "BD", _lib.EXPAND_GE)
+    if model_code == 2:
+        for t, k0 in zip(tmp_names, base):
+            for k, lev in enumerate(env_levels):
+                out[f"{lev}_{t}" if multi else str(lev)] = entry(k0, "BD", _lib.EXPAND_ENV, k)
+    if intercept_random:
+        out["Gi"] = entry(None, "D", _lib.EXPAND_GI)
     return out

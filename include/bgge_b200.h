@@ -153,6 +153,24 @@ int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64
  */
 int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K, int64_t ldk, int on_device,
                                  const int64_t* ne, int n_ne, double tol, int canonical_sign);
+/*
+ * setDEC() of an expanded kernel WITHOUT materialising the n x n matrix: the kernel is described by its
+ * L x L base kernel K0 (host or device pointer, leading dimension ldk; ignored for mode GI), the 0-based
+ * genotype / environment codes of the n rows (host pointers) and the expansion mode of bgge_getk_expand.
+ * Each block is decomposed through the |T| x |T| matrix C^{1/2} K0[T,T] C^{1/2} (T = genotypes present,
+ * C = their counts), which has the same eigenpairs > tol as the block itself; blocks whose mask is not
+ * constant fall back to the direct m x m decomposition.  Sets mean(diag(K)) as well.
+ */
+int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double* K0, int64_t L, int64_t ldk,
+                                   int on_device, const int32_t* gid, const int32_t* env, int mode, int env_k,
+                                   const int64_t* ne, int n_ne, double tol, int canonical_sign);
+/* eigen blocks currently attached to kernel j (valid before bgge_gibbs_init; U is rows x nr, leading dimension ldu) */
+int bgge_gibbs_block_count(bgge_gibbs* h, int j, int* n_blocks);
+int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* rows, int64_t* nr, double* s, double* U,
+                           int64_t ldu);
+/* device pointer / leading dimension of a block's U (owned by handle h; other handles may borrow it with
+ * bgge_gibbs_add_block(..., on_device = 1) while h is alive: one decomposition, many chains) */
+int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int64_t* ldu);
 /* sweep implementation: 1 (default) = fused single-pass kernel step where the block shapes fit (U read
  * once per kernel per iteration), 0 = two-pass proj/back kernels only.  Call before bgge_gibbs_init. */
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode);

@@ -14,6 +14,6 @@ print("    paths", s.get("kernel_paths"))
 g = d.get("getk")
 if g:
     print("    getk contraction", [round(x, 4) for x in g.get("contraction_s_all", [])], "TF", round(g["contraction_tflops"], 2), "frac", round(g["frac_of_dgemm_burst"], 3),
-          "quantile+exp", round(g["quantile_exp_s"], 4), "expand", round(g["expansion_s"], 4), "eig", round(d["eigen"]["syevd_L_s"], 2))
+          "quantile+exp", round(g["quantile_exp_s"], 4), "expand", round(g["expansion_s"], 4), "setDEC", round(d["eigen"]["setdec_s"], 2), "s for", d["eigen"]["problems"], "blocks")
 if d.get("cpu_baseline"):
     print("    cpu", d["cpu_baseline"])
