@@ -391,7 +391,9 @@ def main():
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
                                                  "strides": None}
         bpos, brows, bptr, bld, bnr, bs = blocks[-1][0]                       # an L-row block: U (L x nr), s
-        Ub = torch.as_tensor(_Dev(bptr, (bnr, bld)), device=device)[:, :brows]
+        # first L rows of any block give a root of K0: an L-row block has (V, s); the n-row G block has
+        # (Zg V / sqrt(E), E s), whose first L rows times sqrt(E s) are V sqrt(s) again
+        Ub = torch.as_tensor(_Dev(bptr, (bnr, bld)), device=device)[:, :L]
         root = Ub * torch.sqrt(torch.from_numpy(bs).to(device)).unsqueeze(1)  # (nr, L): K0 = root' root
         gen = torch.Generator(device=device)
         gen.manual_seed(20260000 + 40)

@@ -254,21 +254,6 @@ __global__ void xf_apply_kernel(long long n, int q, const double* __restrict__ x
 }
 
 // ------------------------------------------------------------------ end-of-iteration scalars
-__device__ double block_sum(double v, double* sh) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double tot = 0.0;
-  if (threadIdx.x < 32) {
-    tot = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
-    tot = warp_sum(tot);
-    if (threadIdx.x == 0) sh[32] = tot;
-  }
-  __syncthreads();
-  return sh[32];
-}
-
 struct ScalarArgs {
   long long n;
   int nk, q;
@@ -291,57 +276,104 @@ struct ScalarArgs {
 
 __global__ void __launch_bounds__(S_THREADS)
 scalar_kernel(const ScalarArgs a, DrawCfg dc) {
-  __shared__ double sh[33];
-  __shared__ double sh_sigsq;
+  // Latency matters here (one CTA, every iteration): all draws are made up front by separate warps (they
+  // do not depend on the data), the b^2/s partials are summed one kernel per warp, and the two vector
+  // reductions (sum e^2 for sigsq, sum r for the next intercept) share one pass and one block reduction.
+  __shared__ double sh_a[33], sh_b[33];
+  __shared__ double sh_chi[MAXK + 1];
+  __shared__ double sh_zmu, sh_sigsq;
   Scal* sc = a.sc;
   const long long it = sc->it;        // iteration that just finished (0 right after init)
   const double shift = sc->shift;
   const double mu = sc->mu;
-  if (it > 0) {
-    // variance of each random effect (R/BGGE.R:95-98, 360)
-    for (int j = 0; j < a.nk; ++j) {
-      double zq = 0.0;
-      for (int k = threadIdx.x; k < a.n_bpart[j]; k += blockDim.x) zq += a.bpart[j][k];
-      zq = block_sum(zq, sh);
-      if (threadIdx.x == 0) {
-        const double df = (double)a.nr[j] + NU;
-        const double c = draw_chisq(dc, it, STREAM_CHI_K + (uint32_t)j, df, (it - 1) * dc.c_per_it + j);
-        sc->sigb[j] = (zq + NU * sc->Sc[j]) / c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+
+  // ---- draws (warp w, lane 0): chi-squares of this iteration, normal of the next intercept
+  if (lane == 0) {
+    if (it > 0) {
+      for (int j = warp; j <= a.nk; j += nwarps) {
+        if (j < a.nk)
+          sh_chi[j] = draw_chisq(dc, it, STREAM_CHI_K + (uint32_t)j, (double)a.nr[j] + NU, (it - 1) * dc.c_per_it + j);
+        else
+          sh_chi[a.nk] = draw_chisq(dc, it, STREAM_CHI_E, (double)a.n + NU, (it - 1) * dc.c_per_it + a.nk);
       }
     }
-    // residual variance (R/BGGE.R:101-103, 364-367)
-    double sse = 0.0;
-    for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
-      const double e = a.r[i] - shift;
-      sse = fma(e, e, sse);
+    if (warp == nwarps - 1) sh_zmu = draw_normal(dc, it + 1, STREAM_MU, 0ull, z_pos(dc, it + 1, 0));
+  }
+  // ---- one pass over r: sum e^2 and sum r
+  double sse = 0.0, sr = 0.0;
+  for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const double rv = a.r[i];
+    const double e = rv - shift;
+    sse = fma(e, e, sse);
+    sr += rv;
+  }
+  sse = warp_sum(sse);
+  sr = warp_sum(sr);
+  if (lane == 0) {
+    sh_a[warp] = sse;
+    sh_b[warp] = sr;
+  }
+  __syncthreads();   // also publishes sh_chi / sh_zmu
+  if (it > 0) {
+    // variance of each random effect (R/BGGE.R:95-98, 360): warp j sums kernel j's partials
+    for (int j = warp; j < a.nk; j += nwarps) {
+      double zq = 0.0;
+      for (int k = lane; k < a.n_bpart[j]; k += 32) zq += a.bpart[j][k];
+      zq = warp_sum(zq);
+      if (lane == 0) sc->sigb[j] = (zq + NU * sc->Sc[j]) / sh_chi[j];
     }
-    sse = block_sum(sse, sh);
-    if (threadIdx.x == 0) {
-      const double df = (double)a.n + NU;
-      const double c = draw_chisq(dc, it, STREAM_CHI_E, df, (it - 1) * dc.c_per_it + a.nk);
-      const double s2 = (sse + sc->Sce) / c;
-      sc->sigsq = s2;
-      sc->tau = 1.0 / s2;
-      sh_sigsq = s2;
+  }
+  if (warp == 0) {
+    double ta = lane < nwarps ? sh_a[lane] : 0.0;
+    double tb = lane < nwarps ? sh_b[lane] : 0.0;
+    ta = warp_sum(ta);
+    tb = warp_sum(tb);
+    if (lane == 0) {
+      sh_b[32] = tb;
+      if (it > 0) {   // residual variance (R/BGGE.R:101-103, 364-367)
+        const double s2 = (ta + sc->Sce) / sh_chi[a.nk];
+        sc->sigsq = s2;
+        sc->tau = 1.0 / s2;
+        sh_sigsq = s2;
+      } else {
+        sh_sigsq = sc->sigsq;
+      }
+    }
+  }
+  __syncthreads();
+  double sr_tot = sh_b[32];
+  if (it > 0 && a.n_na > 0) {
+    // missing phenotypes (R/BGGE.R:370-381); the change of sum r is reduced separately
+    const double sd = sqrt(sh_sigsq);
+    double dsum = 0.0;
+    for (long long k = threadIdx.x; k < a.n_na; k += blockDim.x) {
+      const long long i = a.na_idx[k];
+      double uhat = 0.0;
+      for (int j = 0; j < a.nk; ++j) uhat = (j == 0) ? a.u[i] : uhat + a.u[(long long)j * a.n + i];
+      double aux = 0.0;
+      for (int k2 = 0; k2 < a.q; ++k2) aux += a.xf[i + (long long)k2 * a.n] * a.bet[k2];
+      const double z = draw_normal(dc, it, STREAM_NA, (unsigned long long)k, z_pos(dc, it, dc.z_off_na + k));
+      const double yv = ((aux + mu) + uhat) + sd * z;
+      a.y[i] = yv;
+      const double rn = (((yv - uhat) - aux) - mu) + shift;
+      dsum += rn - a.r[i];
+      a.r[i] = rn;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) sh_a[warp] = dsum;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < nwarps ? sh_a[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) sh_a[32] = t;
     }
     __syncthreads();
-    // missing phenotypes (R/BGGE.R:370-381)
-    if (a.n_na > 0) {
-      const double sd = sqrt(sh_sigsq);
-      for (long long k = threadIdx.x; k < a.n_na; k += blockDim.x) {
-        const long long i = a.na_idx[k];
-        double uhat = 0.0;
-        for (int j = 0; j < a.nk; ++j) uhat = (j == 0) ? a.u[i] : uhat + a.u[(long long)j * a.n + i];
-        double aux = 0.0;
-        for (int k2 = 0; k2 < a.q; ++k2) aux += a.xf[i + (long long)k2 * a.n] * a.bet[k2];
-        const double z = draw_normal(dc, it, STREAM_NA, (unsigned long long)k, z_pos(dc, it, dc.z_off_na + k));
-        const double yv = ((aux + mu) + uhat) + sd * z;
-        a.y[i] = yv;
-        a.r[i] = (((yv - uhat) - aux) - mu) + shift;
-      }
-    }
-    // thinned chain (R/BGGE.R:384-395)
-    if (threadIdx.x == 0 && it % a.thin == 0) {
+    sr_tot += sh_a[32];
+  }
+  if (threadIdx.x == 0) {
+    if (it > 0 && it % a.thin == 0) {   // thinned chain (R/BGGE.R:384-395)
       const long long slot = it / a.thin - 1;
       if (slot < a.ncum) {
         a.chain_varE[slot] = sh_sigsq;
@@ -350,20 +382,12 @@ scalar_kernel(const ScalarArgs a, DrawCfg dc) {
         for (int k2 = 0; k2 < a.q; ++k2) a.chain_bet[slot * a.q + k2] = a.bet[k2];
       }
     }
-    __syncthreads();
-  }
-  // intercept of the next iteration (R/BGGE.R:278-281): mean(temp + mu) = mean(r) + mu0
-  double sr = 0.0;
-  for (long long i = threadIdx.x; i < a.n; i += blockDim.x) sr += a.r[i];
-  sr = block_sum(sr, sh);
-  if (threadIdx.x == 0) {
-    const long long nit = it + 1;
-    const double z = draw_normal(dc, nit, STREAM_MU, 0ull, z_pos(dc, nit, 0));
-    const double nmu = (sr / (double)a.n + sc->mu0) + sqrt(sc->sigsq / (double)a.n) * z;
+    // intercept of the next iteration (R/BGGE.R:278-281): mean(temp + mu) = mean(r) + mu0
+    const double nmu = (sr_tot / (double)a.n + sc->mu0) + sqrt(sh_sigsq / (double)a.n) * sh_zmu;
     sc->mu_done = mu;
     sc->mu = nmu;
     sc->shift = nmu - sc->mu0;
-    sc->it = nit;
+    sc->it = it + 1;
   }
 }
 
