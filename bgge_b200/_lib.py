@@ -94,6 +94,19 @@ SIGNATURES = {
     "bgge_gibbs_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgge_gibbs_summary": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgge_batch_create": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, c_void_pp]),
+    "bgge_batch_destroy": (None, [C.c_void_p]),
+    "bgge_batch_set_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgge_batch_set_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "bgge_batch_add_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_int]),
+    "bgge_batch_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_uint32]),
+    "bgge_batch_run": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bgge_batch_sync": (C.c_int, [C.c_void_p]),
+    "bgge_batch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_int64_p, C.POINTER(C.c_int)]),
+    "bgge_batch_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgge_batch_summary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "bgge_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_void_pp, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                            C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int,
                            C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, c_double_p,

@@ -206,3 +206,94 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     out["ite"], out["burn"], out["thin"] = ite, burn, thin
     out["y"] = yout
     return out
+
+
+def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, seed=0, chain0=0, eig=None, device=None):
+    """B independent BGGE() chains / cross-validation folds sharing one eigen decomposition (config C4).
+
+    Y is a (B, n) array: row b is the phenotype vector of chain b (NaN = masked fold / missing).  Chain b
+    uses the RNG stream (seed, chain0 + b), i.e. it reproduces BGGE(Y[b], K, ..., seed=seed, chain=chain0 + b).
+    The eigen blocks are computed once (setDEC on the device) and the per-kernel U'e / U b passes of all
+    chains run as skinny FP64 tensor-core GEMMs.  Returns a list of BGGEFit objects.
+    """
+    Y = np.ascontiguousarray(np.atleast_2d(np.asarray(Y, dtype=np.float64)))
+    B, n = Y.shape
+    if not hasattr(K, "items"):
+        K = OrderedDict((f"K{i + 1}", k) for i, k in enumerate(K))
+    names = list(K.keys())
+    nk = len(names)
+    types = [k["Type"] for k in K.values()]
+    if not all(t in ("BD", "D") for t in types):
+        raise ValueError("Matrix should be of types BD or D")
+    if ne is None and "BD" in types:
+        raise ValueError("For type BD, number of subjects in each sub matrices should be provided")
+    if ne is not None and np.size(ne) == 1 and "BD" in types:
+        raise ValueError("Type BD should be used only for block diagonal matrices")
+    ne_arr = None if ne is None else np.ascontiguousarray(np.atleast_1d(ne), dtype=np.int64)
+    if device is not None:
+        _lib.call("bgge_set_device", int(device))
+    h0, hb = C.c_void_p(), C.c_void_p()
+    _lib.call("bgge_gibbs_create", n, nk, 0, None, C.byref(h0))      # owns the decomposition
+    try:
+        _lib.call("bgge_batch_create", n, nk, B, None, C.byref(hb))
+        _lib.call("bgge_batch_set_y", hb, _lib.ptr(Y), None)
+        for j, k in enumerate(K.values()):
+            tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
+            if eig is not None:
+                md = k["mean_diag"] if "mean_diag" in k else (_factor_mean_diag(k["factor"]) if "factor" in k
+                                                              else float(np.mean(np.diag(k["Kernel"]))))
+                for blk in eig[j]:
+                    U = _lib.f64(blk["U"])
+                    s = np.ascontiguousarray(blk["s"], dtype=np.float64)
+                    pos0 = 0 if blk["pos"] is None else int(blk["pos"][0])
+                    _lib.call("bgge_gibbs_add_block", h0, j, pos0, U.shape[0], U.shape[1], _lib.ptr(s), _lib.ptr(U),
+                              U.shape[0], 0)
+            elif "factor" in k:
+                md = _factor_mean_diag(k["factor"])
+                _add_factored(h0, j, k, ne_arr, tol, True)
+            else:
+                Km = _lib.f64(k["Kernel"])
+                md = float(np.mean(np.diag(Km)))
+                _lib.call("bgge_gibbs_add_kernel_matrix", h0, j, tcode, _lib.ptr(Km), n, 0,
+                          None if ne_arr is None else _lib.ptr(ne_arr), 0 if ne_arr is None else ne_arr.shape[0],
+                          float(tol), 1)
+            _lib.call("bgge_batch_set_kernel", hb, j, tcode, md)
+            nb = C.c_int()
+            _lib.call("bgge_gibbs_block_count", h0, j, C.byref(nb))
+            for b in range(nb.value):
+                pos0, rows, nr, ldu = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+                _lib.call("bgge_gibbs_fetch_block", h0, j, b, C.byref(pos0), C.byref(rows), C.byref(nr), None, None, 0)
+                s = np.empty(nr.value)
+                _lib.call("bgge_gibbs_fetch_block", h0, j, b, None, None, None, _lib.ptr(s), None, 0)
+                dptr = C.c_void_p()
+                _lib.call("bgge_gibbs_block_device", h0, j, b, C.byref(dptr), C.byref(ldu))
+                _lib.call("bgge_batch_add_block", hb, j, pos0.value, rows.value, nr.value, _lib.ptr(s), dptr, ldu.value, 1)
+        _lib.call("bgge_batch_init", hb, int(ite), int(burn), int(thin), float(R2), int(seed), int(chain0))
+        _lib.call("bgge_batch_run", hb, int(ite))
+        _lib.call("bgge_batch_sync", hb)
+        ncum = ite // thin
+        yHat, yout = np.empty((B, n)), np.empty((B, n))
+        u, usd = np.empty((nk, B, n)), np.empty((nk, B, n))
+        varE, varEsd, varu, varusd = np.empty(B), np.empty(B), np.empty((nk, B)), np.empty((nk, B))
+        _lib.call("bgge_batch_summary", hb, _lib.ptr(yHat), _lib.ptr(varE), _lib.ptr(varEsd), _lib.ptr(u), _lib.ptr(usd),
+                  _lib.ptr(varu), _lib.ptr(varusd), _lib.ptr(yout))
+        cmu, cve, cvu = np.empty((B, ncum)), np.empty((B, ncum)), np.empty((nk, B, ncum))
+        _lib.call("bgge_batch_chain", hb, _lib.ptr(cmu), _lib.ptr(cve), _lib.ptr(cvu))
+    finally:
+        if hb:
+            _lib.load().bgge_batch_destroy(hb)
+        _lib.load().bgge_gibbs_destroy(h0)
+    fits = []
+    for b in range(B):
+        out = BGGEFit()
+        out["yHat"] = yHat[b].copy()
+        out["varE"] = float(varE[b])
+        out["varE.sd"] = float(varEsd[b])
+        out["K"] = OrderedDict((nm, {"u": u[j, b].copy(), "u.sd": usd[j, b].copy(), "varu": float(varu[j, b]),
+                                     "varu.sd": float(varusd[j, b])}) for j, nm in enumerate(names))
+        out["chain"] = {"mu": cmu[b].copy(), "varE": cve[b].copy(),
+                        "K": OrderedDict((nm, {"varU": cvu[j, b].copy()}) for j, nm in enumerate(names))}
+        out["ite"], out["burn"], out["thin"] = ite, burn, thin
+        out["y"] = yout[b].copy()
+        fits.append(out)
+    return fits

@@ -3,6 +3,7 @@
 #include "../../include/bgge_b200.h"
 #include "common.cuh"
 #include "gibbs.cuh"
+#include "batch.cuh"
 #include "kernels.h"
 #include "rng.cuh"
 #include <cmath>
@@ -245,6 +246,10 @@ using namespace bgge;
 
 struct bgge_gibbs {
   Gibbs g;
+};
+
+struct bgge_batch {
+  Batch g;
 };
 
 extern "C" {
@@ -1044,6 +1049,214 @@ int bgge_gibbs_summary(bgge_gibbs* h, double* yHat, double* varE, double* varE_s
     }
   }
   if (y) BGGE_CUDA(cudaMemcpy(y, g.y.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+// ====================================================================== batched chains / folds
+int bgge_batch_create(int64_t n, int nk, int n_chains, void* stream, bgge_batch** out) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(out != nullptr, "batch_create: NULL output");
+  BGGE_REQUIRE(n > 1 && nk >= 1 && nk <= MAXK && n_chains >= 1 && n_chains <= 4096 && n * (int64_t)n_chains < (1ll << 40),
+               "batch_create: bad sizes n=%lld nk=%d chains=%d", (long long)n, nk, n_chains);
+  std::unique_ptr<bgge_batch> h(new (std::nothrow) bgge_batch());
+  BGGE_REQUIRE(h != nullptr, "batch_create: out of host memory");
+  Batch& g = h->g;
+  g.n = n;
+  g.nk = nk;
+  g.B = n_chains;
+  g.kernels.resize((size_t)nk);
+  BGGE_CUDA(cudaGetDevice(&g.device));
+  if (stream) {
+    g.stream = as_stream(stream);
+  } else {
+    BGGE_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.own_stream = true;
+  }
+  *out = h.release();
+  return OK;
+}
+
+void bgge_batch_destroy(bgge_batch* h) { delete h; }
+
+int bgge_batch_set_y(bgge_batch* h, const double* Y, const uint8_t* na_mask) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(Y != nullptr, "batch_set_y: NULL Y");
+  Batch& g = h->g;
+  g.y_host.assign(Y, Y + g.n * g.B);
+  if (na_mask) g.na_host.assign(na_mask, na_mask + g.n * g.B); else g.na_host.clear();
+  return OK;
+}
+
+int bgge_batch_set_kernel(bgge_batch* h, int j, int type, double mean_diag) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(j >= 0 && j < g.nk, "batch_set_kernel: kernel index %d outside [0,%d)", j, g.nk);
+  BGGE_REQUIRE(type == BGGE_TYPE_D || type == BGGE_TYPE_BD, "Matrix should be of types BD or D");
+  BGGE_REQUIRE(mean_diag > 0.0 && std::isfinite(mean_diag), "batch_set_kernel: mean(diag(K)) must be positive");
+  g.kernels[(size_t)j].mean_diag = mean_diag;
+  return OK;
+}
+
+int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64_t nr, const double* s, const double* U,
+                         int64_t ldu, int on_device) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "batch_add_block: handle already initialised");
+  BGGE_REQUIRE(j >= 0 && j < g.nk, "batch_add_block: kernel index %d outside [0,%d)", j, g.nk);
+  BGGE_REQUIRE(s && U && rows > 0 && nr > 0 && pos0 >= 0 && pos0 + rows <= g.n && ldu >= rows,
+               "batch_add_block: bad block pos0=%lld rows=%lld nr=%lld ldu=%lld", (long long)pos0, (long long)rows,
+               (long long)nr, (long long)ldu);
+  for (int64_t c = 0; c < nr; ++c) BGGE_REQUIRE(s[c] > 0.0, "batch_add_block: eigenvalue %lld is not positive", (long long)c);
+  BatchKernel& bk = g.kernels[(size_t)j];
+  BatchBlock bl;
+  bl.pos0 = pos0;
+  bl.rows = rows;
+  bl.nr = nr;
+  if (on_device) {
+    BGGE_REQUIRE(ldu % 2 == 0 && (reinterpret_cast<uintptr_t>(U) & 15u) == 0,
+                 "batch_add_block: device U needs an even leading dimension and a 16-byte aligned base");
+    bl.dU = const_cast<double*>(U);
+    bl.ldu = ldu;
+  } else {
+    bl.ldu = round_up(rows, 16);
+    BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+    bl.owns = true;
+    bk.blocks.push_back(bl);
+    bk.s_host.insert(bk.s_host.end(), s, s + nr);
+    BGGE_CUDA(cudaMemset(bl.dU, 0, (size_t)bl.ldu * nr * sizeof(double)));
+    BGGE_CUDA(cudaMemcpy2D(bl.dU, (size_t)bl.ldu * sizeof(double), U, (size_t)ldu * sizeof(double),
+                           (size_t)rows * sizeof(double), (size_t)nr, cudaMemcpyHostToDevice));
+    return OK;
+  }
+  bk.blocks.push_back(bl);
+  bk.s_host.insert(bk.s_host.end(), s, s + nr);
+  return OK;
+}
+
+int bgge_batch_init(bgge_batch* h, int64_t ite, int64_t burn, int64_t thin, double R2, uint64_t seed, uint32_t chain0) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "batch_init: handle already initialised");
+  g.ite = ite;
+  g.burn = burn;
+  g.thin = thin;
+  g.R2 = R2;
+  g.draw = DrawCfg{};
+  g.draw.mode = 0;
+  g.draw.seed = seed;
+  g.draw.chain = chain0;
+  return batch_init(&g);
+}
+
+int bgge_batch_run(bgge_batch* h, int64_t iters) {
+  BGGE_HANDLE(h);
+  return batch_run(&h->g, iters);
+}
+
+int bgge_batch_sync(bgge_batch* h) {
+  BGGE_HANDLE(h);
+  BGGE_CUDA(cudaStreamSynchronize(h->g.stream));
+  return OK;
+}
+
+int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_iter, int* launches_per_iter) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(g.initialised, "batch_info: handle not initialised");
+  if (padded_chains) *padded_chains = g.Bp;
+  int64_t fl = 0;
+  for (auto& k : g.kernels)
+    for (auto& b : k.blocks) fl += 4 * b.rows * b.nr * (int64_t)g.Bp;
+  if (gemm_flops_per_iter) *gemm_flops_per_iter = fl;
+  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 5;
+  return OK;
+}
+
+// chains: mu[B x ncum], varE[B x ncum] chain-major; varU[nk x B x ncum]
+int bgge_batch_chain(bgge_batch* h, double* mu, double* varE, double* varU) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(g.initialised, "batch_chain: handle not initialised");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  const size_t nc = (size_t)g.ncum, Bp = (size_t)g.Bp, B = (size_t)g.B;
+  if (nc == 0) return OK;
+  std::vector<double> t(nc * Bp);
+  auto pull = [&](const double* src, double* dst) -> int {
+    BGGE_CUDA(cudaMemcpy(t.data(), src, nc * Bp * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+      for (size_t k = 0; k < nc; ++k) dst[b * nc + k] = t[k * Bp + b];
+    return OK;
+  };
+  if (mu) BGGE_TRY(pull(g.chain_mu.p, mu));
+  if (varE) BGGE_TRY(pull(g.chain_varE.p, varE));
+  if (varU)
+    for (int j = 0; j < g.nk; ++j) BGGE_TRY(pull(g.chain_varU.p + (size_t)j * nc * Bp, varU + (size_t)j * B * nc));
+  return OK;
+}
+
+// per chain summaries over the kept draws (R/BGGE.R:408-433); all outputs chain-major:
+// yHat[B x n], varE[B], varE_sd[B], u[nk x B x n], u_sd[nk x B x n], varu[nk x B], varu_sd[nk x B], y[B x n]
+int bgge_batch_summary(bgge_batch* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd, double* varu,
+                       double* varu_sd, double* y) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(g.initialised, "batch_summary: handle not initialised");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  const size_t nc = (size_t)g.ncum, B = (size_t)g.B, Bp = (size_t)g.Bp, n = (size_t)g.n;
+  std::vector<double> cmu(B * nc), cve(B * nc), cvu((size_t)g.nk * B * nc);
+  BGGE_TRY(bgge_batch_chain(h, cmu.data(), cve.data(), cvu.data()));
+  std::vector<size_t> kept;
+  for (size_t slot = 0; slot < nc; ++slot) {
+    const int64_t it = (int64_t)(slot + 1) * g.thin;
+    if (it > g.burn && it <= g.done) kept.push_back(slot);
+  }
+  const size_t k = kept.size();
+  std::vector<double> mu_est(B, NAN);
+  for (size_t b = 0; b < B; ++b) {
+    std::vector<double> a, e;
+    for (size_t sl : kept) {
+      a.push_back(cmu[b * nc + sl]);
+      e.push_back(cve[b * nc + sl]);
+    }
+    mu_est[b] = mean_sd(a, nullptr);
+    double sd = NAN;
+    const double m = mean_sd(e, &sd);
+    if (varE) varE[b] = m;
+    if (varE_sd) varE_sd[b] = sd;
+    for (int j = 0; j < g.nk; ++j) {
+      std::vector<double> v;
+      for (size_t sl : kept) v.push_back(cvu[((size_t)j * B + b) * nc + sl]);
+      double sdj = NAN;
+      const double mj = mean_sd(v, &sdj);
+      if (varu) varu[(size_t)j * B + b] = mj;
+      if (varu_sd) varu_sd[(size_t)j * B + b] = sdj;
+    }
+  }
+  std::vector<double> t(n * Bp);
+  if (yHat)
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < n; ++i) yHat[b * n + i] = mu_est[b];
+  for (int j = 0; j < g.nk; ++j) {
+    if (yHat || u) {
+      BGGE_CUDA(cudaMemcpy(t.data(), g.Um.p + (size_t)j * n * Bp, n * Bp * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < n; ++i) {
+          const double v = k ? t[i * Bp + b] : NAN;
+          if (u) u[((size_t)j * B + b) * n + i] = v;
+          if (yHat) yHat[b * n + i] += v;
+        }
+    }
+    if (u_sd) {
+      BGGE_CUDA(cudaMemcpy(t.data(), g.Um2.p + (size_t)j * n * Bp, n * Bp * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < n; ++i) u_sd[((size_t)j * B + b) * n + i] = k > 1 ? std::sqrt(t[i * Bp + b] / (double)(k - 1)) : NAN;
+    }
+  }
+  if (y) {
+    BGGE_CUDA(cudaMemcpy(t.data(), g.Y.p, n * Bp * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < n; ++i) y[b * n + i] = t[i * Bp + b];
+  }
   return OK;
 }
 

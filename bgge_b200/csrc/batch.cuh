@@ -1,0 +1,52 @@
+// Batched (multi-chain / multi-fold) Gibbs sampler state.  Internal header.
+#pragma once
+#include "gibbs.cuh"
+#include "kernels.h"
+
+namespace bgge {
+
+struct BatchBlock {
+  int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, ldt = 0, col_off = 0;
+  double* dU = nullptr;   // rows x nr, column-major (A operand of u = U b)
+  double* dT = nullptr;   // nr x rows, column-major = t(U) (A operand of d = U'e), owned
+  bool owns = false;
+};
+
+struct BatchKernel {
+  std::vector<BatchBlock> blocks;
+  std::vector<double> s_host;
+  double mean_diag = 1.0;
+  int64_t nr_total = 0, nr_pad = 0;
+  int ksplit_proj = 1, ksplit_back = 1, n_proj = 0, n_back = 0, n_ctiles = 0;
+  DevBuf<double> s, Dpart, Bm, zqpart;
+  DevBuf<GemmItem> proj_items, back_items;
+  DevBuf<unsigned char> cover;           // 1 for rows some block of this kernel covers
+};
+
+struct Batch {
+  int64_t n = 0;
+  int nk = 0, B = 0, Bp = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false, initialised = false, any_na = false;
+  std::vector<BatchKernel> kernels;
+  std::vector<double> y_host;            // chain-major: y of chain b at [b*n, (b+1)*n)
+  std::vector<unsigned char> na_host;
+  int64_t ite = 0, burn = 0, thin = 1, ncum = 0, done = 0;
+  double R2 = 0.5;
+  DrawCfg draw{};
+  int rows_per_chunk = 0, nchunks = 0;
+  // all matrices are row-major n x Bp (chain index fastest)
+  DevBuf<double> Y, R, Ep, U, Um, Um2, Upart, part, part2;
+  DevBuf<int> narank;
+  DevBuf<double> mu, mu0, shift, sigsq, tau, Sce, Sc, sigb;
+  DevBuf<long long> it;
+  DevBuf<double> chain_mu, chain_varE, chain_varU;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~Batch();
+};
+
+int batch_init(Batch* g);
+int batch_run(Batch* g, int64_t iters);
+
+}  // namespace bgge

@@ -1,0 +1,167 @@
+// Skinny FP64 tensor-core GEMM for batched chains / folds (north_star (3): "multiple chains or
+// cross-validation folds batch the GEMVs into skinny GEMMs"):
+//     C[m][n] = sum_{k in [k0,k1)} A[m + k*lda] * B[n + k*ldb]        (C row-major, ldc)
+// i.e. A is "M-fast" (column-major M x K), B is "N-fast" (row-major K x N), the same operand form as the
+// Gram kernel (gram.cu), so   d = U'E  uses A = t(U)  and  u = U b  uses A = U  unchanged.
+// Work items = (M tile of 128, N tile of TN, K split); every item writes its own partial C (no atomics,
+// the consumers sum the K splits in fixed order).  Per CTA: TMA producer warp (cp.async.bulk rows into a
+// padded 4-stage ring), 8 consumer warps x 16 rows x TN columns of mma.sync.m8n8k4.f64 (DMMA.8x8x4).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgge {
+namespace {
+
+constexpr int GM = 128;          // M tile
+constexpr int GK = 16;           // K slab
+constexpr int GSLD_A = 132;      // padded shared leading dimensions (== 4 mod 16: conflict-free DMMA fragments)
+constexpr int GSTAGES = 4;
+constexpr int GCONS = 8;
+constexpr int GTHREADS = 384;    // 2 consumer warpgroups + producer warpgroup
+
+template <int TN>
+struct GemmSmem {
+  static constexpr int SLD_B = TN + 4;
+  static constexpr int STAGE_DOUBLES = GK * GSLD_A + GK * SLD_B;
+  static constexpr size_t BYTES = (size_t)GSTAGES * STAGE_DOUBLES * sizeof(double) + 2 * GSTAGES * sizeof(uint64_t);
+};
+
+template <int TN>
+__global__ void __launch_bounds__(GTHREADS, 1)
+dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
+  using SM = GemmSmem<TN>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)GSTAGES * SM::STAGE_DOUBLES);
+  uint64_t* empty = full + GSTAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // stale shared memory must be finite: clipped tail rows are never loaded and multiply zero operands
+  for (int i = threadIdx.x; i < GSTAGES * SM::STAGE_DOUBLES; i += GTHREADS) sm[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], GCONS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp >= GCONS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp != GCONS) return;
+    // producer: lane l < 16 copies A slab row l, lane >= 16 copies B slab row l-16
+    const int row = lane & 15;
+    const bool isB = lane >= 16;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+      const GemmItem gi = items[w];
+      const int mrows = min(GM, gi.M - gi.m0);
+      const int ncols = min(TN, gi.N - gi.n0);
+      const uint32_t bytesA = (uint32_t)((mrows + 1) & ~1) * 8u;
+      const uint32_t bytesB = (uint32_t)((ncols + 1) & ~1) * 8u;
+      for (int kb = gi.kb0; kb < gi.kb1; ++kb, ++it) {
+        const int stage = it % GSTAGES;
+        mbar_wait(&empty[stage], ((it / GSTAGES) & 1u) ^ 1u);
+        const int k = kb * GK + row;
+        const bool live = k < gi.K;
+        // every lane announces its own bytes; lane 0 arrives
+        uint32_t mine = live ? (isB ? bytesB : bytesA) : 0u;
+        uint32_t tot = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) mbar_expect_tx(&full[stage], tot);
+        __syncwarp();
+        if (live) {
+          double* dst = sm + (size_t)stage * SM::STAGE_DOUBLES + (isB ? GK * GSLD_A + row * SM::SLD_B : row * GSLD_A);
+          const double* src = isB ? gi.B + gi.n0 + (long long)k * gi.ldb : gi.A + gi.m0 + (long long)k * gi.lda;
+          bulk_g2s(dst, src, mine, &full[stage]);
+        }
+      }
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  constexpr int NT8 = TN / 8;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int m_w = warp * 16;
+  uint32_t it = 0;
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+    const GemmItem gi = items[w];
+    double acc[2][NT8][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kb = gi.kb0; kb < gi.kb1; ++kb, ++it) {
+      const int stage = it % GSTAGES;
+      mbar_wait(&full[stage], (it / GSTAGES) & 1u);
+      const double* As = sm + (size_t)stage * SM::STAGE_DOUBLES + m_w + fr;
+      const double* Bs = sm + (size_t)stage * SM::STAGE_DOUBLES + GK * GSLD_A + fr;
+      const int klive = min(GK, gi.K - kb * GK);   // rows >= klive hold stale (finite) data: skip them
+#pragma unroll
+      for (int kk = 0; kk < GK / 4; ++kk) {
+        if (kk * 4 < klive) {
+          const int k = kk * 4 + fk;
+          const bool kv = k < klive;
+          double a[2], b[NT8];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a[i] = kv ? As[k * GSLD_A + i * 8] : 0.0;
+#pragma unroll
+          for (int j = 0; j < NT8; ++j) b[j] = kv ? Bs[k * SM::SLD_B + j * 8] : 0.0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NT8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+    // epilogue: C fragment (row = lane/4, cols 2*(lane%4) + {0,1}) -> this item's partial C
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = gi.m0 + m_w + i * 8 + fr;
+      if (m >= gi.M) continue;
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) {
+        const int nn = gi.n0 + j * 8 + 2 * fk;
+        double* c = gi.C + (long long)m * gi.ldc + nn;
+        if (nn + 1 < gi.N) {
+          *reinterpret_cast<double2*>(c) = make_double2(acc[i][j][0], acc[i][j][1]);
+        } else if (nn < gi.N) {
+          c[0] = acc[i][j][0];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
+  if (nitems <= 0) return OK;
+  const int grid = nitems < sm_count() ? nitems : sm_count();
+  static bool attr64 = false, attr128 = false;
+  if (tn == 64) {
+    if (!attr64) {
+      BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64>::BYTES));
+      attr64 = true;
+    }
+    dgemm_dmma_kernel<64><<<grid, GTHREADS, GemmSmem<64>::BYTES, st>>>(d_items, nitems);
+  } else if (tn == 128) {
+    if (!attr128) {
+      BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<128>::BYTES));
+      attr128 = true;
+    }
+    dgemm_dmma_kernel<128><<<grid, GTHREADS, GemmSmem<128>::BYTES, st>>>(d_items, nitems);
+  } else {
+    set_error("dgemm: unsupported N tile %d", tn);
+    return ERR_INVALID;
+  }
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
+
+}  // namespace bgge

@@ -31,4 +31,16 @@ int gather_scale_launch(const double* dK0, int64_t ldk, const int* dT, const dou
 int expand_rows_launch(const double* dW, int64_t ldw, const int* d_loc, const double* d_isq, int64_t rows, int64_t nr,
                        double* dU, int64_t ldu, cudaStream_t st);
 
+// dgemm.cu -- one work item of the skinny DMMA GEMM: C[m][n] (row-major, ldc) = sum_k A[m + k lda] B[n + k ldb]
+struct GemmItem {
+  const double* A;
+  const double* B;
+  double* C;
+  long long lda, ldb, ldc;
+  int M, N, K;          // full extents (for edge clipping)
+  int m0, n0;           // tile origin
+  int kb0, kb1;         // 16-deep k-blocks [kb0, kb1)
+};
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st);
+
 }  // namespace bgge

@@ -205,6 +205,31 @@ int bgge_gibbs_chain(bgge_gibbs* h, double* mu, double* varE, double* varU, doub
 int bgge_gibbs_summary(bgge_gibbs* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd,
                        double* varu, double* varu_sd, double* y);
 
+/* ------------------------------------------------------------------ batched chains / CV folds */
+/*
+ * B independent BGGE() chains (different y / NA masks = folds, different RNG streams) that share the eigen
+ * blocks of every kernel: the two U passes of each kernel step run as skinny FP64 tensor-core GEMMs
+ * (nr x B and n x B).  Chain b draws with key (seed, chain0 + b) and reproduces a single-chain handle
+ * initialised with bgge_gibbs_init(..., seed, chain0 + b).  Device RNG only, no XF.
+ * All per-chain inputs / outputs are chain-major (chain b's vector contiguous).
+ */
+typedef struct bgge_batch bgge_batch;
+int bgge_batch_create(int64_t n, int nk, int n_chains, void* stream, bgge_batch** out);
+void bgge_batch_destroy(bgge_batch* h);
+int bgge_batch_set_y(bgge_batch* h, const double* Y, const uint8_t* na_mask);              /* B x n */
+int bgge_batch_set_kernel(bgge_batch* h, int j, int type, double mean_diag);
+int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64_t nr, const double* s, const double* U,
+                         int64_t ldu, int on_device);
+int bgge_batch_init(bgge_batch* h, int64_t ite, int64_t burn, int64_t thin, double R2, uint64_t seed, uint32_t chain0);
+int bgge_batch_run(bgge_batch* h, int64_t iters);
+int bgge_batch_sync(bgge_batch* h);
+int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_iter, int* launches_per_iter);
+/* mu[B x n_cum], varE[B x n_cum], varU[nk x B x n_cum] */
+int bgge_batch_chain(bgge_batch* h, double* mu, double* varE, double* varU);
+/* yHat[B x n], varE[B], varE_sd[B], u[nk x B x n], u_sd[nk x B x n], varu[nk x B], varu_sd[nk x B], y[B x n] */
+int bgge_batch_summary(bgge_batch* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd, double* varu,
+                       double* varu_sd, double* y);
+
 /* ------------------------------------------------------------------ one-shot BGGE() */
 /*
  * What the .Call shim under BGGE() invokes: eigen of every kernel (setDEC), `ite` sweeps and the
