@@ -45,6 +45,9 @@ WORKLOADS = {
     "c2": (599, 1279, 4, "GK", "MDs", "C2: wheat-shaped 599 x 1279 x 4 envs (n=2396) getK GK MDs + BGGE sweep"),
     "c1": (599, 1279, 4, "GB", "MM", "C1: wheat-shaped 599 x 1279 x 4 envs (n=2396) getK GB MM + BGGE sweep"),
     "tiny": (256, 512, 3, "GK", "MDs", "tiny smoke workload"),
+    "c4": (2000, 20000, 5, "GB", "MM", "C4: 64 chains x 5 folds = 320 runs sharing one U, 2000 lines x 20000 SNPs x 5 envs "
+           "(n=10000) GB MM, sharded across the GPUs"),
+    "c4tiny": (300, 600, 3, "GB", "MM", "tiny batched smoke workload (12 chains)"),
 }
 METRIC = "Gibbs iterations/sec at n=40k (MDs GK)"
 
@@ -260,6 +263,157 @@ def gram_build(torch, dist, lib, Xp, ldx, L, pp, divisor, world, rank, stream):
     return S
 
 
+def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
+    """Config C4: B chains x folds sharing one decomposition; the chains are sharded over the ranks (no
+    data-path collective) and each rank runs its share as one batched sampler (skinny DMMA GEMMs)."""
+    from bgge_b200 import multigpu
+    L, p, E, kernel, model, desc = WORKLOADS[args.workload]
+    n = L * E
+    n_total = 320 if args.workload == "c4" else 12
+    units = list(multigpu.shard_units(n_total, world, rank))
+    B = len(units)
+    iters = args.iters or (200 if args.workload == "c4" else 20)
+    with torch.cuda.stream(stream_t):
+        stream = C.c_void_p(stream_t.cuda_stream)
+        Xp, ldx, pp = build_markers(torch, lib, L, p, 20260000 + 3, device)
+        dg_burst, dg_sust = dgemm_peak(torch, device)
+        t_contr = min(timed(torch, lambda: gram_build(torch, dist, lib, Xp, ldx, L, pp, float(p), 1, 0, stream)) for _ in range(3))
+        K0 = gram_build(torch, dist, lib, Xp, ldx, L, pp, float(p), 1, 0, stream)
+        del Xp
+        gid_h = np.tile(np.arange(L, dtype=np.int32), E)
+        env_h = np.repeat(np.arange(E, dtype=np.int32), L)
+        h0 = C.c_void_p()
+        lib.call("bgge_gibbs_create", n, 1, 0, stream, C.byref(h0))
+        torch.cuda.synchronize()
+        t_eig = time.perf_counter()
+        lib.call("bgge_gibbs_add_expanded_kernel", h0, 0, 0, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), 0, 0, None, 0,
+                 1e-10, 1)
+        torch.cuda.synchronize()
+        t_eig = time.perf_counter() - t_eig
+        pos0, rows, nr_b, ldu_b = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        lib.call("bgge_gibbs_fetch_block", h0, 0, 0, C.byref(pos0), C.byref(rows), C.byref(nr_b), None, None, 0)
+        sv = np.empty(nr_b.value)
+        lib.call("bgge_gibbs_fetch_block", h0, 0, 0, None, None, None, lib.ptr(sv), None, 0)
+        dptr = C.c_void_p()
+        lib.call("bgge_gibbs_block_device", h0, 0, 0, C.byref(dptr), C.byref(ldu_b))
+        mean_diag = float(torch.diagonal(K0).mean().item())
+        # phenotypes + folds (SURVEY.md 8d): fold f masks the lines with perm % 5 == f in all environments
+        rng = np.random.default_rng(20260000 + 3)
+        g = rng.standard_normal(L)
+        y = np.concatenate([0.3 * (e - E / 2) + g + 0.7 * rng.standard_normal(L) for e in range(E)])
+        y = y + rng.standard_normal(n) * y.std()
+        perm = rng.permutation(L)
+        Y = np.empty((B, n))
+        for k, unit in enumerate(units):
+            fold = unit % 5
+            yy = y.copy()
+            mask = np.tile(perm % 5 == fold, E)
+            yy[mask] = np.nan
+            Y[k] = yy
+        Y_pinned = torch.from_numpy(Y).pin_memory()
+        Yh = Y_pinned.numpy()
+        total_iters = (args.warmup + args.steps) * iters + 8
+
+        def make_batch(ite):
+            hb = C.c_void_p()
+            lib.call("bgge_batch_create", n, 1, B, stream, C.byref(hb))
+            lib.call("bgge_batch_set_y", hb, lib.ptr(Yh), None)
+            lib.call("bgge_batch_set_kernel", hb, 0, 0, mean_diag)
+            lib.call("bgge_batch_add_block", hb, 0, pos0.value, rows.value, nr_b.value, lib.ptr(sv), dptr, ldu_b.value, 1)
+            lib.call("bgge_batch_init", hb, ite, ite // 5, 3, 0.5, 1000, units[0])
+            return hb
+        hb = make_batch(total_iters)
+        bp, fl, nl = C.c_int(), C.c_int64(), C.c_int()
+        lib.call("bgge_batch_info", hb, C.byref(bp), C.byref(fl), C.byref(nl))
+        for _ in range(args.warmup):
+            lib.call("bgge_batch_run", hb, iters)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            lib.call("bgge_batch_run", hb, iters)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else {}
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        lib.load().bgge_batch_destroy(hb)
+        value = n_total * args.steps * iters / (ms_total * 1e-3)                     # chain-iterations / s, whole job
+        it_s = args.steps * iters / (ms_total * 1e-3)
+        tflops = fl.value * it_s / 1e12
+        # e2e: host Y -> batch handle -> sweeps -> per-chain summaries back on the host
+        yHat = np.empty((B, n))
+        vE, vEs, vu, vus = np.empty(B), np.empty(B), np.empty((1, B)), np.empty((1, B))
+        ncum = max(1, iters // 3)
+        cm, cv, cu = np.empty((B, ncum)), np.empty((B, ncum)), np.empty((1, B, ncum))
+
+        def e2e_step():
+            hh = make_batch(iters)
+            lib.call("bgge_batch_run", hh, iters)
+            lib.call("bgge_batch_summary", hh, lib.ptr(yHat), lib.ptr(vE), lib.ptr(vEs), None, None, lib.ptr(vu), lib.ptr(vus), None)
+            lib.call("bgge_batch_chain", hh, lib.ptr(cm), lib.ptr(cv), lib.ptr(cu))
+            lib.load().bgge_batch_destroy(hh)
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_val = n_total * args.steps * iters / float(te.item())
+        lib.load().bgge_gibbs_destroy(h0)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref_it = args.ref_iters or default_ref_iters(L, False)
+        prob = cpu_problem(L, E, model, kernel)
+        cpu_sweep_time(prob, max(1, ref_it // 20))
+        dt = cpu_sweep_time(prob, ref_it)
+        cpu_base = {"value": ref_it / dt, "unit": "chain-it/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"{ref_it} sweep iterations of ONE chain (the reference runs chains one after another), numpy/"
+                              f"OpenBLAS restatement of R/BGGE.R:274-403, eigen block of the true shape, {dt:.1f} s"}
+    if rank == 0:
+        line = {
+            "metric": "chain-iterations/sec, 320 chains x folds (C4)", "value": value, "unit": "chain-it/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "iters_per_step": iters, "chains_total": n_total, "chains_per_gpu": B,
+                       "padded_chains_per_gpu": bp.value, "n": n, "L": L, "p": p, "E": E, "kept_eigen": int(nr_b.value),
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+                       "l2": "U and t(U) (2 x 160 MB) exceed L2; compute-bound above ~23 chains"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "chain-it/s", "h2d_bytes_per_step": 8 * n * B, "d2h_bytes_per_step": 8 * (n * B + 4 * B + 3 * B * ncum),
+                    "covers": "bgge_batch_create + set_y (host) + add_block (resident eigen) + init + sweeps + summaries/chains"},
+            "gpu_launches": args.steps * iters * nl.value,
+            "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel (d = U'E and u = U b over all chains)",
+                         "achieved": tflops, "peak": dg_burst, "unit": "TFLOP/s", "frac": tflops / dg_burst, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst)",
+                         "note": "flops counted on the padded chain count; whole-iteration time (GEMMs + elementwise)"},
+            "cpu_baseline": cpu_base,
+            "getk": {"contraction_s": t_contr, "contraction_tflops": float(L) * (L + 1) * p / t_contr / 1e12,
+                     "dgemm_peak_tflops_burst": dg_burst, "dgemm_peak_tflops_sustained": dg_sust},
+            "eigen": {"setdec_s": t_eig, "L": L},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,6 +446,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     lib.call("bgge_set_device", local)
     stream_t = torch.cuda.Stream(device=device)
+    if args.workload in ("c4", "c4tiny"):
+        return run_c4(args, torch, dist, lib, world, rank, local, device, stream_t)
     L, p, E, kernel, model, desc = WORKLOADS[args.workload]
     n = L * E
     iters = args.iters or (200 if n >= 30000 else 500 if n >= 10000 else 2000)

@@ -447,11 +447,20 @@ int batch_init(Batch* g) {
     for (auto& bl : bk.blocks) std::fill(cover.begin() + bl.pos0, cover.begin() + bl.pos0 + bl.rows, (unsigned char)1);
     BGGE_TRY(up(bk.cover, cover, st));
     const int ntile_n = Bp / 64;
+    // K splits: enough work items that the persistent CTAs end within a few percent of each other
+    // (>= 6 items per SM), but at least 24 k-blocks per item so the 4-stage ring fill stays amortised
     auto pick_split = [&](int64_t tiles, int64_t kmax) {
-      int sp = 1;
       const int64_t kblocks = (kmax + 15) / 16;
-      while (tiles * ntile_n * sp < 2 * sms && sp * 2 <= kblocks / 8 && sp < 32) sp *= 2;
-      return sp;
+      int best = 1;
+      double best_cost = 1e300;
+      for (int sp = 1; sp <= 32 && kblocks / sp >= 24; ++sp) {
+        const int64_t items = tiles * ntile_n * sp;
+        const double waves = (double)((items + sms - 1) / sms);
+        const double per_item = (double)kblocks / sp + 6.0;          // + ring fill / epilogue, in k-block units
+        const double cost = waves * per_item + 0.02 * sp * kblocks;  // + partial-sum traffic
+        if (cost < best_cost) { best_cost = cost; best = sp; }
+      }
+      return best;
     };
     bk.ksplit_proj = pick_split(proj_tiles, max_rows);
     bk.ksplit_back = pick_split(back_tiles, max_nr);
