@@ -34,6 +34,7 @@ constexpr int F_THREADS = 2 * F_ROLE + 32;       // + one producer warp (one ele
 constexpr int F_ROWS_PER_STEP = 2 * F_ROLE;      // each role thread owns row pairs (16-byte shared loads)
 constexpr int F_MAX_NS = 10;                     // data ring depth limit
 constexpr int NPX = 32;                          // partial-exchange ring depth (see protocol note)
+constexpr int F_MAXCS = 16;                      // largest cluster (16 needs the non-portable opt-in)
 
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t r;
@@ -83,7 +84,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   const size_t slot_doubles = (size_t)G * max_rs;
   double* ring = reinterpret_cast<double*>(fsm);
   double* parts = ring + (size_t)ns * slot_doubles;
-  double* red = parts + (size_t)NPX * 8 * G;
+  double* red = parts + (size_t)NPX * F_MAXCS * G;
   double* tvb = red + 2 * 8 * G;                 // tau * v       per column of a draw batch
   double* zsb = tvb + 2 * ZB;                    // sqrt(v) * z
   double* isb = zsb + 2 * ZB;                    // 1 / s
@@ -179,7 +180,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
             p += __shfl_xor_sync(0xffffffffu, p, 2);
             p += __shfl_xor_sync(0xffffffffu, p, 1);
             if (lane < (int)cs) {
-              const uint32_t dst = smem_u32(parts + (size_t)pg * 8 * G + (size_t)rank * G + g);
+              const uint32_t dst = smem_u32(parts + (size_t)pg * F_MAXCS * G + (size_t)rank * G + g);
               st_async_f64(map_to_rank(dst, (uint32_t)lane), p, map_to_rank(bar_addr, (uint32_t)lane));
             }
           }
@@ -226,7 +227,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
         for (int g = 0; g < G; ++g) {
           bv[g] = 0.0;
           if (g < gc) {
-            const double* pp = parts + (size_t)pg * 8 * G + g;
+            const double* pp = parts + (size_t)pg * F_MAXCS * G + g;
             double d = 0.0;
             for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * G];             // rank order
             const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
@@ -344,6 +345,7 @@ int occupancy_t(int cs, size_t smem, int* nclusters) {
   (void)dev;
   BGGE_REQUIRE((size_t)optin >= smem, "fused plan: %zu bytes of shared memory exceed the device limit %d", smem, optin);
   BGGE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  if (cs > 8) BGGE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
   cfg.blockDim = dim3(F_THREADS, 1, 1);
@@ -402,7 +404,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   while (cs < 8 && max_rows > (int64_t)cs * 12 * F_ROWS_PER_STEP) cs *= 2;
   if (const char* ev = getenv("BGGE_FUSED_CS")) {   // tuning hook
     const int v = atoi(ev);
-    if (v == 1 || v == 2 || v == 4 || v == 8) cs = std::max(cs, v);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cs = std::max(cs, v);
   }
   const int64_t rs_max = round_up((max_rows + cs - 1) / cs, 16);
   const int rpt_need = (int)((rs_max + F_ROWS_PER_STEP - 1) / F_ROWS_PER_STEP);
@@ -415,7 +417,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   hk.fused_g = combo->gcols;
   const size_t slot_bytes = (size_t)combo->gcols * rs_max * sizeof(double);
   const size_t zb = (size_t)combo->gcols * (F_ROLE / combo->gcols);
-  const size_t fixed = ((size_t)NPX * 8 * combo->gcols + 2 * 8 * combo->gcols + 6 * zb) * sizeof(double) +
+  const size_t fixed = ((size_t)NPX * F_MAXCS * combo->gcols + 2 * 8 * combo->gcols + 6 * zb) * sizeof(double) +
                        (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
   int dev = 0, optin = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
