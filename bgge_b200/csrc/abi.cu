@@ -150,21 +150,6 @@ namespace {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// lower-triangular tile list for tile rows [tr0, tr1)
-int build_tiles(int64_t tr0, int64_t tr1, DevBuf<int2>& out, int* ntiles, cudaStream_t st) {
-  std::vector<int2> t;
-  // walk anti-diagonal-ish: longest rows first so the tail of the persistent loop is short
-  for (int64_t ti = tr1 - 1; ti >= tr0; --ti)
-    for (int64_t tj = 0; tj <= ti; ++tj) t.push_back(make_int2((int)ti, (int)tj));
-  *ntiles = (int)t.size();
-  BGGE_CUDA(out.alloc(t.size()));
-  if (!t.empty()) {
-    BGGE_CUDA(cudaMemcpyAsync(out.p, t.data(), t.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    BGGE_CUDA(cudaStreamSynchronize(st));   // t goes out of scope
-  }
-  return OK;
-}
-
 // host X (L x p) -> padded device copy
 int upload_markers(const double* X, int64_t L, int64_t p, DevBuf<double>& dX, int64_t* ldx, int64_t* p_pad) {
   *ldx = round_up(L, 128);
@@ -183,14 +168,11 @@ int base_kernels_device(const double* dX, int64_t ldx, int64_t L, int64_t p, int
   BGGE_REQUIRE(kind == BGGE_KERNEL_GB || kind == BGGE_KERNEL_GK,
                "kernel selected is not available. Please choose one method available or make available other "
                "kernel through argument K");
-  DevBuf<int2> tiles;
-  int ntiles = 0;
   const int64_t T = (L + 127) / 128;
-  BGGE_TRY(build_tiles(0, T, tiles, &ntiles, st));
   if (kind == BGGE_KERNEL_GB) {
     K0.resize(1);
     BGGE_CUDA(K0[0].alloc((size_t)L * L));
-    BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, K0[0].p, L, 0, (double)p, 1, st));
+    BGGE_TRY(gram_launch(dX, ldx, L, p_pad, 0, T, K0[0].p, L, 0, (double)p, 1, st));
     BGGE_CUDA(cudaStreamSynchronize(st));
     return OK;
   }
@@ -201,7 +183,7 @@ int base_kernels_device(const double* dX, int64_t ldx, int64_t L, int64_t p, int
   BGGE_CUDA(diag.alloc((size_t)L));
   BGGE_CUDA(q.alloc(1));
   BGGE_CUDA(scratch.alloc(quantile_scratch_bytes()));
-  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, D.p, L, 0, 1.0, 1, st));
+  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, 0, T, D.p, L, 0, 1.0, 1, st));
   BGGE_TRY(gk_distance_launch(D.p, L, L, diag.p, st));
   BGGE_TRY(quantile7_launch(D.p, L, L, quantil, scratch.p, q.p, st));
   K0.resize((size_t)nb);
@@ -308,12 +290,7 @@ int bgge_dev_gram(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64
   BGGE_REQUIRE(0 <= tile_row0 && tile_row0 <= tile_row1 && tile_row1 <= T, "dev_gram: tile rows [%lld,%lld) outside [0,%lld)",
                (long long)tile_row0, (long long)tile_row1, (long long)T);
   BGGE_REQUIRE(divisor != 0.0, "dev_gram: zero divisor");
-  DevBuf<int2> tiles;
-  int ntiles = 0;
-  BGGE_TRY(build_tiles(tile_row0, tile_row1, tiles, &ntiles, as_stream(stream)));
-  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, tiles.p, ntiles, dS, lds, row_off, divisor, mirror, as_stream(stream)));
-  BGGE_CUDA(cudaStreamSynchronize(as_stream(stream)));   // the tile list is freed on return
-  return OK;
+  return gram_launch(dX, ldx, L, p_pad, tile_row0, tile_row1, dS, lds, row_off, divisor, mirror, as_stream(stream));
 }
 
 int bgge_dev_symmetrize(double* dS, int64_t lds, int64_t L, void* stream) {

@@ -14,9 +14,16 @@
 // per half-warp.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 namespace bgge {
 namespace {
+
+struct GramItem {                // one work item: tile (ti, tj) of the lower triangle, k-blocks [kb0, kb1)
+  int ti, tj, kb0, kb1, split;
+};
 
 constexpr int TM = 128;          // tile rows
 constexpr int TN = 128;          // tile cols
@@ -30,9 +37,9 @@ constexpr uint32_t STAGE_TX_BYTES = 2u * BK * TM * sizeof(double);
 constexpr size_t GRAM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const int2* __restrict__ tiles,
-                 int ntiles, double* __restrict__ S, int64_t lds, int64_t L, int64_t row_off,
-                 double divisor, int mirror) {
+gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __restrict__ tiles,
+                 int ntiles, double* __restrict__ S, double* __restrict__ Spart, int64_t part_stride, int64_t lds,
+                 int64_t L, int64_t row_off, double divisor, int mirror) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)STAGES * STAGE_DOUBLES);
@@ -60,9 +67,9 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
     const int op = lane >> 4;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int2 tc = tiles[t];
-      const double* src = X + (int64_t)(op ? tc.y : tc.x) * TM + (int64_t)row * ldx;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+      const GramItem tc = tiles[t];
+      const double* src = X + (int64_t)(op ? tc.tj : tc.ti) * TM + (int64_t)row * ldx;
+      for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
         const int stage = it % STAGES;
         mbar_wait(&empty[stage], ((it / STAGES) & 1u) ^ 1u);
         if (lane == 0) mbar_expect_tx(&full[stage], STAGE_TX_BYTES);
@@ -82,14 +89,14 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
   const int fk = lane & 3;     // fragment k 0..3
   uint32_t it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int2 tc = tiles[t];
+    const GramItem tc = tiles[t];
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+    for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
       const int stage = it % STAGES;
       mbar_wait(&full[stage], (it / STAGES) & 1u);
       const double* As = sm + (size_t)stage * STAGE_DOUBLES + wm * 64 + fr;
@@ -111,10 +118,13 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
       if (lane == 0) mbar_arrive(&empty[stage]);
     }
 
-    // epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}); scale and store
-    const int64_t gi0 = (int64_t)tc.x * TM + wm * 64 + fr;
-    const int64_t gj0 = (int64_t)tc.y * TN + wn * 32 + 2 * fk;
-    const bool offdiag = mirror && (tc.x != tc.y);
+    // epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}).  Unsplit tiles are scaled and stored
+    // (with the mirror); K-split tiles store their raw partial, gram_reduce_kernel finishes them.
+    const int64_t gi0 = (int64_t)tc.ti * TM + wm * 64 + fr;
+    const int64_t gj0 = (int64_t)tc.tj * TN + wn * 32 + 2 * fk;
+    const bool direct = Spart == nullptr;
+    const bool offdiag = direct && mirror && (tc.ti != tc.tj);
+    double* out = direct ? S : Spart + (int64_t)tc.split * part_stride;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t gi = gi0 + i * 8;
@@ -125,8 +135,8 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
         for (int h = 0; h < 2; ++h) {
           const int64_t gj = gj0 + j * 8 + h;
           if (gj >= L) continue;
-          const double v = acc[i][j][h] / divisor;
-          S[(gi - row_off) + gj * lds] = v;
+          const double v = direct ? acc[i][j][h] / divisor : acc[i][j][h];
+          out[(gi - row_off) + gj * lds] = v;
           if (offdiag) S[gj + gi * lds] = v;
         }
       }
@@ -134,23 +144,94 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, int kblocks, const i
   }
 }
 
+// sums the K-split partials of every tile in fixed order, scales, stores (+ mirror)
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const GramItem* __restrict__ tiles, int nsplit, const double* __restrict__ Spart,
+                   int64_t part_stride, double* __restrict__ S, int64_t lds, int64_t L, int64_t row_off, double divisor,
+                   int mirror) {
+  const GramItem tc = tiles[blockIdx.x];   // the split-0 item of each tile
+  const int64_t i = (int64_t)tc.ti * TM + (threadIdx.x & 127);
+  if (i >= L) return;
+  for (int c = threadIdx.x >> 7; c < TN; c += 2) {
+    const int64_t jx = (int64_t)tc.tj * TN + c;
+    if (jx >= L) break;
+    const int64_t off = (i - row_off) + jx * lds;
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) v += Spart[(int64_t)sp * part_stride + off];
+    v /= divisor;
+    S[off] = v;
+    if (mirror && tc.ti != tc.tj) S[jx + i * lds] = v;
+  }
+}
+
 }  // namespace
 
-int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, const int2* d_tiles, int ntiles,
-                double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st) {
+// Lower-triangle tiles of tile rows [tr0, tr1).  When the tile count leaves a poor last wave on the
+// persistent grid (mid-size L), the marker dimension is split so that the items spread evenly; partials go
+// to a workspace and are summed in fixed order by gram_reduce_kernel (deterministic).
+int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tr0, int64_t tr1, double* dS,
+                int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st) {
   BGGE_REQUIRE(ldx % TM == 0 && ldx >= round_up(L, TM), "gram: ldx=%lld must be a multiple of 128 >= L", (long long)ldx);
   BGGE_REQUIRE(p_pad % BK == 0 && p_pad > 0, "gram: padded marker count %lld must be a positive multiple of 16", (long long)p_pad);
   BGGE_REQUIRE(!(mirror && row_off != 0), "gram: mirror store needs the full square output");
+  std::vector<int2> tl;
+  for (int64_t ti = tr1 - 1; ti >= tr0; --ti)   // longest tile rows first
+    for (int64_t tj = 0; tj <= ti; ++tj) tl.push_back(make_int2((int)ti, (int)tj));
+  const int64_t ntiles = (int64_t)tl.size();
   if (ntiles == 0) return OK;
+  const int sms = sm_count();
+  const int kblocks = (int)(p_pad / BK);
+  int nsplit = 1;
+  {
+    // the split is a function of (L, p) only -- computed on the full triangle, not on this panel -- so that
+    // a row-panel build (multi-GPU) stays bit-identical to the one-shot build
+    const int64_t Tfull = (L + TM - 1) / TM;
+    const int64_t nfull = Tfull * (Tfull + 1) / 2;
+    auto cost = [&](int sp) {
+      const double waves = (double)((nfull * sp + sms - 1) / sms);
+      return waves * ((double)kblocks / sp + 8.0) + (sp > 1 ? 0.03 * sp * kblocks / std::max<int64_t>(1, nfull / sms + 1) : 0.0);
+    };
+    double best = cost(1);
+    for (int sp = 2; sp <= 16 && kblocks / sp >= 64; ++sp)
+      if (cost(sp) < 0.95 * best && cost(sp) < cost(nsplit)) nsplit = sp;
+  }
+  if (const char* ev = getenv("BGGE_GRAM_SPLIT")) {
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 16) nsplit = v;
+  }
+  std::vector<GramItem> items;
+  for (int sp = 0; sp < nsplit; ++sp)
+    for (auto& t : tl) {
+      GramItem g{};
+      g.ti = t.x;
+      g.tj = t.y;
+      g.kb0 = (int)((int64_t)kblocks * sp / nsplit);
+      g.kb1 = (int)((int64_t)kblocks * (sp + 1) / nsplit);
+      g.split = sp;
+      items.push_back(g);
+    }
+  DevBuf<GramItem> d_items;
+  DevBuf<double> part;
+  BGGE_CUDA(d_items.alloc(items.size()));
+  BGGE_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(GramItem), cudaMemcpyHostToDevice, st));
+  const int64_t part_stride = lds * L;
+  if (nsplit > 1) BGGE_CUDA(part.alloc((size_t)part_stride * nsplit));
   static bool attr_set = false;
   if (!attr_set) {
     BGGE_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
     attr_set = true;
   }
-  int grid = ntiles < sm_count() ? ntiles : sm_count();
-  gram_dmma_kernel<<<grid, NTHREADS, GRAM_SMEM, st>>>(dX, ldx, (int)(p_pad / BK), d_tiles, ntiles, dS, lds, L,
-                                                             row_off, divisor, mirror);
+  const int nitems = (int)items.size();
+  const int grid = nitems < sms ? nitems : sms;
+  gram_dmma_kernel<<<grid, NTHREADS, GRAM_SMEM, st>>>(dX, ldx, d_items.p, nitems, dS, nsplit > 1 ? part.p : nullptr,
+                                                       part_stride, lds, L, row_off, divisor, mirror);
   BGGE_CUDA(cudaGetLastError());
+  if (nsplit > 1) {
+    gram_reduce_kernel<<<(unsigned)ntiles, 256, 0, st>>>(d_items.p, nsplit, part.p, part_stride, dS, lds, L, row_off,
+                                                        divisor, mirror);
+    BGGE_CUDA(cudaGetLastError());
+  }
+  BGGE_CUDA(cudaStreamSynchronize(st));   // the item list and the workspace die here
   return OK;
 }
 

@@ -6,7 +6,7 @@
 namespace bgge {
 
 // gram.cu
-int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, const int2* d_tiles, int ntiles,
+int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tile_row0, int64_t tile_row1,
                 double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st);
 
 // getk.cu
