@@ -1,0 +1,113 @@
+"""The remaining C-ABI entry points exercised directly through ctypes: one-shot bgge_fit, the device-pointer
+getK pipeline, chunked runs (verbose semantics), the device-memory cache."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import design, markers, phenotype, relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_bgge_fit_one_shot_matches_wrapper(lib):
+    """bgge_fit (what the .Call shim calls) == handle API driven by the Python wrapper, same tape."""
+    import bgge_b200
+    L, E, p = 21, 3, 40
+    X = markers(L, p, 1)
+    Y, names = design(L, E)
+    K = oracle.getK(Y, X, kernel="GK", model="MDs", rownames=names)
+    y = phenotype(oracle.gb_kernel(X), L, E, 2)
+    y[[3, 30]] = np.nan
+    n, nk, ite, burn, thin = L * E, 2, 30, 6, 2
+    ne = np.array([L] * E, dtype=np.int64)
+    Ei = bgge_b200.setDEC(K, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    nz, nc = oracle.tape_sizes(n, nrs, ite, n_na=2)
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    want = bgge_b200.BGGE(y, K, ne=ne, ite=ite, burn=burn, thin=thin, draws=(z, c))
+    mats = [lib.f64(k["Kernel"]) for k in K.values()]
+    kp = (C.c_void_p * nk)(*[m.ctypes.data for m in mats])
+    types = np.array([0, 1], dtype=np.int32)
+    ncum = ite // thin
+    yHat, u, usd, yout = np.empty(n), np.empty((nk, n)), np.empty((nk, n)), np.empty(n)
+    varu, varusd = np.empty(nk), np.empty(nk)
+    cmu, cve, cvu = np.empty(ncum), np.empty(ncum), np.empty((nk, ncum))
+    varE, varEsd = C.c_double(), C.c_double()
+    na = np.isnan(y).astype(np.uint8)
+    yy = np.where(np.isnan(y), 0.0, y)                       # NA passed as a byte mask, as the R shim does
+    lib.call("bgge_fit", lib.ptr(yy), lib.ptr(na), n, kp, lib.ptr(types), nk, None, 0, lib.ptr(ne), E, ite, burn, thin, 1e-10,
+             0.5, lib.RNG_TAPE, 0, lib.ptr(z), z.shape[0], lib.ptr(c), c.shape[0], lib.ptr(yHat), C.byref(varE),
+             C.byref(varEsd), lib.ptr(u), lib.ptr(usd), lib.ptr(varu), lib.ptr(varusd), lib.ptr(yout), lib.ptr(cmu),
+             lib.ptr(cve), lib.ptr(cvu))
+    assert relmax(yHat, want["yHat"]) <= 1e-12
+    assert relmax(cve, want["chain"]["varE"]) <= 1e-12
+    assert relmax(cvu[1], want["chain"]["K"]["GE"]["varU"]) <= 1e-12
+    assert relmax(u[0], want["K"]["G"]["u"]) <= 1e-12
+    assert relmax(yout, want["y"]) <= 1e-12
+    assert abs(varE.value - want["varE"]) <= 1e-12 * want["varE"]
+
+
+def test_device_pointer_getk_pipeline_matches_host_entry(lib):
+    import torch
+    L, p, E = 150, 130, 2
+    X = markers(L, p, 5)
+    Y, names = design(L, E)
+    ref = oracle.getK(Y, X, kernel="GK", model="MDs", rownames=names, bandwidth=[0.7])
+    ldx, pp = C.c_int64(), C.c_int64()
+    lib.call("bgge_marker_ld", L, C.byref(ldx))
+    lib.call("bgge_marker_cols", p, C.byref(pp))
+    Xp = torch.zeros((pp.value, ldx.value), dtype=torch.float64, device="cuda")
+    Xp[:p, :L] = torch.from_numpy(X.T.copy()).cuda()
+    S = torch.empty((L, L), dtype=torch.float64, device="cuda")
+    lib.call("bgge_dev_gram", vp(Xp), ldx.value, L, pp.value, 0, (L + 127) // 128, vp(S), L, 0, 1.0, 1, None)
+    lib.call("bgge_dev_gk_distance", vp(S), L, L, None)
+    q = torch.empty(1, dtype=torch.float64, device="cuda")
+    hq = C.c_double()
+    lib.call("bgge_dev_quantile7", vp(S), L, L, 0.5, vp(q), C.byref(hq), None)
+    K0 = torch.empty_like(S)
+    lib.call("bgge_dev_gk_exp", vp(S), L, L, 0.7, vp(q), vp(K0), L, None)
+    n = L * E
+    gid = torch.arange(L, dtype=torch.int32, device="cuda").repeat(E)
+    env = torch.arange(E, dtype=torch.int32, device="cuda").repeat_interleave(L)
+    out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    for mode, nm in [(lib.EXPAND_G, "G"), (lib.EXPAND_GE, "GE")]:
+        lib.call("bgge_dev_expand", vp(K0), L, L, vp(gid), vp(env), n, mode, 0, vp(out), n, None)
+        torch.cuda.synchronize()
+        assert relmax(out.cpu().numpy().T, ref[nm]["Kernel"]) <= 1e-12, nm
+    D = oracle.gk_distance(X)
+    assert abs(hq.value - oracle.quantile7(D, 0.5)) <= 1e-12 * hq.value
+
+
+def test_chunked_runs_equal_one_run():
+    """verbose=k runs the sweep in chunks of k iterations (R/BGGE.R:398-401); the chain must not depend on it."""
+    import bgge_b200
+    L, E = 18, 2
+    X = markers(L, 30, 7)
+    Y, names = design(L, E)
+    K = bgge_b200.getK(Y, X, kernel="GB", model="MDs", rownames=names)
+    y = phenotype(oracle.gb_kernel(X), L, E, 8)
+    a = bgge_b200.BGGE(y, K, ne=[L] * E, ite=60, burn=10, thin=3, seed=4)
+    b = bgge_b200.BGGE(y, K, ne=[L] * E, ite=60, burn=10, thin=3, seed=4, verbose=7)
+    assert np.array_equal(a["chain"]["varE"], b["chain"]["varE"])
+    assert np.array_equal(a["yHat"], b["yHat"])
+
+
+def test_release_cache_and_memory_query(lib):
+    free0, tot = C.c_uint64(), C.c_uint64()
+    lib.call("bgge_device_memory", C.byref(free0), C.byref(tot))
+    assert 0 < free0.value <= tot.value
+    out = np.empty((64, 64), order="F")
+    lib.call("bgge_getk_base", lib.ptr(lib.f64(np.random.default_rng(0).standard_normal((64, 32)))), 64, 32, lib.GB, None, 1,
+             0.5, lib.ptr(out), None)
+    lib.call("bgge_release_cache")
+    free1 = C.c_uint64()
+    lib.call("bgge_device_memory", C.byref(free1), None)
+    assert free1.value > 0
