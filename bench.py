@@ -521,34 +521,34 @@ def main():
                      lib.ptr(ne_h), E, 1e-10, 1)
         torch.cuda.synchronize()
         t_eig = time.perf_counter() - t_eig
-        blocks, types, mean_diags = [], [], []       # per kernel: list of (pos0, rows, dU ptr, ldu, nr, s)
+        blocks = []                                   # per kernel: list of (pos0, rows, nr) for the bookkeeping below
         n_eig_problems = 0
-        for j, (tp, mode, k) in enumerate(kspec):
+        for j in range(nk):
             nb = C.c_int()
             lib.call("bgge_gibbs_block_count", h0, j, C.byref(nb))
             bl = []
             for b in range(nb.value):
-                pos0, rows, nr_b, ldu_b = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+                pos0, rows, nr_b = C.c_int64(), C.c_int64(), C.c_int64()
                 lib.call("bgge_gibbs_fetch_block", h0, j, b, C.byref(pos0), C.byref(rows), C.byref(nr_b), None, None, 0)
-                sv = np.empty(nr_b.value)
-                lib.call("bgge_gibbs_fetch_block", h0, j, b, None, None, None, lib.ptr(sv), None, 0)
-                dptr = C.c_void_p()
-                lib.call("bgge_gibbs_block_device", h0, j, b, C.byref(dptr), C.byref(ldu_b))
-                bl.append((pos0.value, rows.value, dptr.value, ldu_b.value, nr_b.value, sv))
+                bl.append((pos0.value, rows.value, nr_b.value))
                 n_eig_problems += 1
             blocks.append(bl)
-            types.append(tp)
-            mean_diags.append(mean_diag0 if mode != 2 else mean_diag0 / E)
-        nr = blocks[0][0][4]
+        nr = blocks[0][0][2]
 
         # phenotypes: y = mu_env + g + ge + eps, h2 ~ 0.5; one chain per rank (chain id = rank)
         class _Dev:   # torch view of a library-owned device block
             def __init__(self, ptr, shape):
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
                                                  "strides": None}
-        bpos, brows, bptr, bld, bnr, bs = blocks[-1][0]                       # an L-row block: U (L x nr), s
         # first L rows of any block give a root of K0: an L-row block has (V, s); the n-row G block has
         # (Zg V / sqrt(E), E s), whose first L rows times sqrt(E s) are V sqrt(s) again
+        jb = nk - 1
+        bpos, brows, bnr = blocks[jb][0]
+        bs = np.empty(bnr)
+        lib.call("bgge_gibbs_fetch_block", h0, jb, 0, None, None, None, lib.ptr(bs), None, 0)
+        bptr_c, bld_c = C.c_void_p(), C.c_int64()
+        lib.call("bgge_gibbs_block_device", h0, jb, 0, C.byref(bptr_c), C.byref(bld_c))   # expands a factorised block
+        bptr, bld = bptr_c.value, bld_c.value
         Ub = torch.as_tensor(_Dev(bptr, (bnr, bld)), device=device)[:, :L]
         root = Ub * torch.sqrt(torch.from_numpy(bs).to(device)).unsqueeze(1)  # (nr, L): K0 = root' root
         gen = torch.Generator(device=device)
@@ -572,9 +572,7 @@ def main():
             lib.call("bgge_gibbs_create", n, nk, 0, stream, C.byref(h))
             lib.call("bgge_gibbs_set_y", h, lib.ptr(y_np), None)
             for j in range(nk):
-                lib.call("bgge_gibbs_set_kernel", h, j, types[j], mean_diags[j])
-                for (pos0, rows, dptr, ldu, nr_b, sv) in blocks[j]:
-                    lib.call("bgge_gibbs_add_block", h, j, pos0, rows, nr_b, lib.ptr(sv), C.c_void_p(dptr), ldu, 1)
+                lib.call("bgge_gibbs_share_kernel", h, j, h0, j)      # borrow the decomposition (dense or factorised)
             if args.two_pass:
                 lib.call("bgge_gibbs_set_mode", h, 0)
             lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + rank, rank)
@@ -617,7 +615,10 @@ def main():
         for j in range(nk):
             f_, cs_, ncl_, nl_ = C.c_int(), C.c_int(), C.c_int(), C.c_int()
             lib.call("bgge_gibbs_kernel_info", h, j, C.byref(f_), C.byref(cs_), C.byref(ncl_), C.byref(nl_))
-            kinfo.append({"fused": bool(f_.value), "cluster_size": cs_.value, "clusters": ncl_.value})
+            bb_, nf_ = C.c_int64(), C.c_int()
+            lib.call("bgge_gibbs_kernel_bytes", h, j, C.byref(bb_), C.byref(nf_))
+            kinfo.append({"fused": bool(f_.value), "cluster_size": cs_.value, "clusters": ncl_.value,
+                          "basis_bytes": bb_.value, "factored_blocks": nf_.value, "launches": nl_.value})
         lib.load().bgge_gibbs_destroy(h)
 
         # ------------------------------------------------------------- e2e: host-buffer BGGE() call per step
@@ -665,23 +666,22 @@ def main():
 
     # ----------------------------------------------------------------- roofline bookkeeping
     # fused kernel steps read U once per iteration, two-pass steps twice; the accounting follows the path used
-    sum_nr = sum(b[4] for blk in blocks for b in blk)
+    sum_nr = sum(b[2] for blk in blocks for b in blk)
     kern = []
     u_bytes = 0
     for j in range(nk):
-        rn = sum(b[1] * b[4] for b in blocks[j])
         cov = sum(b[1] for b in blocks[j])
-        nrj = sum(b[4] for b in blocks[j])
+        nrj = sum(b[2] for b in blocks[j])
+        basis = kinfo[j]["basis_bytes"]                   # W (not U) for blocks the sweep keeps factorised
+        u_bytes += basis
         if kinfo[j]["fused"]:
             ncl = kinfo[j]["clusters"]
-            u_bytes += 8 * rn
             kern.append({"name": f"sweep_fused_kernel[{j}]", "ms": prof_ms[2 * j],
-                         "bytes": 8 * rn + 16 * cov + 8 * nrj + 8 * cov * 1})
+                         "bytes": basis + 24 * cov + 8 * nrj})
             kern.append({"name": f"fused_finalize_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * cov * ncl + 32 * n})
         else:
-            u_bytes += 16 * rn
-            kern.append({"name": f"proj_kernel[{j}]", "ms": prof_ms[2 * j], "bytes": 8 * rn + 16 * cov + 24 * nrj})
-            kern.append({"name": f"back_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * rn + 32 * n + 8 * nrj})
+            kern.append({"name": f"proj_kernel[{j}]", "ms": prof_ms[2 * j], "bytes": basis // 2 + 16 * cov + 24 * nrj})
+            kern.append({"name": f"back_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": basis // 2 + 32 * n + 8 * nrj})
     bytes_iter = u_bytes + 8 * n * (4 * nk + 3) + 40 * sum_nr
     sweep_gbs = bytes_iter * (world * args.steps * iters) / (ms_total * 1e-3) / 1e9 / world
     kern.append({"name": "scalar_kernel", "ms": prof_ms[2 * nk], "bytes": 16 * n})
@@ -725,15 +725,17 @@ def main():
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "step_s": e2e_steps, "phase_s_create_run_fetch_destroy": e2e_phase[1:],
                     "covers": "bgge_gibbs_create + set_y (pinned host) + add_block (device-resident eigen) + init + "
                               f"{iters} sweeps + summary/chain download; eigen and getK are one-off setup below"},
-            "gpu_launches": args.steps * iters * (2 * nk + 1),
+            "gpu_launches": args.steps * iters * (sum(k["launches"] for k in kinfo) + 1),
             "roofline": roofline,
             "cpu_baseline": cpu_base,
             "sweep": {"algorithmic_bytes_per_iter": bytes_iter, "achieved_gbs_per_gpu": sweep_gbs,
-                      "frac_of_hbm_peak": sweep_gbs / pk["hbm_gbs"], "accounting": ("1-pass: U read from HBM once per kernel step (fused proj+draw+back kernel)"
+                      "frac_of_hbm_peak": sweep_gbs / pk["hbm_gbs"], "accounting": (("1-pass: eigen basis read from HBM once per kernel step (fused proj+draw+back kernel)"
+                                      + ("; expanded kernels stay factorised (U = Z C^-1/2 W): the sweep streams W"
+                                         if any(k["factored_blocks"] for k in kinfo) else ""))
                                      if all(k["fused"] for k in kinfo) else
                                      "2-pass (U read for U'e and for U b)" if not any(k["fused"] for k in kinfo)
                                      else "mixed: fused kernels 1-pass, others 2-pass"),
-                      "two_pass_equivalent_gbs_per_gpu": (16 * sum(b[1] * b[4] for blk in blocks for b in blk)
+                      "two_pass_equivalent_gbs_per_gpu": (16 * sum(b[1] * b[2] for blk in blocks for b in blk)
                                                           + 8 * n * (4 * nk + 3) + 40 * sum_nr)
                                                          * (args.steps * iters) / (ms_total * 1e-3) / 1e9,
                       "kernel_paths": kinfo,

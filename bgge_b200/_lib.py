@@ -82,6 +82,8 @@ SIGNATURES = {
     "bgge_gibbs_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgge_gibbs_kernel_bytes": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.POINTER(C.c_int)]),
+    "bgge_gibbs_share_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "bgge_gibbs_set_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "bgge_gibbs_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_uint64,
                                   C.c_uint32]),

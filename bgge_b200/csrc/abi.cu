@@ -718,37 +718,71 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         loc[(size_t)i] = slot[(size_t)gid[pos + i]];
         isq[(size_t)i] = 1.0 / sqc[(size_t)loc[(size_t)i]];
       }
-      DevBuf<int> dT, dloc;
-      DevBuf<double> dsqc, disq, dM, dW, dS, dWc;
+      DevBuf<int> dT;
+      DevBuf<double> dsqc, dM, dW, dS, dWc, dwts;
       BGGE_CUDA(dT.alloc((size_t)t));
-      BGGE_CUDA(dloc.alloc((size_t)m));
       BGGE_CUDA(dsqc.alloc((size_t)t));
-      BGGE_CUDA(disq.alloc((size_t)m));
       BGGE_CUDA(dM.alloc((size_t)t * t));
       BGGE_CUDA(dW.alloc((size_t)t));
       BGGE_CUDA(cudaMemcpyAsync(dT.p, T.data(), (size_t)t * sizeof(int), cudaMemcpyHostToDevice, st));
-      BGGE_CUDA(cudaMemcpyAsync(dloc.p, loc.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
       BGGE_CUDA(cudaMemcpyAsync(dsqc.p, sqc.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
-      BGGE_CUDA(cudaMemcpyAsync(disq.p, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
       BGGE_TRY(gather_scale_launch(dK0, ld0, dT.p, dsqc.p, t, dM.p, st));
       int64_t nr = 0;
       BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
       if (nr == 0) continue;                                        // R/BGGE.R:162
       bl.nr = nr;
+      const int64_t ldw = round_up(t, 16);
       BGGE_CUDA(dS.alloc((size_t)nr));
-      BGGE_CUDA(dWc.alloc((size_t)t * nr));
-      BGGE_TRY(eig_compact(dM.p, t, dW.p, t, nr, 0, dS.p, dWc.p, t, st));
-      BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
-      bl.owns = true;
-      hk.blocks.push_back(bl);
-      BGGE_TRY(expand_rows_launch(dWc.p, t, dloc.p, disq.p, m, nr, bl.dU, bl.ldu, st));
-      if (canonical_sign) {   // same convention as the direct route: largest-|.| entry of each U column positive
-        DevBuf<double> tmpS, tmpU;
-        BGGE_CUDA(tmpS.alloc((size_t)nr));
-        BGGE_CUDA(tmpU.alloc((size_t)bl.ldu * nr));
-        BGGE_CUDA(cudaMemcpyAsync(tmpU.p, bl.dU, (size_t)bl.ldu * nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        BGGE_TRY(sign_fix_launch(tmpU.p, bl.ldu, m, nr, bl.dU, st));
+      BGGE_CUDA(dWc.alloc((size_t)ldw * nr));
+      BGGE_TRY(eig_compact(dM.p, t, dW.p, t, nr, 0, dS.p, dWc.p, ldw, st));
+      // row map of the block: loc (row -> genotype slot), 1/sqrt(count), and its CSR transpose
+      double* dWfinal = nullptr;
+      BGGE_CUDA(pool_alloc((void**)&dWfinal, (size_t)ldw * nr * sizeof(double)));
+      if (canonical_sign) {
+        // same convention as the dense route: the largest-|.| entry of the EXPANDED vector is positive,
+        // i.e. the largest |W[a,c]| / sqrt(count_a)
+        std::vector<double> wts((size_t)t);
+        for (int64_t a = 0; a < t; ++a) wts[(size_t)a] = 1.0 / sqc[(size_t)a];
+        BGGE_CUDA(dwts.alloc((size_t)t));
+        BGGE_CUDA(cudaMemcpyAsync(dwts.p, wts.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
+        BGGE_TRY(sign_fix_launch(dWc.p, ldw, t, nr, dwts.p, dWfinal, st));
+      } else {
+        BGGE_CUDA(cudaMemcpyAsync(dWfinal, dWc.p, (size_t)ldw * nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      }
+      int* d_loc = nullptr;
+      double* d_isq = nullptr;
+      BGGE_CUDA(pool_alloc((void**)&d_loc, (size_t)m * sizeof(int)));
+      BGGE_CUDA(pool_alloc((void**)&d_isq, (size_t)m * sizeof(double)));
+      BGGE_CUDA(cudaMemcpyAsync(d_loc, loc.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+      BGGE_CUDA(cudaMemcpyAsync(d_isq, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+      const bool keep_factored = 3 * t <= 2 * m && !getenv("BGGE_NO_FACTORED_SWEEP");   // >= 1.5x fewer rows to stream
+      if (keep_factored) {
+        std::vector<int> rowptr((size_t)t + 1, 0), rowidx((size_t)m);
+        for (int64_t i = 0; i < m; ++i) ++rowptr[(size_t)loc[(size_t)i] + 1];
+        for (int64_t a = 0; a < t; ++a) rowptr[(size_t)a + 1] += rowptr[(size_t)a];
+        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t i = 0; i < m; ++i) rowidx[(size_t)fill[(size_t)loc[(size_t)i]]++] = (int)i;
+        BGGE_CUDA(pool_alloc((void**)&bl.d_rowptr, ((size_t)t + 1) * sizeof(int)));
+        BGGE_CUDA(pool_alloc((void**)&bl.d_rowidx, (size_t)m * sizeof(int)));
+        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowptr, rowptr.data(), ((size_t)t + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowidx, rowidx.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+        bl.dU = dWfinal;       // W, t x nr
+        bl.ldu = ldw;
+        bl.vrows = t;
+        bl.d_loc = d_loc;
+        bl.d_isq = d_isq;
+        bl.owns = true;
+        hk.blocks.push_back(bl);
+        BGGE_CUDA(cudaStreamSynchronize(st));   // host staging vectors die at the end of this scope
+      } else {
+        BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
+        bl.owns = true;
+        hk.blocks.push_back(bl);
+        BGGE_TRY(expand_rows_launch(dWfinal, ldw, d_loc, d_isq, m, nr, bl.dU, bl.ldu, st));
         BGGE_CUDA(cudaStreamSynchronize(st));
+        pool_free(dWfinal);
+        pool_free(d_loc);
+        pool_free(d_isq);
       }
       s_host.resize((size_t)nr);
       BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -798,9 +832,11 @@ int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int6
   BGGE_REQUIRE(j >= 0 && j < g.nk && dU && ldu, "gibbs_block_device: bad arguments");
   HostKernel& hk = g.kernels[(size_t)j];
   BGGE_REQUIRE(b >= 0 && b < (int)hk.blocks.size(), "gibbs_block_device: bad block index");
+  HostBlock& bl = hk.blocks[(size_t)b];
+  BGGE_TRY(ensure_dense(bl, g.stream));        // a factorised block is expanded on first request
   BGGE_CUDA(cudaStreamSynchronize(g.stream));
-  *dU = hk.blocks[(size_t)b].dU;
-  *ldu = hk.blocks[(size_t)b].ldu;
+  *dU = bl.vrows > 0 ? bl.dU_dense : bl.dU;
+  *ldu = bl.vrows > 0 ? bl.ldu_dense : bl.ldu;
   return OK;
 }
 
@@ -811,7 +847,7 @@ int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* 
   BGGE_REQUIRE(j >= 0 && j < g.nk, "gibbs_fetch_block: bad kernel index");
   HostKernel& hk = g.kernels[(size_t)j];
   BGGE_REQUIRE(b >= 0 && b < (int)hk.blocks.size(), "gibbs_fetch_block: bad block index");
-  const HostBlock& bl = hk.blocks[(size_t)b];
+  HostBlock& bl = hk.blocks[(size_t)b];
   if (pos0) *pos0 = bl.pos0;
   if (rows) *rows = bl.rows;
   if (nr) *nr = bl.nr;
@@ -822,8 +858,10 @@ int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* 
   }
   if (U) {
     BGGE_REQUIRE(ldu >= bl.rows, "gibbs_fetch_block: ldu too small");
+    BGGE_TRY(ensure_dense(bl, g.stream));
     BGGE_CUDA(cudaStreamSynchronize(g.stream));
-    BGGE_CUDA(cudaMemcpy2D(U, (size_t)ldu * sizeof(double), bl.dU, (size_t)bl.ldu * sizeof(double),
+    BGGE_CUDA(cudaMemcpy2D(U, (size_t)ldu * sizeof(double), bl.vrows > 0 ? bl.dU_dense : bl.dU,
+                           (size_t)(bl.vrows > 0 ? bl.ldu_dense : bl.ldu) * sizeof(double),
                            (size_t)bl.rows * sizeof(double), (size_t)bl.nr, cudaMemcpyDeviceToHost));
   }
   return OK;
@@ -875,6 +913,31 @@ int bgge_gibbs_set_mode(bgge_gibbs* h, int mode) {
   return OK;
 }
 
+// dst's kernel j_dst borrows every eigen block (dense or factorised) of src's kernel j_src: one
+// decomposition, many chains.  src must outlive dst.
+int bgge_gibbs_share_kernel(bgge_gibbs* dst, int j_dst, bgge_gibbs* src, int j_src) {
+  BGGE_HANDLE(dst);
+  BGGE_REQUIRE(src != nullptr, "gibbs_share_kernel: NULL source handle");
+  Gibbs& d = dst->g;
+  Gibbs& sg = src->g;
+  BGGE_REQUIRE(!d.initialised, "gibbs_share_kernel: destination already initialised");
+  BGGE_REQUIRE(j_dst >= 0 && j_dst < d.nk && j_src >= 0 && j_src < sg.nk && d.n == sg.n && d.device == sg.device,
+               "gibbs_share_kernel: kernel index out of range or handles of different size / device");
+  HostKernel& hd = d.kernels[(size_t)j_dst];
+  const HostKernel& hs = sg.kernels[(size_t)j_src];
+  BGGE_REQUIRE(hd.blocks.empty() && !hs.blocks.empty(), "gibbs_share_kernel: destination kernel not empty or source kernel empty");
+  BGGE_CUDA(cudaStreamSynchronize(sg.stream));
+  for (const HostBlock& b : hs.blocks) {
+    HostBlock c = b;
+    c.owns = false;
+    c.owns_dense = false;
+    hd.blocks.push_back(c);
+  }
+  hd.s_host = hs.s_host;
+  hd.mean_diag = hs.mean_diag;
+  return OK;
+}
+
 int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches) {
   BGGE_HANDLE(h);
   Gibbs& g = h->g;
@@ -883,7 +946,29 @@ int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, 
   if (fused) *fused = hk.fused ? 1 : 0;
   if (cluster_size) *cluster_size = hk.fused ? hk.fused_cs : hk.cs;
   if (clusters) *clusters = hk.fused ? hk.fused_clusters : hk.n_btasks;
-  if (launches) *launches = 2;
+  if (launches) {
+    int nv = 0;
+    for (auto& b : hk.blocks) nv += b.vrows > 0 ? 1 : 0;
+    *launches = 2 + (hk.fused ? nv : 0);
+  }
+  return OK;
+}
+
+// bytes of eigen basis one kernel step of kernel j streams from HBM (W for factorised blocks; two-pass
+// steps read it twice) and how many of its blocks are kept factorised
+int bgge_gibbs_kernel_bytes(bgge_gibbs* h, int j, int64_t* basis_bytes, int* factored_blocks) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && j >= 0 && j < g.nk, "gibbs_kernel_bytes: bad kernel index or handle not initialised");
+  HostKernel& hk = g.kernels[(size_t)j];
+  int64_t bytes = 0;
+  int nv = 0;
+  for (auto& b : hk.blocks) {
+    bytes += 8 * (hk.fused ? b.stream_rows() : 2 * b.rows) * b.nr;
+    nv += (hk.fused && b.vrows > 0) ? 1 : 0;
+  }
+  if (basis_bytes) *basis_bytes = bytes;
+  if (factored_blocks) *factored_blocks = nv;
   return OK;
 }
 

@@ -101,7 +101,8 @@ __global__ void expand_rows_kernel(const double* __restrict__ W, int64_t ldw, co
 }
 
 // dst[:, c] = +-src[:, c] so that the largest-|.| entry (first on ties) is positive; pad rows zeroed
-__global__ void sign_fix_kernel(const double* __restrict__ src, int64_t ld, int64_t rows, double* __restrict__ dst) {
+__global__ void sign_fix_kernel(const double* __restrict__ src, int64_t ld, int64_t rows, const double* __restrict__ wts,
+                                double* __restrict__ dst) {
   const int64_t c = blockIdx.x;
   const double* v = src + c * ld;
   __shared__ double sa[32];
@@ -109,7 +110,7 @@ __global__ void sign_fix_kernel(const double* __restrict__ src, int64_t ld, int6
   double best = -1.0;
   long long bi = 0;
   for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
-    const double a = fabs(v[i]);
+    const double a = fabs(v[i]) * (wts ? wts[i] : 1.0);   // weights: |U| of the expanded vector is |W| / sqrt(count)
     if (a > best) { best = a; bi = i; }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -138,9 +139,10 @@ __global__ void sign_fix_kernel(const double* __restrict__ src, int64_t ld, int6
 
 }  // namespace
 
-int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, double* dDst, cudaStream_t st) {
+int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, const double* d_wts, double* dDst,
+                    cudaStream_t st) {
   if (nr <= 0) return OK;
-  sign_fix_kernel<<<(unsigned)nr, 256, 0, st>>>(dSrc, ld, rows, dDst);
+  sign_fix_kernel<<<(unsigned)nr, 256, 0, st>>>(dSrc, ld, rows, d_wts, dDst);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }

@@ -552,6 +552,14 @@ int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
 
 }  // namespace
 
+int ensure_dense(HostBlock& bl, cudaStream_t st) {
+  if (bl.vrows == 0 || bl.dU_dense) return OK;
+  bl.ldu_dense = round_up(bl.rows, 16);
+  BGGE_CUDA(pool_alloc((void**)&bl.dU_dense, (size_t)bl.ldu_dense * bl.nr * sizeof(double)));
+  bl.owns_dense = true;
+  return expand_rows_launch(bl.dU, bl.ldu, bl.d_loc, bl.d_isq, bl.rows, bl.nr, bl.dU_dense, bl.ldu_dense, st);
+}
+
 Gibbs::~Gibbs() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);   // pooled blocks may be reused as soon as they are released
@@ -559,7 +567,16 @@ Gibbs::~Gibbs() {
   if (graph) cudaGraphDestroy(graph);
   for (auto& k : kernels)
     for (auto& bl : k.blocks)
-      if (bl.owns && bl.dU) pool_free(bl.dU);
+    {
+      if (bl.owns) {
+        if (bl.dU) pool_free(bl.dU);
+        if (bl.d_loc) pool_free(bl.d_loc);
+        if (bl.d_isq) pool_free(bl.d_isq);
+        if (bl.d_rowptr) pool_free(bl.d_rowptr);
+        if (bl.d_rowidx) pool_free(bl.d_rowidx);
+      }
+      if (bl.owns_dense && bl.dU_dense) pool_free(bl.dU_dense);
+    }
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -635,70 +652,84 @@ int gibbs_init(Gibbs* g) {
   long long z_off = 1 + q;
   long long sum_nr = 0;
   int max_clusters = 0;
+  int64_t max_vpart = 0;
   for (int j = 0; j < g->nk; ++j) {
     HostKernel& hk = g->kernels[j];
     BGGE_REQUIRE(!hk.blocks.empty(), "gibbs: kernel %d has no eigen blocks (all eigenvalues <= tol)", j);
     std::sort(hk.blocks.begin(), hk.blocks.end(), [](const HostBlock& a, const HostBlock& b) { return a.pos0 < b.pos0; });
     hk.nr_total = 0;
     int64_t cursor = 0;
-    std::vector<BTask> bt;
-    auto add_rows = [&](const HostBlock* bl, int64_t pos0, int64_t rows) {
-      for (int64_t r0 = 0; r0 < rows; r0 += B_ROWS) {
-        BTask t{};
-        t.U = bl ? bl->dU : nullptr;
-        t.ldu = bl ? bl->ldu : 0;
-        t.rows = (int)std::min<int64_t>(B_ROWS, rows - r0);
-        t.row0 = (int)(pos0 + r0);
-        t.urow0 = (int)r0;
-        t.nr = bl ? (int)bl->nr : 0;
-        t.col_off = bl ? (int)bl->col_off : 0;
-        bt.push_back(t);
-      }
-    };
     int64_t max_nr = 0;
     for (auto& bl : hk.blocks) {
       BGGE_REQUIRE(bl.pos0 >= cursor && bl.pos0 + bl.rows <= n, "gibbs: kernel %d has overlapping / out-of-range blocks", j);
-      BGGE_REQUIRE(bl.nr > 0 && bl.ldu % 2 == 0 && bl.ldu >= bl.rows, "gibbs: kernel %d block layout invalid", j);
+      BGGE_REQUIRE(bl.nr > 0 && bl.ldu % 2 == 0 && bl.ldu >= bl.stream_rows(), "gibbs: kernel %d block layout invalid", j);
       bl.col_off = hk.nr_total;
       hk.nr_total += bl.nr;
       max_nr = std::max(max_nr, bl.nr);
-      if (bl.pos0 > cursor) add_rows(nullptr, cursor, bl.pos0 - cursor);   // rows no block covers
-      add_rows(&bl, bl.pos0, bl.rows);
       cursor = bl.pos0 + bl.rows;
     }
-    if (cursor < n) add_rows(nullptr, cursor, n - cursor);
     BGGE_REQUIRE((int64_t)hk.s_host.size() == hk.nr_total, "gibbs: kernel %d eigenvalue count mismatch", j);
-    // columns per proj CTA: largest CT that still gives >= 2 CTAs per SM
-    hk.ct = 2;
-    for (int ct : {16, 8, 4}) {
-      int64_t tasks = 0;
-      for (auto& bl : hk.blocks) tasks += (bl.nr + ct - 1) / ct;
-      if (tasks >= 2 * sms) { hk.ct = ct; break; }
-    }
-    std::vector<ATask> at;
-    for (auto& bl : hk.blocks)
-      for (int64_t c = 0; c < bl.nr; c += hk.ct) {
-        ATask t{};
-        t.U = bl.dU + c * bl.ldu;
-        t.ldu = bl.ldu;
-        t.rows = (int)bl.rows;
-        t.pos0 = (int)bl.pos0;
-        t.ncols = (int)std::min<int64_t>(hk.ct, bl.nr - c);
-        t.col_off = (int)(bl.col_off + c);
-        at.push_back(t);
-      }
-    // column split of the back-transform: enough CTAs to fill the machine, >= 32 columns each
-    int cs = 1;
-    while (cs < 8 && (int64_t)bt.size() * cs < 4 * sms && max_nr / (cs * 2) >= 32) cs *= 2;
-    hk.cs = cs;
-    hk.n_atasks = (int)at.size();
-    hk.n_btasks = (int)bt.size();
-    BGGE_TRY(upload(hk.atasks, at, st));
-    BGGE_TRY(upload(hk.btasks, bt, st));
     BGGE_TRY(upload(hk.s, hk.s_host, st));
     BGGE_CUDA(hk.b.alloc((size_t)hk.nr_total));
     if (g->mode == 1) BGGE_TRY(plan_fused(g, hk, st));
+    hk.n_atasks = hk.n_btasks = 0;
+    if (!hk.fused) {
+      // two-pass kernels work on dense U: materialise factorised blocks
+      for (auto& bl : hk.blocks) BGGE_TRY(ensure_dense(bl, st));
+      std::vector<BTask> bt;
+      auto add_rows = [&](const HostBlock* bl, int64_t pos0, int64_t rows) {
+        for (int64_t r0 = 0; r0 < rows; r0 += B_ROWS) {
+          BTask t{};
+          t.U = bl ? (bl->vrows > 0 ? bl->dU_dense : bl->dU) : nullptr;
+          t.ldu = bl ? (bl->vrows > 0 ? bl->ldu_dense : bl->ldu) : 0;
+          t.rows = (int)std::min<int64_t>(B_ROWS, rows - r0);
+          t.row0 = (int)(pos0 + r0);
+          t.urow0 = (int)r0;
+          t.nr = bl ? (int)bl->nr : 0;
+          t.col_off = bl ? (int)bl->col_off : 0;
+          bt.push_back(t);
+        }
+      };
+      int64_t cur2 = 0;
+      for (auto& bl : hk.blocks) {
+        if (bl.pos0 > cur2) add_rows(nullptr, cur2, bl.pos0 - cur2);   // rows no block covers
+        add_rows(&bl, bl.pos0, bl.rows);
+        cur2 = bl.pos0 + bl.rows;
+      }
+      if (cur2 < n) add_rows(nullptr, cur2, n - cur2);
+      // columns per proj CTA: largest CT that still gives >= 2 CTAs per SM
+      hk.ct = 2;
+      for (int ct : {16, 8, 4}) {
+        int64_t tasks = 0;
+        for (auto& bl : hk.blocks) tasks += (bl.nr + ct - 1) / ct;
+        if (tasks >= 2 * sms) { hk.ct = ct; break; }
+      }
+      std::vector<ATask> at;
+      for (auto& bl : hk.blocks) {
+        const double* Ud = bl.vrows > 0 ? bl.dU_dense : bl.dU;
+        const int64_t ld = bl.vrows > 0 ? bl.ldu_dense : bl.ldu;
+        for (int64_t c = 0; c < bl.nr; c += hk.ct) {
+          ATask t{};
+          t.U = Ud + c * ld;
+          t.ldu = ld;
+          t.rows = (int)bl.rows;
+          t.pos0 = (int)bl.pos0;
+          t.ncols = (int)std::min<int64_t>(hk.ct, bl.nr - c);
+          t.col_off = (int)(bl.col_off + c);
+          at.push_back(t);
+        }
+      }
+      // column split of the back-transform: enough CTAs to fill the machine, >= 32 columns each
+      int cs = 1;
+      while (cs < 8 && (int64_t)bt.size() * cs < 4 * sms && max_nr / (cs * 2) >= 32) cs *= 2;
+      hk.cs = cs;
+      hk.n_atasks = (int)at.size();
+      hk.n_btasks = (int)bt.size();
+      BGGE_TRY(upload(hk.atasks, at, st));
+      BGGE_TRY(upload(hk.btasks, bt, st));
+    }
     max_clusters = std::max(max_clusters, hk.fused ? hk.fused_clusters : 0);
+    max_vpart = std::max<int64_t>(max_vpart, hk.fused ? hk.vtotal * hk.fused_clusters : 0);
     BGGE_CUDA(hk.bpart.alloc((size_t)std::max(std::max(1, hk.n_atasks), hk.fused_clusters)));
     hk.z_off = z_off;
     z_off += hk.nr_total;
@@ -728,6 +759,7 @@ int gibbs_init(Gibbs* g) {
   g->ncum = g->ite / g->thin;                                       // R/BGGE.R:229
   BGGE_CUDA(g->r.alloc((size_t)n));
   if (max_clusters > 0) BGGE_CUDA(g->upart.alloc((size_t)n * max_clusters));
+  if (max_vpart > 0) BGGE_CUDA(g->vupart.alloc((size_t)max_vpart));
   BGGE_CUDA(g->u.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->umean.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->um2.alloc((size_t)n * g->nk));

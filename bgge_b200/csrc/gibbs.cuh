@@ -56,21 +56,38 @@ struct BTask {                   // one row tile of one block (or of a gap: nr =
 };
 
 struct FPanel {                  // fused path: columns [c0, c1) of one block, handled by one cluster
-  const double* U;
+  const double* U;               // dense U (rows x nr) or, for a factorised block, W (vrows x nr)
   long long ldu;
-  int rows, pos0, c0, c1, col_off;
+  int rows, pos0, c0, c1, col_off;   // rows = rows the kernel streams (vrows for a factorised block)
   int rs;                        // rows per CTA of the cluster (multiple of 16)
   int slot;                      // upart slot (= cluster index)
+  int virt;                      // 1: rows live in the kernel's virtual vectors at offset voff
+  long long voff;
 };
 
-struct FTile {                   // fused finalize: 256 rows, clusters [qlo, qhi] contributed (qlo > qhi: none)
+struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo, qhi] contributed (qlo > qhi: none)
   int row0, rows, qlo, qhi;
+  const int* loc;                // factorised block: row -> virtual row (already offset to row0), else nullptr
+  const double* isq;             // 1/sqrt(count) per row (offset to row0)
+  long long voff;
 };
 
+// An eigen block.  Dense: U (rows x nr).  Factorised (bgge_gibbs_add_expanded_kernel, repeated genotypes):
+// U = Z C^{-1/2} W is kept as W (vrows x nr) + the row map, so the sweep streams W only:
+// U'e = W'(C^{-1/2} Z'e),  U b = Z C^{-1/2} (W b).
 struct HostBlock {
   int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, col_off = 0;
-  double* dU = nullptr;
+  double* dU = nullptr;          // dense U, or W when vrows > 0
   bool owns = false;
+  int64_t vrows = 0, voff = 0;   // factorised: number of distinct genotypes, offset in the virtual vectors
+  int* d_loc = nullptr;          // [rows]
+  double* d_isq = nullptr;       // [rows]
+  int* d_rowptr = nullptr;       // [vrows + 1] rows of each virtual row (CSR, ascending)
+  int* d_rowidx = nullptr;       // [rows]
+  double* dU_dense = nullptr;    // lazily materialised dense copy (two-pass path, fetch / borrow)
+  int64_t ldu_dense = 0;
+  bool owns_dense = false;
+  int64_t stream_rows() const { return vrows > 0 ? vrows : rows; }
 };
 
 struct HostKernel {
@@ -92,6 +109,8 @@ struct HostKernel {
   DevBuf<FPanel> fpanels;
   DevBuf<int2> fcluster;
   DevBuf<FTile> ftiles;
+  int64_t vtotal = 0;            // total virtual rows of the factorised blocks
+  DevBuf<double> ve;             // virtual residual  C^{-1/2} Z'(e + u_old), [vtotal]
 };
 
 struct Gibbs {
@@ -107,7 +126,7 @@ struct Gibbs {
   std::vector<double> xf_host;
   int64_t n_na = 0;
   // device state
-  DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart;
+  DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart, vupart;
   int mode = 1;                  // 0: two-pass kernels only, 1: fused single-pass where the shape fits
   DevBuf<int> na_idx;
   DevBuf<Scal> scal;
@@ -133,5 +152,6 @@ int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
 int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st);
 int launch_fused(Gibbs* g, HostKernel& hk, int j);
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j);
+int ensure_dense(HostBlock& bl, cudaStream_t st);   // materialise U = Z C^{-1/2} W of a factorised block
 
 }  // namespace bgge

@@ -25,7 +25,8 @@ int eig_decompose(double* dA, int64_t m, int64_t lda, double tol, double* d_W, i
 int eig_compact(const double* dV, int64_t ldv, const double* d_W, int64_t m, int64_t nr, int canonical, double* d_s,
                 double* dU, int64_t ldu, cudaStream_t st);
 
-int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, double* dDst, cudaStream_t st);
+int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, const double* d_wts, double* dDst,
+                    cudaStream_t st);
 int gather_scale_launch(const double* dK0, int64_t ldk, const int* dT, const double* d_sqc, int64_t t, double* dM,
                         cudaStream_t st);
 int expand_rows_launch(const double* dW, int64_t ldw, const int* d_loc, const double* d_isq, int64_t rows, int64_t nr,

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cluster_panels,
                    const double* __restrict__ r, const double* __restrict__ u_old, const double* __restrict__ s,
                    double* __restrict__ upart, double* __restrict__ bpart, long long n,
+                   const double* __restrict__ ve, double* __restrict__ vupart, long long vtotal,
                    const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns) {
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
@@ -142,9 +143,15 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const int row = k * F_ROWS_PER_STEP + 2 * tid;
-        const long long gi = (long long)pn.pos0 + row0 + row;
-        e[k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
-        e[k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
+        if (pn.virt) {   // factorised block: the residual was already gathered to genotype space
+          const long long gi = pn.voff + row0 + row;
+          e[k].x = row < my_rows ? ve[gi] : 0.0;
+          e[k].y = row + 1 < my_rows ? ve[gi + 1] : 0.0;
+        } else {
+          const long long gi = (long long)pn.pos0 + row0 + row;
+          e[k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
+          e[k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
+        }
       }
       for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
         const int slot = cc % ns;
@@ -255,7 +262,8 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
         if (lane == 0) mbar_arrive(&empty[slot]);
       }
       // this cluster's contribution to u over the block's rows
-      double* up = upart + (size_t)pn.slot * n + pn.pos0 + row0;
+      double* up = pn.virt ? vupart + (size_t)pn.slot * vtotal + pn.voff + row0
+                           : upart + (size_t)pn.slot * n + pn.pos0 + row0;
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const int row = k * F_ROWS_PER_STEP + 2 * tid;
@@ -276,7 +284,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
 constexpr int FIN_ROWS = 32, FIN_Q = 8;
 __global__ void __launch_bounds__(FIN_ROWS * FIN_Q)
 fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict__ upart, long long n,
-                      double* __restrict__ r, double* __restrict__ u, double* __restrict__ umean,
+                      const double* __restrict__ vupart, long long vtotal, double* __restrict__ r, double* __restrict__ u, double* __restrict__ umean,
                       double* __restrict__ um2, const Scal* __restrict__ sc, long long thin, long long burn) {
   __shared__ double part[FIN_Q][FIN_ROWS];
   const FTile t = tiles[blockIdx.x];
@@ -288,13 +296,20 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
     const int row = row0 + lane;
     const long long g = (long long)t.row0 + row;
     double a = 0.0;
-    if (row < t.rows)
-      for (int q = t.qlo + ql; q <= t.qhi; q += FIN_Q) a += upart[(size_t)q * n + g];
+    if (row < t.rows) {
+      if (t.loc) {   // factorised block: u_i = isq_i * (W b)[loc_i]
+        const long long v = t.voff + t.loc[row];
+        for (int q = t.qlo + ql; q <= t.qhi; q += FIN_Q) a += vupart[(size_t)q * vtotal + v];
+      } else {
+        for (int q = t.qlo + ql; q <= t.qhi; q += FIN_Q) a += upart[(size_t)q * n + g];
+      }
+    }
     part[ql][lane] = a;
     __syncthreads();
     if (ql == 0 && row < t.rows) {
-      const double un = ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane])) +
-                        ((part[4][lane] + part[5][lane]) + (part[6][lane] + part[7][lane]));
+      double un = ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane])) +
+                  ((part[4][lane] + part[5][lane]) + (part[6][lane] + part[7][lane]));
+      if (t.loc) un *= t.isq[row];
       r[g] = (r[g] + u[g]) - un;
       u[g] = un;
       if (keep) {
@@ -307,6 +322,22 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
     }
     __syncthreads();
   }
+}
+
+// factorised block: ve[a] = sum over the rows i of genotype a of isq_i * ((r_i - shift) + u_old_i), CSR order
+__global__ void __launch_bounds__(256)
+virt_gather_kernel(int vrows, const int* __restrict__ rowptr, const int* __restrict__ rowidx,
+                   const double* __restrict__ isq, const double* __restrict__ r, const double* __restrict__ u_old,
+                   const Scal* __restrict__ sc, double* __restrict__ ve) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= vrows) return;
+  const double shift = sc->shift;
+  double acc = 0.0;
+  for (int k = rowptr[a]; k < rowptr[a + 1]; ++k) {
+    const int i = rowidx[k];
+    acc = fma(isq[i], (r[i] - shift) + u_old[i], acc);
+  }
+  ve[a] = acc;
 }
 
 template <int RPT, int G>
@@ -327,6 +358,7 @@ int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
   BGGE_CUDA(cudaLaunchKernelEx(&cfg, kfn, (const FPanel*)hk.fpanels.p, (const int2*)hk.fcluster.p,
                                (const double*)g->r.p, (const double*)(g->u.p + (size_t)j * g->n),
                                (const double*)hk.s.p, g->upart.p, hk.bpart.p, (long long)g->n,
+                               (const double*)hk.ve.p, g->vupart.p, (long long)hk.vtotal,
                                (const Scal*)g->scal.p, j, g->draw, hk.z_off, hk.fused_ns));
   return OK;
 }
@@ -378,12 +410,20 @@ int occupancy_dispatch(HostKernel& hk, int cs, size_t smem, int* ncl) { BGGE_FUS
 }  // namespace
 
 int launch_fused(Gibbs* g, HostKernel& hk, int j) {
+  for (auto& bl : hk.blocks)
+    if (bl.vrows > 0) {
+      virt_gather_kernel<<<(unsigned)((bl.vrows + 255) / 256), 256, 0, g->stream>>>(
+          (int)bl.vrows, bl.d_rowptr, bl.d_rowidx, bl.d_isq, g->r.p + bl.pos0, g->u.p + (size_t)j * g->n + bl.pos0,
+          g->scal.p, hk.ve.p + bl.voff);
+      BGGE_CUDA(cudaGetLastError());
+    }
   auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
   return run();
 }
 
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
-  fused_finalize_kernel<<<hk.n_ftiles, dim3(FIN_ROWS, FIN_Q), 0, g->stream>>>(hk.ftiles.p, g->upart.p, (long long)g->n, g->r.p,
+  fused_finalize_kernel<<<hk.n_ftiles, dim3(FIN_ROWS, FIN_Q), 0, g->stream>>>(hk.ftiles.p, g->upart.p, (long long)g->n,
+                                                            g->vupart.p, (long long)hk.vtotal, g->r.p,
                                                             g->u.p + (size_t)j * g->n, g->umean.p + (size_t)j * g->n,
                                                             g->um2.p + (size_t)j * g->n, g->scal.p,
                                                             (long long)g->thin, (long long)g->burn);
@@ -395,8 +435,15 @@ int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
 // Returns OK with hk.fused == false when the shape does not fit (caller keeps the two-pass kernels).
 int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   hk.fused = false;
-  int64_t max_rows = 0;
-  for (auto& bl : hk.blocks) max_rows = std::max(max_rows, bl.rows);
+  int64_t max_rows = 0;   // rows the kernel streams: genotype count for a factorised block
+  hk.vtotal = 0;
+  for (auto& bl : hk.blocks) {
+    max_rows = std::max(max_rows, bl.stream_rows());
+    if (bl.vrows > 0) {
+      bl.voff = hk.vtotal;
+      hk.vtotal += round_up(bl.vrows, 16);
+    }
+  }
   if (max_rows <= 0) return OK;
   // smallest cluster whose row slice fits the register budget (<= 12 row pairs per thread): long
   // contiguous column slices (~40 KB) stream best and small clusters leave no SM idle
@@ -432,7 +479,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   if (ncl < 1) return OK;
   // work-balanced contiguous split of the (block, column) space over the clusters
   double total = 0.0;
-  for (auto& bl : hk.blocks) total += (double)bl.rows * (double)bl.nr;
+  for (auto& bl : hk.blocks) total += (double)bl.stream_rows() * (double)bl.nr;
   int64_t total_cols = 0;
   for (auto& bl : hk.blocks) total_cols += bl.nr;
   ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, combo->gcols)));
@@ -452,24 +499,26 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
         const int64_t avail = bl.nr - col;
         int64_t take = avail;
         if (!last) {
-          const int64_t want = (int64_t)std::ceil(need / (double)bl.rows);
+          const int64_t want = (int64_t)std::ceil(need / (double)bl.stream_rows());
           take = std::min<int64_t>(avail, (want + combo->gcols - 1) / combo->gcols * combo->gcols);
         }
         if (take <= 0) break;
         FPanel p{};
         p.U = bl.dU;
         p.ldu = bl.ldu;
-        p.rows = (int)bl.rows;
+        p.rows = (int)bl.stream_rows();
         p.pos0 = (int)bl.pos0;
         p.c0 = (int)col;
         p.c1 = (int)(col + take);
         p.col_off = (int)bl.col_off;
-        p.rs = (int)round_up((bl.rows + cs - 1) / cs, 16);
+        p.rs = (int)round_up((bl.stream_rows() + cs - 1) / cs, 16);
         p.slot = q;
+        p.virt = bl.vrows > 0 ? 1 : 0;
+        p.voff = bl.voff;
         panels.push_back(p);
         block_q[bi].first = std::min(block_q[bi].first, q);
         block_q[bi].second = std::max(block_q[bi].second, q);
-        need -= (double)bl.rows * (double)take;
+        need -= (double)bl.stream_rows() * (double)take;
         col += take;
         if (col >= bl.nr) {
           ++bi;
@@ -483,25 +532,34 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   // finalize tiles: every row of y, gaps included (qlo > qhi -> zero)
   std::vector<FTile> tiles;
   int64_t cursor = 0;
-  auto add_rows = [&](int64_t pos0, int64_t rows, int qlo, int qhi) {
+  auto add_rows = [&](int64_t pos0, int64_t rows, int qlo, int qhi, const HostBlock* vb = nullptr) {
     for (int64_t r0 = 0; r0 < rows; r0 += 64) {
       FTile t{};
       t.row0 = (int)(pos0 + r0);
       t.rows = (int)std::min<int64_t>(64, rows - r0);
       t.qlo = qlo;
       t.qhi = qhi;
+      if (vb) {
+        t.loc = vb->d_loc + r0;
+        t.isq = vb->d_isq + r0;
+        t.voff = vb->voff;
+      }
       tiles.push_back(t);
     }
   };
   for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
     HostBlock& bl = hk.blocks[bi];
     if (bl.pos0 > cursor) add_rows(cursor, bl.pos0 - cursor, 1, 0);
-    add_rows(bl.pos0, bl.rows, block_q[bi].first, block_q[bi].second);
+    add_rows(bl.pos0, bl.rows, block_q[bi].first, block_q[bi].second, bl.vrows > 0 ? &bl : nullptr);
     cursor = bl.pos0 + bl.rows;
   }
   if (cursor < g->n) add_rows(cursor, g->n - cursor, 1, 0);
   hk.fused_clusters = ncl;
   hk.n_ftiles = (int)tiles.size();
+  if (hk.vtotal > 0) {
+    BGGE_CUDA(hk.ve.alloc((size_t)hk.vtotal));
+    BGGE_CUDA(cudaMemsetAsync(hk.ve.p, 0, (size_t)hk.vtotal * sizeof(double), st));
+  }
   BGGE_CUDA(hk.fpanels.alloc(panels.size()));
   BGGE_CUDA(cudaMemcpyAsync(hk.fpanels.p, panels.data(), panels.size() * sizeof(FPanel), cudaMemcpyHostToDevice, st));
   BGGE_CUDA(hk.fcluster.alloc(cpan.size()));

@@ -160,6 +160,9 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
  * Each block is decomposed through the |T| x |T| matrix C^{1/2} K0[T,T] C^{1/2} (T = genotypes present,
  * C = their counts), which has the same eigenpairs > tol as the block itself; blocks whose mask is not
  * constant fall back to the direct m x m decomposition.  Sets mean(diag(K)) as well.
+ * When genotypes repeat inside a block (|T| <= 2/3 of its rows, e.g. the G kernel of a multi-environment
+ * trial) the block stays factorised: the sweep streams W (|T| x nr) and applies Z C^{-1/2} on the fly, so
+ * that kernel step moves |T|/rows of the bytes.  bgge_gibbs_fetch_block / block_device expand it on demand.
  */
 int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double* K0, int64_t L, int64_t ldk,
                                    int on_device, const int32_t* gid, const int32_t* env, int mode, int env_k,
@@ -176,6 +179,12 @@ int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int6
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode);
 /* after init: which path kernel j uses, its cluster size / cluster (or tile) count, launches per step */
 int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches);
+/* after init: bytes of eigen basis one step of kernel j streams (W, not U, for blocks kept factorised; twice
+ * for two-pass steps) and the number of its blocks kept factorised */
+int bgge_gibbs_kernel_bytes(bgge_gibbs* h, int j, int64_t* basis_bytes, int* factored_blocks);
+/* kernel j_dst of dst borrows all eigen blocks (dense or factorised), eigenvalues and mean(diag) of kernel
+ * j_src of src; src must stay alive.  One decomposition, many chains. */
+int bgge_gibbs_share_kernel(bgge_gibbs* dst, int j_dst, bgge_gibbs* src, int j_src);
 /* injected draws in the reference's call order; copied to the device */
 int bgge_gibbs_set_tape(bgge_gibbs* h, const double* normals, int64_t n_normals, const double* chisq,
                         int64_t n_chisq);

@@ -53,9 +53,13 @@ def test_factored_blocks_reconstruct_dense_kernels(kernel, model):
                 assert np.max(np.abs(rec - blk)) <= 1e-9 * max(1.0, np.max(np.abs(blk))), (label, nm)
 
 
-def test_fit_from_factored_kernels_matches_oracle_per_iteration():
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("L,E", [(28, 3), (700, 4)])
+def test_fit_from_factored_kernels_matches_oracle_per_iteration(L, E, mode):
+    """mode 1: the G kernel stays factorised in the sweep (streams W, L rows, instead of U, L*E rows);
+    mode 0: the two-pass kernels on the expanded U.  Both against the oracle on the dense kernels."""
     import bgge_b200
-    L, E, p = 28, 3, 50
+    p = 50
     X = markers(L, p, 2)
     Y, names = design(L, E)
     ne = [L] * E
@@ -64,14 +68,14 @@ def test_fit_from_factored_kernels_matches_oracle_per_iteration():
     y = phenotype(oracle.gb_kernel(X), L, E, 3)
     y[[5, 40]] = np.nan
     Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    ite = 20 if L < 100 else 6
     nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
-    ite = 20
     nz, nc = oracle.tape_sizes(L * E, nrs, ite, n_na=2)
     rng = np.random.default_rng(4)
     z = rng.standard_normal(nz)
     c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [L * E + 3], dtype=float), ite))
     ref = oracle.BGGE(y, Kd, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
-    got = bgge_b200.BGGE(y, Kf, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c))      # decomposes inside the library
+    got = bgge_b200.BGGE(y, Kf, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), mode=mode)   # decomposes inside the library
     assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9
     assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9
     for nm in ref["K"]:
