@@ -551,6 +551,7 @@ int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64
     bl.ldu = round_up(rows, 16);
     BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
     bl.owns = true;
+    bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
     hk.blocks.push_back(bl);   // owned from here on (freed by the handle even on failure below)
     BGGE_CUDA(cudaMemset(bl.dU, 0, (size_t)bl.ldu * nr * sizeof(double)));
     BGGE_CUDA(cudaMemcpy2D(bl.dU, (size_t)bl.ldu * sizeof(double), U, (size_t)ldu * sizeof(double),
@@ -558,7 +559,8 @@ int bgge_gibbs_add_block(bgge_gibbs* h, int j, int64_t pos0, int64_t rows, int64
     hk.s_host.insert(hk.s_host.end(), s, s + nr);
     return OK;
   }
-  hk.blocks.push_back(bl);
+  bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
+    hk.blocks.push_back(bl);
   hk.s_host.insert(hk.s_host.end(), s, s + nr);
   return OK;
 }
@@ -610,6 +612,7 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
     bl.ldu = round_up(m, 16);
     BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
     bl.owns = true;
+    bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
     hk.blocks.push_back(bl);
     BGGE_CUDA(dS.alloc((size_t)nr));
     BGGE_TRY(eig_compact(dA.p, m, dW.p, m, nr, canonical_sign, dS.p, bl.dU, bl.ldu, g.stream));
@@ -684,6 +687,29 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
   }
   HostKernel& hk = g.kernels[(size_t)j];
   DevBuf<int> dgid_all, denv_all;   // only for the fallback route
+  // Identical blocks (same genotypes with the same counts, e.g. every environment of a balanced trial) are
+  // the same matrix: decompose it once, let the blocks share W and sweep them as one multi-RHS panel.
+  struct Decomp {
+    std::vector<int> T, cnt;
+    double* W;
+    int64_t ldw, nr;
+    std::vector<double> s;
+  };
+  std::vector<Decomp> cache;
+  const bool share_blocks = !getenv("BGGE_NO_SHARED_BLOCKS") && !getenv("BGGE_NO_FACTORED_SWEEP");
+  std::map<std::pair<std::vector<int>, std::vector<int>>, int> key_count;
+  auto block_key = [&](int64_t pos, int64_t m) {
+    std::vector<int> cnt((size_t)L, 0), T, c;
+    for (int64_t i = 0; i < m; ++i) ++cnt[(size_t)gid[pos + i]];
+    for (int64_t gidx = 0; gidx < L; ++gidx)
+      if (cnt[(size_t)gidx] > 0) {
+        T.push_back((int)gidx);
+        c.push_back(cnt[(size_t)gidx]);
+      }
+    return std::make_pair(T, c);
+  };
+  if (share_blocks && spans.size() > 1)
+    for (auto& sp : spans) ++key_count[block_key(sp.first, sp.second)];
   for (auto& sp : spans) {
     const int64_t pos = sp.first, m = sp.second;
     // is the mask constant on this block?  (first row decides; every pair is checked through the row classes)
@@ -718,6 +744,54 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         loc[(size_t)i] = slot[(size_t)gid[pos + i]];
         isq[(size_t)i] = 1.0 / sqc[(size_t)loc[(size_t)i]];
       }
+      // row map of the block (every factorised block owns one, even when W is shared)
+      int* d_loc = nullptr;
+      double* d_isq = nullptr;
+      auto upload_map = [&]() -> int {
+        BGGE_CUDA(pool_alloc((void**)&d_loc, (size_t)m * sizeof(int)));
+        BGGE_CUDA(pool_alloc((void**)&d_isq, (size_t)m * sizeof(double)));
+        BGGE_CUDA(cudaMemcpyAsync(d_loc, loc.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+        BGGE_CUDA(cudaMemcpyAsync(d_isq, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+        return OK;
+      };
+      auto make_virtual = [&](double* W, int64_t ldw, int64_t nr, bool owns_w) -> int {
+        std::vector<int> rowptr((size_t)t + 1, 0), rowidx((size_t)m);
+        for (int64_t i = 0; i < m; ++i) ++rowptr[(size_t)loc[(size_t)i] + 1];
+        for (int64_t a = 0; a < t; ++a) rowptr[(size_t)a + 1] += rowptr[(size_t)a];
+        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t i = 0; i < m; ++i) rowidx[(size_t)fill[(size_t)loc[(size_t)i]]++] = (int)i;
+        BGGE_CUDA(pool_alloc((void**)&bl.d_rowptr, ((size_t)t + 1) * sizeof(int)));
+        BGGE_CUDA(pool_alloc((void**)&bl.d_rowidx, (size_t)m * sizeof(int)));
+        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowptr, rowptr.data(), ((size_t)t + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowidx, rowidx.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+        bl.dU = W;
+        bl.ldu = ldw;
+        bl.nr = nr;
+        bl.vrows = t;
+        bl.d_loc = d_loc;
+        bl.d_isq = d_isq;
+        bl.owns = owns_w;
+        bl.owns_map = true;
+        bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
+    hk.blocks.push_back(bl);
+        BGGE_CUDA(cudaStreamSynchronize(st));   // host staging vectors die at the end of this scope
+        return OK;
+      };
+      std::vector<int> cntT((size_t)t);
+      for (int64_t a = 0; a < t; ++a) cntT[(size_t)a] = cnt[(size_t)T[(size_t)a]];
+      const bool duplicated = share_blocks && spans.size() > 1 && key_count[std::make_pair(T, cntT)] > 1;
+      if (duplicated) {
+        const Decomp* hit = nullptr;
+        for (auto& d : cache)
+          if (d.T == T && d.cnt == cntT) hit = &d;
+        if (hit) {   // an identical block was decomposed already: share its W and eigenvalues
+          if (hit->nr == 0) continue;
+          BGGE_TRY(upload_map());
+          BGGE_TRY(make_virtual(hit->W, hit->ldw, hit->nr, false));
+          hk.s_host.insert(hk.s_host.end(), hit->s.begin(), hit->s.end());
+          continue;
+        }
+      }
       DevBuf<int> dT;
       DevBuf<double> dsqc, dM, dW, dS, dWc, dwts;
       BGGE_CUDA(dT.alloc((size_t)t));
@@ -729,7 +803,10 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       BGGE_TRY(gather_scale_launch(dK0, ld0, dT.p, dsqc.p, t, dM.p, st));
       int64_t nr = 0;
       BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
-      if (nr == 0) continue;                                        // R/BGGE.R:162
+      if (nr == 0) {                                                // R/BGGE.R:162
+        if (duplicated) cache.push_back(Decomp{T, cntT, nullptr, 0, 0, {}});
+        continue;
+      }
       bl.nr = nr;
       const int64_t ldw = round_up(t, 16);
       BGGE_CUDA(dS.alloc((size_t)nr));
@@ -749,35 +826,21 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       } else {
         BGGE_CUDA(cudaMemcpyAsync(dWfinal, dWc.p, (size_t)ldw * nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
       }
-      int* d_loc = nullptr;
-      double* d_isq = nullptr;
-      BGGE_CUDA(pool_alloc((void**)&d_loc, (size_t)m * sizeof(int)));
-      BGGE_CUDA(pool_alloc((void**)&d_isq, (size_t)m * sizeof(double)));
-      BGGE_CUDA(cudaMemcpyAsync(d_loc, loc.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
-      BGGE_CUDA(cudaMemcpyAsync(d_isq, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
-      const bool keep_factored = 3 * t <= 2 * m && !getenv("BGGE_NO_FACTORED_SWEEP");   // >= 1.5x fewer rows to stream
-      if (keep_factored) {
-        std::vector<int> rowptr((size_t)t + 1, 0), rowidx((size_t)m);
-        for (int64_t i = 0; i < m; ++i) ++rowptr[(size_t)loc[(size_t)i] + 1];
-        for (int64_t a = 0; a < t; ++a) rowptr[(size_t)a + 1] += rowptr[(size_t)a];
-        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
-        for (int64_t i = 0; i < m; ++i) rowidx[(size_t)fill[(size_t)loc[(size_t)i]]++] = (int)i;
-        BGGE_CUDA(pool_alloc((void**)&bl.d_rowptr, ((size_t)t + 1) * sizeof(int)));
-        BGGE_CUDA(pool_alloc((void**)&bl.d_rowidx, (size_t)m * sizeof(int)));
-        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowptr, rowptr.data(), ((size_t)t + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        BGGE_CUDA(cudaMemcpyAsync(bl.d_rowidx, rowidx.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
-        bl.dU = dWfinal;       // W, t x nr
-        bl.ldu = ldw;
-        bl.vrows = t;
-        bl.d_loc = d_loc;
-        bl.d_isq = d_isq;
-        bl.owns = true;
-        hk.blocks.push_back(bl);
-        BGGE_CUDA(cudaStreamSynchronize(st));   // host staging vectors die at the end of this scope
+      BGGE_TRY(upload_map());
+      s_host.resize((size_t)nr);
+      BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+      BGGE_CUDA(cudaStreamSynchronize(st));
+      const bool keep_factored = (duplicated || 3 * t <= 2 * m) && !getenv("BGGE_NO_FACTORED_SWEEP");
+      if (keep_factored) {   // fewer rows to stream (repeated genotypes) or W shared with identical blocks
+        BGGE_TRY(make_virtual(dWfinal, ldw, nr, true));
+        if (duplicated) cache.push_back(Decomp{T, cntT, dWfinal, ldw, nr, s_host});
+        hk.s_host.insert(hk.s_host.end(), s_host.begin(), s_host.end());
+        continue;
       } else {
         BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
         bl.owns = true;
-        hk.blocks.push_back(bl);
+        bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
+    hk.blocks.push_back(bl);
         BGGE_TRY(expand_rows_launch(dWfinal, ldw, d_loc, d_isq, m, nr, bl.dU, bl.ldu, st));
         BGGE_CUDA(cudaStreamSynchronize(st));
         pool_free(dWfinal);
@@ -805,7 +868,8 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       bl.nr = nr;
       BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
       bl.owns = true;
-      hk.blocks.push_back(bl);
+      bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
+    hk.blocks.push_back(bl);
       BGGE_CUDA(dS.alloc((size_t)nr));
       BGGE_TRY(eig_compact(dA.p, m, dW.p, m, nr, canonical_sign, dS.p, bl.dU, bl.ldu, st));
       s_host.resize((size_t)nr);
@@ -852,9 +916,7 @@ int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* 
   if (rows) *rows = bl.rows;
   if (nr) *nr = bl.nr;
   if (s) {
-    int64_t off = 0;   // blocks are appended to s_host in insertion order until init sorts them
-    for (int k = 0; k < b; ++k) off += hk.blocks[(size_t)k].nr;
-    std::memcpy(s, hk.s_host.data() + off, (size_t)bl.nr * sizeof(double));
+    std::memcpy(s, hk.s_host.data() + bl.col_off, (size_t)bl.nr * sizeof(double));   // col_off tracks s_host
   }
   if (U) {
     BGGE_REQUIRE(ldu >= bl.rows, "gibbs_fetch_block: ldu too small");
@@ -931,6 +993,7 @@ int bgge_gibbs_share_kernel(bgge_gibbs* dst, int j_dst, bgge_gibbs* src, int j_s
     HostBlock c = b;
     c.owns = false;
     c.owns_dense = false;
+    c.owns_map = false;
     hd.blocks.push_back(c);
   }
   hd.s_host = hs.s_host;
@@ -963,9 +1026,29 @@ int bgge_gibbs_kernel_bytes(bgge_gibbs* h, int j, int64_t* basis_bytes, int* fac
   HostKernel& hk = g.kernels[(size_t)j];
   int64_t bytes = 0;
   int nv = 0;
+  std::vector<const double*> seen;   // fused: a W shared by identical blocks is streamed once per <= 4 of them
+  std::vector<int> uses;
   for (auto& b : hk.blocks) {
-    bytes += 8 * (hk.fused ? b.stream_rows() : 2 * b.rows) * b.nr;
-    nv += (hk.fused && b.vrows > 0) ? 1 : 0;
+    if (!hk.fused) {
+      bytes += 16 * b.rows * b.nr;
+      continue;
+    }
+    nv += b.vrows > 0 ? 1 : 0;
+    bool counted = false;
+    if (b.vrows > 0)
+      for (size_t k = 0; k < seen.size(); ++k)
+        if (seen[k] == b.dU && uses[k] < 4) {
+          ++uses[k];
+          counted = true;
+          break;
+        }
+    if (!counted) {
+      bytes += 8 * b.stream_rows() * b.nr;
+      if (b.vrows > 0) {
+        seen.push_back(b.dU);
+        uses.push_back(1);
+      }
+    }
   }
   if (basis_bytes) *basis_bytes = bytes;
   if (factored_blocks) *factored_blocks = nv;
@@ -1183,6 +1266,7 @@ int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64
     bl.ldu = round_up(rows, 16);
     BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
     bl.owns = true;
+    bl.col_off = (int64_t)bk.s_host.size();
     bk.blocks.push_back(bl);
     bk.s_host.insert(bk.s_host.end(), s, s + nr);
     BGGE_CUDA(cudaMemset(bl.dU, 0, (size_t)bl.ldu * nr * sizeof(double)));
@@ -1190,6 +1274,7 @@ int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64
                            (size_t)rows * sizeof(double), (size_t)nr, cudaMemcpyHostToDevice));
     return OK;
   }
+  bl.col_off = (int64_t)bk.s_host.size();
   bk.blocks.push_back(bl);
   bk.s_host.insert(bk.s_host.end(), s, s + nr);
   return OK;

@@ -424,7 +424,15 @@ int batch_init(Batch* g) {
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     BGGE_REQUIRE(!bk.blocks.empty(), "batch: kernel %d has no eigen blocks", j);
-    std::sort(bk.blocks.begin(), bk.blocks.end(), [](const BatchBlock& a, const BatchBlock& b) { return a.pos0 < b.pos0; });
+    {   // blocks in row order, eigenvalues re-concatenated to match (col_off = insertion offset until here)
+      int64_t tot = 0;
+      for (auto& bl : bk.blocks) tot += bl.nr;
+      BGGE_REQUIRE((int64_t)bk.s_host.size() == tot, "batch: kernel %d eigenvalue count mismatch", j);
+      std::sort(bk.blocks.begin(), bk.blocks.end(), [](const BatchBlock& a, const BatchBlock& b) { return a.pos0 < b.pos0; });
+      std::vector<double> ss;
+      for (auto& bl : bk.blocks) ss.insert(ss.end(), bk.s_host.begin() + bl.col_off, bk.s_host.begin() + bl.col_off + bl.nr);
+      bk.s_host.swap(ss);
+    }
     bk.nr_total = 0;
     int64_t cursor = 0, proj_tiles = 0, back_tiles = 0, max_rows = 0, max_nr = 0;
     for (auto& bl : bk.blocks) {

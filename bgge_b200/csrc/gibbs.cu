@@ -568,8 +568,8 @@ Gibbs::~Gibbs() {
   for (auto& k : kernels)
     for (auto& bl : k.blocks)
     {
-      if (bl.owns) {
-        if (bl.dU) pool_free(bl.dU);
+      if (bl.owns && bl.dU) pool_free(bl.dU);
+      if (bl.owns_map) {
         if (bl.d_loc) pool_free(bl.d_loc);
         if (bl.d_isq) pool_free(bl.d_isq);
         if (bl.d_rowptr) pool_free(bl.d_rowptr);
@@ -656,7 +656,16 @@ int gibbs_init(Gibbs* g) {
   for (int j = 0; j < g->nk; ++j) {
     HostKernel& hk = g->kernels[j];
     BGGE_REQUIRE(!hk.blocks.empty(), "gibbs: kernel %d has no eigen blocks (all eigenvalues <= tol)", j);
-    std::sort(hk.blocks.begin(), hk.blocks.end(), [](const HostBlock& a, const HostBlock& b) { return a.pos0 < b.pos0; });
+    {   // blocks in row order, eigenvalues re-concatenated to match (col_off = insertion offset until here)
+      int64_t tot = 0;
+      for (auto& bl : hk.blocks) tot += bl.nr;
+      BGGE_REQUIRE((int64_t)hk.s_host.size() == tot, "gibbs: kernel %d eigenvalue count mismatch", j);
+      std::sort(hk.blocks.begin(), hk.blocks.end(), [](const HostBlock& a, const HostBlock& b) { return a.pos0 < b.pos0; });
+      std::vector<double> ss;
+      ss.reserve((size_t)tot);
+      for (auto& bl : hk.blocks) ss.insert(ss.end(), hk.s_host.begin() + bl.col_off, hk.s_host.begin() + bl.col_off + bl.nr);
+      hk.s_host.swap(ss);
+    }
     hk.nr_total = 0;
     int64_t cursor = 0;
     int64_t max_nr = 0;

@@ -63,6 +63,12 @@ struct FPanel {                  // fused path: columns [c0, c1) of one block, h
   int slot;                      // upart slot (= cluster index)
   int virt;                      // 1: rows live in the kernel's virtual vectors at offset voff
   long long voff;
+  // multi-right-hand-side panels: nb factorised blocks that share this W (identical diagonal blocks of a BD
+  // kernel) are swept together; member k reads / writes the virtual vectors at voffs[k] and draws with the
+  // column offset col_offs[k].  nb == 1: voffs[0] == voff, col_offs[0] == col_off.
+  int nb;
+  long long voffs[4];
+  int col_offs[4];
 };
 
 struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo, qhi] contributed (qlo > qhi: none)
@@ -70,6 +76,14 @@ struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo
   const int* loc;                // factorised block: row -> virtual row (already offset to row0), else nullptr
   const double* isq;             // 1/sqrt(count) per row (offset to row0)
   long long voff;
+};
+
+struct VDesc {                   // one factorised block for virt_gather_kernel
+  int vrows, pos0, cta0;         // CTAs [cta0, cta0 + ceil(vrows/256)) of the gather launch belong to it
+  long long voff;
+  const int* rowptr;
+  const int* rowidx;
+  const double* isq;
 };
 
 // An eigen block.  Dense: U (rows x nr).  Factorised (bgge_gibbs_add_expanded_kernel, repeated genotypes):
@@ -87,6 +101,7 @@ struct HostBlock {
   double* dU_dense = nullptr;    // lazily materialised dense copy (two-pass path, fetch / borrow)
   int64_t ldu_dense = 0;
   bool owns_dense = false;
+  bool owns_map = false;         // loc / isq / CSR arrays (dU may be shared with an identical block)
   int64_t stream_rows() const { return vrows > 0 ? vrows : rows; }
 };
 
@@ -111,6 +126,9 @@ struct HostKernel {
   DevBuf<FTile> ftiles;
   int64_t vtotal = 0;            // total virtual rows of the factorised blocks
   DevBuf<double> ve;             // virtual residual  C^{-1/2} Z'(e + u_old), [vtotal]
+  int fused_nb = 1;              // right-hand sides per panel the fused kernel is instantiated for (1, 2 or 4)
+  DevBuf<VDesc> vdesc;           // factorised blocks of this kernel (one gather launch for all of them)
+  int n_vdesc = 0, vgrid = 0;
 };
 
 struct Gibbs {

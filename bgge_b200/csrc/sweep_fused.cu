@@ -33,8 +33,8 @@ constexpr int F_ROLE = 256;                      // threads per compute role (do
 constexpr int F_THREADS = 2 * F_ROLE + 32;       // + one producer warp (one elected lane issues TMA)
 constexpr int F_ROWS_PER_STEP = 2 * F_ROLE;      // each role thread owns row pairs (16-byte shared loads)
 constexpr int F_MAX_NS = 10;                     // data ring depth limit
-constexpr int NPX = 32;                          // partial-exchange ring depth (see protocol note)
-constexpr int F_MAXCS = 16;                      // largest cluster (16 needs the non-portable opt-in)
+constexpr int NPX = 32;                          // max partial-exchange ring depth; runtime depth is 2 ns + 4
+constexpr int F_MAXCS = 8;                       // largest cluster (portable limit; 16 brought 7 clusters and no gain)
 
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t r;
@@ -46,8 +46,43 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                "l"(__double_as_longlong(v)), "r"(remote_bar)
                : "memory");
 }
+// waiting warps share issue slots with working ones: back off between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++polls > 8) __nanosleep(32);   // short waits (small, latency-bound problems) never sleep
+}
 __device__ __forceinline__ void role_barrier(int id) {   // named barrier over one 256-thread role
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(F_ROLE) : "memory");
+}
+
+// Sums P values (P a power of two <= 32) over the 32 lanes with P - 1 + (5 - log2 P) 64-bit shuffles instead of
+// 5 P: at every step a lane keeps half of its values and hands the other half to its partner.  On return
+// a[0] of the lanes with lane % (32/P) == 0 ... (every lane) holds the total of value index
+// idx = (lane * P) >> 5  (the top log2 P lane bits); all lanes of one idx agree.
+template <int P>
+__device__ __forceinline__ double warp_multi_reduce(double (&a)[P], int lane, int& idx) {
+  int n = P;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if (n > 1) {
+      const int half = n >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        if (i < half) {
+          const double send = upper ? a[i] : a[i + half];
+          const double keep = upper ? a[i + half] : a[i];
+          a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = half;
+    } else {
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
+    }
+  }
+  idx = (lane * P) >> 5;
+  return a[0];
 }
 
 // Warp-specialised CTA:
@@ -62,14 +97,14 @@ __device__ __forceinline__ void role_barrier(int id) {   // named barrier over o
 //                                 release the slot (empty[slot]).
 // Protocol note: a remote CTA can send group h only after its axpy finished h - ns (slot reuse), which
 // needs my partials of h - ns; my axpy can lag my dots by ns groups, so up to 2 ns + 1 partial entries
-// are live; NPX = 32 >= 2 * F_MAX_NS + 2 leaves a margin of several microseconds for in-flight stores.
-template <int RPT, int G>
+// are live; the exchange ring holds 2 ns + 4 entries (<= NPX).
+template <int RPT, int G, int NB>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cluster_panels,
                    const double* __restrict__ r, const double* __restrict__ u_old, const double* __restrict__ s,
                    double* __restrict__ upart, double* __restrict__ bpart, long long n,
                    const double* __restrict__ ve, double* __restrict__ vupart, long long vtotal,
-                   const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns) {
+                   const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns, int npx) {
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
   const uint32_t cs = cluster.num_blocks();
@@ -78,27 +113,36 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   constexpr int ZB = G * (F_ROLE / G);           // columns per draw batch
 
   extern __shared__ __align__(128) unsigned char fsm[];
-  // carve: ring[ns] | parts[NPX][8][G] | red[2][8][G] | tvb,zsb,isb[2][ZB] | full[F_MAX_NS] | empty[F_MAX_NS] | pbar[NPX]
+  // carve: ring[ns] | parts[NPX][F_MAXCS][NB*G] | red[2][8][NB*G] | bsm[2][NB*G] | tvb,isb[2][ZB] | zsb[NB][2][ZB] |
+  //        full[F_MAX_NS] | empty[F_MAX_NS] | pbar[NPX]
+  constexpr int NG = NB * G;
   const int2 cp = cluster_panels[cid];
   int max_rs = 0;
   for (int pi = 0; pi < cp.y; ++pi) max_rs = max(max_rs, panels[cp.x + pi].rs);
   const size_t slot_doubles = (size_t)G * max_rs;
   double* ring = reinterpret_cast<double*>(fsm);
   double* parts = ring + (size_t)ns * slot_doubles;
-  double* red = parts + (size_t)NPX * F_MAXCS * G;
-  double* tvb = red + 2 * 8 * G;                 // tau * v       per column of a draw batch
-  double* zsb = tvb + 2 * ZB;                    // sqrt(v) * z
-  double* isb = zsb + 2 * ZB;                    // 1 / s
-  uint64_t* full = reinterpret_cast<uint64_t*>(isb + 2 * ZB);
+  double* red = parts + (size_t)npx * F_MAXCS * NG;
+  double* bsm = red + 2 * 8 * NG;                // NB > 1: coefficients of the current group (double buffered)
+  double* tvb = bsm + 2 * NG;                    // tau * v       per column of a draw batch (same for all members)
+  double* isb = tvb + 2 * ZB;                    // 1 / s
+  double* zsb = isb + 2 * ZB;                    // sqrt(v) * z,  [NB][2][ZB]
+  uint64_t* full = reinterpret_cast<uint64_t*>(zsb + (size_t)NB * 2 * ZB);
   uint64_t* empty = full + F_MAX_NS;
   uint64_t* pbar = empty + F_MAX_NS;
 
+  // Rows of a ring slot beyond this CTA's slice are never written by the TMA copies; zero the ring once so
+  // they stay finite: the hot loops then need no per-row predicates (such rows meet e = 0 in the dots and
+  // their u accumulators are never written back).
+  // (a read of the last row pairs may run past a slot into the next slot or into the small arrays behind the
+  // ring, so everything up to the barriers is zeroed, not only the ring)
+  for (size_t i = threadIdx.x; i < (size_t)(reinterpret_cast<double*>(full) - ring); i += F_THREADS) ring[i] = 0.0;
   if (threadIdx.x == 0) {
     for (int k = 0; k < ns; ++k) {
       mbar_init(&full[k], 1);
       mbar_init(&empty[k], F_ROLE / 32);
     }
-    for (int k = 0; k < NPX; ++k) mbar_init(&pbar[k], 1);
+    for (int k = 0; k < npx; ++k) mbar_init(&pbar[k], 1);
     mbar_fence_init();
   }
   cluster.sync();   // barriers of every CTA exist before anybody sends
@@ -111,17 +155,22 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   if (warp == 2 * (F_ROLE / 32)) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      uint32_t lc = 0;
+      int pslot = 0;
+      uint32_t pphase = 0;
       for (int pi = 0; pi < cp.y; ++pi) {
-        const FPanel pn = panels[cp.x + pi];
+        const FPanel& pn = panels[cp.x + pi];   // stays in global memory: members are indexed dynamically
         const int row0 = (int)rank * pn.rs;
         const int my_rows = max(0, min(pn.rs, pn.rows - row0));
         const uint32_t slice_bytes = (uint32_t)((my_rows + 1) & ~1) * (uint32_t)sizeof(double);
         const double* Ubase = pn.U + row0;
-        for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++lc) {
-          const int slot = lc % ns;
+        for (int c0 = pn.c0; c0 < pn.c1; c0 += G) {
+          const int slot = pslot;
           const int gc = min(G, pn.c1 - c0);
-          mbar_wait(&empty[slot], ((lc / ns) & 1u) ^ 1u);
+          mbar_wait_relaxed(&empty[slot], pphase ^ 1u);
+          if (++pslot == ns) {
+            pslot = 0;
+            pphase ^= 1u;
+          }
           mbar_expect_tx(&full[slot], slice_bytes * (uint32_t)gc);
           if (slice_bytes > 0) {
             double* dst = ring + (size_t)slot * slot_doubles;
@@ -135,61 +184,87 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
     // ------------------------------------------------------------------ dot warps
     const int tid = threadIdx.x;
     uint32_t cc = 0;
+    int dslot = 0, dpg = 0;
+    uint32_t dphase = 0;
     for (int pi = 0; pi < cp.y; ++pi) {
-      const FPanel pn = panels[cp.x + pi];
+      const FPanel& pn = panels[cp.x + pi];   // stays in global memory: members are indexed dynamically
       const int row0 = (int)rank * pn.rs;
       const int my_rows = max(0, min(pn.rs, pn.rows - row0));
-      double2 e[RPT];   // residual slice e = (r - shift) + u_old, register resident for the whole panel
+      // residual slices e = (r - shift) + u_old (one per member block), register resident for the whole panel
+      double2 e[NB][RPT];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const int row = k * F_ROWS_PER_STEP + 2 * tid;
-        if (pn.virt) {   // factorised block: the residual was already gathered to genotype space
-          const long long gi = pn.voff + row0 + row;
-          e[k].x = row < my_rows ? ve[gi] : 0.0;
-          e[k].y = row + 1 < my_rows ? ve[gi + 1] : 0.0;
-        } else {
-          const long long gi = (long long)pn.pos0 + row0 + row;
-          e[k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
-          e[k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
+      for (int m = 0; m < NB; ++m) {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int row = k * F_ROWS_PER_STEP + 2 * tid;
+          e[m][k] = make_double2(0.0, 0.0);
+          if (m < pn.nb) {
+            if (pn.virt) {   // factorised block: the residual was already gathered to genotype space
+              const long long gi = pn.voffs[m] + row0 + row;
+              e[m][k].x = row < my_rows ? ve[gi] : 0.0;
+              e[m][k].y = row + 1 < my_rows ? ve[gi + 1] : 0.0;
+            } else {
+              const long long gi = (long long)pn.pos0 + row0 + row;
+              e[m][k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
+              e[m][k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
+            }
+          }
         }
       }
       for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
-        const int slot = cc % ns;
+        const int slot = dslot;
         const int gc = min(G, pn.c1 - c0);
-        mbar_wait(&full[slot], (cc / ns) & 1u);
+        mbar_wait_relaxed(&full[slot], dphase);
+        if (++dslot == ns) {
+          dslot = 0;
+          dphase ^= 1u;
+        }
         const double* src = ring + (size_t)slot * slot_doubles + 2 * tid;
-        double* rd = red + (cc & 1u) * 8 * G;
+        double* rd = red + (cc & 1u) * 8 * NG;
+        constexpr int PV = NG <= 1 ? 1 : NG <= 2 ? 2 : NG <= 4 ? 4 : NG <= 8 ? 8 : NG <= 16 ? 16 : 32;
+        double a[PV];
+#pragma unroll
+        for (int v = 0; v < PV; ++v) a[v] = 0.0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          double a = 0.0;
           if (g < gc) {
+            const double* sg = src + (size_t)g * max_rs;
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
-              if (k * F_ROWS_PER_STEP + 2 * tid < my_rows) {
-                const double2 x = *reinterpret_cast<const double2*>(src + (size_t)g * max_rs + k * F_ROWS_PER_STEP);
-                a = fma(x.x, e[k].x, a);
-                a = fma(x.y, e[k].y, a);
+              // no row predicate: rows past the slice are finite (zeroed ring) and meet e = 0
+              const double2 x = *reinterpret_cast<const double2*>(sg + k * F_ROWS_PER_STEP);
+#pragma unroll
+              for (int m = 0; m < NB; ++m) {
+                a[m * G + g] = fma(x.x, e[m][k].x, a[m * G + g]);
+                a[m * G + g] = fma(x.y, e[m][k].y, a[m * G + g]);
               }
             }
           }
-          a = warp_sum(a);
-          if (lane == 0) rd[warp * G + g] = a;
+        }
+        {
+          int vi;
+          const double tot = warp_multi_reduce<PV>(a, lane, vi);
+          if ((lane & (32 / PV - 1)) == 0 && vi < NG) rd[warp * NG + vi] = tot;
         }
         role_barrier(1);
+        const uint32_t pg = (uint32_t)dpg;
+        if (++dpg == npx) dpg = 0;
         if (warp == 0) {
-          const uint32_t pg = cc % NPX;
-          if (lane == 0) mbar_expect_tx(&pbar[pg], cs * (uint32_t)gc * (uint32_t)sizeof(double));
+          if (lane == 0) mbar_expect_tx(&pbar[pg], cs * (uint32_t)(gc * pn.nb) * (uint32_t)sizeof(double));
           __syncwarp();
-          const uint32_t bar_addr = smem_u32(&pbar[pg]);
-          for (int g = 0; g < gc; ++g) {
-            double p = lane < 8 ? rd[lane * G + g] : 0.0;   // fixed tree: deterministic
-            p += __shfl_xor_sync(0xffffffffu, p, 4);
-            p += __shfl_xor_sync(0xffffffffu, p, 2);
-            p += __shfl_xor_sync(0xffffffffu, p, 1);
-            if (lane < (int)cs) {
-              const uint32_t dst = smem_u32(parts + (size_t)pg * F_MAXCS * G + (size_t)rank * G + g);
-              st_async_f64(map_to_rank(dst, (uint32_t)lane), p, map_to_rank(bar_addr, (uint32_t)lane));
-            }
+          // lane l owns value v = l % 16 (member m = v / G, column g = v % G): it adds the 8 warp partials in
+          // warp order (deterministic) and pushes the sum to half of the cluster (l / 16 selects the half)
+          const int v = NG <= 16 ? (lane & 15) : lane;
+          const uint32_t q0 = NG <= 16 ? (uint32_t)(lane >> 4) : 0u, qstep = NG <= 16 ? 2u : 1u;
+          const int m = v / G, gq = v % G;
+          if (v < NG && m < pn.nb && gq < gc) {
+            double p = 0.0;
+#pragma unroll
+            for (int w = 0; w < F_ROLE / 32; ++w) p += rd[w * NG + v];
+            const uint32_t dst = smem_u32(parts + (size_t)pg * F_MAXCS * NG + (size_t)rank * NG + v);
+            const uint32_t bar_addr = smem_u32(&pbar[pg]);
+            for (uint32_t q = q0; q < cs; q += qstep)
+              st_async_f64(map_to_rank(dst, q), p, map_to_rank(bar_addr, q));
           }
         }
       }
@@ -198,62 +273,103 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
     // ------------------------------------------------------------------ axpy warps
     const int tid = threadIdx.x - F_ROLE;
     uint32_t cc = 0;
+    int aslot = 0, apg = 0;
+    uint32_t aphase = 0, pphase2 = 0;
     double zq = 0.0;   // thread 0 of the role: sum of b^2 / s (R/BGGE.R:96)
     for (int pi = 0; pi < cp.y; ++pi) {
-      const FPanel pn = panels[cp.x + pi];
+      const FPanel& pn = panels[cp.x + pi];   // stays in global memory: members are indexed dynamically
       const int row0 = (int)rank * pn.rs;
       const int my_rows = max(0, min(pn.rs, pn.rows - row0));
       const int ncols = pn.c1 - pn.c0;
-      double2 uacc[RPT];
+      double2 uacc[NB][RPT];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) uacc[k] = make_double2(0.0, 0.0);
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) uacc[m][k] = make_double2(0.0, 0.0);
       for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
-        const int slot = cc % ns;
+        const int slot = aslot;
+        const uint32_t sphase = aphase;
+        if (++aslot == ns) {
+          aslot = 0;
+          aphase ^= 1u;
+        }
         const int gc = min(G, pn.c1 - c0);
         const int rel0 = c0 - pn.c0;
         if (rel0 % ZB == 0) {
           // draw batch for panel columns [rel0, rel0 + ZB): the normal draw does not depend on d
           const int rel = rel0 + tid;
           if (tid < ZB && rel < ncols) {
-            const long long col = (long long)pn.col_off + pn.c0 + rel;
+            const long long col = (long long)pn.col_offs[0] + pn.c0 + rel;   // members share s (same matrix)
             const double sv = s[col];
             const double vari = sv * lam / (1.0 + sv * lam * tau);                 // R/BGGE.R:302
-            const double z = draw_normal(dc, it, (uint32_t)j, (unsigned long long)col,
-                                         dc.z_init + (it - 1) * dc.z_per_it + z_off + col);
             const int zb = ((rel0 / ZB) & 1) * ZB + tid;
             tvb[zb] = tau * vari;
-            zsb[zb] = sqrt(vari) * z;
             isb[zb] = 1.0 / sv;
+            const double sq = sqrt(vari);
+            for (int m = 0; m < pn.nb; ++m) {
+              const long long cm = (long long)pn.col_offs[m] + pn.c0 + rel;
+              const double z = draw_normal(dc, it, (uint32_t)j, (unsigned long long)cm,
+                                           dc.z_init + (it - 1) * dc.z_per_it + z_off + cm);
+              zsb[(size_t)m * 2 * ZB + zb] = sq * z;
+            }
           }
           role_barrier(2);
         }
-        const uint32_t pg = cc % NPX;
-        mbar_wait(&pbar[pg], (cc / NPX) & 1u);
-        double bv[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          bv[g] = 0.0;
-          if (g < gc) {
-            const double* pp = parts + (size_t)pg * F_MAXCS * G + g;
-            double d = 0.0;
-            for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * G];             // rank order
-            const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
-            const double media = tvb[zb] * d;                                       // (tau vari) d   R/BGGE.R:303
-            bv[g] = media + zsb[zb];                                                // + sqrt(vari) z R/BGGE.R:89-92
-            if (tid == 0) zq += bv[g] * bv[g] * isb[zb];
-          }
+        const uint32_t pg = (uint32_t)apg;
+        mbar_wait_relaxed(&pbar[pg], pphase2);
+        if (++apg == npx) {
+          apg = 0;
+          pphase2 ^= 1u;
         }
-        mbar_wait(&full[slot], (cc / ns) & 1u);   // acquire the TMA-written slot for this role too
+        double bv[NB == 1 ? G : 1];
+        const double* bcur = bsm + (cc & 1u) * NG;
+        if constexpr (NB == 1) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            bv[g] = 0.0;
+            if (g < gc) {
+              const double* pp = parts + (size_t)pg * F_MAXCS * NG + g;
+              double d = 0.0;
+              for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * NG];          // rank order
+              const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
+              const double media = tvb[zb] * d;                                     // (tau vari) d   R/BGGE.R:303
+              bv[g] = media + zsb[zb];                                              // + sqrt(vari) z R/BGGE.R:89-92
+              if (tid == 0) zq += bv[g] * bv[g] * isb[zb];
+            }
+          }
+        } else {
+          // one lane per (member, column) forms the coefficient once; everybody reads it after the barrier
+          if (tid < pn.nb * G) {
+            const int m = tid / G, g = tid % G;
+            double bcoef = 0.0;
+            if (g < gc) {
+              const double* pp = parts + (size_t)pg * F_MAXCS * NG + m * G + g;
+              double d = 0.0;
+              for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * NG];
+              const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
+              bcoef = tvb[zb] * d + zsb[(size_t)m * 2 * ZB + zb];
+              zq += bcoef * bcoef * isb[zb];
+            }
+            bsm[(cc & 1u) * NG + m * G + g] = bcoef;
+          }
+          role_barrier(2);
+        }
+        mbar_wait_relaxed(&full[slot], sphase);   // acquire the TMA-written slot for this role too
         const double* src = ring + (size_t)slot * slot_doubles + 2 * tid;
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-          if (k * F_ROWS_PER_STEP + 2 * tid < my_rows) {
+        for (int g = 0; g < G; ++g) {
+          if (g < gc) {
+            double2 x[RPT];
+            const double* sg = src + (size_t)g * max_rs;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (g < gc) {
-                const double2 x = *reinterpret_cast<const double2*>(src + (size_t)g * max_rs + k * F_ROWS_PER_STEP);
-                uacc[k].x = fma(x.x, bv[g], uacc[k].x);
-                uacc[k].y = fma(x.y, bv[g], uacc[k].y);
+            for (int k = 0; k < RPT; ++k) x[k] = *reinterpret_cast<const double2*>(sg + k * F_ROWS_PER_STEP);
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+              const double bb = NB == 1 ? bv[NB == 1 ? g : 0] : bcur[m * G + g];
+#pragma unroll
+              for (int k = 0; k < RPT; ++k) {
+                uacc[m][k].x = fma(x[k].x, bb, uacc[m][k].x);
+                uacc[m][k].y = fma(x[k].y, bb, uacc[m][k].y);
               }
             }
           }
@@ -262,15 +378,23 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
         if (lane == 0) mbar_arrive(&empty[slot]);
       }
       // this cluster's contribution to u over the block's rows
-      double* up = pn.virt ? vupart + (size_t)pn.slot * vtotal + pn.voff + row0
-                           : upart + (size_t)pn.slot * n + pn.pos0 + row0;
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const int row = k * F_ROWS_PER_STEP + 2 * tid;
-        if (row < my_rows) up[row] = uacc[k].x;
-        if (row + 1 < my_rows) up[row + 1] = uacc[k].y;
+      for (int m = 0; m < NB; ++m) {
+        if (m < pn.nb) {
+          double* up = pn.virt ? vupart + (size_t)pn.slot * vtotal + pn.voffs[m] + row0
+                               : upart + (size_t)pn.slot * n + pn.pos0 + row0;
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) {
+            const int row = k * F_ROWS_PER_STEP + 2 * tid;
+            if (row < my_rows) up[row] = uacc[m][k].x;
+            if (row + 1 < my_rows) up[row + 1] = uacc[m][k].y;
+          }
+        }
       }
       role_barrier(2);   // batch buffers are reused by the next panel
+    }
+    if constexpr (NB > 1) {   // the (member, column) lanes of warp 0 of this role hold the pieces of sum b^2/s
+      zq = warp_sum(tid < 32 ? zq : 0.0);
     }
     if (rank == 0 && tid == 0) bpart[cid] = zq;
   }
@@ -324,25 +448,30 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
   }
 }
 
-// factorised block: ve[a] = sum over the rows i of genotype a of isq_i * ((r_i - shift) + u_old_i), CSR order
+// factorised blocks: ve[voff + a] = sum over the rows i of genotype a of isq_i * ((r_i - shift) + u_old_i), in
+// CSR order (deterministic); one launch covers every factorised block of the kernel
 __global__ void __launch_bounds__(256)
-virt_gather_kernel(int vrows, const int* __restrict__ rowptr, const int* __restrict__ rowidx,
-                   const double* __restrict__ isq, const double* __restrict__ r, const double* __restrict__ u_old,
-                   const Scal* __restrict__ sc, double* __restrict__ ve) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= vrows) return;
+virt_gather_kernel(const VDesc* __restrict__ desc, int ndesc, const double* __restrict__ r,
+                   const double* __restrict__ u_old, const Scal* __restrict__ sc, double* __restrict__ ve) {
+  int d = 0;
+  while (d + 1 < ndesc && (int)blockIdx.x >= desc[d + 1].cta0) ++d;
+  const VDesc vd = desc[d];
+  const int a = ((int)blockIdx.x - vd.cta0) * blockDim.x + threadIdx.x;
+  if (a >= vd.vrows) return;
   const double shift = sc->shift;
+  const double* rp = r + vd.pos0;
+  const double* up = u_old + vd.pos0;
   double acc = 0.0;
-  for (int k = rowptr[a]; k < rowptr[a + 1]; ++k) {
-    const int i = rowidx[k];
-    acc = fma(isq[i], (r[i] - shift) + u_old[i], acc);
+  for (int k = vd.rowptr[a]; k < vd.rowptr[a + 1]; ++k) {
+    const int i = vd.rowidx[k];
+    acc = fma(vd.isq[i], (rp[i] - shift) + up[i], acc);
   }
-  ve[a] = acc;
+  ve[vd.voff + a] = acc;
 }
 
-template <int RPT, int G>
+template <int RPT, int G, int NB>
 int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
-  auto kfn = sweep_fused_kernel<RPT, G>;
+  auto kfn = sweep_fused_kernel<RPT, G, NB>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(hk.fused_clusters * hk.fused_cs), 1, 1);
   cfg.blockDim = dim3(F_THREADS, 1, 1);
@@ -359,16 +488,17 @@ int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
                                (const double*)g->r.p, (const double*)(g->u.p + (size_t)j * g->n),
                                (const double*)hk.s.p, g->upart.p, hk.bpart.p, (long long)g->n,
                                (const double*)hk.ve.p, g->vupart.p, (long long)hk.vtotal,
-                               (const Scal*)g->scal.p, j, g->draw, hk.z_off, hk.fused_ns));
+                               (const Scal*)g->scal.p, j, g->draw, hk.z_off, hk.fused_ns, 2 * hk.fused_ns + 4));
   return OK;
 }
 
 struct Combo { int rpt, gcols; };
 constexpr Combo kCombos[] = {{1, 8}, {2, 6}, {3, 4}, {4, 3}, {6, 2}, {8, 1}, {10, 1}, {12, 1}};   // slot <= 48 KB
+// register budget: NB * RPT <= 12 row pairs per thread -> NB = 2 up to RPT 6, NB = 4 up to RPT 3
 
-template <int RPT, int G>
+template <int RPT, int G, int NB>
 int occupancy_t(int cs, size_t smem, int* nclusters) {
-  auto kfn = sweep_fused_kernel<RPT, G>;
+  auto kfn = sweep_fused_kernel<RPT, G, NB>;
   // one template instantiation serves several model kernels with different ring sizes: opt in to the
   // device maximum once instead of per launch
   int dev = 0, optin = 0;
@@ -393,30 +523,42 @@ int occupancy_t(int cs, size_t smem, int* nclusters) {
   return OK;
 }
 
+#define BGGE_FUSED_CASE(FN, R, GG, ...)                                  \
+  case R:                                                                \
+    if (hk.fused_nb == 1) return FN<R, GG, 1>(__VA_ARGS__);              \
+    if constexpr (R <= 6) {                                              \
+      if (hk.fused_nb == 2) return FN<R, GG, 2>(__VA_ARGS__);            \
+    }                                                                    \
+    if constexpr (R <= 3) {                                              \
+      if (hk.fused_nb == 4) return FN<R, GG, 4>(__VA_ARGS__);            \
+    }                                                                    \
+    break;
+
 #define BGGE_FUSED_DISPATCH(FN, ...)                       \
   switch (hk.fused_rpt) {                                  \
-    case 1: return FN<1, 8>(__VA_ARGS__);                  \
-    case 2: return FN<2, 6>(__VA_ARGS__);                  \
-    case 3: return FN<3, 4>(__VA_ARGS__);                  \
-    case 4: return FN<4, 3>(__VA_ARGS__);                  \
-    case 6: return FN<6, 2>(__VA_ARGS__);                  \
-    case 8: return FN<8, 1>(__VA_ARGS__);                  \
-    case 10: return FN<10, 1>(__VA_ARGS__);                \
-    default: return FN<12, 1>(__VA_ARGS__);                \
-  }
+    BGGE_FUSED_CASE(FN, 1, 8, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 2, 6, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 3, 4, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 4, 3, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 6, 2, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 8, 1, __VA_ARGS__)                 \
+    BGGE_FUSED_CASE(FN, 10, 1, __VA_ARGS__)                \
+    BGGE_FUSED_CASE(FN, 12, 1, __VA_ARGS__)                \
+    default: break;                                        \
+  }                                                        \
+  set_error("fused sweep: no kernel instantiation for rpt=%d nb=%d", hk.fused_rpt, hk.fused_nb); \
+  return ERR_INVALID;
 
 int occupancy_dispatch(HostKernel& hk, int cs, size_t smem, int* ncl) { BGGE_FUSED_DISPATCH(occupancy_t, cs, smem, ncl) }
 
 }  // namespace
 
 int launch_fused(Gibbs* g, HostKernel& hk, int j) {
-  for (auto& bl : hk.blocks)
-    if (bl.vrows > 0) {
-      virt_gather_kernel<<<(unsigned)((bl.vrows + 255) / 256), 256, 0, g->stream>>>(
-          (int)bl.vrows, bl.d_rowptr, bl.d_rowidx, bl.d_isq, g->r.p + bl.pos0, g->u.p + (size_t)j * g->n + bl.pos0,
-          g->scal.p, hk.ve.p + bl.voff);
-      BGGE_CUDA(cudaGetLastError());
-    }
+  if (hk.n_vdesc > 0) {
+    virt_gather_kernel<<<(unsigned)hk.vgrid, 256, 0, g->stream>>>(hk.vdesc.p, hk.n_vdesc, g->r.p,
+                                                                 g->u.p + (size_t)j * g->n, g->scal.p, hk.ve.p);
+    BGGE_CUDA(cudaGetLastError());
+  }
   auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
   return run();
 }
@@ -435,99 +577,162 @@ int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
 // Returns OK with hk.fused == false when the shape does not fit (caller keeps the two-pass kernels).
 int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   hk.fused = false;
-  int64_t max_rows = 0;   // rows the kernel streams: genotype count for a factorised block
+  // groups of blocks that stream the same matrix: a dense / unshared block alone, or up to 4 factorised
+  // blocks sharing one W (identical diagonal blocks) swept as one multi-RHS panel
+  struct Group {
+    std::vector<int> members;
+    int64_t rows, nr;
+  };
+  std::vector<Group> groups;
   hk.vtotal = 0;
-  for (auto& bl : hk.blocks) {
-    max_rows = std::max(max_rows, bl.stream_rows());
+  int64_t max_rows = 0;
+  int nbmax = 1;
+  for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
+    HostBlock& bl = hk.blocks[bi];
     if (bl.vrows > 0) {
       bl.voff = hk.vtotal;
       hk.vtotal += round_up(bl.vrows, 16);
     }
+    max_rows = std::max(max_rows, bl.stream_rows());
+    bool placed = false;
+    if (bl.vrows > 0)
+      for (auto& gr : groups) {
+        const HostBlock& b0 = hk.blocks[(size_t)gr.members[0]];
+        if (b0.vrows > 0 && b0.dU == bl.dU && b0.vrows == bl.vrows && b0.nr == bl.nr && gr.members.size() < 4) {
+          gr.members.push_back((int)bi);
+          nbmax = std::max(nbmax, (int)gr.members.size());
+          placed = true;
+          break;
+        }
+      }
+    if (!placed) groups.push_back(Group{{(int)bi}, bl.stream_rows(), bl.nr});
   }
   if (max_rows <= 0) return OK;
-  // smallest cluster whose row slice fits the register budget (<= 12 row pairs per thread): long
-  // contiguous column slices (~40 KB) stream best and small clusters leave no SM idle
+  const int nb_t = nbmax > 2 ? 4 : nbmax;            // instantiated right-hand-side counts: 1, 2, 4
+  const int rpt_cap = 12 / nb_t;                     // register budget: NB * RPT <= 12 row pairs per thread
+  // smallest cluster whose row slice fits the register budget: long contiguous column slices (~40 KB)
+  // stream best and small clusters leave no SM idle
   int cs = 1;
-  while (cs < 8 && max_rows > (int64_t)cs * 12 * F_ROWS_PER_STEP) cs *= 2;
+  while (cs < 8 && max_rows > (int64_t)cs * rpt_cap * F_ROWS_PER_STEP) cs *= 2;
   if (const char* ev = getenv("BGGE_FUSED_CS")) {   // tuning hook
     const int v = atoi(ev);
-    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cs = std::max(cs, v);
+    if (v == 1 || v == 2 || v == 4 || v == 8) cs = std::max(cs, v);
   }
   const int64_t rs_max = round_up((max_rows + cs - 1) / cs, 16);
   const int rpt_need = (int)((rs_max + F_ROWS_PER_STEP - 1) / F_ROWS_PER_STEP);
   const Combo* combo = nullptr;
   for (const Combo& c : kCombos)
-    if (c.rpt >= rpt_need) { combo = &c; break; }
+    if (c.rpt >= rpt_need && c.rpt <= rpt_cap) { combo = &c; break; }
   if (!combo) return OK;   // slices too long for the register budget: two-pass path
   hk.fused_cs = cs;
   hk.fused_rpt = combo->rpt;
   hk.fused_g = combo->gcols;
+  hk.fused_nb = nb_t;
   const size_t slot_bytes = (size_t)combo->gcols * rs_max * sizeof(double);
   const size_t zb = (size_t)combo->gcols * (F_ROLE / combo->gcols);
-  const size_t fixed = ((size_t)NPX * F_MAXCS * combo->gcols + 2 * 8 * combo->gcols + 6 * zb) * sizeof(double) +
-                       (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
+  const size_t ng = (size_t)nb_t * combo->gcols;
   int dev = 0, optin = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
   BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t budget = (size_t)optin > fixed + 2048 ? (size_t)optin - fixed - 1024 : 0;
-  int ns = (int)std::min<size_t>(F_MAX_NS, budget / std::max<size_t>(slot_bytes, 16));
+  auto fixed_bytes = [&](int nsv) {   // exchange ring depth 2 ns + 4 (protocol note) -> grows with the data ring
+    return ((size_t)(2 * nsv + 4) * F_MAXCS * ng + 2 * 8 * ng + 2 * ng + 4 * zb + (size_t)nb_t * 2 * zb) * sizeof(double) +
+           (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
+  };
+  int ns = 0;
+  for (int c = F_MAX_NS; c >= 3; --c)
+    if ((size_t)c * slot_bytes + fixed_bytes(c) + 1024 <= (size_t)optin) { ns = c; break; }
   if (ns < 3) return OK;
+  const size_t fixed = fixed_bytes(ns);
   hk.fused_ns = ns;
   hk.fused_smem = ns * slot_bytes + fixed;
   int ncl = 0;
   BGGE_TRY(occupancy_dispatch(hk, cs, hk.fused_smem, &ncl));
   if (ncl < 1) return OK;
-  // work-balanced contiguous split of the (block, column) space over the clusters
+  // work-balanced contiguous split of the (group, column) space over the clusters
   double total = 0.0;
-  for (auto& bl : hk.blocks) total += (double)bl.stream_rows() * (double)bl.nr;
   int64_t total_cols = 0;
-  for (auto& bl : hk.blocks) total_cols += bl.nr;
+  for (auto& gr : groups) {
+    total += (double)gr.rows * (double)gr.nr;
+    total_cols += gr.nr;
+  }
   ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, combo->gcols)));
   std::vector<FPanel> panels;
   std::vector<int2> cpan((size_t)ncl, make_int2(0, 0));
   std::vector<std::pair<int, int>> block_q(hk.blocks.size(), {1 << 30, -1});
   {
     const double quota = total / (double)ncl;
-    size_t bi = 0;
-    int64_t col = 0;   // next unassigned column of block bi
+    size_t gi = 0;
+    int64_t col = 0;   // next unassigned column of group gi
     for (int q = 0; q < ncl; ++q) {
       const bool last = q == ncl - 1;
       double need = quota;
       cpan[(size_t)q].x = (int)panels.size();
-      while (bi < hk.blocks.size() && (last || need > 0.02 * quota)) {
-        HostBlock& bl = hk.blocks[bi];
-        const int64_t avail = bl.nr - col;
+      while (gi < groups.size() && (last || need > 0.02 * quota)) {
+        Group& gr = groups[gi];
+        const int64_t avail = gr.nr - col;
         int64_t take = avail;
         if (!last) {
-          const int64_t want = (int64_t)std::ceil(need / (double)bl.stream_rows());
+          const int64_t want = (int64_t)std::ceil(need / (double)gr.rows);
           take = std::min<int64_t>(avail, (want + combo->gcols - 1) / combo->gcols * combo->gcols);
         }
         if (take <= 0) break;
+        const HostBlock& b0 = hk.blocks[(size_t)gr.members[0]];
         FPanel p{};
-        p.U = bl.dU;
-        p.ldu = bl.ldu;
-        p.rows = (int)bl.stream_rows();
-        p.pos0 = (int)bl.pos0;
+        p.U = b0.dU;
+        p.ldu = b0.ldu;
+        p.rows = (int)gr.rows;
+        p.pos0 = (int)b0.pos0;
         p.c0 = (int)col;
         p.c1 = (int)(col + take);
-        p.col_off = (int)bl.col_off;
-        p.rs = (int)round_up((bl.stream_rows() + cs - 1) / cs, 16);
+        p.col_off = (int)b0.col_off;
+        p.rs = (int)round_up((gr.rows + cs - 1) / cs, 16);
         p.slot = q;
-        p.virt = bl.vrows > 0 ? 1 : 0;
-        p.voff = bl.voff;
+        p.virt = b0.vrows > 0 ? 1 : 0;
+        p.voff = b0.voff;
+        p.nb = (int)gr.members.size();
+        for (size_t m = 0; m < gr.members.size(); ++m) {
+          const HostBlock& bm = hk.blocks[(size_t)gr.members[m]];
+          p.voffs[m] = bm.voff;
+          p.col_offs[m] = (int)bm.col_off;
+          block_q[(size_t)gr.members[m]].first = std::min(block_q[(size_t)gr.members[m]].first, q);
+          block_q[(size_t)gr.members[m]].second = std::max(block_q[(size_t)gr.members[m]].second, q);
+        }
         panels.push_back(p);
-        block_q[bi].first = std::min(block_q[bi].first, q);
-        block_q[bi].second = std::max(block_q[bi].second, q);
-        need -= (double)bl.stream_rows() * (double)take;
+        need -= (double)gr.rows * (double)take;
         col += take;
-        if (col >= bl.nr) {
-          ++bi;
+        if (col >= gr.nr) {
+          ++gi;
           col = 0;
         }
       }
       cpan[(size_t)q].y = (int)panels.size() - cpan[(size_t)q].x;
     }
-    BGGE_REQUIRE(bi == hk.blocks.size(), "fused plan: internal error (columns left unassigned)");
+    BGGE_REQUIRE(gi == groups.size(), "fused plan: internal error (columns left unassigned)");
+  }
+  // gather descriptors of the factorised blocks
+  {
+    std::vector<VDesc> vd;
+    int cta = 0;
+    for (auto& bl : hk.blocks)
+      if (bl.vrows > 0) {
+        VDesc d{};
+        d.vrows = (int)bl.vrows;
+        d.pos0 = (int)bl.pos0;
+        d.cta0 = cta;
+        d.voff = bl.voff;
+        d.rowptr = bl.d_rowptr;
+        d.rowidx = bl.d_rowidx;
+        d.isq = bl.d_isq;
+        vd.push_back(d);
+        cta += (int)((bl.vrows + 255) / 256);
+      }
+    hk.n_vdesc = (int)vd.size();
+    hk.vgrid = cta;
+    if (!vd.empty()) {
+      BGGE_CUDA(hk.vdesc.alloc(vd.size()));
+      BGGE_CUDA(cudaMemcpyAsync(hk.vdesc.p, vd.data(), vd.size() * sizeof(VDesc), cudaMemcpyHostToDevice, st));
+      BGGE_CUDA(cudaStreamSynchronize(st));
+    }
   }
   // finalize tiles: every row of y, gaps included (qlo > qhi -> zero)
   std::vector<FTile> tiles;
@@ -568,6 +773,10 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   BGGE_CUDA(cudaMemcpyAsync(hk.ftiles.p, tiles.data(), tiles.size() * sizeof(FTile), cudaMemcpyHostToDevice, st));
   BGGE_CUDA(cudaStreamSynchronize(st));
   hk.fused = true;
+  if (getenv("BGGE_DEBUG"))
+    fprintf(stderr, "[bgge] fused plan: cs=%d clusters=%d rpt=%d g=%d nb=%d ns=%d smem=%zu groups=%zu panels=%zu vtotal=%lld\n",
+            hk.fused_cs, hk.fused_clusters, hk.fused_rpt, hk.fused_g, hk.fused_nb, hk.fused_ns, hk.fused_smem,
+            groups.size(), panels.size(), (long long)hk.vtotal);
   return OK;
 }
 
