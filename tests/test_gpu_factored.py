@@ -81,3 +81,74 @@ def test_fit_from_factored_kernels_matches_oracle_per_iteration(L, E, mode):
     for nm in ref["K"]:
         assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9
     assert relmax(got["yHat"], ref["yHat"]) <= 1e-9
+
+
+@pytest.mark.parametrize("E,drop_env", [(2, None), (6, None), (5, 2)])
+def test_shared_blocks_multi_rhs_sweep(E, drop_env):
+    """Identical diagonal blocks (balanced environments) share one decomposition and are swept as a
+    multi-right-hand-side panel: E = 2 -> one group of 2, E = 6 -> groups of 4 + 2, and a design where one
+    environment misses genotypes (its block differs, so it must NOT be shared).  Per-iteration parity against
+    the oracle run on the dense kernels with the same eigen blocks."""
+    import bgge_b200
+    L, p = 40, 64
+    X = markers(L, p, 9)
+    Y, names = design(L, E)
+    if drop_env is not None:
+        Y = [r for k, r in enumerate(Y) if not (r[0] == f"env{drop_env + 1:02d}" and k % 7 == 0)]
+    envs = [r[0] for r in Y]
+    ne = [envs.count(e) for e in sorted(set(envs))]
+    n = len(Y)
+    Kf = bgge_b200.getK(Y, X, kernel="GB", model="MDs", rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel="GB", model="MDs", rownames=names)
+    rng = np.random.default_rng(E)
+    y = rng.standard_normal(n)
+    y[rng.choice(n, 5, replace=False)] = np.nan
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    assert len(Ei[1]) == E
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    ite = 12
+    nz, nc = oracle.tape_sizes(n, nrs, ite, n_na=5)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    ref = oracle.BGGE(y, Kd, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
+    for mode in (1, 0):
+        got = bgge_b200.BGGE(y, Kf, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), mode=mode)
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
+        for nm in ref["K"]:
+            assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9, (mode, nm)
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (mode, nm)
+        assert relmax(got["yHat"], ref["yHat"]) <= 1e-9, mode
+
+
+def test_shared_kernel_handles_reproduce_owner(lib):
+    """bgge_gibbs_share_kernel: chains that borrow a decomposition (factorised + shared blocks included) give
+    the same chain as a handle that built it itself."""
+    import ctypes as C
+    import bgge_b200
+    L, E, p = 36, 4, 48
+    X = markers(L, p, 3)
+    Y, names = design(L, E)
+    Kf = bgge_b200.getK(Y, X, kernel="GK", model="MDs", rownames=names, factored=True)
+    n = L * E
+    y = np.random.default_rng(1).standard_normal(n)
+    want = bgge_b200.BGGE(y, Kf, ne=[L] * E, ite=30, burn=6, thin=2, seed=21, chain=2)
+    ne = np.array([L] * E, dtype=np.int64)
+    h0 = C.c_void_p()
+    lib.call("bgge_gibbs_create", n, 2, 0, None, C.byref(h0))
+    for j, k in enumerate(Kf.values()):
+        f = k["factor"]
+        lib.call("bgge_gibbs_add_expanded_kernel", h0, j, 0 if k["Type"] == "D" else 1, lib.ptr(lib.f64(f["K0"])), L, L, 0,
+                 lib.ptr(f["gid"]), lib.ptr(f["env"]), f["mode"], f["env_k"], lib.ptr(ne), E, 1e-10, 1)
+    for rep in range(2):
+        h = C.c_void_p()
+        lib.call("bgge_gibbs_create", n, 2, 0, None, C.byref(h))
+        lib.call("bgge_gibbs_set_y", h, lib.ptr(y), None)
+        for j in range(2):
+            lib.call("bgge_gibbs_share_kernel", h, j, h0, j)
+        lib.call("bgge_gibbs_init", h, 30, 6, 2, 0.5, lib.RNG_PHILOX, 21, 2)
+        lib.call("bgge_gibbs_run", h, 30)
+        cv = np.empty(15)
+        lib.call("bgge_gibbs_chain", h, None, lib.ptr(cv), None, None)
+        lib.load().bgge_gibbs_destroy(h)
+        assert np.array_equal(cv, want["chain"]["varE"]), rep
+    lib.load().bgge_gibbs_destroy(h0)
