@@ -14,6 +14,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _lib
+from .getk import factor_matches
 
 
 class BGGEFit(OrderedDict):
@@ -59,7 +60,7 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
     ne_arr = None if ne is None else np.ascontiguousarray(np.atleast_1d(ne), dtype=np.int64)
     out = []
     for k in K.values():
-        if "factor" in k:
+        if "factor" in k and factor_matches(k):
             n = k["factor"]["gid"].shape[0]
             h = C.c_void_p()
             _lib.call("bgge_gibbs_create", n, 1, 0, None, C.byref(h))
@@ -141,7 +142,8 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
             _lib.call("bgge_gibbs_set_mode", h, int(mode))
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
-            if eig is None and "factor" in k:
+            if eig is None and "factor" in k and factor_matches(k):
+                # getK() output: decompose through the L x L problem instead of the n x n matrix
                 _add_factored(h, j, k, ne_arr, tol, True)
                 continue
             if eig is not None and ("mean_diag" in k or "factor" in k):
@@ -248,7 +250,7 @@ def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, 
                     pos0 = 0 if blk["pos"] is None else int(blk["pos"][0])
                     _lib.call("bgge_gibbs_add_block", h0, j, pos0, U.shape[0], U.shape[1], _lib.ptr(s), _lib.ptr(U),
                               U.shape[0], 0)
-            elif "factor" in k:
+            elif "factor" in k and factor_matches(k):
                 md = _factor_mean_diag(k["factor"])
                 _add_factored(h0, j, k, ne_arr, tol, True)
             else:

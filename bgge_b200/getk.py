@@ -45,6 +45,27 @@ def _named_matrix(km):
     return None, None
 
 
+def factor_matches(entry, samples=256, seed=0):
+    """Cheap check that entry["Kernel"] still is the expansion its "factor" describes (a caller may have
+    edited the matrix after getK): a few hundred sampled entries and the full diagonal must agree exactly."""
+    f, K = entry.get("factor"), entry.get("Kernel")
+    if f is None or K is None:
+        return f is not None
+    gid, env, mode, k = f["gid"], f["env"], f["mode"], f["env_k"]
+    n = gid.shape[0]
+    if K.shape != (n, n):
+        return False
+    rng = np.random.default_rng(seed)
+    i = np.concatenate([rng.integers(0, n, samples), np.arange(n)])
+    j = np.concatenate([rng.integers(0, n, samples), np.arange(n)])
+    base = (gid[i] == gid[j]).astype(np.float64) if f["K0"] is None else f["K0"][gid[i], gid[j]]
+    if mode == _lib.EXPAND_GE:
+        base = base * (env[i] == env[j])
+    elif mode == _lib.EXPAND_ENV:
+        base = base * ((env[i] == k) & (env[j] == k))
+    return bool(np.array_equal(np.asarray(K)[i, j], base))
+
+
 def materialize(entry):
     """Dense n x n matrix of a factored kernel entry (see getK(..., factored=True))."""
     if "Kernel" in entry and entry["Kernel"] is not None:
@@ -67,7 +88,8 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
     kernel   : "GB" (X X'/p) or "GK" (Gaussian, exp(-bandwidth * D / quantile(D, quantil))).
     setKernel: dict/list of user kernels, each a (matrix, names) tuple or a DataFrame.
     model    : "SM", "MM", "MDs" or "MDe".
-    Returns an OrderedDict name -> {"Kernel": n x n float64 (Fortran order), "Type": "D"|"BD"}.
+    Returns an OrderedDict name -> {"Kernel": n x n float64 (Fortran order), "Type": "D"|"BD"} (every entry
+    also carries "factor", the L x L description it was expanded from).
 
     factored=True (extension): the n x n matrices are not built; each entry carries
     {"Type", "factor": {"K0": L x L base kernel, "gid", "env", "mode", "env_k", "L"}} instead, which BGGE()
@@ -98,7 +120,6 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
         raise ValueError("Model selected is not available ")
     model_code = _MODELS[model]
 
-    n_per_base = 1 if model_code == 0 else (2 if model_code == 1 else 1 + n_env)
     if setKernel is None:
         if hasattr(X, "index") and hasattr(X, "to_numpy") and rownames is None:
             rownames = list(X.index)
@@ -118,19 +139,20 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
             raise ValueError("kernel selected is not available. Please choose one method available or make "
                              "available other kernel through argument K")
         nbase = 1 if kind == _lib.GB else bw.shape[0]
-        n_out = nbase * n_per_base + (1 if intercept_random else 0)
+        # base kernels over the L genotypes (R/getK.R:136, 142-146) ...
+        K0s = np.empty((nbase, L, L), dtype=np.float64)
+        _lib.call("bgge_getk_base", _lib.ptr(Xs), L, p, kind, _lib.ptr(bw), nbase, float(quantil), _lib.ptr(K0s), None)
+        base_f = [np.asfortranarray(K0s[b].T) for b in range(nbase)]   # symmetric: layout only
+        fres = _factored_result(base_f, [str(i + 1) for i in range(nbase)], gid, env, env_levels, L, model_code,
+                                intercept_random)
         if factored:
-            K0s = np.empty((nbase, L, L), dtype=np.float64)
-            _lib.call("bgge_getk_base", _lib.ptr(Xs), L, p, kind, _lib.ptr(bw), nbase, float(quantil), _lib.ptr(K0s), None)
-            base_f = [np.asfortranarray(K0s[b].T) for b in range(nbase)]   # symmetric: layout only
-            return _factored_result(base_f, [str(i + 1) for i in range(nbase)], gid, env, env_levels, L, model_code,
-                                    intercept_random)
-        outs = [np.empty((n, n), dtype=np.float64, order="F") for _ in range(n_out)]
-        arr = (C.c_void_p * n_out)(*[o.ctypes.data for o in outs])
-        q = C.c_double(0.0)
-        _lib.call("bgge_getk", _lib.ptr(Xs), L, p, kind, _lib.ptr(bw), nbase, float(quantil), _lib.ptr(gid),
-                  _lib.ptr(env), n, n_env, model_code, int(bool(intercept_random)), arr, n_out, C.byref(q))
-        tmp_names = [str(i + 1) for i in range(nbase)]
+            return fres
+        # ... and their n x n expansions (R/getK.R:138, 148, 199-201, 207-218, 232).  Every dense entry also keeps
+        # its factored description, so BGGE() can decompose through the L x L problem (it verifies first that the
+        # matrix still matches the description).
+        for ent in fres.values():
+            ent["Kernel"] = materialize(ent)
+        return fres
     else:
         items = list(setKernel.items()) if hasattr(setKernel, "items") else [(None, k) for k in setKernel]
         base = []
@@ -146,43 +168,11 @@ def getK(Y, X=None, kernel=("GK", "GB"), setKernel=None, bandwidth=1, model=("SM
             base.append(_lib.f64(mat[np.ix_(idx, idx)]))
         tmp_names = [str(k) for k, _ in items] if hasattr(setKernel, "items") else [str(i + 1) for i in range(len(base))]
         nbase = len(base)
-        if factored:
-            return _factored_result(base, tmp_names, gid, env, env_levels, L, model_code, intercept_random)
-        outs = []
-
-        def emit(k0, mode, k=0):
-            o = np.empty((n, n), dtype=np.float64, order="F")
-            _lib.call("bgge_getk_expand", _lib.ptr(k0), L, _lib.ptr(gid), _lib.ptr(env), n, mode, k, _lib.ptr(o))
-            outs.append(o)
-
-        for k0 in base:
-            emit(k0, _lib.EXPAND_G)
-        if model_code == 1:
-            for k0 in base:
-                emit(k0, _lib.EXPAND_GE)
-        if model_code == 2:
-            for k0 in base:
-                for k in range(n_env):
-                    emit(k0, _lib.EXPAND_ENV, k)
-        if intercept_random:
-            emit(None, _lib.EXPAND_GI)
-
-    # names (R/getK.R:184-185, 202, 220-224, 233)
-    out = OrderedDict()
-    it = iter(outs)
-    multi = nbase > 1
-    for t in tmp_names:
-        out["G_" + t if multi else "G"] = {"Kernel": next(it), "Type": "D"}
-    if model_code == 1:
-        for t in tmp_names:
-            out["GE_" + t if multi else "GE"] = {"Kernel": next(it), "Type": "BD"}
-    if model_code == 2:
-        for t in tmp_names:
-            for lev in env_levels:
-                out[f"{lev}_{t}" if multi else str(lev)] = {"Kernel": next(it), "Type": "BD"}
-    if intercept_random:
-        out["Gi"] = {"Kernel": next(it), "Type": "D"}
-    return out
+        fres = _factored_result(base, tmp_names, gid, env, env_levels, L, model_code, intercept_random)
+        if not factored:
+            for ent in fres.values():
+                ent["Kernel"] = materialize(ent)
+        return fres
 
 
 def _factored_result(base, tmp_names, gid, env, env_levels, L, model_code, intercept_random):

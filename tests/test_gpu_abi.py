@@ -111,3 +111,47 @@ def test_release_cache_and_memory_query(lib):
     free1 = C.c_uint64()
     lib.call("bgge_device_memory", C.byref(free1), None)
     assert free1.value > 0
+
+
+def test_bgge_getk_single_call_matches_oracle(lib):
+    """bgge_getk: the one-call entry point the .Call shim uses (one upload of X, all kernels of the model)."""
+    L, p, E = 37, 29, 3
+    X = markers(L, p, 4)
+    Y, names = design(L, E)
+    ref = oracle.getK(Y, X, kernel="GK", model="MDe", rownames=names, bandwidth=[1.0, 0.3], intercept_random=True)
+    n = L * E
+    gid = np.tile(np.arange(L, dtype=np.int32), E)
+    env = np.repeat(np.arange(E, dtype=np.int32), L)
+    bw = np.array([1.0, 0.3])
+    n_out = 2 * (1 + E) + 1
+    outs = [np.empty((n, n), order="F") for _ in range(n_out)]
+    arr = (C.c_void_p * n_out)(*[o.ctypes.data for o in outs])
+    q = C.c_double()
+    lib.call("bgge_getk", lib.ptr(lib.f64(X)), L, p, lib.GK, lib.ptr(bw), 2, 0.5, lib.ptr(gid), lib.ptr(env), n, E, 2, 1, arr,
+             n_out, C.byref(q))
+    assert len(ref) == n_out
+    for o, (nm, k) in zip(outs, ref.items()):
+        assert relmax(o, k["Kernel"]) <= 1e-12, nm
+
+
+def test_default_getk_output_takes_the_factorised_route():
+    """getK() (dense, R-compatible output) + BGGE(): the fit goes through the L x L decomposition; editing a
+    kernel matrix afterwards makes BGGE fall back to the dense n x n route for that kernel."""
+    import bgge_b200
+    from bgge_b200.getk import factor_matches
+    L, E = 26, 3
+    X = markers(L, 40, 5)
+    Y, names = design(L, E)
+    K = bgge_b200.getK(Y, X, kernel="GB", model="MDs", rownames=names)
+    assert all(factor_matches(k) for k in K.values())
+    y = phenotype(oracle.gb_kernel(X), L, E, 6)
+    a = bgge_b200.BGGE(y, K, ne=[L] * E, ite=40, burn=10, thin=2, seed=3)
+    Kd = {nm: {"Kernel": k["Kernel"], "Type": k["Type"]} for nm, k in K.items()}      # no factor: dense route
+    b = bgge_b200.BGGE(y, Kd, ne=[L] * E, ite=40, burn=10, thin=2, seed=3)
+    # different eigen routes give the same eigenpairs up to rounding -> same chain up to rounding amplification
+    assert relmax(a["chain"]["varE"], b["chain"]["varE"]) <= 1e-6
+    K["GE"]["Kernel"] = K["GE"]["Kernel"].copy()
+    K["GE"]["Kernel"][0, 0] += 1.0
+    assert not factor_matches(K["GE"])
+    c = bgge_b200.BGGE(y, K, ne=[L] * E, ite=10, burn=2, thin=2, seed=3)
+    assert np.isfinite(c["yHat"]).all()
