@@ -970,7 +970,7 @@ int bgge_gibbs_run(bgge_gibbs* h, int64_t iters) {
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode) {
   BGGE_HANDLE(h);
   BGGE_REQUIRE(!h->g.initialised, "gibbs_set_mode: handle already initialised");
-  BGGE_REQUIRE(mode == 0 || mode == 1, "gibbs_set_mode: mode must be 0 (two-pass) or 1 (fused)");
+  BGGE_REQUIRE(mode >= 0 && mode <= 2, "gibbs_set_mode: mode must be 0 (two-pass), 1 (resident / fused) or 2 (fused)");
   h->g.mode = mode;
   return OK;
 }
@@ -1014,6 +1014,17 @@ int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, 
     for (auto& b : hk.blocks) nv += b.vrows > 0 ? 1 : 0;
     *launches = 2 + (hk.fused ? nv : 0);
   }
+  return OK;
+}
+
+// after init: does the model run in the resident (on-chip basis, one launch per run) kernel?
+int bgge_gibbs_resident_info(bgge_gibbs* h, int* enabled, int* ctas, int64_t* smem_bytes) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised, "gibbs_resident_info: handle not initialised");
+  if (enabled) *enabled = g.resident.enabled ? 1 : 0;
+  if (ctas) *ctas = g.resident.enabled ? g.resident.ncta : 0;
+  if (smem_bytes) *smem_bytes = g.resident.enabled ? (int64_t)g.resident.smem : 0;
   return OK;
 }
 

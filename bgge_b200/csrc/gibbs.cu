@@ -680,7 +680,7 @@ int gibbs_init(Gibbs* g) {
     BGGE_REQUIRE((int64_t)hk.s_host.size() == hk.nr_total, "gibbs: kernel %d eigenvalue count mismatch", j);
     BGGE_TRY(upload(hk.s, hk.s_host, st));
     BGGE_CUDA(hk.b.alloc((size_t)hk.nr_total));
-    if (g->mode == 1) BGGE_TRY(plan_fused(g, hk, st));
+    if (g->mode >= 1) BGGE_TRY(plan_fused(g, hk, st));
     hk.n_atasks = hk.n_btasks = 0;
     if (!hk.fused) {
       // two-pass kernels work on dense U: materialise factorised blocks
@@ -813,6 +813,7 @@ int gibbs_init(Gibbs* g) {
   BGGE_CUDA(cudaGetLastError());
   BGGE_TRY(launch_scalar(g));   // it = 0: draws the intercept of iteration 1
   BGGE_CUDA(cudaStreamSynchronize(st));
+  BGGE_TRY(plan_resident(g));
   g->done = 0;
   g->initialised = true;
   return OK;
@@ -825,6 +826,11 @@ int gibbs_run(Gibbs* g, int64_t iters) {
   }
   BGGE_REQUIRE(iters >= 0 && g->done + iters <= g->ite, "gibbs: asked for %lld iterations, %lld of %lld already done",
                (long long)iters, (long long)g->done, (long long)g->ite);
+  if (g->resident.enabled) {   // the whole run is one cooperative launch
+    if (iters > 0) BGGE_TRY(launch_resident(g, iters));
+    g->done += iters;
+    return OK;
+  }
   if (g->use_graph && !g->graph_exec) {
     BGGE_CUDA(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     int s = launch_iteration(g);

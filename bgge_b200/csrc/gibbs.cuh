@@ -131,6 +131,51 @@ struct HostKernel {
   int n_vdesc = 0, vgrid = 0;
 };
 
+// Resident path (resident.cu): small models whose whole basis fits the shared memory of the chip.
+struct RGroup {                  // one basis matrix W (t x nr) and the <= 4 blocks of one kernel that share it
+  const double* W;
+  long long ldw;
+  const double* s;               // eigenvalues of the columns (identical for every member)
+  int t, t_pad, nr, nb, mem0;    // members [mem0, mem0 + nb)
+  int maxcols;                   // columns per CTA (upper bound)
+  long long woff;                // offset (doubles) of this group's slice in a CTA's shared memory
+  long long z_off;               // offset of the kernel's coefficient normals inside an iteration (tape mode)
+};
+struct RMember {                 // one eigen block
+  int pos0, rows, col_off;
+  long long part_off;            // offset of its virtual rows inside a part row / the kernel's etil0 and wsum
+};
+struct REntry {                  // one row of y in the row phase of step j, ordered by the units of the next kernel
+  int row;
+  int poff;                      // kernel j: part offset of the row's virtual row, -1 if no block covers the row
+  double isq;                    // kernel j: row weight (1/sqrt(count); 1 for a dense block)
+  double w;                      // next kernel: row weight
+};
+struct RUnit {                   // one virtual row of the next kernel: entries [e0, e1), eoff < 0: rows it does not cover
+  int e0, e1, eoff, pad;
+};
+struct RStep {
+  const REntry* entries;
+  const RUnit* units;
+  int nunits, g0, g1, next;      // groups [g0, g1) of this kernel; next = index of the following kernel step
+  long long nr_total;
+  const double* wsum;            // this kernel: sum of the row weights per virtual row
+  double* etil0;                 // this kernel: C^-1/2 Z'(r + u_j) per virtual row, written by the previous row phase
+};
+struct ResidentPlan {
+  bool enabled = false;
+  int ncta = 0, etp = 0, max_entries = 0;
+  size_t smem = 0;
+  long long pstride = 0, smem_w = 0;
+  DevBuf<RGroup> groups;
+  DevBuf<RMember> members;
+  DevBuf<RStep> steps;
+  std::vector<DevBuf<REntry>> entries;
+  std::vector<DevBuf<RUnit>> units;
+  std::vector<DevBuf<double>> wsum, etil0;
+  DevBuf<double> part, zqpart, sspart;
+};
+
 struct Gibbs {
   int64_t n = 0;
   int nk = 0, q = 0, n_chains = 1;
@@ -145,7 +190,9 @@ struct Gibbs {
   int64_t n_na = 0;
   // device state
   DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart, vupart;
-  int mode = 1;                  // 0: two-pass kernels only, 1: fused single-pass where the shape fits
+  int mode = 1;                  // 0: two-pass kernels only, 1: resident kernel if the model fits on chip, else
+                                 // fused single-pass where the shape fits, 2: as 1 without the resident kernel
+  ResidentPlan resident;
   DevBuf<int> na_idx;
   DevBuf<Scal> scal;
   DevBuf<double> chain_mu, chain_varE, chain_varU, chain_bet;
@@ -170,6 +217,8 @@ int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
 int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st);
 int launch_fused(Gibbs* g, HostKernel& hk, int j);
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j);
+int plan_resident(Gibbs* g);
+int launch_resident(Gibbs* g, int64_t iters);
 int ensure_dense(HostBlock& bl, cudaStream_t st);   // materialise U = Z C^{-1/2} W of a factorised block
 
 }  // namespace bgge

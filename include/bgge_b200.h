@@ -174,9 +174,13 @@ int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* 
 /* device pointer / leading dimension of a block's U (owned by handle h; other handles may borrow it with
  * bgge_gibbs_add_block(..., on_device = 1) while h is alive: one decomposition, many chains) */
 int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int64_t* ldu);
-/* sweep implementation: 1 (default) = fused single-pass kernel step where the block shapes fit (U read
- * once per kernel per iteration), 0 = two-pass proj/back kernels only.  Call before bgge_gibbs_init. */
+/* sweep implementation: 1 (default) = resident kernel when the whole eigen basis fits the chip's shared memory
+ * (small models: one cooperative launch runs all iterations), else the fused single-pass kernel step where
+ * the block shapes fit (U read once per kernel per iteration); 2 = as 1 but never resident; 0 = two-pass
+ * proj/back kernels only.  Call before bgge_gibbs_init. */
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode);
+/* after init: whether bgge_gibbs_run uses the resident kernel, its grid size and shared memory per CTA */
+int bgge_gibbs_resident_info(bgge_gibbs* h, int* enabled, int* ctas, int64_t* smem_bytes);
 /* after init: which path kernel j uses, its cluster size / cluster (or tile) count, launches per step */
 int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches);
 /* after init: bytes of eigen basis one step of kernel j streams (W, not U, for blocks kept factorised; twice

@@ -53,7 +53,7 @@ def test_rank_one_and_dropped_blocks():
     z = rng.standard_normal(nz)
     c = rng.chisquare(np.tile(np.array([n + 3, 2 + 3, n + 3], dtype=float), ite))
     ref = oracle.BGGE(y, K, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         got = bgge_b200.BGGE(y, K, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), eig=Ei, mode=mode)
         assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9
         assert relmax(got["K"]["B"]["u"], ref["K"]["B"]["u"]) <= 1e-9

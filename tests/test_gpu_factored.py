@@ -53,7 +53,7 @@ def test_factored_blocks_reconstruct_dense_kernels(kernel, model):
                 assert np.max(np.abs(rec - blk)) <= 1e-9 * max(1.0, np.max(np.abs(blk))), (label, nm)
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0])
 @pytest.mark.parametrize("L,E", [(28, 3), (700, 4)])
 def test_fit_from_factored_kernels_matches_oracle_per_iteration(L, E, mode):
     """mode 1: the G kernel stays factorised in the sweep (streams W, L rows, instead of U, L*E rows);
@@ -111,7 +111,7 @@ def test_shared_blocks_multi_rhs_sweep(E, drop_env):
     z = rng.standard_normal(nz)
     c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
     ref = oracle.BGGE(y, Kd, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         got = bgge_b200.BGGE(y, Kf, ne=ne, ite=ite, burn=0, thin=1, draws=(z, c), mode=mode)
         assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
         for nm in ref["K"]:

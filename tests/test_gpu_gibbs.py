@@ -50,7 +50,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0])
 @pytest.mark.parametrize("L,E,p,model,kernel,n_na,q", CASES)
 def test_per_iteration_parity(L, E, p, model, kernel, n_na, q, mode):
     import bgge_b200
@@ -215,7 +215,7 @@ BIG = [
 ]
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0])
 @pytest.mark.parametrize("n,spec", BIG)
 def test_parity_on_large_blocks(n, spec, mode):
     import bgge_b200
@@ -243,6 +243,58 @@ def test_fused_and_two_pass_agree_with_device_rng():
     import bgge_b200
     K, y, XF, ne = _problem(40, 3, 60, "MDs", seed=8, n_na=7)
     a = bgge_b200.BGGE(y, K, ne=ne, ite=200, burn=50, thin=2, seed=5, mode=1)
-    b = bgge_b200.BGGE(y, K, ne=ne, ite=200, burn=50, thin=2, seed=5, mode=0)
-    assert relmax(a["chain"]["varE"], b["chain"]["varE"]) <= 1e-8
-    assert relmax(a["yHat"], b["yHat"]) <= 1e-8
+    for mode in (2, 0):
+        b = bgge_b200.BGGE(y, K, ne=ne, ite=200, burn=50, thin=2, seed=5, mode=mode)
+        assert relmax(a["chain"]["varE"], b["chain"]["varE"]) <= 1e-8, mode
+        assert relmax(a["yHat"], b["yHat"]) <= 1e-8, mode
+
+
+def test_small_models_run_resident_and_chunked_runs_continue(lib):
+    """A model whose basis fits on chip runs in the resident kernel (mode 1); splitting the run into several
+    bgge_gibbs_run calls (state handed back through device memory each time) gives the same chain as one call,
+    and mode 2 on the same handle layout is not resident."""
+    K, y, XF, ne = _problem(30, 3, 40, "MDs", seed=4, n_na=3)
+    n, nk, ite = y.shape[0], len(K), 24
+    import bgge_b200
+    Ei = bgge_b200.setDEC(K, ne, 1e-10)
+
+    def make(mode):
+        h = C.c_void_p()
+        lib.call("bgge_gibbs_create", n, nk, 0, None, C.byref(h))
+        lib.call("bgge_gibbs_set_y", h, lib.ptr(y), None)
+        for j, k in enumerate(K.values()):
+            lib.call("bgge_gibbs_set_kernel", h, j, 0 if k["Type"] == "D" else 1, float(np.mean(np.diag(k["Kernel"]))))
+            for blk in Ei[j]:
+                U = lib.f64(blk["U"])
+                lib.call("bgge_gibbs_add_block", h, j, 0 if blk["pos"] is None else blk["pos"][0], U.shape[0], U.shape[1],
+                         lib.ptr(blk["s"]), lib.ptr(U), U.shape[0], 0)
+        lib.call("bgge_gibbs_set_mode", h, mode)
+        lib.call("bgge_gibbs_init", h, ite, 4, 2, 0.5, lib.RNG_PHILOX, 11, 0)
+        en, ctas, smem = C.c_int(), C.c_int(), C.c_int64()
+        lib.call("bgge_gibbs_resident_info", h, C.byref(en), C.byref(ctas), C.byref(smem))
+        return h, en.value, ctas.value, smem.value
+
+    def chains(h):
+        ncum = ite // 2
+        mu, ve, vu = np.empty(ncum), np.empty(ncum), np.empty((nk, ncum))
+        lib.call("bgge_gibbs_sync", h)
+        lib.call("bgge_gibbs_chain", h, lib.ptr(mu), lib.ptr(ve), lib.ptr(vu), None)
+        return mu, ve, vu
+
+    h1, en1, ctas1, smem1 = make(1)
+    assert en1 == 1 and ctas1 >= 1 and 0 < smem1 <= 200 * 1024
+    lib.call("bgge_gibbs_run", h1, ite)
+    one = chains(h1)
+    h2, en2, _, _ = make(1)
+    for k in (1, 7, 3, 13):
+        lib.call("bgge_gibbs_run", h2, k)
+    parts = chains(h2)
+    for a, b in zip(one, parts):
+        assert np.array_equal(a, b)
+    h3, en3, ctas3, _ = make(2)
+    assert en3 == 0 and ctas3 == 0
+    lib.call("bgge_gibbs_run", h3, ite)
+    for a, b in zip(one, chains(h3)):
+        assert relmax(a, b) <= 1e-9
+    for h in (h1, h2, h3):
+        lib.load().bgge_gibbs_destroy(h)
