@@ -140,6 +140,9 @@ struct RGroup {                  // one basis matrix W (t x nr) and the <= 4 blo
   int maxcols;                   // columns per CTA (upper bound)
   long long woff;                // offset (doubles) of this group's slice in a CTA's shared memory
   long long z_off;               // offset of the kernel's coefficient normals inside an iteration (tape mode)
+  int kidx;                      // kernel (random effect) the group belongs to
+  int doff, coff;                // offsets of its draws / column constants in a CTA's shared memory
+  int pad;
 };
 struct RMember {                 // one eigen block
   int pos0, rows, col_off;
@@ -148,6 +151,7 @@ struct RMember {                 // one eigen block
 struct REntry {                  // one row of y in the row phase of step j, ordered by the units of the next kernel
   int row;
   int poff;                      // kernel j: part offset of the row's virtual row, -1 if no block covers the row
+  int vpos, pad;                 // slot of its value in the CTA's staging array (entries are stored sorted by poff)
   double isq;                    // kernel j: row weight (1/sqrt(count); 1 for a dense block)
   double w;                      // next kernel: row weight
 };
@@ -159,12 +163,14 @@ struct RStep {
   const RUnit* units;
   int nunits, g0, g1, next;      // groups [g0, g1) of this kernel; next = index of the following kernel step
   long long nr_total;
+  int woff, nws;                 // this kernel's wsum in a CTA's shared memory: offset and length
   const double* wsum;            // this kernel: sum of the row weights per virtual row
   double* etil0;                 // this kernel: C^-1/2 Z'(r + u_j) per virtual row, written by the previous row phase
 };
 struct ResidentPlan {
   bool enabled = false;
-  int ncta = 0, etp = 0, max_entries = 0;
+  int ncta = 0, etp = 0, max_entries = 0, max_units = 0, ndraw = 0, ncolc = 0, ngroups = 0, nwsum = 0;
+  DevBuf<unsigned long long> bar;
   size_t smem = 0;
   long long pstride = 0, smem_w = 0;
   DevBuf<RGroup> groups;

@@ -31,15 +31,17 @@ namespace {
 
 constexpr int R_THREADS = 512;
 constexpr int R_WARPS = R_THREADS / 32;
-constexpr int R_SUB = 8;                      // lanes that share one row in P5
+constexpr int R_SUB = 8;                      // lanes that share one row in the row phase
+constexpr int R_NPL = 19;                     // partials per lane: supports up to R_SUB * R_NPL = 152 CTAs
 constexpr int R_MAXCOLS = 64;                 // columns of one matrix per CTA (bsm capacity)
-constexpr int R_MAXV = MAXK + 2;
+constexpr int R_MAXG = 32;                    // basis matrices (groups) per model
+constexpr int R_MAXKR = 16;                   // kernels per model
 
 struct RParams {
   const RGroup* groups;
   const RMember* members;
   const RStep* steps;
-  int nk, ncta;
+  int nk, ncta, ngroups;
   long long n;
   double* r;
   double* u;
@@ -60,52 +62,160 @@ struct RParams {
   long long iters;
   int etp;                    // padded length of one e~ vector in shared memory
   long long smem_w;           // doubles of basis slices per CTA
-  int max_entries;
+  int max_entries, max_units, ndraw, ncolc, nwsum;
+  unsigned long long* bar;    // grid barrier counter (zeroed before the launch)
+  unsigned long long* timing; // debug (BGGE_RESIDENT_TIMING): ns per phase, accumulated by CTA 0
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define R_TICK(slot)                                         \
+  if (TIMED && timed) {                                      \
+    const unsigned long long now_ = gtime();                 \
+    tacc[slot] += now_ - tlast;                              \
+    tlast = now_;                                            \
+  }
 
 struct RShared {
-  double red[R_MAXV][R_WARPS];
+  RGroup groups[R_MAXG];
+  RMember members[4 * R_MAXG];
+  RStep steps[R_MAXKR];
+  int nent[R_MAXKR], nun[R_MAXKR];
+  int c0[R_MAXG], ncol[R_MAXG];        // my columns of every basis matrix
+  double red[2][R_WARPS];
+  double tot[R_MAXKR + 2];
   double bsm[4 * R_MAXCOLS];
-  double chi[MAXK + 1];
-  double sigb[MAXK];
-  double Sc[MAXK];
-  double zmu;
+  double dpart[4 * R_MAXCOLS];
+  double chi[2][R_MAXKR + 1];
+  double zmu[2];
+  double sigb[R_MAXKR];
+  double Sc[R_MAXKR];
 };
 
-// P5 of step j (update = true), or only the gather of the next step's etil0 (update = false: prologue of a
-// launch and after the imputation of missing phenotypes).
-__device__ __forceinline__ void rows_phase(const RParams& p, const RStep& S, int j, bool update, bool last, double shift,
-                                           bool keep, double kcount, double* vals, RShared& sh) {
+// Split grid barrier (all CTAs are co-resident: cooperative launch).  Work placed between arrive and wait
+// overlaps the barrier latency; it must be CTA-local.
+struct GridBar {
+  unsigned long long* ctr;
+  unsigned long long target;
+  unsigned ncta;
+};
+__device__ __forceinline__ void bar_arrive(GridBar& b) {
+  __syncthreads();
+  b.target += b.ncta;
+  if (threadIdx.x == 0)   // release: orders the CTA's writes (made visible to this thread by the bar.sync) before the count
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(b.ctr), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ void bar_wait(const GridBar& b) {
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(b.ctr) : "memory");
+    } while (v < b.target);
+  }
+  __syncthreads();
+}
+
+struct RSmem {                 // dynamic shared memory carve-up
+  double* wsm;                 // basis slices
+  double* etil;                // [4][etp]
+  double* vals;                // [max_entries]
+  double* zbuf;                // [2][ndraw] coefficient normals of my columns, by iteration parity
+  double* svs;                 // [ncolc] eigenvalues of my columns
+  double* isv;                 // 1 / eigenvalue
+  double* tv;                  // tau * v        (R/BGGE.R:302-303)
+  double* sd;                  // sqrt(v)
+  double* wsum;                // [nwsum] row-weight sums per virtual row, all kernels (offset RStep::woff)
+  REntry* sent;                // [nk][max_entries] my rows of every row phase
+  RUnit* sunit;                // [nk][max_units]
+};
+
+// Draws of iteration itn that do not depend on the data: the normals of my coefficient columns, the chi-squares
+// and the normal of the intercept that follows itn.  Stored under parity itn & 1.
+__device__ __forceinline__ void draws_for(const RParams& p, const DrawCfg& dc, RShared& sh, const RSmem& m, long long itn,
+                                          bool normals, bool scalars) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int par = (int)(itn & 1);
+  if (normals)
+  for (int idx = tid; idx < p.ndraw; idx += R_THREADS) {
+    int g = 0;
+    while (g + 1 < p.ngroups && idx >= sh.groups[g + 1].doff) ++g;
+    const RGroup& gr = sh.groups[g];
+    const int f = idx - gr.doff, mm = f / gr.maxcols, cc = f % gr.maxcols;
+    if (cc < sh.ncol[g]) {
+      const long long col = (long long)sh.members[gr.mem0 + mm].col_off + sh.c0[g] + cc;
+      m.zbuf[(size_t)par * p.ndraw + idx] = draw_normal(dc, itn, (uint32_t)gr.kidx, (unsigned long long)col,
+                                                        dc.z_init + (itn - 1) * dc.z_per_it + gr.z_off + col);
+    }
+  }
+  if (scalars && lane == 0) {
+    for (int d = R_WARPS - 1 - warp; d <= p.nk + 1; d += R_WARPS) {
+      if (d < p.nk)
+        sh.chi[par][d] = draw_chisq(dc, itn, STREAM_CHI_K + (uint32_t)d, (double)sh.steps[d].nr_total + NU, (itn - 1) * dc.c_per_it + d);
+      else if (d == p.nk)
+        sh.chi[par][p.nk] = draw_chisq(dc, itn, STREAM_CHI_E, (double)p.n + NU, (itn - 1) * dc.c_per_it + p.nk);
+      else
+        sh.zmu[par] = draw_normal(dc, itn + 1, STREAM_MU, 0ull, dc.z_init + itn * dc.z_per_it);
+    }
+  }
+}
+
+// per-column constants of the coefficient draw for the current sigb / tau (R/BGGE.R:302-303)
+__device__ __forceinline__ void column_constants(const RParams& p, RShared& sh, const RSmem& m, double tau) {
+  for (int idx = threadIdx.x; idx < p.ncolc; idx += R_THREADS) {
+    int g = 0;
+    while (g + 1 < p.ngroups && idx >= sh.groups[g + 1].coff) ++g;
+    const double sv = m.svs[idx];
+    const double lam = sh.sigb[sh.groups[g].kidx];
+    const double vari = sv * lam / (1.0 + sv * lam * tau);
+    m.tv[idx] = tau * vari;
+    m.sd[idx] = sqrt(vari);
+  }
+}
+
+// Row phase of step j (update = true), or only the gather of the next step's etil0 (update = false: prologue
+// of a launch and after the imputation of missing phenotypes).
+__device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const RSmem& m, int j, bool update, bool last,
+                                           double shift, bool keep, double kcount) {
   const int cta = blockIdx.x, tid = threadIdx.x;
   const int sub = tid / R_SUB, sl = tid % R_SUB;
-  const int u0 = (int)((long long)S.nunits * cta / p.ncta), u1 = (int)((long long)S.nunits * (cta + 1) / p.ncta);
-  const int eb = u0 < u1 ? S.units[u0].e0 : 0, ee = u0 < u1 ? S.units[u1 - 1].e1 : 0;
-  const int jn = S.next;
+  const int ne = sh.nent[j], nu = sh.nun[j];
+  const REntry* ent = m.sent + (size_t)j * p.max_entries;
+  const RUnit* units = m.sunit + (size_t)j * p.max_units;
+  const int jn = sh.steps[j].next;
   double* uj = p.u + (size_t)j * p.n;
   const double* ujn_p = p.u + (size_t)jn * p.n;
   double sse = 0.0, sr = 0.0;
-  for (int k0 = eb; k0 < ee; k0 += R_THREADS / R_SUB) {
+  for (int k0 = 0; k0 < ne; k0 += R_THREADS / R_SUB) {
     const int k = k0 + sub;
-    const bool valid = k < ee;
+    const bool valid = k < ne;
     REntry E{};
-    if (valid) E = S.entries[k];
+    if (valid) E = ent[k];
     double rold = 0.0, uold = 0.0, ujn = 0.0, mm = 0.0, m2 = 0.0;
     if (valid && sl == 0) {
-      rold = p.r[E.row];
-      if (update) uold = uj[E.row];
-      if (!update || jn != j) ujn = ujn_p[E.row];
+      rold = __ldcg(p.r + E.row);
+      if (update) uold = __ldcg(uj + E.row);
+      if (!update || jn != j) ujn = __ldcg(ujn_p + E.row);
       if (update && keep) {
-        mm = p.umean[(size_t)j * p.n + E.row];
-        m2 = p.um2[(size_t)j * p.n + E.row];
+        mm = __ldcg(p.umean + (size_t)j * p.n + E.row);
+        m2 = __ldcg(p.um2 + (size_t)j * p.n + E.row);
       }
     }
     double v;
     if (update) {
-      double un = 0.0;
-      if (valid && E.poff >= 0) {
-        const double* pp = p.part + E.poff;
-        for (int c = sl; c < p.ncta; c += R_SUB) un += pp[(size_t)c * p.pstride];
+      double x[R_NPL];
+      const bool live = valid && E.poff >= 0;
+      const double* pp = p.part + (live ? E.poff : 0);
+#pragma unroll
+      for (int q = 0; q < R_NPL; ++q) {
+        const int c = sl + R_SUB * q;
+        x[q] = (live && c < p.ncta) ? __ldcg(pp + (size_t)c * p.pstride) : 0.0;
       }
+      double un = ((((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]))) +
+                   (((x[8] + x[9]) + (x[10] + x[11])) + ((x[12] + x[13]) + (x[14] + x[15])))) +
+                  ((x[16] + x[17]) + x[18]);
       un += __shfl_xor_sync(0xffffffffu, un, 4);
       un += __shfl_xor_sync(0xffffffffu, un, 2);
       un += __shfl_xor_sync(0xffffffffu, un, 1);
@@ -130,15 +240,15 @@ __device__ __forceinline__ void rows_phase(const RParams& p, const RStep& S, int
     } else {
       v = E.w * (rold + ujn);
     }
-    if (valid && sl == 0) vals[k - eb] = v;
+    if (valid && sl == 0) m.vals[E.vpos] = v;
   }
   __syncthreads();
-  double* etil0 = p.steps[jn].etil0;
-  for (int un = u0 + tid; un < u1; un += R_THREADS) {
-    const RUnit U = S.units[un];
+  double* etil0 = sh.steps[jn].etil0;
+  for (int un = tid; un < nu; un += R_THREADS) {
+    const RUnit U = units[un];
     if (U.eoff < 0) continue;
     double acc = 0.0;
-    for (int k = U.e0; k < U.e1; ++k) acc += vals[k - eb];
+    for (int k = U.e0; k < U.e1; ++k) acc += m.vals[k];
     etil0[U.eoff] = acc;
   }
   if (last) {   // per-CTA pieces of sum e^2 and sum r (fixed order)
@@ -158,24 +268,74 @@ __device__ __forceinline__ void rows_phase(const RParams& p, const RStep& S, int
   }
 }
 
+template <bool TIMED>
 __global__ void __launch_bounds__(R_THREADS, 1)
 resident_sweep_kernel(const RParams p, DrawCfg dc) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char rsm[];
   __shared__ RShared sh;
-  double* wsm = reinterpret_cast<double*>(rsm);                 // per group: slice [maxcols][t_pad]
-  double* etil = wsm + p.smem_w;                                // [4][etp]
-  double* vals = etil + 4 * p.etp;                              // [max_entries]
   const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ngroups = p.steps[p.nk - 1].g1;
+  RSmem m;
+  m.wsm = reinterpret_cast<double*>(rsm);
+  m.etil = m.wsm + p.smem_w;
+  m.vals = m.etil + 4 * p.etp;
+  m.zbuf = m.vals + p.max_entries;
+  m.svs = m.zbuf + 2 * p.ndraw;
+  m.isv = m.svs + p.ncolc;
+  m.tv = m.isv + p.ncolc;
+  m.sd = m.tv + p.ncolc;
+  m.wsum = m.sd + p.ncolc;
+  m.sent = reinterpret_cast<REntry*>(m.wsum + p.nwsum);
+  m.sunit = reinterpret_cast<RUnit*>(m.sent + (size_t)p.nk * p.max_entries);
+  GridBar gb{p.bar, 0ull, (unsigned)p.ncta};
 
-  // ---- load my column slices of every basis matrix once
-  for (int g = 0; g < ngroups; ++g) {
-    const RGroup& gr = p.groups[g];
-    const int c0 = (int)((long long)gr.nr * cta / p.ncta), c1 = (int)((long long)gr.nr * (cta + 1) / p.ncta);
-    double* dst = wsm + gr.woff;
+  // ---- descriptors into shared memory (every later phase starts from them: no dependent global loads)
+  {
+    auto copy8 = [&](void* dst, const void* src, size_t bytes) {
+      unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+      const unsigned long long* s_ = reinterpret_cast<const unsigned long long*>(src);
+      for (size_t i = tid; i < bytes / 8; i += R_THREADS) d[i] = s_[i];
+    };
+    copy8(sh.groups, p.groups, (size_t)p.ngroups * sizeof(RGroup));
+    copy8(sh.members, p.members, (size_t)p.ngroups * 4 * sizeof(RMember));
+    copy8(sh.steps, p.steps, (size_t)p.nk * sizeof(RStep));
+  }
+  __syncthreads();
+  if (tid < p.ngroups) {
+    const int nr = sh.groups[tid].nr;
+    const int c0 = (int)((long long)nr * cta / p.ncta), c1 = (int)((long long)nr * (cta + 1) / p.ncta);
+    sh.c0[tid] = c0;
+    sh.ncol[tid] = c1 - c0;
+  }
+  __syncthreads();
+  // ---- my column slices of every basis matrix, their eigenvalues, row weights, my rows of every row phase
+  for (int g = 0; g < p.ngroups; ++g) {
+    const RGroup& gr = sh.groups[g];
+    const int c0 = sh.c0[g], c1 = c0 + sh.ncol[g];
+    double* dst = m.wsm + gr.woff;
     for (int c = c0; c < c1; ++c)
       for (int a = tid; a < gr.t; a += R_THREADS) dst[(size_t)(c - c0) * gr.t_pad + a] = gr.W[(long long)c * gr.ldw + a];
+    for (int cc = tid; cc < gr.maxcols; cc += R_THREADS) {
+      const double sv = cc < c1 - c0 ? gr.s[c0 + cc] : 1.0;
+      m.svs[gr.coff + cc] = sv;
+      m.isv[gr.coff + cc] = 1.0 / sv;
+    }
+  }
+  for (int j = 0; j < p.nk; ++j) {
+    const RStep& S = sh.steps[j];
+    for (int a = tid; a < S.nws; a += R_THREADS) m.wsum[S.woff + a] = S.wsum[a];
+    const int u0 = (int)((long long)S.nunits * cta / p.ncta), u1 = (int)((long long)S.nunits * (cta + 1) / p.ncta);
+    const int eb = u0 < u1 ? S.units[u0].e0 : 0, ee = u0 < u1 ? S.units[u1 - 1].e1 : 0;
+    for (int k = eb + tid; k < ee; k += R_THREADS) m.sent[(size_t)j * p.max_entries + (k - eb)] = S.entries[k];
+    for (int un = u0 + tid; un < u1; un += R_THREADS) {
+      RUnit U = S.units[un];
+      U.e0 -= eb;
+      U.e1 -= eb;
+      m.sunit[(size_t)j * p.max_units + (un - u0)] = U;
+    }
+    if (tid == 0) {
+      sh.nent[j] = ee - eb;
+      sh.nun[j] = u1 - u0;
+    }
   }
   // chain scalars: every CTA holds (and updates identically) its own copy
   Scal* sc = p.sc;
@@ -186,127 +346,138 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     sh.sigb[j] = sc->sigb[j];
     sh.Sc[j] = sc->Sc[j];
   }
+  __syncthreads();
+  column_constants(p, sh, m, tau);
+  draws_for(p, dc, sh, m, it, true, true);
   // first kernel's etil0 from the state in memory
-  rows_phase(p, p.steps[p.nk - 1], p.nk - 1, false, false, 0.0, false, 1.0, vals, sh);
-  grid.sync();
+  rows_phase(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+  bar_arrive(gb);
+  bar_wait(gb);
 
+  const bool timed = p.timing && cta == 0 && tid == 0;
+  unsigned long long tacc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tlast = gtime();
+  long long tmod = it % p.thin, qit = it / p.thin;   // it % thin and it / thin, kept incrementally
+  const long long qburn = p.burn / p.thin;
   for (long long step = 0; step < p.iters; ++step, ++it) {
-    const bool keep = (it % p.thin == 0) && (it > p.burn);
-    const double kcount = keep ? (double)(it / p.thin - p.burn / p.thin) : 1.0;
-    // draws that do not depend on the data: made up front by the warps P2 uses last
-    if (lane == 0) {
-      for (int d = R_WARPS - 1 - warp; d <= p.nk + 1; d += R_WARPS) {
-        if (d < p.nk)
-          sh.chi[d] = draw_chisq(dc, it, STREAM_CHI_K + (uint32_t)d, (double)p.steps[d].nr_total + NU, (it - 1) * dc.c_per_it + d);
-        else if (d == p.nk)
-          sh.chi[p.nk] = draw_chisq(dc, it, STREAM_CHI_E, (double)p.n + NU, (it - 1) * dc.c_per_it + p.nk);
-        else
-          sh.zmu = draw_normal(dc, it + 1, STREAM_MU, 0ull, dc.z_init + it * dc.z_per_it);
-      }
-    }
+    const bool keep = (tmod == 0) && (it > p.burn);
+    const double kcount = keep ? (double)(qit - qburn) : 1.0;
+    const int par = (int)(it & 1);
     for (int j = 0; j < p.nk; ++j) {
-      const RStep& S = p.steps[j];
+      const RStep& S = sh.steps[j];
       double zq = 0.0;
-      const double lam = sh.sigb[j];
       for (int g = S.g0; g < S.g1; ++g) {
-        const RGroup& gr = p.groups[g];
-        const int c0 = (int)((long long)gr.nr * cta / p.ncta), c1 = (int)((long long)gr.nr * (cta + 1) / p.ncta);
-        const int ncol = c1 - c0;
-        const double* W = wsm + gr.woff;
+        const RGroup& gr = sh.groups[g];
+        const int ncol = sh.ncol[g], nb = gr.nb;
+        const double* W = m.wsm + gr.woff;
         // P1: residual in genotype space for every member block
-        for (int m = 0; m < gr.nb; ++m) {
-          const long long po = p.members[gr.mem0 + m].part_off;
-          for (int a = tid; a < gr.t; a += R_THREADS) etil[m * p.etp + a] = S.etil0[po + a] - shift * S.wsum[po + a];
+        for (int mb = 0; mb < nb; ++mb) {
+          const long long po = sh.members[gr.mem0 + mb].part_off;
+          for (int a = tid; a < gr.t; a += R_THREADS)
+            m.etil[mb * p.etp + a] = __ldcg(S.etil0 + po + a) - shift * m.wsum[S.woff + po + a];
         }
         __syncthreads();
-        // P2: one warp per (column, member): dot, draw
-        for (int w = warp; w < ncol * gr.nb; w += R_WARPS) {
-          const int cc = w / gr.nb, m = w % gr.nb;
+        R_TICK(5)
+        // P2: W[:,c]' e~ for all members at once; a column is split over nch warps
+        int nch = ncol > 0 ? max(1, R_WARPS / ncol) : 1;
+        nch = min(nch, (gr.t + 63) >> 6);
+        const int clen = (((gr.t + nch - 1) / nch) + 31) & ~31;
+        for (int w = warp; w < ncol * nch; w += R_WARPS) {
+          const int cc = w / nch, ch = w - cc * nch;
+          const int a0 = ch * clen, a1 = min(gr.t, a0 + clen);
           const double* wc = W + (size_t)cc * gr.t_pad;
-          const double* em = etil + m * p.etp;
-          double d0 = 0.0, d1 = 0.0;
-          int a = lane;
-          for (; a + 32 < gr.t; a += 64) {
-            d0 = fma(wc[a], em[a], d0);
-            d1 = fma(wc[a + 32], em[a + 32], d1);
+          double d[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int a = a0 + lane; a < a1; a += 32) {
+            const double wv = wc[a];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+              if (mb < nb) d[mb] = fma(wv, m.etil[mb * p.etp + a], d[mb]);
           }
-          if (a < gr.t) d0 = fma(wc[a], em[a], d0);
-          const double d = warp_sum(d0 + d1);
-          if (lane == 0) {
-            const long long col = (long long)p.members[gr.mem0 + m].col_off + c0 + cc;
-            const double sv = gr.s[c0 + cc];
-            const double vari = sv * lam / (1.0 + sv * lam * tau);          // R/BGGE.R:302
-            const double media = tau * vari * d;                            // R/BGGE.R:303
-            const double z = draw_normal(dc, it, (uint32_t)j, (unsigned long long)col,
-                                         dc.z_init + (it - 1) * dc.z_per_it + gr.z_off + col);
-            const double bv = media + sqrt(vari) * z;
-            sh.bsm[m * R_MAXCOLS + cc] = bv;
-            zq += bv * bv * (1.0 / sv);                                     // R/BGGE.R:96
-          }
+#pragma unroll
+          for (int mb = 0; mb < 4; ++mb)
+            if (mb < nb) {
+              const double t = warp_sum(d[mb]);
+              if (lane == 0) sh.dpart[w * 4 + mb] = t;
+            }
         }
         __syncthreads();
+        R_TICK(6)
+        // coefficient draw: one thread per (column, member)   R/BGGE.R:298-305
+        if (tid < ncol * nb) {
+          const int cc = tid / nb, mb = tid % nb;
+          double d = 0.0;
+          for (int ch = 0; ch < nch; ++ch) d += sh.dpart[(cc * nch + ch) * 4 + mb];
+          const double z = m.zbuf[(size_t)par * p.ndraw + gr.doff + mb * gr.maxcols + cc];
+          const double bv = m.tv[gr.coff + cc] * d + m.sd[gr.coff + cc] * z;
+          sh.bsm[mb * R_MAXCOLS + cc] = bv;
+          zq += bv * bv * m.isv[gr.coff + cc];                              // R/BGGE.R:96
+        }
+        __syncthreads();
+        R_TICK(7)
         // P3: my columns' contribution to W b, per member
-        for (int m = 0; m < gr.nb; ++m) {
-          double* out = p.part + (size_t)cta * p.pstride + p.members[gr.mem0 + m].part_off;
-          const double* bm = sh.bsm + m * R_MAXCOLS;
+        for (int mb = 0; mb < nb; ++mb) {
+          double* out = p.part + (size_t)cta * p.pstride + sh.members[gr.mem0 + mb].part_off;
+          const double* bm = sh.bsm + mb * R_MAXCOLS;
           for (int a = tid; a < gr.t; a += R_THREADS) {
             double acc = 0.0;
             for (int cc = 0; cc < ncol; ++cc) acc = fma(W[(size_t)cc * gr.t_pad + a], bm[cc], acc);
             out[a] = acc;
           }
         }
-        __syncthreads();
+        if (g + 1 < S.g1) __syncthreads();
+        R_TICK(8)
       }
-      // sum of b^2/s of my columns (lanes 0 hold the pieces)
+      // sum of b^2/s of my columns
+      zq = warp_sum(zq);
       if (lane == 0) sh.red[0][warp] = zq;
       __syncthreads();
       if (tid == 0) {
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < R_WARPS; ++w) t += sh.red[0][w];
-        p.zqpart[((size_t)(it & 1) * p.nk + j) * p.ncta + cta] = t;
+        p.zqpart[((size_t)par * p.nk + j) * p.ncta + cta] = t;
       }
-      grid.sync();
-      rows_phase(p, S, j, true, j == p.nk - 1, shift, keep, kcount, vals, sh);
-      grid.sync();
+      R_TICK(0)
+      bar_arrive(gb);
+      R_TICK(9)
+      if (j == 0 && step + 1 < p.iters) draws_for(p, dc, sh, m, it + 1, true, false);   // hidden behind the barrier
+      R_TICK(10)
+      bar_wait(gb);
+      R_TICK(1)
+      rows_phase(p, sh, m, j, true, j == p.nk - 1, shift, keep, kcount);
+      R_TICK(2)
+      bar_arrive(gb);
+      if (j == 0 && step + 1 < p.iters) draws_for(p, dc, sh, m, it + 1, false, true);
+      bar_wait(gb);
+      R_TICK(3)
     }
     // ---- scalars, identically in every CTA: sum the per-CTA pieces (R/BGGE.R:360-367)
-    const int nv = p.nk + 2;
-    for (int v = 0; v < nv; ++v) {
+    for (int v = warp; v < p.nk + 2; v += R_WARPS) {
+      const double* src = v < p.nk ? p.zqpart + ((size_t)par * p.nk + v) * p.ncta : p.sspart + (size_t)(v - p.nk) * p.ncta;
       double x = 0.0;
-      if (tid < p.ncta)
-        x = v < p.nk ? p.zqpart[((size_t)(it & 1) * p.nk + v) * p.ncta + tid] : p.sspart[(size_t)(v - p.nk) * p.ncta + tid];
+      for (int c = lane; c < p.ncta; c += 32) x += __ldcg(src + c);
       x = warp_sum(x);
-      if (lane == 0) sh.red[v][warp] = x;
+      if (lane == 0) sh.tot[v] = x;
     }
     __syncthreads();
-    double sse = 0.0, sr = 0.0;
-#pragma unroll
-    for (int w = 0; w < R_WARPS; ++w) {
-      sse += sh.red[p.nk][w];
-      sr += sh.red[p.nk + 1][w];
-    }
-    if (tid < p.nk) {
-      double zq = 0.0;
-#pragma unroll
-      for (int w = 0; w < R_WARPS; ++w) zq += sh.red[tid][w];
-      sh.sigb[tid] = (zq + NU * sh.Sc[tid]) / sh.chi[tid];
-    }
-    sigsq = (sse + Sce) / sh.chi[p.nk];
+    double sr = sh.tot[p.nk + 1];
+    sigsq = (sh.tot[p.nk] + Sce) / sh.chi[par][p.nk];
     tau = 1.0 / sigsq;
+    if (tid < p.nk) sh.sigb[tid] = (sh.tot[tid] + NU * sh.Sc[tid]) / sh.chi[par][tid];
     __syncthreads();
+    column_constants(p, sh, m, tau);
     if (p.n_na > 0) {   // missing phenotypes (R/BGGE.R:370-381): rows split over the CTAs
       const double sd = sqrt(sigsq);
       double dsum = 0.0;
       for (long long k = (long long)cta * R_THREADS + tid; k < p.n_na; k += (long long)p.ncta * R_THREADS) {
         const long long i = p.na_idx[k];
         double uhat = 0.0;
-        for (int j = 0; j < p.nk; ++j) uhat = (j == 0) ? p.u[i] : uhat + p.u[(size_t)j * p.n + i];
+        for (int j = 0; j < p.nk; ++j) uhat = (j == 0) ? __ldcg(p.u + i) : uhat + __ldcg(p.u + (size_t)j * p.n + i);
         const double z = draw_normal(dc, it, STREAM_NA, (unsigned long long)k, dc.z_init + (it - 1) * dc.z_per_it + dc.z_off_na + k);
         const double yv = ((0.0 + mu) + uhat) + sd * z;
         p.y[i] = yv;
         const double rn = (((yv - uhat) - 0.0) - mu) + shift;
-        dsum += rn - p.r[i];
+        dsum += rn - __ldcg(p.r + i);
         p.r[i] = rn;
       }
       dsum = warp_sum(dsum);
@@ -318,19 +489,17 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
         for (int w = 0; w < R_WARPS; ++w) t += sh.red[0][w];
         p.sspart[(size_t)2 * p.ncta + cta] = t;
       }
-      grid.sync();
-      rows_phase(p, p.steps[p.nk - 1], p.nk - 1, false, false, 0.0, false, 1.0, vals, sh);
-      grid.sync();
-      double x = tid < p.ncta ? p.sspart[(size_t)2 * p.ncta + tid] : 0.0;
-      x = warp_sum(x);
-      if (lane == 0) sh.red[0][warp] = x;
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < R_WARPS; ++w) sr += sh.red[0][w];
-      __syncthreads();
+      bar_arrive(gb);
+      bar_wait(gb);
+      rows_phase(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+      bar_arrive(gb);
+      bar_wait(gb);
+      double x = 0.0;
+      for (int c = lane; c < p.ncta; c += 32) x += __ldcg(p.sspart + (size_t)2 * p.ncta + c);
+      sr += warp_sum(x);   // every warp computes the same sum
     }
-    if (cta == 0 && tid == 0 && it % p.thin == 0) {   // thinned chain (R/BGGE.R:384-395)
-      const long long slot = it / p.thin - 1;
+    if (cta == 0 && tid == 0 && tmod == 0) {   // thinned chain (R/BGGE.R:384-395)
+      const long long slot = qit - 1;
       if (slot < p.ncum) {
         p.chain_varE[slot] = sigsq;
         p.chain_mu[slot] = mu;
@@ -339,9 +508,17 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     }
     // next intercept (R/BGGE.R:278-281): mean(temp + mu) = mean(r) + mu0
     mu_done = mu;
-    mu = (sr / (double)p.n + mu0) + sqrt(sigsq / (double)p.n) * sh.zmu;
+    mu = (sr / (double)p.n + mu0) + sqrt(sigsq / (double)p.n) * sh.zmu[par];
     shift = mu - mu0;
-    __syncthreads();   // sh.zmu / sh.chi are redrawn at the top of the next iteration
+    if (++tmod == p.thin) {
+      tmod = 0;
+      ++qit;
+    }
+    R_TICK(4)
+  }
+  if (TIMED && timed) {
+#pragma unroll
+    for (int k = 0; k < 11; ++k) p.timing[k] = tacc[k];
   }
   if (cta == 0 && tid == 0) {   // hand the chain state back (fetch functions, streaming path)
     sc->mu = mu;
@@ -368,7 +545,7 @@ int plan_resident(Gibbs* g) {
   ResidentPlan& rp = g->resident;
   rp.enabled = false;
   if (g->q > 0 || g->mode != 1 || getenv("BGGE_NO_RESIDENT")) return OK;
-  if (g->n > 32768) return OK;
+  if (g->n > 32768 || g->nk > R_MAXKR) return OK;
   cudaStream_t st = g->stream;
   const int sms = sm_count();
   const int64_t n = g->n;
@@ -411,6 +588,7 @@ int plan_resident(Gibbs* g) {
         gr.mem0 = (int)members.size();   // members of a group are contiguous: reserve 4 slots
         gr.s = hk.s.p + bl.col_off;
         gr.z_off = hk.z_off;
+        gr.kidx = j;
         members.resize(members.size() + 4);
         groups.push_back(gr);
         first_of_group.push_back((int)bi);
@@ -444,13 +622,13 @@ int plan_resident(Gibbs* g) {
     pstride = std::max(pstride, poff);
   }
   kg0.push_back((int)groups.size());
-  if (groups.empty() || pstride >= (1ll << 30)) return OK;
+  if (groups.empty() || (int)groups.size() > R_MAXG || pstride >= (1ll << 30)) return OK;
   // grid size: as many CTAs as useful (>= 4 columns of the widest matrix each), at most one per SM
   int max_nr = 0;
   for (auto& gr : groups) max_nr = std::max(max_nr, gr.nr);
-  int ncta = std::max(1, std::min(sms, max_nr / 4));
-  if (const char* e = getenv("BGGE_RESIDENT_CTAS")) ncta = std::max(1, std::min(sms, atoi(e)));
-  if (ncta > R_THREADS) return OK;
+  const int cta_cap = std::min(sms, R_SUB * R_NPL);   // the row phase reads R_NPL partials per lane
+  int ncta = std::max(1, std::min(cta_cap, max_nr / 4));
+  if (const char* e = getenv("BGGE_RESIDENT_CTAS")) ncta = std::max(1, std::min(cta_cap, atoi(e)));
   const int etp = (max_t + 3) & ~1;
 
   // units of every kernel (virtual rows that have rows of y, then rows no block covers) and, per step j, the rows
@@ -462,14 +640,18 @@ int plan_resident(Gibbs* g) {
   };
   std::vector<HostStep> hs((size_t)nk);
   int max_entries = 1;
-  auto entries_of = [&](int ncta_) {
+  int max_units = 1, ndraw = 0, ncolc = 0, nwsum = 0;
+  for (int j = 0; j < nk; ++j) nwsum += (int)std::max<long long>(1, kstride[(size_t)j]);
+  auto entries_of = [&](int ncta_) {   // most rows / units one CTA gets in any row phase
     int worst = 1;
+    max_units = 1;
     for (int j = 0; j < nk; ++j) {
       const auto& un = hs[(size_t)j].units;
       const int nu = (int)un.size();
       for (int c = 0; c < ncta_; ++c) {
         const int u0 = (int)((long long)nu * c / ncta_), u1 = (int)((long long)nu * (c + 1) / ncta_);
         if (u0 < u1) worst = std::max(worst, un[(size_t)u1 - 1].e1 - un[(size_t)u0].e0);
+        max_units = std::max(max_units, u1 - u0);
       }
     }
     return worst;
@@ -515,33 +697,56 @@ int plan_resident(Gibbs* g) {
     for (int64_t i = 0; i < n; ++i)
       if (row_poff[(size_t)j][(size_t)i] >= 0) h.wsum[(size_t)row_poff[(size_t)j][(size_t)i]] += row_isq[(size_t)j][(size_t)i];
   }
-  // shared memory: slices of every group + e~ (4 x etp) + the staged row values
+  // shared memory: slices of every group, e~ (4 x etp), staged row values, draws, column constants, row tables
   size_t smem = 0;
   long long smem_w = 0;
   for (;;) {
     long long off = 0;
     bool ok = true;
+    ndraw = ncolc = 0;
     for (auto& gr : groups) {
       gr.maxcols = (gr.nr + ncta - 1) / ncta;
       if (gr.maxcols > R_MAXCOLS) ok = false;
       gr.woff = off;
+      gr.doff = ndraw;
+      gr.coff = ncolc;
+      ndraw += gr.maxcols * gr.nb;
+      ncolc += gr.maxcols;
       off += (long long)gr.maxcols * gr.t_pad;
     }
     off = (off + 1) & ~1ll;
     smem_w = off;
     max_entries = entries_of(ncta);
-    smem = ((size_t)off + 4 * (size_t)etp + (size_t)max_entries + 2) * sizeof(double);
+    smem = ((size_t)off + 4 * (size_t)etp + (size_t)max_entries + 2 * (size_t)ndraw + 4 * (size_t)ncolc + (size_t)nwsum) *
+               sizeof(double) +
+           (size_t)nk * ((size_t)max_entries * sizeof(REntry) + (size_t)max_units * sizeof(RUnit));
     if (ok && smem <= 200 * 1024) break;
-    if (ncta >= sms) return OK;          // does not fit even with one CTA per SM: streaming path
-    ncta = std::min(sms, ncta * 2);
+    if (ncta >= cta_cap) return OK;      // does not fit even with one CTA per SM: streaming path
+    ncta = std::min(cta_cap, ncta * 2);
+  }
+  // inside every CTA's range the rows are processed in part-offset order (neighbouring lanes then read the same
+  // 32-byte sectors of the partial sums); vpos keeps the unit-major slot the unit sums read
+  for (int j = 0; j < nk; ++j) {
+    HostStep& h = hs[(size_t)j];
+    const int nu = (int)h.units.size();
+    for (int c = 0; c < ncta; ++c) {
+      const int u0 = (int)((long long)nu * c / ncta), u1 = (int)((long long)nu * (c + 1) / ncta);
+      if (u0 >= u1) continue;
+      const int eb = h.units[(size_t)u0].e0, ee = h.units[(size_t)u1 - 1].e1;
+      for (int k = eb; k < ee; ++k) h.entries[(size_t)k].vpos = k - eb;
+      std::stable_sort(h.entries.begin() + eb, h.entries.begin() + ee, [](const REntry& a, const REntry& b) {
+        return (unsigned)a.poff < (unsigned)b.poff;   // -1 (no block) last
+      });
+    }
   }
   int dev = 0, coop = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
   BGGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) return OK;
-  BGGE_CUDA(cudaFuncSetAttribute(resident_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BGGE_CUDA(cudaFuncSetAttribute(resident_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BGGE_CUDA(cudaFuncSetAttribute(resident_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int per_sm = 0;
-  BGGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_sweep_kernel, R_THREADS, smem));
+  BGGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_sweep_kernel<true>, R_THREADS, smem));
   if (per_sm < 1 || ncta > per_sm * sms) return OK;
 
   rp.ncta = ncta;
@@ -550,6 +755,12 @@ int plan_resident(Gibbs* g) {
   rp.pstride = pstride;
   rp.etp = etp;
   rp.max_entries = max_entries;
+  rp.max_units = max_units;
+  rp.ndraw = ndraw;
+  rp.ncolc = ncolc;
+  rp.nwsum = nwsum;
+  rp.ngroups = (int)groups.size();
+  BGGE_CUDA(rp.bar.alloc(1));
   rp.entries.resize((size_t)nk);
   rp.units.resize((size_t)nk);
   rp.wsum.resize((size_t)nk);
@@ -569,6 +780,8 @@ int plan_resident(Gibbs* g) {
     S.g1 = kg0[(size_t)j + 1];
     S.nr_total = g->kernels[(size_t)j].nr_total;
     S.wsum = rp.wsum[(size_t)j].p;
+    S.nws = (int)hs[(size_t)j].wsum.size();
+    S.woff = j == 0 ? 0 : steps[(size_t)j - 1].woff + steps[(size_t)j - 1].nws;
     S.etil0 = rp.etil0[(size_t)j].p;
     S.next = (j + 1) % nk;
   }
@@ -617,10 +830,33 @@ int launch_resident(Gibbs* g, int64_t iters) {
   p.etp = rp.etp;
   p.smem_w = rp.smem_w;
   p.max_entries = rp.max_entries;
+  p.max_units = rp.max_units;
+  p.ndraw = rp.ndraw;
+  p.ncolc = rp.ncolc;
+  p.nwsum = rp.nwsum;
+  p.ngroups = rp.ngroups;
+  p.bar = rp.bar.p;
+  BGGE_CUDA(cudaMemsetAsync(rp.bar.p, 0, sizeof(unsigned long long), g->stream));
   DrawCfg dc = g->draw;
+  DevBuf<unsigned long long> timing;
+  if (getenv("BGGE_RESIDENT_TIMING")) {
+    BGGE_CUDA(timing.alloc(16));
+    BGGE_CUDA(cudaMemsetAsync(timing.p, 0, 16 * sizeof(unsigned long long), g->stream));
+    p.timing = timing.p;
+  }
   void* args[] = {&p, &dc};
-  BGGE_CUDA(cudaLaunchCooperativeKernel((void*)resident_sweep_kernel, dim3((unsigned)rp.ncta), dim3(R_THREADS), args, rp.smem,
-                                        g->stream));
+  BGGE_CUDA(cudaLaunchCooperativeKernel(p.timing ? (void*)resident_sweep_kernel<true> : (void*)resident_sweep_kernel<false>,
+                                        dim3((unsigned)rp.ncta), dim3(R_THREADS), args, rp.smem, g->stream));
+  if (p.timing) {
+    unsigned long long t[16];
+    BGGE_CUDA(cudaMemcpyAsync(t, timing.p, sizeof(t), cudaMemcpyDeviceToHost, g->stream));
+    BGGE_CUDA(cudaStreamSynchronize(g->stream));
+    const double k = 1e-3 / (double)std::max<int64_t>(1, iters);
+    fprintf(stderr,
+            "[bgge] resident us/iter (CTA 0): P1 %.2f  P2 %.2f  draw %.2f  P3 %.2f  zq %.2f | arriveA %.2f  slack %.2f  waitA %.2f | rows %.2f  "
+            "barrierB %.2f | scalars %.2f\n",
+            t[5] * k, t[6] * k, t[7] * k, t[8] * k, t[0] * k, t[9] * k, t[10] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k);
+  }
   return OK;
 }
 
