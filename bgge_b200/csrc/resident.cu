@@ -69,7 +69,7 @@ struct RParams {
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
   return t;
 }
 #define R_TICK(slot)                                         \
@@ -133,29 +133,34 @@ struct RSmem {                 // dynamic shared memory carve-up
 };
 
 // Draws of iteration itn that do not depend on the data: the normals of my coefficient columns, the chi-squares
-// and the normal of the intercept that follows itn.  Stored under parity itn & 1.
-__device__ __forceinline__ void draws_for(const RParams& p, const DrawCfg& dc, RShared& sh, const RSmem& m, long long itn,
-                                          bool normals, bool scalars) {
+// and the normal of the intercept that follows itn.  Stored under parity itn & 1.  (One copy of this code: the
+// kernel is instruction-fetch sensitive, every phase runs once per iteration.)
+__device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, int ndraw, int ngroups, int nk, long long n,
+                                       long long itn, bool normals, bool scalars) {
+  RShared& sh = *shp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = (int)(itn & 1);
   if (normals)
-  for (int idx = tid; idx < p.ndraw; idx += R_THREADS) {
-    int g = 0;
-    while (g + 1 < p.ngroups && idx >= sh.groups[g + 1].doff) ++g;
-    const RGroup& gr = sh.groups[g];
-    const int f = idx - gr.doff, mm = f / gr.maxcols, cc = f % gr.maxcols;
-    if (cc < sh.ncol[g]) {
-      const long long col = (long long)sh.members[gr.mem0 + mm].col_off + sh.c0[g] + cc;
-      m.zbuf[(size_t)par * p.ndraw + idx] = draw_normal(dc, itn, (uint32_t)gr.kidx, (unsigned long long)col,
-                                                        dc.z_init + (itn - 1) * dc.z_per_it + gr.z_off + col);
+    for (int idx = tid; idx < ndraw; idx += R_THREADS) {
+      int g = 0;
+      while (g + 1 < ngroups && idx >= sh.groups[g + 1].doff) ++g;
+      const RGroup& gr = sh.groups[g];
+      const int f = idx - gr.doff, mm = f / gr.maxcols, cc = f % gr.maxcols;
+      if (cc < sh.ncol[g]) {
+        const long long col = (long long)sh.members[gr.mem0 + mm].col_off + sh.c0[g] + cc;
+        zbuf[(size_t)par * ndraw + idx] = draw_normal(dc, itn, (uint32_t)gr.kidx, (unsigned long long)col,
+                                                      dc.z_init + (itn - 1) * dc.z_per_it + gr.z_off + col);
+      }
     }
-  }
-  if (scalars && lane == 0) {
-    for (int d = R_WARPS - 1 - warp; d <= p.nk + 1; d += R_WARPS) {
-      if (d < p.nk)
+  // scalar draws, one per warp from the last warp down: the kernels' chi-squares go with the normals (first
+  // barrier of an iteration), the residual chi-square and the intercept normal with the second
+  if (lane == 0) {
+    for (int d = R_WARPS - 1 - warp; d <= nk + 1; d += R_WARPS) {
+      if (!(d < nk ? normals : scalars)) continue;
+      if (d < nk)
         sh.chi[par][d] = draw_chisq(dc, itn, STREAM_CHI_K + (uint32_t)d, (double)sh.steps[d].nr_total + NU, (itn - 1) * dc.c_per_it + d);
-      else if (d == p.nk)
-        sh.chi[par][p.nk] = draw_chisq(dc, itn, STREAM_CHI_E, (double)p.n + NU, (itn - 1) * dc.c_per_it + p.nk);
+      else if (d == nk)
+        sh.chi[par][nk] = draw_chisq(dc, itn, STREAM_CHI_E, (double)n + NU, (itn - 1) * dc.c_per_it + nk);
       else
         sh.zmu[par] = draw_normal(dc, itn + 1, STREAM_MU, 0ull, dc.z_init + itn * dc.z_per_it);
     }
@@ -163,22 +168,28 @@ __device__ __forceinline__ void draws_for(const RParams& p, const DrawCfg& dc, R
 }
 
 // per-column constants of the coefficient draw for the current sigb / tau (R/BGGE.R:302-303)
-__device__ __forceinline__ void column_constants(const RParams& p, RShared& sh, const RSmem& m, double tau) {
-  for (int idx = threadIdx.x; idx < p.ncolc; idx += R_THREADS) {
+__device__ __forceinline__ void column_constants(RShared* shp, const double* svs, double* tv, double* sd, int ncolc, int ngroups,
+                                              double tau) {
+  RShared& sh = *shp;
+  for (int idx = R_THREADS - 1 - (int)threadIdx.x; idx < ncolc; idx += R_THREADS) {
     int g = 0;
-    while (g + 1 < p.ngroups && idx >= sh.groups[g + 1].coff) ++g;
-    const double sv = m.svs[idx];
+    while (g + 1 < ngroups && idx >= sh.groups[g + 1].coff) ++g;
+    const double sv = svs[idx];
     const double lam = sh.sigb[sh.groups[g].kidx];
     const double vari = sv * lam / (1.0 + sv * lam * tau);
-    m.tv[idx] = tau * vari;
-    m.sd[idx] = sqrt(vari);
+    tv[idx] = tau * vari;
+    sd[idx] = sqrt(vari);
   }
 }
 
 // Row phase of step j (update = true), or only the gather of the next step's etil0 (update = false: prologue
 // of a launch and after the imputation of missing phenotypes).
+template <bool TIMED>
 __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const RSmem& m, int j, bool update, bool last,
-                                           double shift, bool keep, double kcount) {
+                                           double shift, bool keep, double kcount, unsigned long long* tacc = nullptr,
+                                           unsigned long long* tlast_p = nullptr) {
+  const bool timed = TIMED && tacc != nullptr;
+  unsigned long long tlast = timed ? *tlast_p : 0ull;
   const int cta = blockIdx.x, tid = threadIdx.x;
   const int sub = tid / R_SUB, sl = tid % R_SUB;
   const int ne = sh.nent[j], nu = sh.nun[j];
@@ -207,12 +218,15 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
     if (update) {
       double x[R_NPL];
       const bool live = valid && E.poff >= 0;
-      const double* pp = p.part + (live ? E.poff : 0);
+      const double* pp = p.part + (live ? E.poff : 0) + (size_t)sl * p.pstride;
+      const size_t pstep = (size_t)R_SUB * p.pstride;
+      const int nq = live ? (p.ncta - sl + R_SUB - 1) / R_SUB : 0;   // partials this lane reads
 #pragma unroll
       for (int q = 0; q < R_NPL; ++q) {
-        const int c = sl + R_SUB * q;
-        x[q] = (live && c < p.ncta) ? __ldcg(pp + (size_t)c * p.pstride) : 0.0;
+        x[q] = q < nq ? __ldcg(pp) : 0.0;
+        pp += pstep;
       }
+      R_TICK(14)
       double un = ((((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]))) +
                    (((x[8] + x[9]) + (x[10] + x[11])) + ((x[12] + x[13]) + (x[14] + x[15])))) +
                   ((x[16] + x[17]) + x[18]);
@@ -220,6 +234,8 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
       un += __shfl_xor_sync(0xffffffffu, un, 2);
       un += __shfl_xor_sync(0xffffffffu, un, 1);
       un *= E.isq;
+      if (TIMED && timed && un == 123.456) tacc[0] += 1;   // force the sum to be complete at the tick
+      R_TICK(15)
       const double rn = (rold + uold) - un;
       if (valid && sl == 0) {
         p.r[E.row] = rn;
@@ -242,7 +258,9 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
     }
     if (valid && sl == 0) m.vals[E.vpos] = v;
   }
+  R_TICK(11)
   __syncthreads();
+  R_TICK(12)
   double* etil0 = sh.steps[jn].etil0;
   for (int un = tid; un < nu; un += R_THREADS) {
     const RUnit U = units[un];
@@ -251,6 +269,7 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
     for (int k = U.e0; k < U.e1; ++k) acc += m.vals[k];
     etil0[U.eoff] = acc;
   }
+  R_TICK(13)
   if (last) {   // per-CTA pieces of sum e^2 and sum r (fixed order)
     sse = warp_sum(sse);
     sr = warp_sum(sr);
@@ -266,6 +285,7 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
       p.sspart[(size_t)tid * p.ncta + cta] = t;
     }
   }
+  if (timed) *tlast_p = tlast;
 }
 
 template <bool TIMED>
@@ -347,15 +367,15 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     sh.Sc[j] = sc->Sc[j];
   }
   __syncthreads();
-  column_constants(p, sh, m, tau);
-  draws_for(p, dc, sh, m, it, true, true);
+  column_constants(&sh, m.svs, m.tv, m.sd, p.ncolc, p.ngroups, tau);
+  draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it, true, true);
   // first kernel's etil0 from the state in memory
-  rows_phase(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+  rows_phase<false>(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
   bar_arrive(gb);
   bar_wait(gb);
 
   const bool timed = p.timing && cta == 0 && tid == 0;
-  unsigned long long tacc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long tlast = gtime();
   long long tmod = it % p.thin, qit = it / p.thin;   // it % thin and it / thin, kept incrementally
   const long long qburn = p.burn / p.thin;
@@ -370,11 +390,27 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
         const RGroup& gr = sh.groups[g];
         const int ncol = sh.ncol[g], nb = gr.nb;
         const double* W = m.wsm + gr.woff;
-        // P1: residual in genotype space for every member block
-        for (int mb = 0; mb < nb; ++mb) {
-          const long long po = sh.members[gr.mem0 + mb].part_off;
-          for (int a = tid; a < gr.t; a += R_THREADS)
-            m.etil[mb * p.etp + a] = __ldcg(S.etil0 + po + a) - shift * m.wsum[S.woff + po + a];
+        // P1: residual in genotype space for every member block (the members' virtual rows are contiguous:
+        // one flat vector of nb * t entries); loads are issued four deep
+        const int tg = gr.t, tot = nb * tg;
+        {
+          const long long po = sh.members[gr.mem0].part_off;
+          const double* e0 = S.etil0 + po;
+          const double* ws = m.wsum + S.woff + po;
+          double* et = m.etil;
+          for (int i0 = tid; i0 < tot; i0 += 4 * R_THREADS) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int idx = i0 + q * R_THREADS;
+              v[q] = idx < tot ? __ldcg(e0 + idx) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int idx = i0 + q * R_THREADS;
+              if (idx < tot) et[idx] = v[q] - shift * ws[idx];
+            }
+          }
         }
         __syncthreads();
         R_TICK(5)
@@ -387,11 +423,12 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
           const int a0 = ch * clen, a1 = min(gr.t, a0 + clen);
           const double* wc = W + (size_t)cc * gr.t_pad;
           double d[4] = {0.0, 0.0, 0.0, 0.0};
+          const double* et = m.etil;
           for (int a = a0 + lane; a < a1; a += 32) {
             const double wv = wc[a];
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb)
-              if (mb < nb) d[mb] = fma(wv, m.etil[mb * p.etp + a], d[mb]);
+              if (mb < nb) d[mb] = fma(wv, et[mb * tg + a], d[mb]);
           }
 #pragma unroll
           for (int mb = 0; mb < 4; ++mb)
@@ -414,14 +451,21 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
         }
         __syncthreads();
         R_TICK(7)
-        // P3: my columns' contribution to W b, per member
-        for (int mb = 0; mb < nb; ++mb) {
-          double* out = p.part + (size_t)cta * p.pstride + sh.members[gr.mem0 + mb].part_off;
-          const double* bm = sh.bsm + mb * R_MAXCOLS;
-          for (int a = tid; a < gr.t; a += R_THREADS) {
-            double acc = 0.0;
-            for (int cc = 0; cc < ncol; ++cc) acc = fma(W[(size_t)cc * gr.t_pad + a], bm[cc], acc);
-            out[a] = acc;
+        // P3: my columns' contribution to W b, all members of the group per row
+        {
+          double* out = p.part + (size_t)cta * p.pstride + sh.members[gr.mem0].part_off;
+          const int tp = gr.t_pad;
+          for (int a = tid; a < tg; a += R_THREADS) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int cc = 0; cc < ncol; ++cc) {
+              const double wv = W[(size_t)cc * tp + a];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb)
+                if (mb < nb) acc[mb] = fma(wv, sh.bsm[mb * R_MAXCOLS + cc], acc[mb]);
+            }
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+              if (mb < nb) out[mb * tg + a] = acc[mb];
           }
         }
         if (g + 1 < S.g1) __syncthreads();
@@ -440,14 +484,14 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       R_TICK(0)
       bar_arrive(gb);
       R_TICK(9)
-      if (j == 0 && step + 1 < p.iters) draws_for(p, dc, sh, m, it + 1, true, false);   // hidden behind the barrier
+      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it + 1, true, false);   // hidden behind the barrier
       R_TICK(10)
       bar_wait(gb);
       R_TICK(1)
-      rows_phase(p, sh, m, j, true, j == p.nk - 1, shift, keep, kcount);
+      rows_phase<TIMED>(p, sh, m, j, true, j == p.nk - 1, shift, keep, kcount, timed ? tacc : nullptr, &tlast);
       R_TICK(2)
       bar_arrive(gb);
-      if (j == 0 && step + 1 < p.iters) draws_for(p, dc, sh, m, it + 1, false, true);
+      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it + 1, false, true);
       bar_wait(gb);
       R_TICK(3)
     }
@@ -465,7 +509,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     tau = 1.0 / sigsq;
     if (tid < p.nk) sh.sigb[tid] = (sh.tot[tid] + NU * sh.Sc[tid]) / sh.chi[par][tid];
     __syncthreads();
-    column_constants(p, sh, m, tau);
+    column_constants(&sh, m.svs, m.tv, m.sd, p.ncolc, p.ngroups, tau);
     if (p.n_na > 0) {   // missing phenotypes (R/BGGE.R:370-381): rows split over the CTAs
       const double sd = sqrt(sigsq);
       double dsum = 0.0;
@@ -491,7 +535,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       }
       bar_arrive(gb);
       bar_wait(gb);
-      rows_phase(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+      rows_phase<false>(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
       bar_arrive(gb);
       bar_wait(gb);
       double x = 0.0;
@@ -518,7 +562,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
   }
   if (TIMED && timed) {
 #pragma unroll
-    for (int k = 0; k < 11; ++k) p.timing[k] = tacc[k];
+    for (int k = 0; k < 16; ++k) p.timing[k] = tacc[k];
   }
   if (cta == 0 && tid == 0) {   // hand the chain state back (fetch functions, streaming path)
     sc->mu = mu;
@@ -599,24 +643,33 @@ int plan_resident(Gibbs* g) {
       mb.pos0 = (int)bl.pos0;
       mb.rows = (int)bl.rows;
       mb.col_off = (int)bl.col_off;
-      mb.part_off = poff;
-      std::vector<int> loc;
-      std::vector<double> isq;
-      if (bl.vrows > 0) {
-        loc.resize((size_t)bl.rows);
-        isq.resize((size_t)bl.rows);
-        BGGE_CUDA(cudaMemcpyAsync(loc.data(), bl.d_loc, loc.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-        BGGE_CUDA(cudaMemcpyAsync(isq.data(), bl.d_isq, isq.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        BGGE_CUDA(cudaStreamSynchronize(st));
-      }
-      for (int64_t i = 0; i < bl.rows; ++i) {
-        row_poff[(size_t)j][(size_t)(bl.pos0 + i)] = (int)(poff + (bl.vrows > 0 ? loc[(size_t)i] : i));
-        row_isq[(size_t)j][(size_t)(bl.pos0 + i)] = bl.vrows > 0 ? isq[(size_t)i] : 1.0;
-      }
-      poff += gr.t;
+      mb.part_off = (long long)bi;       // block index for now; offsets are assigned group by group below
       members[(size_t)(gr.mem0 + gr.nb)] = mb;
       ++gr.nb;
       max_t = std::max(max_t, gr.t);
+    }
+    // virtual rows of the members of one group are contiguous (the kernel treats them as one vector of nb * t)
+    for (size_t gi = (size_t)kg0.back(); gi < groups.size(); ++gi) {
+      const RGroup& gr = groups[gi];
+      for (int mi = 0; mi < gr.nb; ++mi) {
+        RMember& mb = members[(size_t)(gr.mem0 + mi)];
+        HostBlock& bl = hk.blocks[(size_t)mb.part_off];
+        mb.part_off = poff;
+        std::vector<int> loc;
+        std::vector<double> isq;
+        if (bl.vrows > 0) {
+          loc.resize((size_t)bl.rows);
+          isq.resize((size_t)bl.rows);
+          BGGE_CUDA(cudaMemcpyAsync(loc.data(), bl.d_loc, loc.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+          BGGE_CUDA(cudaMemcpyAsync(isq.data(), bl.d_isq, isq.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+          BGGE_CUDA(cudaStreamSynchronize(st));
+        }
+        for (int64_t i = 0; i < bl.rows; ++i) {
+          row_poff[(size_t)j][(size_t)(bl.pos0 + i)] = (int)(poff + (bl.vrows > 0 ? loc[(size_t)i] : i));
+          row_isq[(size_t)j][(size_t)(bl.pos0 + i)] = bl.vrows > 0 ? isq[(size_t)i] : 1.0;
+        }
+        poff += gr.t;
+      }
     }
     kstride[(size_t)j] = poff;
     pstride = std::max(pstride, poff);
@@ -853,9 +906,10 @@ int launch_resident(Gibbs* g, int64_t iters) {
     BGGE_CUDA(cudaStreamSynchronize(g->stream));
     const double k = 1e-3 / (double)std::max<int64_t>(1, iters);
     fprintf(stderr,
-            "[bgge] resident us/iter (CTA 0): P1 %.2f  P2 %.2f  draw %.2f  P3 %.2f  zq %.2f | arriveA %.2f  slack %.2f  waitA %.2f | rows %.2f  "
-            "barrierB %.2f | scalars %.2f\n",
-            t[5] * k, t[6] * k, t[7] * k, t[8] * k, t[0] * k, t[9] * k, t[10] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k);
+            "[bgge] resident us/iter (CTA 0): P1 %.2f  P2 %.2f  draw %.2f  P3 %.2f  zq %.2f | arriveA %.2f  slack %.2f  waitA %.2f | rows: "
+            "issue %.2f  arrive %.2f  update %.2f  sync %.2f  units %.2f  sums %.2f | barrierB %.2f | scalars %.2f\n",
+            t[5] * k, t[6] * k, t[7] * k, t[8] * k, t[0] * k, t[9] * k, t[10] * k, t[1] * k, t[14] * k, t[15] * k, t[11] * k, t[12] * k, t[13] * k, t[2] * k,
+            t[3] * k, t[4] * k);
   }
   return OK;
 }
