@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from .getk import factor_matches
+from .rrng import r_tapes
 
 
 class BGGEFit(OrderedDict):
@@ -103,14 +104,22 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
 
 
 def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=1e-10, R2=0.5, *, seed=0, chain=0,
-         draws=None, eig=None, device=None, mode=None):
+         draws=None, eig=None, device=None, mode=None, rng="philox"):
     """Fit the G x E model by Gibbs sampling (signature of R/BGGE.R:84 plus keyword-only extras).
 
     draws : optional (normals, chisq) tapes -> injected-draw mode.
     eig   : optional precomputed setDEC() result (shared eigenbasis); kernel entries may then carry
             "mean_diag" instead of the n x n "Kernel".
-    mode  : None/1 = fused single-pass sweep kernels where the shapes fit, 0 = two-pass kernels only.
+    mode  : None/1 = resident kernel (small models) or fused single-pass sweep kernels where the shapes fit,
+            2 = never resident, 0 = two-pass kernels only.
+    rng   : "philox" (default) = counter-based device draws keyed by (seed, chain); "R" = the stream of R's
+            `set.seed(seed)` (Mersenne-Twister, inversion normals, Ahrens-Dieter gammas) consumed in the
+            reference's call order and injected as tapes (bgge_b200.rrng).
     """
+    if rng not in ("philox", "R"):
+        raise ValueError("rng must be 'philox' or 'R'")
+    if rng == "R" and draws is not None:
+        raise ValueError("rng='R' builds its own tapes: do not pass draws")
     y = np.array(y, dtype=np.float64).ravel()
     n = y.shape[0]
     if not hasattr(K, "items"):
@@ -168,6 +177,17 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
                     _lib.call("bgge_gibbs_add_block", h, j, pos0, U.shape[0], U.shape[1], _lib.ptr(s), _lib.ptr(U),
                               U.shape[0], 0)
         mode = _lib.RNG_PHILOX
+        if rng == "R":
+            nrs = []
+            for j in range(nk):
+                nb_, tot = C.c_int(), 0
+                _lib.call("bgge_gibbs_block_count", h, j, C.byref(nb_))
+                for b in range(nb_.value):
+                    nr_ = C.c_int64()
+                    _lib.call("bgge_gibbs_fetch_block", h, j, b, None, None, C.byref(nr_), None, None, 0)
+                    tot += nr_.value
+                nrs.append(tot)
+            draws = r_tapes(int(seed), n, nrs, q, int(np.isnan(y).sum()), int(ite))
         if draws is not None:
             z = np.ascontiguousarray(draws[0], dtype=np.float64)
             c = np.ascontiguousarray(draws[1], dtype=np.float64)
