@@ -689,13 +689,6 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
   DevBuf<int> dgid_all, denv_all;   // only for the fallback route
   // Identical blocks (same genotypes with the same counts, e.g. every environment of a balanced trial) are
   // the same matrix: decompose it once, let the blocks share W and sweep them as one multi-RHS panel.
-  struct Decomp {
-    std::vector<int> T, cnt;
-    double* W;
-    int64_t ldw, nr;
-    std::vector<double> s;
-  };
-  std::vector<Decomp> cache;
   const bool share_blocks = !getenv("BGGE_NO_SHARED_BLOCKS") && !getenv("BGGE_NO_FACTORED_SWEEP");
   std::map<std::pair<std::vector<int>, std::vector<int>>, int> key_count;
   auto block_key = [&](int64_t pos, int64_t m) {
@@ -779,21 +772,25 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       };
       std::vector<int> cntT((size_t)t);
       for (int64_t a = 0; a < t; ++a) cntT[(size_t)a] = cnt[(size_t)T[(size_t)a]];
+      bool identity = t == m;   // every genotype once, rows in genotype order: U = W
+      for (int64_t i = 0; i < m && identity; ++i) identity = loc[(size_t)i] == (int)i;
+      const bool env_mode = mode == BGGE_EXPAND_ENV;
       const bool duplicated = share_blocks && spans.size() > 1 && key_count[std::make_pair(T, cntT)] > 1;
-      if (duplicated) {
-        const Decomp* hit = nullptr;
-        for (auto& d : cache)
-          if (d.T == T && d.cnt == cntT) hit = &d;
-        if (hit) {   // an identical block was decomposed already: share its W and eigenvalues
-          if (hit->nr == 0) continue;
-          BGGE_TRY(upload_map());
-          BGGE_TRY(make_virtual(hit->W, hit->ldw, hit->nr, false));
-          hk.s_host.insert(hk.s_host.end(), hit->s.begin(), hit->s.end());
-          continue;
-        }
-      }
+      // the environment kernels of MDe are one block each and, in a balanced trial, the same matrix: shared through
+      // the handle-level cache (bgge::SharedDecomp) like the identical blocks of one BD kernel
+      const bool shareable = share_blocks && (duplicated || env_mode);
+      auto add_dense_shared = [&](double* W, int64_t ldw, int64_t nr, bool owns_w) -> int {
+        bl.dU = W;
+        bl.ldu = ldw;
+        bl.nr = nr;
+        bl.owns = owns_w;
+        bl.col_off = (int64_t)hk.s_host.size();
+        hk.blocks.push_back(bl);
+        return OK;
+      };
       DevBuf<int> dT;
       DevBuf<double> dsqc, dM, dW, dS, dWc, dwts;
+      DevBuf<unsigned long long> dhash;
       BGGE_CUDA(dT.alloc((size_t)t));
       BGGE_CUDA(dsqc.alloc((size_t)t));
       BGGE_CUDA(dM.alloc((size_t)t * t));
@@ -801,10 +798,31 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       BGGE_CUDA(cudaMemcpyAsync(dT.p, T.data(), (size_t)t * sizeof(int), cudaMemcpyHostToDevice, st));
       BGGE_CUDA(cudaMemcpyAsync(dsqc.p, sqc.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
       BGGE_TRY(gather_scale_launch(dK0, ld0, dT.p, dsqc.p, t, dM.p, st));
+      unsigned long long hh[2] = {0, 0};
+      if (shareable) {
+        BGGE_CUDA(dhash.alloc(2));
+        BGGE_TRY(hash_bits_launch(dM.p, t * t, dhash.p, st));
+        BGGE_CUDA(cudaMemcpyAsync(hh, dhash.p, sizeof(hh), cudaMemcpyDeviceToHost, st));
+        BGGE_CUDA(cudaStreamSynchronize(st));
+        const SharedDecomp* hit = nullptr;
+        for (auto& d : g.decomps)
+          if (d.h1 == hh[0] && d.h2 == hh[1] && d.T == T && d.cnt == cntT) hit = &d;
+        if (hit) {   // this matrix was decomposed already: share its W and eigenvalues
+          if (hit->nr == 0) continue;
+          if (env_mode && identity && !duplicated) {
+            BGGE_TRY(add_dense_shared(hit->W, hit->ldw, hit->nr, false));
+          } else {
+            BGGE_TRY(upload_map());
+            BGGE_TRY(make_virtual(hit->W, hit->ldw, hit->nr, false));
+          }
+          hk.s_host.insert(hk.s_host.end(), hit->s.begin(), hit->s.end());
+          continue;
+        }
+      }
       int64_t nr = 0;
       BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
       if (nr == 0) {                                                // R/BGGE.R:162
-        if (duplicated) cache.push_back(Decomp{T, cntT, nullptr, 0, 0, {}});
+        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, nullptr, 0, 0, {}});
         continue;
       }
       bl.nr = nr;
@@ -812,7 +830,6 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       BGGE_CUDA(dS.alloc((size_t)nr));
       BGGE_CUDA(dWc.alloc((size_t)ldw * nr));
       BGGE_TRY(eig_compact(dM.p, t, dW.p, t, nr, 0, dS.p, dWc.p, ldw, st));
-      // row map of the block: loc (row -> genotype slot), 1/sqrt(count), and its CSR transpose
       double* dWfinal = nullptr;
       BGGE_CUDA(pool_alloc((void**)&dWfinal, (size_t)ldw * nr * sizeof(double)));
       if (canonical_sign) {
@@ -826,30 +843,30 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       } else {
         BGGE_CUDA(cudaMemcpyAsync(dWfinal, dWc.p, (size_t)ldw * nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
       }
-      BGGE_TRY(upload_map());
       s_host.resize((size_t)nr);
       BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
       BGGE_CUDA(cudaStreamSynchronize(st));
-      const bool keep_factored = (duplicated || 3 * t <= 2 * m) && !getenv("BGGE_NO_FACTORED_SWEEP");
+      const bool no_fact = getenv("BGGE_NO_FACTORED_SWEEP") != nullptr;
+      const bool keep_factored = (duplicated || 3 * t <= 2 * m) && !no_fact;
       if (keep_factored) {   // fewer rows to stream (repeated genotypes) or W shared with identical blocks
+        BGGE_TRY(upload_map());
         BGGE_TRY(make_virtual(dWfinal, ldw, nr, true));
-        if (duplicated) cache.push_back(Decomp{T, cntT, dWfinal, ldw, nr, s_host});
-        hk.s_host.insert(hk.s_host.end(), s_host.begin(), s_host.end());
-        continue;
+        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, dWfinal, ldw, nr, s_host});
+      } else if (shareable && identity) {   // U = W: the block streams W itself, later identical kernels share it
+        BGGE_TRY(add_dense_shared(dWfinal, ldw, nr, true));
+        g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, dWfinal, ldw, nr, s_host});
       } else {
+        BGGE_TRY(upload_map());
         BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
         bl.owns = true;
         bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
-    hk.blocks.push_back(bl);
+        hk.blocks.push_back(bl);
         BGGE_TRY(expand_rows_launch(dWfinal, ldw, d_loc, d_isq, m, nr, bl.dU, bl.ldu, st));
         BGGE_CUDA(cudaStreamSynchronize(st));
         pool_free(dWfinal);
         pool_free(d_loc);
         pool_free(d_isq);
       }
-      s_host.resize((size_t)nr);
-      BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
-      BGGE_CUDA(cudaStreamSynchronize(st));
     } else {
       // ---- mixed mask inside the block: materialise the m x m block and decompose it directly
       if (!dgid_all.p) {

@@ -4,6 +4,7 @@
 // sign of each eigenvector so that its largest-|.| component is positive.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 #include <cusolverDn.h>
 #include <vector>
 #include <mutex>
@@ -88,6 +89,30 @@ __global__ void gather_scale_kernel(const double* __restrict__ K0, int64_t ldk, 
   }
 }
 
+// Two independent 64-bit hashes of the bit patterns of x[0..count): position-weighted sums mod 2^64 (integer
+// addition is associative, so the result does not depend on the launch shape).  Identifies identical
+// matrices across kernels of one model (the environment kernels of MDe are the same L x L matrix).
+__global__ void hash_bits_kernel(const double* __restrict__ x, long long count, unsigned long long* __restrict__ out) {
+  unsigned long long h1 = 0, h2 = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x[i]);
+    h1 += b * (2ull * (unsigned long long)i + 1ull);
+    unsigned long long m = b ^ (b >> 29);
+    m *= 0x9E3779B97F4A7C15ull;
+    m ^= m >> 32;
+    h2 += m * (0xD6E8FEB86659FD93ull * (unsigned long long)(i + 1) | 1ull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+    h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, h1);
+    atomicAdd(out + 1, h2);
+  }
+}
+
 // U[i, c] = W[loc[i], c] * isq[i]   (rows x nr into the padded layout, pad rows zero)
 __global__ void expand_rows_kernel(const double* __restrict__ W, int64_t ldw, const int* __restrict__ loc,
                                    const double* __restrict__ isq, int64_t rows, int64_t nr, double* __restrict__ U,
@@ -154,6 +179,14 @@ int gather_scale_launch(const double* dK0, int64_t ldk, const int* dT, const dou
   if (gx > 32) gx = 32;
   BGGE_REQUIRE(t <= 65535, "expanded eigen: %lld distinct genotypes in one block exceed 65535", (long long)t);
   gather_scale_kernel<<<dim3(gx, (unsigned)t), 256, 0, st>>>(dK0, ldk, dT, d_sqc, t, dM);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int hash_bits_launch(const double* dX, int64_t count, unsigned long long* d_out2, cudaStream_t st) {
+  BGGE_CUDA(cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned long long), st));
+  unsigned grid = (unsigned)std::min<int64_t>(2048, (count + 255) / 256);
+  hash_bits_kernel<<<grid ? grid : 1, 256, 0, st>>>(dX, (long long)count, d_out2);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }

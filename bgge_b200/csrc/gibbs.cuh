@@ -182,6 +182,16 @@ struct ResidentPlan {
   DevBuf<double> part, zqpart, sspart;
 };
 
+// One decomposed base matrix C^{1/2} K0[T,T] C^{1/2}, kept per handle: identical blocks of one kernel and identical
+// blocks of different kernels (the environment kernels of MDe) share W and the eigenvalues.
+struct SharedDecomp {
+  unsigned long long h1, h2;     // content hash of the matrix that was decomposed
+  std::vector<int> T, cnt;
+  double* W;
+  int64_t ldw, nr;
+  std::vector<double> s;
+};
+
 struct Gibbs {
   int64_t n = 0;
   int nk = 0, q = 0, n_chains = 1;
@@ -189,6 +199,7 @@ struct Gibbs {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::vector<HostKernel> kernels;
+  std::vector<SharedDecomp> decomps;
   // data
   std::vector<double> y_host;
   std::vector<unsigned char> na_host;

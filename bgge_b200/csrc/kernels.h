@@ -29,6 +29,7 @@ int sign_fix_launch(const double* dSrc, int64_t ld, int64_t rows, int64_t nr, co
                     cudaStream_t st);
 int gather_scale_launch(const double* dK0, int64_t ldk, const int* dT, const double* d_sqc, int64_t t, double* dM,
                         cudaStream_t st);
+int hash_bits_launch(const double* dX, int64_t count, unsigned long long* d_out2, cudaStream_t st);
 int expand_rows_launch(const double* dW, int64_t ldw, const int* d_loc, const double* d_isq, int64_t rows, int64_t nr,
                        double* dU, int64_t ldu, cudaStream_t st);
 
