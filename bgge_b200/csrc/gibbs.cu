@@ -827,6 +827,12 @@ int gibbs_run(Gibbs* g, int64_t iters) {
   BGGE_REQUIRE(iters >= 0 && g->done + iters <= g->ite, "gibbs: asked for %lld iterations, %lld of %lld already done",
                (long long)iters, (long long)g->done, (long long)g->ite);
   if (g->resident.enabled) {   // the whole run is one cooperative launch
+    if (g->resident.has_merged && g->done == 0 && iters > 0) {
+      // merged steps rely on u_k = 0 outside kernel k's block, true once every kernel has been swept once
+      BGGE_TRY(launch_iteration(g));
+      g->done += 1;
+      iters -= 1;
+    }
     if (iters > 0) BGGE_TRY(launch_resident(g, iters));
     g->done += iters;
     return OK;

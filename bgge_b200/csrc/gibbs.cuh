@@ -139,36 +139,38 @@ struct RGroup {                  // one basis matrix W (t x nr) and the <= 4 blo
   int t, t_pad, nr, nb, mem0;    // members [mem0, mem0 + nb)
   int maxcols;                   // columns per CTA (upper bound)
   long long woff;                // offset (doubles) of this group's slice in a CTA's shared memory
-  long long z_off;               // offset of the kernel's coefficient normals inside an iteration (tape mode)
-  int kidx;                      // kernel (random effect) the group belongs to
-  int doff, coff;                // offsets of its draws / column constants in a CTA's shared memory
-  int pad;
+  int doff, coff;                // offsets of its (member, column) draws / its column eigenvalues in shared memory
 };
 struct RMember {                 // one eigen block
   int pos0, rows, col_off;
-  long long part_off;            // offset of its virtual rows inside a part row / the kernel's etil0 and wsum
+  int kidx;                      // kernel (random effect) the block belongs to: its sigb, draw stream, u
+  long long part_off;            // offset of its virtual rows inside a part row / the step's etil0 and wsum
+  long long z_off;               // offset of the kernel's coefficient normals inside an iteration (tape mode)
 };
 struct REntry {                  // one row of y in the row phase of step j, ordered by the units of the next kernel
   int row;
   int poff;                      // kernel j: part offset of the row's virtual row, -1 if no block covers the row
-  int vpos, pad;                 // slot of its value in the CTA's staging array (entries are stored sorted by poff)
+  int vpos;                      // slot of its value in the CTA's staging array (entries are stored sorted by poff)
+  int kj;                        // kernel of this step that owns the row (-1: none; merged steps only)
+  int kn, pad;                   // kernel whose u enters the next step's residual for the row (-1: none)
   double isq;                    // kernel j: row weight (1/sqrt(count); 1 for a dense block)
   double w;                      // next kernel: row weight
 };
 struct RUnit {                   // one virtual row of the next kernel: entries [e0, e1), eoff < 0: rows it does not cover
   int e0, e1, eoff, pad;
 };
-struct RStep {
+struct RStep {                   // one kernel, or up to 4 kernels sharing a matrix on disjoint rows (merged)
   const REntry* entries;
   const RUnit* units;
-  int nunits, g0, g1, next;      // groups [g0, g1) of this kernel; next = index of the following kernel step
-  long long nr_total;
-  int woff, nws;                 // this kernel's wsum in a CTA's shared memory: offset and length
-  const double* wsum;            // this kernel: sum of the row weights per virtual row
-  double* etil0;                 // this kernel: C^-1/2 Z'(r + u_j) per virtual row, written by the previous row phase
+  int nunits, g0, g1, next;      // groups [g0, g1) of this step; next = index of the following step
+  int merged, zk[4];             // zk[m]: kernel that receives sum b^2/s of member slot m (all equal unless merged)
+  int woff, nws, pad;            // this step's wsum in a CTA's shared memory: offset and length
+  const double* wsum;            // sum of the row weights per virtual row
+  double* etil0;                 // C^-1/2 Z'(r + u) per virtual row, written by the previous row phase
 };
 struct ResidentPlan {
-  bool enabled = false;
+  bool enabled = false, has_merged = false;
+  int nsteps = 0;
   int ncta = 0, etp = 0, max_entries = 0, max_units = 0, ndraw = 0, ncolc = 0, ngroups = 0, nwsum = 0;
   DevBuf<unsigned long long> bar;
   size_t smem = 0;

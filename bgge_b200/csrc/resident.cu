@@ -17,6 +17,12 @@
 // and after the last kernel step every CTA computes sigb_j, sigsq, tau and the next intercept from per-CTA
 // partial sums (R/BGGE.R:360-367, 278-281); missing phenotypes (R/BGGE.R:370-381) cost two more barriers.
 // All sums run in a fixed order: results do not depend on how a run is split into launches.
+//
+// Merged steps: consecutive kernels that consist of one block each, share one basis matrix and cover disjoint
+// rows (the environment kernels of MDe in a balanced trial) are conditionally independent given the rest, so up
+// to 4 of them are swept as ONE step (one group, one member per kernel, each with its own sigb / draws / u).
+// This needs u_k = 0 outside kernel k's block, which holds after the first iteration: gibbs_run runs iteration
+// 1 on the streaming path when the plan contains a merged step.
 #include "gibbs.cuh"
 #include "kernels.h"
 #include "rng.cuh"
@@ -41,8 +47,9 @@ struct RParams {
   const RGroup* groups;
   const RMember* members;
   const RStep* steps;
-  int nk, ncta, ngroups;
+  int nk, nsteps, ncta, ngroups;
   long long n;
+  long long nr_k[R_MAXKR];     // kept eigenvalues per kernel (chi-square degrees of freedom)
   double* r;
   double* u;
   double* y;
@@ -85,7 +92,7 @@ struct RShared {
   RStep steps[R_MAXKR];
   int nent[R_MAXKR], nun[R_MAXKR];
   int c0[R_MAXG], ncol[R_MAXG];        // my columns of every basis matrix
-  double red[2][R_WARPS];
+  double red[4][R_WARPS];
   double tot[R_MAXKR + 2];
   double bsm[4 * R_MAXCOLS];
   double dpart[4 * R_MAXCOLS];
@@ -93,6 +100,7 @@ struct RShared {
   double zmu[2];
   double sigb[R_MAXKR];
   double Sc[R_MAXKR];
+  long long nrk[R_MAXKR];
 };
 
 // Split grid barrier (all CTAs are co-resident: cooperative launch).  Work placed between arrive and wait
@@ -125,8 +133,8 @@ struct RSmem {                 // dynamic shared memory carve-up
   double* zbuf;                // [2][ndraw] coefficient normals of my columns, by iteration parity
   double* svs;                 // [ncolc] eigenvalues of my columns
   double* isv;                 // 1 / eigenvalue
-  double* tv;                  // tau * v        (R/BGGE.R:302-303)
-  double* sd;                  // sqrt(v)
+  double* tv;                  // [ndraw] tau * v per (member, column)   (R/BGGE.R:302-303)
+  double* sd;                  // [ndraw] sqrt(v)
   double* wsum;                // [nwsum] row-weight sums per virtual row, all kernels (offset RStep::woff)
   REntry* sent;                // [nk][max_entries] my rows of every row phase
   RUnit* sunit;                // [nk][max_units]
@@ -147,9 +155,10 @@ __device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, i
       const RGroup& gr = sh.groups[g];
       const int f = idx - gr.doff, mm = f / gr.maxcols, cc = f % gr.maxcols;
       if (cc < sh.ncol[g]) {
-        const long long col = (long long)sh.members[gr.mem0 + mm].col_off + sh.c0[g] + cc;
-        zbuf[(size_t)par * ndraw + idx] = draw_normal(dc, itn, (uint32_t)gr.kidx, (unsigned long long)col,
-                                                      dc.z_init + (itn - 1) * dc.z_per_it + gr.z_off + col);
+        const RMember& mbr = sh.members[gr.mem0 + mm];
+        const long long col = (long long)mbr.col_off + sh.c0[g] + cc;
+        zbuf[(size_t)par * ndraw + idx] = draw_normal(dc, itn, (uint32_t)mbr.kidx, (unsigned long long)col,
+                                                      dc.z_init + (itn - 1) * dc.z_per_it + mbr.z_off + col);
       }
     }
   // scalar draws, one per warp from the last warp down: the kernels' chi-squares go with the normals (first
@@ -158,7 +167,7 @@ __device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, i
     for (int d = R_WARPS - 1 - warp; d <= nk + 1; d += R_WARPS) {
       if (!(d < nk ? normals : scalars)) continue;
       if (d < nk)
-        sh.chi[par][d] = draw_chisq(dc, itn, STREAM_CHI_K + (uint32_t)d, (double)sh.steps[d].nr_total + NU, (itn - 1) * dc.c_per_it + d);
+        sh.chi[par][d] = draw_chisq(dc, itn, STREAM_CHI_K + (uint32_t)d, (double)sh.nrk[d] + NU, (itn - 1) * dc.c_per_it + d);
       else if (d == nk)
         sh.chi[par][nk] = draw_chisq(dc, itn, STREAM_CHI_E, (double)n + NU, (itn - 1) * dc.c_per_it + nk);
       else
@@ -167,15 +176,18 @@ __device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, i
   }
 }
 
-// per-column constants of the coefficient draw for the current sigb / tau (R/BGGE.R:302-303)
-__device__ __forceinline__ void column_constants(RShared* shp, const double* svs, double* tv, double* sd, int ncolc, int ngroups,
-                                              double tau) {
+// per-(member, column) constants of the coefficient draw for the current sigb / tau (R/BGGE.R:302-303); same
+// layout as the normals (group offset doff, member-major)
+__device__ __forceinline__ void column_constants(RShared* shp, const double* svs, double* tv, double* sd, int ndraw, int ngroups,
+                                                 double tau) {
   RShared& sh = *shp;
-  for (int idx = R_THREADS - 1 - (int)threadIdx.x; idx < ncolc; idx += R_THREADS) {
+  for (int idx = R_THREADS - 1 - (int)threadIdx.x; idx < ndraw; idx += R_THREADS) {
     int g = 0;
-    while (g + 1 < ngroups && idx >= sh.groups[g + 1].coff) ++g;
-    const double sv = svs[idx];
-    const double lam = sh.sigb[sh.groups[g].kidx];
+    while (g + 1 < ngroups && idx >= sh.groups[g + 1].doff) ++g;
+    const RGroup& gr = sh.groups[g];
+    const int f = idx - gr.doff, mm = f / gr.maxcols, cc = f - mm * gr.maxcols;
+    const double sv = svs[gr.coff + cc];
+    const double lam = sh.sigb[sh.members[gr.mem0 + mm].kidx];
     const double vari = sv * lam / (1.0 + sv * lam * tau);
     tv[idx] = tau * vari;
     sd[idx] = sqrt(vari);
@@ -196,28 +208,31 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
   const REntry* ent = m.sent + (size_t)j * p.max_entries;
   const RUnit* units = m.sunit + (size_t)j * p.max_units;
   const int jn = sh.steps[j].next;
-  double* uj = p.u + (size_t)j * p.n;
-  const double* ujn_p = p.u + (size_t)jn * p.n;
   double sse = 0.0, sr = 0.0;
   for (int k0 = 0; k0 < ne; k0 += R_THREADS / R_SUB) {
     const int k = k0 + sub;
     const bool valid = k < ne;
     REntry E{};
+    E.kj = E.kn = -1;
     if (valid) E = ent[k];
+    // kj: the kernel of this step that owns the row (-1: none, a merged step away from its blocks);
+    // kn: the kernel whose u enters the next step's residual for this row (-1: none)
+    const bool upd = update && E.kj >= 0;
+    double* ujp = p.u + (size_t)(upd ? E.kj : 0) * p.n + E.row;
     double rold = 0.0, uold = 0.0, ujn = 0.0, mm = 0.0, m2 = 0.0;
     if (valid && sl == 0) {
       rold = __ldcg(p.r + E.row);
-      if (update) uold = __ldcg(uj + E.row);
-      if (!update || jn != j) ujn = __ldcg(ujn_p + E.row);
-      if (update && keep) {
-        mm = __ldcg(p.umean + (size_t)j * p.n + E.row);
-        m2 = __ldcg(p.um2 + (size_t)j * p.n + E.row);
+      if (upd) uold = __ldcg(ujp);
+      if (E.kn >= 0 && !(upd && E.kn == E.kj)) ujn = __ldcg(p.u + (size_t)E.kn * p.n + E.row);
+      if (upd && keep) {
+        mm = __ldcg(p.umean + (size_t)E.kj * p.n + E.row);
+        m2 = __ldcg(p.um2 + (size_t)E.kj * p.n + E.row);
       }
     }
     double v;
     if (update) {
       double x[R_NPL];
-      const bool live = valid && E.poff >= 0;
+      const bool live = valid && upd && E.poff >= 0;
       const double* pp = p.part + (live ? E.poff : 0) + (size_t)sl * p.pstride;
       const size_t pstep = (size_t)R_SUB * p.pstride;
       const int nq = live ? (p.ncta - sl + R_SUB - 1) / R_SUB : 0;   // partials this lane reads
@@ -236,15 +251,17 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
       un *= E.isq;
       if (TIMED && timed && un == 123.456) tacc[0] += 1;   // force the sum to be complete at the tick
       R_TICK(15)
-      const double rn = (rold + uold) - un;
+      const double rn = upd ? (rold + uold) - un : rold;
       if (valid && sl == 0) {
-        p.r[E.row] = rn;
-        uj[E.row] = un;
-        if (keep) {
-          const double dlt = un - mm;
-          const double mn = mm + dlt / kcount;
-          p.umean[(size_t)j * p.n + E.row] = mn;
-          p.um2[(size_t)j * p.n + E.row] = m2 + dlt * (un - mn);
+        if (upd) {
+          p.r[E.row] = rn;
+          *ujp = un;
+          if (keep) {
+            const double dlt = un - mm;
+            const double mn = mm + dlt / kcount;
+            p.umean[(size_t)E.kj * p.n + E.row] = mn;
+            p.um2[(size_t)E.kj * p.n + E.row] = m2 + dlt * (un - mn);
+          }
         }
         if (last) {
           const double e = rn - shift;
@@ -252,7 +269,7 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
           sr += rn;
         }
       }
-      v = E.w * (rn + (jn == j ? un : ujn));
+      v = E.w * (rn + (upd && E.kn == E.kj ? un : ujn));
     } else {
       v = E.w * (rold + ujn);
     }
@@ -302,10 +319,10 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
   m.svs = m.zbuf + 2 * p.ndraw;
   m.isv = m.svs + p.ncolc;
   m.tv = m.isv + p.ncolc;
-  m.sd = m.tv + p.ncolc;
-  m.wsum = m.sd + p.ncolc;
+  m.sd = m.tv + p.ndraw;
+  m.wsum = m.sd + p.ndraw;
   m.sent = reinterpret_cast<REntry*>(m.wsum + p.nwsum);
-  m.sunit = reinterpret_cast<RUnit*>(m.sent + (size_t)p.nk * p.max_entries);
+  m.sunit = reinterpret_cast<RUnit*>(m.sent + (size_t)p.nsteps * p.max_entries);
   GridBar gb{p.bar, 0ull, (unsigned)p.ncta};
 
   // ---- descriptors into shared memory (every later phase starts from them: no dependent global loads)
@@ -317,7 +334,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     };
     copy8(sh.groups, p.groups, (size_t)p.ngroups * sizeof(RGroup));
     copy8(sh.members, p.members, (size_t)p.ngroups * 4 * sizeof(RMember));
-    copy8(sh.steps, p.steps, (size_t)p.nk * sizeof(RStep));
+    copy8(sh.steps, p.steps, (size_t)p.nsteps * sizeof(RStep));
   }
   __syncthreads();
   if (tid < p.ngroups) {
@@ -340,7 +357,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       m.isv[gr.coff + cc] = 1.0 / sv;
     }
   }
-  for (int j = 0; j < p.nk; ++j) {
+  for (int j = 0; j < p.nsteps; ++j) {
     const RStep& S = sh.steps[j];
     for (int a = tid; a < S.nws; a += R_THREADS) m.wsum[S.woff + a] = S.wsum[a];
     const int u0 = (int)((long long)S.nunits * cta / p.ncta), u1 = (int)((long long)S.nunits * (cta + 1) / p.ncta);
@@ -365,12 +382,13 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
   for (int j = tid; j < p.nk; j += R_THREADS) {
     sh.sigb[j] = sc->sigb[j];
     sh.Sc[j] = sc->Sc[j];
+    sh.nrk[j] = p.nr_k[j];
   }
   __syncthreads();
-  column_constants(&sh, m.svs, m.tv, m.sd, p.ncolc, p.ngroups, tau);
+  column_constants(&sh, m.svs, m.tv, m.sd, p.ndraw, p.ngroups, tau);
   draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it, true, true);
   // first kernel's etil0 from the state in memory
-  rows_phase<false>(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+  rows_phase<false>(p, sh, m, p.nsteps - 1, false, false, 0.0, false, 1.0);
   bar_arrive(gb);
   bar_wait(gb);
 
@@ -383,9 +401,9 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     const bool keep = (tmod == 0) && (it > p.burn);
     const double kcount = keep ? (double)(qit - qburn) : 1.0;
     const int par = (int)(it & 1);
-    for (int j = 0; j < p.nk; ++j) {
+    for (int j = 0; j < p.nsteps; ++j) {
       const RStep& S = sh.steps[j];
-      double zq = 0.0;
+      double zq = 0.0;   // b^2 / s of the (column, member) this thread draws; member slot = tid % nb of the group
       for (int g = S.g0; g < S.g1; ++g) {
         const RGroup& gr = sh.groups[g];
         const int ncol = sh.ncol[g], nb = gr.nb;
@@ -444,8 +462,9 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
           const int cc = tid / nb, mb = tid % nb;
           double d = 0.0;
           for (int ch = 0; ch < nch; ++ch) d += sh.dpart[(cc * nch + ch) * 4 + mb];
-          const double z = m.zbuf[(size_t)par * p.ndraw + gr.doff + mb * gr.maxcols + cc];
-          const double bv = m.tv[gr.coff + cc] * d + m.sd[gr.coff + cc] * z;
+          const int di = gr.doff + mb * gr.maxcols + cc;
+          const double z = m.zbuf[(size_t)par * p.ndraw + di];
+          const double bv = m.tv[di] * d + m.sd[di] * z;
           sh.bsm[mb * R_MAXCOLS + cc] = bv;
           zq += bv * bv * m.isv[gr.coff + cc];                              // R/BGGE.R:96
         }
@@ -471,15 +490,23 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
         if (g + 1 < S.g1) __syncthreads();
         R_TICK(8)
       }
-      // sum of b^2/s of my columns
-      zq = warp_sum(zq);
-      if (lane == 0) sh.red[0][warp] = zq;
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
+      // sum of b^2/s of my columns: one kernel (every member slot adds up), or one kernel per member slot (merged step)
+      {
+        const int slot = S.merged ? tid % sh.groups[S.g0].nb : 0;   // the drawing threads are tid = cc * nb + mb
 #pragma unroll
-        for (int w = 0; w < R_WARPS; ++w) t += sh.red[0][w];
-        p.zqpart[((size_t)par * p.nk + j) * p.ncta + cta] = t;
+        for (int q = 0; q < 4; ++q) {
+          if (q == 0 || S.merged) {
+            const double t = warp_sum(slot == q ? zq : 0.0);
+            if (lane == 0) sh.red[q][warp] = t;
+          }
+        }
+        __syncthreads();
+        if (tid < (S.merged ? sh.groups[S.g0].nb : 1)) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < R_WARPS; ++w) t += sh.red[tid][w];
+          p.zqpart[((size_t)par * p.nk + S.zk[tid]) * p.ncta + cta] = t;
+        }
       }
       R_TICK(0)
       bar_arrive(gb);
@@ -488,7 +515,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       R_TICK(10)
       bar_wait(gb);
       R_TICK(1)
-      rows_phase<TIMED>(p, sh, m, j, true, j == p.nk - 1, shift, keep, kcount, timed ? tacc : nullptr, &tlast);
+      rows_phase<TIMED>(p, sh, m, j, true, j == p.nsteps - 1, shift, keep, kcount, timed ? tacc : nullptr, &tlast);
       R_TICK(2)
       bar_arrive(gb);
       if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it + 1, false, true);
@@ -509,7 +536,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     tau = 1.0 / sigsq;
     if (tid < p.nk) sh.sigb[tid] = (sh.tot[tid] + NU * sh.Sc[tid]) / sh.chi[par][tid];
     __syncthreads();
-    column_constants(&sh, m.svs, m.tv, m.sd, p.ncolc, p.ngroups, tau);
+    column_constants(&sh, m.svs, m.tv, m.sd, p.ndraw, p.ngroups, tau);
     if (p.n_na > 0) {   // missing phenotypes (R/BGGE.R:370-381): rows split over the CTAs
       const double sd = sqrt(sigsq);
       double dsum = 0.0;
@@ -535,7 +562,7 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       }
       bar_arrive(gb);
       bar_wait(gb);
-      rows_phase<false>(p, sh, m, p.nk - 1, false, false, 0.0, false, 1.0);
+      rows_phase<false>(p, sh, m, p.nsteps - 1, false, false, 0.0, false, 1.0);
       bar_arrive(gb);
       bar_wait(gb);
       double x = 0.0;
@@ -588,73 +615,115 @@ int upload_vec(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
 int plan_resident(Gibbs* g) {
   ResidentPlan& rp = g->resident;
   rp.enabled = false;
+  rp.has_merged = false;
   if (g->q > 0 || g->mode != 1 || getenv("BGGE_NO_RESIDENT")) return OK;
   if (g->n > 32768 || g->nk > R_MAXKR) return OK;
   cudaStream_t st = g->stream;
   const int sms = sm_count();
   const int64_t n = g->n;
   const int nk = g->nk;
-  // groups: blocks sharing one matrix (same rule as the fused plan), up to 4 members
+  const bool allow_merge = !getenv("BGGE_NO_MERGED_STEPS");
+
+  // ---- steps: one kernel, or up to 4 consecutive single-block kernels sharing one matrix on disjoint rows
+  struct StepDef {
+    std::vector<int> kernels;
+    bool merged;
+  };
+  std::vector<StepDef> sdef;
+  for (int j = 0; j < nk;) {
+    StepDef sd{{j}, false};
+    const HostKernel& h0 = g->kernels[(size_t)j];
+    if (allow_merge && h0.blocks.size() == 1) {
+      const HostBlock& b0 = h0.blocks[0];
+      while ((int)sd.kernels.size() < 4) {
+        const int jn = j + (int)sd.kernels.size();
+        if (jn >= nk || g->kernels[(size_t)jn].blocks.size() != 1) break;
+        const HostBlock& bn = g->kernels[(size_t)jn].blocks[0];
+        if (bn.dU != b0.dU || bn.nr != b0.nr || bn.stream_rows() != b0.stream_rows() || (bn.vrows > 0) != (b0.vrows > 0)) break;
+        bool disjoint = true;
+        for (int kk : sd.kernels) {
+          const HostBlock& bk = g->kernels[(size_t)kk].blocks[0];
+          if (bn.pos0 < bk.pos0 + bk.rows && bk.pos0 < bn.pos0 + bn.rows) disjoint = false;
+        }
+        if (!disjoint) break;
+        sd.kernels.push_back(jn);
+      }
+      sd.merged = sd.kernels.size() > 1;
+    }
+    j += (int)sd.kernels.size();
+    sdef.push_back(sd);
+  }
+  const int nsteps = (int)sdef.size();
+
+  // ---- groups (blocks streaming one matrix, up to 4 members) and, per step and row, where the row's
+  // virtual row sits in a part row, its weight and the kernel that owns it
   std::vector<RGroup> groups;
   std::vector<RMember> members;
-  std::vector<int> kg0;
-  // per kernel, per row: offset into a part row (-1: no block covers the row) and the row weight
-  std::vector<std::vector<int>> row_poff((size_t)nk, std::vector<int>((size_t)n, -1));
-  std::vector<std::vector<double>> row_isq((size_t)nk, std::vector<double>((size_t)n, 0.0));
-  std::vector<long long> kstride((size_t)nk, 0);
+  std::vector<int> sg0;
+  std::vector<std::vector<int>> row_poff((size_t)nsteps, std::vector<int>((size_t)n, -1));
+  std::vector<std::vector<int>> row_k((size_t)nsteps, std::vector<int>((size_t)n, -1));
+  std::vector<std::vector<double>> row_isq((size_t)nsteps, std::vector<double>((size_t)n, 0.0));
+  std::vector<long long> sstride((size_t)nsteps, 0);
   int max_t = 0;
   long long pstride = 0;
-  for (int j = 0; j < nk; ++j) {
-    HostKernel& hk = g->kernels[(size_t)j];
-    kg0.push_back((int)groups.size());
-    long long poff = 0;
-    std::vector<int> first_of_group;   // block index of the first member of each group of this kernel
-    for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
-      HostBlock& bl = hk.blocks[bi];
-      int gi = -1;
-      if (bl.vrows > 0)
-        for (size_t k = 0; k < first_of_group.size(); ++k) {
-          const HostBlock& b0 = hk.blocks[(size_t)first_of_group[k]];
-          const RGroup& gr = groups[(size_t)kg0.back() + k];
-          if (b0.vrows > 0 && b0.dU == bl.dU && b0.vrows == bl.vrows && b0.nr == bl.nr && gr.nb < 4) {
-            gi = (int)k;
-            break;
+  for (int si = 0; si < nsteps; ++si) {
+    const StepDef& sd = sdef[(size_t)si];
+    sg0.push_back((int)groups.size());
+    struct Ref {
+      int k, b;
+    };
+    std::vector<std::vector<Ref>> gmem;   // members of the groups of this step
+    for (int k : sd.kernels) {
+      HostKernel& hk = g->kernels[(size_t)k];
+      for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
+        HostBlock& bl = hk.blocks[bi];
+        int gi = -1;
+        if (sd.merged) {
+          gi = gmem.empty() ? -1 : 0;
+        } else if (bl.vrows > 0) {
+          for (size_t q = 0; q < gmem.size(); ++q) {
+            const HostBlock& b0 = g->kernels[(size_t)gmem[q][0].k].blocks[(size_t)gmem[q][0].b];
+            if (b0.vrows > 0 && b0.dU == bl.dU && b0.vrows == bl.vrows && b0.nr == bl.nr && gmem[q].size() < 4) {
+              gi = (int)q;
+              break;
+            }
           }
         }
-      if (gi < 0) {
-        RGroup gr{};
-        gr.W = bl.dU;
-        gr.ldw = bl.ldu;
-        gr.t = (int)bl.stream_rows();
-        gr.t_pad = (gr.t + 1) | 1;       // odd stride: P3 rows and P2 columns both conflict-free enough
-        gr.nr = (int)bl.nr;
-        gr.nb = 0;
-        gr.mem0 = (int)members.size();   // members of a group are contiguous: reserve 4 slots
-        gr.s = hk.s.p + bl.col_off;
-        gr.z_off = hk.z_off;
-        gr.kidx = j;
-        members.resize(members.size() + 4);
-        groups.push_back(gr);
-        first_of_group.push_back((int)bi);
-        gi = (int)first_of_group.size() - 1;
+        if (gi < 0) {
+          RGroup gr{};
+          gr.W = bl.dU;
+          gr.ldw = bl.ldu;
+          gr.t = (int)bl.stream_rows();
+          gr.t_pad = (gr.t + 1) | 1;
+          gr.nr = (int)bl.nr;
+          gr.nb = 0;
+          gr.mem0 = (int)members.size();   // members of a group are contiguous: reserve 4 slots
+          gr.s = hk.s.p + bl.col_off;
+          members.resize(members.size() + 4);
+          groups.push_back(gr);
+          gmem.push_back({});
+          gi = (int)gmem.size() - 1;
+          max_t = std::max(max_t, gr.t);
+        }
+        gmem[(size_t)gi].push_back(Ref{k, (int)bi});
       }
-      RGroup& gr = groups[(size_t)kg0.back() + gi];
-      RMember mb{};
-      mb.pos0 = (int)bl.pos0;
-      mb.rows = (int)bl.rows;
-      mb.col_off = (int)bl.col_off;
-      mb.part_off = (long long)bi;       // block index for now; offsets are assigned group by group below
-      members[(size_t)(gr.mem0 + gr.nb)] = mb;
-      ++gr.nb;
-      max_t = std::max(max_t, gr.t);
     }
     // virtual rows of the members of one group are contiguous (the kernel treats them as one vector of nb * t)
-    for (size_t gi = (size_t)kg0.back(); gi < groups.size(); ++gi) {
-      const RGroup& gr = groups[gi];
-      for (int mi = 0; mi < gr.nb; ++mi) {
-        RMember& mb = members[(size_t)(gr.mem0 + mi)];
-        HostBlock& bl = hk.blocks[(size_t)mb.part_off];
+    long long poff = 0;
+    for (size_t q = 0; q < gmem.size(); ++q) {
+      RGroup& gr = groups[(size_t)sg0.back() + q];
+      for (const Ref& rf : gmem[q]) {
+        HostKernel& hk = g->kernels[(size_t)rf.k];
+        HostBlock& bl = hk.blocks[(size_t)rf.b];
+        RMember mb{};
+        mb.pos0 = (int)bl.pos0;
+        mb.rows = (int)bl.rows;
+        mb.col_off = (int)bl.col_off;
+        mb.kidx = rf.k;
+        mb.z_off = hk.z_off;
         mb.part_off = poff;
+        members[(size_t)(gr.mem0 + gr.nb)] = mb;
+        ++gr.nb;
         std::vector<int> loc;
         std::vector<double> isq;
         if (bl.vrows > 0) {
@@ -665,16 +734,21 @@ int plan_resident(Gibbs* g) {
           BGGE_CUDA(cudaStreamSynchronize(st));
         }
         for (int64_t i = 0; i < bl.rows; ++i) {
-          row_poff[(size_t)j][(size_t)(bl.pos0 + i)] = (int)(poff + (bl.vrows > 0 ? loc[(size_t)i] : i));
-          row_isq[(size_t)j][(size_t)(bl.pos0 + i)] = bl.vrows > 0 ? isq[(size_t)i] : 1.0;
+          const size_t row = (size_t)(bl.pos0 + i);
+          row_poff[(size_t)si][row] = (int)(poff + (bl.vrows > 0 ? loc[(size_t)i] : i));
+          row_isq[(size_t)si][row] = bl.vrows > 0 ? isq[(size_t)i] : 1.0;
+          row_k[(size_t)si][row] = rf.k;
         }
         poff += gr.t;
       }
     }
-    kstride[(size_t)j] = poff;
+    if (!sd.merged)   // rows no block of the kernel covers still belong to it: u_j = 0 there (R/BGGE.R:334)
+      for (int64_t i = 0; i < n; ++i) row_k[(size_t)si][(size_t)i] = sd.kernels[0];
+    sstride[(size_t)si] = poff;
     pstride = std::max(pstride, poff);
+    if (sd.merged) rp.has_merged = true;
   }
-  kg0.push_back((int)groups.size());
+  sg0.push_back((int)groups.size());
   if (groups.empty() || (int)groups.size() > R_MAXG || pstride >= (1ll << 30)) return OK;
   // grid size: as many CTAs as useful (>= 4 columns of the widest matrix each), at most one per SM
   int max_nr = 0;
@@ -684,22 +758,21 @@ int plan_resident(Gibbs* g) {
   if (const char* e = getenv("BGGE_RESIDENT_CTAS")) ncta = std::max(1, std::min(cta_cap, atoi(e)));
   const int etp = (max_t + 3) & ~1;
 
-  // units of every kernel (virtual rows that have rows of y, then rows no block covers) and, per step j, the rows
-  // ordered by the units of the next kernel
+  // ---- per step: the rows ordered by the units (virtual rows with rows of y, then uncovered rows) of the next step
   struct HostStep {
     std::vector<REntry> entries;
     std::vector<RUnit> units;
     std::vector<double> wsum;
   };
-  std::vector<HostStep> hs((size_t)nk);
+  std::vector<HostStep> hs((size_t)nsteps);
   int max_entries = 1;
   int max_units = 1, ndraw = 0, ncolc = 0, nwsum = 0;
-  for (int j = 0; j < nk; ++j) nwsum += (int)std::max<long long>(1, kstride[(size_t)j]);
+  for (int si = 0; si < nsteps; ++si) nwsum += (int)std::max<long long>(1, sstride[(size_t)si]);
   auto entries_of = [&](int ncta_) {   // most rows / units one CTA gets in any row phase
     int worst = 1;
     max_units = 1;
-    for (int j = 0; j < nk; ++j) {
-      const auto& un = hs[(size_t)j].units;
+    for (int si = 0; si < nsteps; ++si) {
+      const auto& un = hs[(size_t)si].units;
       const int nu = (int)un.size();
       for (int c = 0; c < ncta_; ++c) {
         const int u0 = (int)((long long)nu * c / ncta_), u1 = (int)((long long)nu * (c + 1) / ncta_);
@@ -709,22 +782,23 @@ int plan_resident(Gibbs* g) {
     }
     return worst;
   };
-  for (int j = 0; j < nk; ++j) {
-    const int jn = (j + 1) % nk;
-    HostStep& h = hs[(size_t)j];
-    // rows of the next kernel grouped by part offset (= virtual row), ascending rows inside a unit
-    std::vector<std::vector<int>> by_off((size_t)kstride[(size_t)jn]);
+  for (int si = 0; si < nsteps; ++si) {
+    const int sn = (si + 1) % nsteps;
+    HostStep& h = hs[(size_t)si];
+    std::vector<std::vector<int>> by_off((size_t)sstride[(size_t)sn]);
     std::vector<int> orphans;
     for (int64_t i = 0; i < n; ++i) {
-      const int po = row_poff[(size_t)jn][(size_t)i];
+      const int po = row_poff[(size_t)sn][(size_t)i];
       if (po >= 0) by_off[(size_t)po].push_back((int)i);
       else orphans.push_back((int)i);
     }
     auto push_entry = [&](int i, double w) {
       REntry e{};
       e.row = i;
-      e.poff = row_poff[(size_t)j][(size_t)i];
-      e.isq = row_isq[(size_t)j][(size_t)i];
+      e.poff = row_poff[(size_t)si][(size_t)i];
+      e.kj = row_k[(size_t)si][(size_t)i];
+      e.kn = row_poff[(size_t)sn][(size_t)i] >= 0 ? row_k[(size_t)sn][(size_t)i] : -1;
+      e.isq = row_isq[(size_t)si][(size_t)i];
       e.w = w;
       h.entries.push_back(e);
     };
@@ -732,7 +806,7 @@ int plan_resident(Gibbs* g) {
       if (by_off[po].empty()) continue;
       RUnit u{};
       u.e0 = (int)h.entries.size();
-      for (int i : by_off[po]) push_entry(i, row_isq[(size_t)jn][(size_t)i]);
+      for (int i : by_off[po]) push_entry(i, row_isq[(size_t)sn][(size_t)i]);
       u.e1 = (int)h.entries.size();
       u.eoff = (int)po;
       h.units.push_back(u);
@@ -745,12 +819,12 @@ int plan_resident(Gibbs* g) {
       u.eoff = -1;
       h.units.push_back(u);
     }
-    // wsum of THIS kernel j: sum of the row weights per virtual row
-    h.wsum.assign((size_t)std::max<long long>(1, kstride[(size_t)j]), 0.0);
+    // wsum of THIS step: sum of the row weights per virtual row
+    h.wsum.assign((size_t)std::max<long long>(1, sstride[(size_t)si]), 0.0);
     for (int64_t i = 0; i < n; ++i)
-      if (row_poff[(size_t)j][(size_t)i] >= 0) h.wsum[(size_t)row_poff[(size_t)j][(size_t)i]] += row_isq[(size_t)j][(size_t)i];
+      if (row_poff[(size_t)si][(size_t)i] >= 0) h.wsum[(size_t)row_poff[(size_t)si][(size_t)i]] += row_isq[(size_t)si][(size_t)i];
   }
-  // shared memory: slices of every group, e~ (4 x etp), staged row values, draws, column constants, row tables
+  // ---- shared memory: slices of every group, e~ (4 x etp), staged row values, draws, column constants, row tables
   size_t smem = 0;
   long long smem_w = 0;
   for (;;) {
@@ -770,17 +844,17 @@ int plan_resident(Gibbs* g) {
     off = (off + 1) & ~1ll;
     smem_w = off;
     max_entries = entries_of(ncta);
-    smem = ((size_t)off + 4 * (size_t)etp + (size_t)max_entries + 2 * (size_t)ndraw + 4 * (size_t)ncolc + (size_t)nwsum) *
+    smem = ((size_t)off + 4 * (size_t)etp + (size_t)max_entries + 4 * (size_t)ndraw + 2 * (size_t)ncolc + (size_t)nwsum) *
                sizeof(double) +
-           (size_t)nk * ((size_t)max_entries * sizeof(REntry) + (size_t)max_units * sizeof(RUnit));
+           (size_t)nsteps * ((size_t)max_entries * sizeof(REntry) + (size_t)max_units * sizeof(RUnit));
     if (ok && smem <= 200 * 1024) break;
     if (ncta >= cta_cap) return OK;      // does not fit even with one CTA per SM: streaming path
     ncta = std::min(cta_cap, ncta * 2);
   }
   // inside every CTA's range the rows are processed in part-offset order (neighbouring lanes then read the same
   // 32-byte sectors of the partial sums); vpos keeps the unit-major slot the unit sums read
-  for (int j = 0; j < nk; ++j) {
-    HostStep& h = hs[(size_t)j];
+  for (int si = 0; si < nsteps; ++si) {
+    HostStep& h = hs[(size_t)si];
     const int nu = (int)h.units.size();
     for (int c = 0; c < ncta; ++c) {
       const int u0 = (int)((long long)nu * c / ncta), u1 = (int)((long long)nu * (c + 1) / ncta);
@@ -812,31 +886,39 @@ int plan_resident(Gibbs* g) {
   rp.ndraw = ndraw;
   rp.ncolc = ncolc;
   rp.nwsum = nwsum;
+  rp.nsteps = nsteps;
   rp.ngroups = (int)groups.size();
   BGGE_CUDA(rp.bar.alloc(1));
-  rp.entries.resize((size_t)nk);
-  rp.units.resize((size_t)nk);
-  rp.wsum.resize((size_t)nk);
-  rp.etil0.resize((size_t)nk);
-  std::vector<RStep> steps((size_t)nk);
-  for (int j = 0; j < nk; ++j) {
-    BGGE_TRY(upload_vec(rp.entries[(size_t)j], hs[(size_t)j].entries, st));
-    BGGE_TRY(upload_vec(rp.units[(size_t)j], hs[(size_t)j].units, st));
-    BGGE_TRY(upload_vec(rp.wsum[(size_t)j], hs[(size_t)j].wsum, st));
-    BGGE_CUDA(rp.etil0[(size_t)j].alloc((size_t)std::max<long long>(1, kstride[(size_t)j])));
-    BGGE_CUDA(cudaMemsetAsync(rp.etil0[(size_t)j].p, 0, (size_t)std::max<long long>(1, kstride[(size_t)j]) * sizeof(double), st));
-    RStep& S = steps[(size_t)j];
-    S.entries = rp.entries[(size_t)j].p;
-    S.units = rp.units[(size_t)j].p;
-    S.nunits = (int)hs[(size_t)j].units.size();
-    S.g0 = kg0[(size_t)j];
-    S.g1 = kg0[(size_t)j + 1];
-    S.nr_total = g->kernels[(size_t)j].nr_total;
-    S.wsum = rp.wsum[(size_t)j].p;
-    S.nws = (int)hs[(size_t)j].wsum.size();
-    S.woff = j == 0 ? 0 : steps[(size_t)j - 1].woff + steps[(size_t)j - 1].nws;
-    S.etil0 = rp.etil0[(size_t)j].p;
-    S.next = (j + 1) % nk;
+  rp.entries.clear();
+  rp.units.clear();
+  rp.wsum.clear();
+  rp.etil0.clear();
+  rp.entries.resize((size_t)nsteps);
+  rp.units.resize((size_t)nsteps);
+  rp.wsum.resize((size_t)nsteps);
+  rp.etil0.resize((size_t)nsteps);
+  std::vector<RStep> steps((size_t)nsteps);
+  for (int si = 0; si < nsteps; ++si) {
+    BGGE_TRY(upload_vec(rp.entries[(size_t)si], hs[(size_t)si].entries, st));
+    BGGE_TRY(upload_vec(rp.units[(size_t)si], hs[(size_t)si].units, st));
+    BGGE_TRY(upload_vec(rp.wsum[(size_t)si], hs[(size_t)si].wsum, st));
+    const size_t ne0 = (size_t)std::max<long long>(1, sstride[(size_t)si]);
+    BGGE_CUDA(rp.etil0[(size_t)si].alloc(ne0));
+    BGGE_CUDA(cudaMemsetAsync(rp.etil0[(size_t)si].p, 0, ne0 * sizeof(double), st));
+    RStep& S = steps[(size_t)si];
+    S.entries = rp.entries[(size_t)si].p;
+    S.units = rp.units[(size_t)si].p;
+    S.nunits = (int)hs[(size_t)si].units.size();
+    S.g0 = sg0[(size_t)si];
+    S.g1 = sg0[(size_t)si + 1];
+    S.next = (si + 1) % nsteps;
+    S.merged = sdef[(size_t)si].merged ? 1 : 0;
+    for (int q = 0; q < 4; ++q)
+      S.zk[q] = sdef[(size_t)si].kernels[std::min<size_t>((size_t)q, sdef[(size_t)si].kernels.size() - 1)];
+    S.wsum = rp.wsum[(size_t)si].p;
+    S.nws = (int)hs[(size_t)si].wsum.size();
+    S.woff = si == 0 ? 0 : steps[(size_t)si - 1].woff + steps[(size_t)si - 1].nws;
+    S.etil0 = rp.etil0[(size_t)si].p;
   }
   BGGE_TRY(upload_vec(rp.steps, steps, st));
   BGGE_TRY(upload_vec(rp.groups, groups, st));
@@ -847,8 +929,8 @@ int plan_resident(Gibbs* g) {
   BGGE_CUDA(cudaStreamSynchronize(st));
   rp.enabled = true;
   if (getenv("BGGE_DEBUG"))
-    fprintf(stderr, "[bgge] resident plan: ncta=%d smem=%zu groups=%zu pstride=%lld max_t=%d max_entries=%d\n", ncta, smem,
-            groups.size(), (long long)pstride, max_t, max_entries);
+    fprintf(stderr, "[bgge] resident plan: ncta=%d smem=%zu steps=%d (merged: %s) groups=%zu pstride=%lld max_t=%d max_entries=%d\n",
+            ncta, smem, nsteps, rp.has_merged ? "yes" : "no", groups.size(), (long long)pstride, max_t, max_entries);
   return OK;
 }
 
@@ -859,6 +941,8 @@ int launch_resident(Gibbs* g, int64_t iters) {
   p.members = rp.members.p;
   p.steps = rp.steps.p;
   p.nk = g->nk;
+  p.nsteps = rp.nsteps;
+  for (int j = 0; j < g->nk; ++j) p.nr_k[j] = g->kernels[(size_t)j].nr_total;
   p.ncta = rp.ncta;
   p.n = g->n;
   p.r = g->r.p;

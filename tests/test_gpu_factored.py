@@ -120,6 +120,48 @@ def test_shared_blocks_multi_rhs_sweep(E, drop_env):
         assert relmax(got["yHat"], ref["yHat"]) <= 1e-9, mode
 
 
+@pytest.mark.parametrize("E,drop_env,kernel", [(3, None, "GB"), (6, None, "GK"), (5, 1, "GB")])
+def test_mde_environment_kernels_share_one_decomposition_and_sweep_together(E, drop_env, kernel):
+    """MDe: one kernel per environment, each one block.  In a balanced trial they are the same L x L matrix: the
+    handle decomposes it once and the resident kernel sweeps up to 4 of them as ONE step (they touch disjoint
+    rows, so this equals the sequential sweep).  E = 6 -> steps of 4 + 2; a design where one environment misses
+    genotypes (its matrix differs: not shared, not merged).  Per-iteration parity with the oracle on the dense
+    kernels, for the resident (1), streaming (2) and two-pass (0) paths, plus thinning / burn-in on mode 1."""
+    import bgge_b200
+    L, p = 36, 48
+    X = markers(L, p, 5)
+    Y, names = design(L, E)
+    if drop_env is not None:
+        Y = [r for k, r in enumerate(Y) if not (r[0] == f"env{drop_env + 1:02d}" and k % 5 == 0)]
+    envs = [r[0] for r in Y]
+    ne = [envs.count(e) for e in sorted(set(envs))]
+    n = len(Y)
+    Kf = bgge_b200.getK(Y, X, kernel=kernel, model="MDe", rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel=kernel, model="MDe", rownames=names)
+    assert len(Kf) == E + 1
+    rng = np.random.default_rng(10 + E)
+    y = rng.standard_normal(n)
+    y[rng.choice(n, 4, replace=False)] = np.nan
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    ite = 14
+    nz, nc = oracle.tape_sizes(n, nrs, ite, n_na=4)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    for burn, thin, modes in ((0, 1, (1, 2, 0)), (4, 3, (1,))):
+        ref = oracle.BGGE(y, Kd, ne=ne, ite=ite, burn=burn, thin=thin, draws=oracle.TapeDraws(z, c), eig=Ei)
+        for mode in modes:
+            got = bgge_b200.BGGE(y, Kf, ne=ne, ite=ite, burn=burn, thin=thin, draws=(z, c), mode=mode)
+            assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
+            assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, mode
+            for nm in ref["K"]:
+                assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9, (mode, nm)
+                assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (mode, nm)
+                assert relmax(got["K"][nm]["u.sd"], ref["K"][nm]["u.sd"]) <= 1e-7, (mode, nm)
+            assert relmax(got["yHat"], ref["yHat"]) <= 1e-9, mode
+            assert relmax(got["y"], ref["y"]) <= 1e-9, mode
+
+
 def test_shared_kernel_handles_reproduce_owner(lib):
     """bgge_gibbs_share_kernel: chains that borrow a decomposition (factorised + shared blocks included) give
     the same chain as a handle that built it itself."""

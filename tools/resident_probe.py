@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bgge_b200
 from bgge_b200 import _lib as lib
 
-model = sys.argv[1] if len(sys.argv) > 1 else "MDs"
+model = sys.argv[1] if len(sys.argv) > 1 else "MDs"   # MM | MDs | MDe
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
 L, E, p = 599, 4, 1279
 rng = np.random.default_rng(0)
