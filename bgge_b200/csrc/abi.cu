@@ -146,6 +146,11 @@ int sm_count() {
   return (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) ? g_sm_count[dev] : 148;
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("BGGE_NO_PDL") == nullptr;
+  return on;
+}
+
 namespace {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -49,6 +49,7 @@ const char* last_error();
 
 int ensure_device();   // checks that the current device is sm_100; caches SM count
 int sm_count();
+bool pdl_enabled();   // BGGE_NO_PDL=1 switches programmatic dependent launch off
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -97,6 +98,14 @@ struct DevBuf {
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and
+// its writes are visible (no-op otherwise).  Everything before it may only touch data no earlier launch of the
+// same iteration writes (tables, the eigen basis).  pdl_trigger() lets the successor's CTAs be scheduled as soon
+// as every CTA of this grid has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

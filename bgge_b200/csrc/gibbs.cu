@@ -282,7 +282,10 @@ scalar_kernel(const ScalarArgs a, DrawCfg dc) {
   __shared__ double sh_a[33], sh_b[33];
   __shared__ double sh_chi[MAXK + 1];
   __shared__ double sh_zmu, sh_sigsq;
+  pdl_trigger();
   Scal* sc = a.sc;
+  // it / shift / mu were written by the previous scalar_kernel, at least two launches upstream: every launch
+  // in between passed its own pdl_wait(), so that kernel has completed and the values are visible here
   const long long it = sc->it;        // iteration that just finished (0 right after init)
   const double shift = sc->shift;
   const double mu = sc->mu;
@@ -301,6 +304,7 @@ scalar_kernel(const ScalarArgs a, DrawCfg dc) {
     }
     if (warp == nwarps - 1) sh_zmu = draw_normal(dc, it + 1, STREAM_MU, 0ull, z_pos(dc, it + 1, 0));
   }
+  pdl_wait();   // the draws above overlap the tail of the previous launch
   // ---- one pass over r: sum e^2 and sum r
   double sse = 0.0, sr = 0.0;
   for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
@@ -509,8 +513,19 @@ int launch_scalar(Gibbs* g) {
     a.n_bpart[j] = g->kernels[j].fused ? g->kernels[j].fused_clusters : g->kernels[j].n_atasks;
     a.nr[j] = g->kernels[j].nr_total;
   }
-  scalar_kernel<<<1, S_THREADS, 0, g->stream>>>(a, g->draw);
-  BGGE_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, 1);
+  cfg.blockDim = dim3(S_THREADS, 1, 1);
+  cfg.stream = g->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // the early reads of it / shift / mu need a launch between two scalar kernels that waits itself (fused steps)
+  bool chain = pdl_enabled() && g->q == 0 && g->initialised;
+  for (int j = 0; j < g->nk; ++j) chain = chain && g->kernels[j].fused;
+  cfg.numAttrs = chain ? 1 : 0;
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, scalar_kernel, a, g->draw));
   return OK;
 }
 

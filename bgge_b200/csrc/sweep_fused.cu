@@ -105,6 +105,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
                    double* __restrict__ upart, double* __restrict__ bpart, long long n,
                    const double* __restrict__ ve, double* __restrict__ vupart, long long vtotal,
                    const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns, int npx) {
+  pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
   const uint32_t cs = cluster.num_blocks();
@@ -147,6 +148,9 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   }
   cluster.sync();   // barriers of every CTA exist before anybody sends
 
+  // The producer only reads the eigen basis (constant) and starts filling the ring while the previous launch
+  // (gather / finalize / scalars of the step before) is still finishing; everybody else needs its results.
+  if (warp != 2 * (F_ROLE / 32)) pdl_wait();
   const double shift = sc->shift;
   const double lam = sc->sigb[j];
   const double tau = sc->tau;
@@ -411,8 +415,10 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
                       const double* __restrict__ vupart, long long vtotal, double* __restrict__ r, double* __restrict__ u, double* __restrict__ umean,
                       double* __restrict__ um2, const Scal* __restrict__ sc, long long thin, long long burn) {
   __shared__ double part[FIN_Q][FIN_ROWS];
+  pdl_trigger();
   const FTile t = tiles[blockIdx.x];
   const int lane = threadIdx.x, ql = threadIdx.y;
+  pdl_wait();
   const long long it = sc->it;
   const bool keep = (it % thin == 0) && (it > burn);
   const double kcount = keep ? (double)(it / thin - burn / thin) : 1.0;
@@ -453,16 +459,19 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
 __global__ void __launch_bounds__(256)
 virt_gather_kernel(const VDesc* __restrict__ desc, int ndesc, const double* __restrict__ r,
                    const double* __restrict__ u_old, const Scal* __restrict__ sc, double* __restrict__ ve) {
+  pdl_trigger();
   int d = 0;
   while (d + 1 < ndesc && (int)blockIdx.x >= desc[d + 1].cta0) ++d;
   const VDesc vd = desc[d];
   const int a = ((int)blockIdx.x - vd.cta0) * blockDim.x + threadIdx.x;
+  const int k0 = a < vd.vrows ? vd.rowptr[a] : 0, k1 = a < vd.vrows ? vd.rowptr[a + 1] : 0;   // constant tables
+  pdl_wait();
   if (a >= vd.vrows) return;
   const double shift = sc->shift;
   const double* rp = r + vd.pos0;
   const double* up = u_old + vd.pos0;
   double acc = 0.0;
-  for (int k = vd.rowptr[a]; k < vd.rowptr[a + 1]; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const int i = vd.rowidx[k];
     acc = fma(vd.isq[i], (rp[i] - shift) + up[i], acc);
   }
@@ -477,13 +486,15 @@ int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
   cfg.blockDim = dim3(F_THREADS, 1, 1);
   cfg.dynamicSmemBytes = hk.fused_smem;
   cfg.stream = g->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)hk.fused_cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   BGGE_CUDA(cudaLaunchKernelEx(&cfg, kfn, (const FPanel*)hk.fpanels.p, (const int2*)hk.fcluster.p,
                                (const double*)g->r.p, (const double*)(g->u.p + (size_t)j * g->n),
                                (const double*)hk.s.p, g->upart.p, hk.bpart.p, (long long)g->n,
@@ -555,21 +566,36 @@ int occupancy_dispatch(HostKernel& hk, int cs, size_t smem, int* ncl) { BGGE_FUS
 
 int launch_fused(Gibbs* g, HostKernel& hk, int j) {
   if (hk.n_vdesc > 0) {
-    virt_gather_kernel<<<(unsigned)hk.vgrid, 256, 0, g->stream>>>(hk.vdesc.p, hk.n_vdesc, g->r.p,
-                                                                 g->u.p + (size_t)j * g->n, g->scal.p, hk.ve.p);
-    BGGE_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)hk.vgrid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = g->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    BGGE_CUDA(cudaLaunchKernelEx(&cfg, virt_gather_kernel, (const VDesc*)hk.vdesc.p, hk.n_vdesc, (const double*)g->r.p,
+                                 (const double*)(g->u.p + (size_t)j * g->n), (const Scal*)g->scal.p, hk.ve.p));
   }
   auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
   return run();
 }
 
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
-  fused_finalize_kernel<<<hk.n_ftiles, dim3(FIN_ROWS, FIN_Q), 0, g->stream>>>(hk.ftiles.p, g->upart.p, (long long)g->n,
-                                                            g->vupart.p, (long long)hk.vtotal, g->r.p,
-                                                            g->u.p + (size_t)j * g->n, g->umean.p + (size_t)j * g->n,
-                                                            g->um2.p + (size_t)j * g->n, g->scal.p,
-                                                            (long long)g->thin, (long long)g->burn);
-  BGGE_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)hk.n_ftiles, 1, 1);
+  cfg.blockDim = dim3(FIN_ROWS, FIN_Q, 1);
+  cfg.stream = g->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, fused_finalize_kernel, (const FTile*)hk.ftiles.p, (const double*)g->upart.p, (long long)g->n,
+                               (const double*)g->vupart.p, (long long)hk.vtotal, g->r.p, g->u.p + (size_t)j * g->n,
+                               g->umean.p + (size_t)j * g->n, g->um2.p + (size_t)j * g->n, (const Scal*)g->scal.p,
+                               (long long)g->thin, (long long)g->burn));
   return OK;
 }
 
