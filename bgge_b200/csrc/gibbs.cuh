@@ -181,7 +181,8 @@ struct ResidentPlan {
   std::vector<DevBuf<REntry>> entries;
   std::vector<DevBuf<RUnit>> units;
   std::vector<DevBuf<double>> wsum, etil0;
-  DevBuf<double> part, zqpart, sspart;
+  DevBuf<double> part, zqpart, sspart, x1, mx0, xrpart;
+  long long ps0 = 0;
 };
 
 // One decomposed base matrix C^{1/2} K0[T,T] C^{1/2}, kept per handle: identical blocks of one kernel and identical

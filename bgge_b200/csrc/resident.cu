@@ -42,6 +42,7 @@ constexpr int R_NPL = 19;                     // partials per lane: supports up 
 constexpr int R_MAXCOLS = 64;                 // columns of one matrix per CTA (bsm capacity)
 constexpr int R_MAXG = 32;                    // basis matrices (groups) per model
 constexpr int R_MAXKR = 16;                   // kernels per model
+constexpr int R_MAXQ = 8;                     // fixed-effect columns
 
 struct RParams {
   const RGroup* groups;
@@ -70,6 +71,18 @@ struct RParams {
   int etp;                    // padded length of one e~ vector in shared memory
   long long smem_w;           // doubles of basis slices per CTA
   int max_entries, max_units, ndraw, ncolc, nwsum;
+  // fixed effects (R/BGGE.R:284-290): the kernel keeps r WITHOUT the fixed-effect part (r_s = r + XF b), so the
+  // XF step needs no pass over the rows: XF'(e + XF b_old) = XF' r_s - shift * XF'1
+  int q;
+  const double* xf;           // n x q, column-major
+  const double* txx;          // (XF'XF)^-1, q x q
+  const double* lchol;        // lower Cholesky factor of txx
+  const double* x1;           // XF'1
+  const double* mx0;          // [q][ps0]: C^-1/2 Z' XF of step 0 (its residual is formed before the new b is known)
+  long long ps0;
+  double* bet;                // [q] current coefficients (state shared with the streaming path)
+  double* chain_bet;
+  double* xrpart;             // [q][ncta]: XF' r_s pieces
   unsigned long long* bar;    // grid barrier counter (zeroed before the launch)
   unsigned long long* timing; // debug (BGGE_RESIDENT_TIMING): ns per phase, accumulated by CTA 0
 };
@@ -92,8 +105,10 @@ struct RShared {
   RStep steps[R_MAXKR];
   int nent[R_MAXKR], nun[R_MAXKR];
   int c0[R_MAXG], ncol[R_MAXG];        // my columns of every basis matrix
-  double red[4][R_WARPS];
-  double tot[R_MAXKR + 2];
+  double red[2 + R_MAXQ][R_WARPS];
+  double tot[R_MAXKR + 2 + R_MAXQ];
+  double bet[R_MAXQ], betn[R_MAXQ], zxf[2][R_MAXQ], x1[R_MAXQ];
+  double txx[R_MAXQ * R_MAXQ], lch[R_MAXQ * R_MAXQ];
   double bsm[4 * R_MAXCOLS];
   double dpart[4 * R_MAXCOLS];
   double chi[2][R_MAXKR + 1];
@@ -130,6 +145,7 @@ struct RSmem {                 // dynamic shared memory carve-up
   double* wsm;                 // basis slices
   double* etil;                // [4][etp]
   double* vals;                // [max_entries]
+  double* rvals;               // [max_entries] updated residuals of my rows (XF' r_s pieces)
   double* zbuf;                // [2][ndraw] coefficient normals of my columns, by iteration parity
   double* svs;                 // [ncolc] eigenvalues of my columns
   double* isv;                 // 1 / eigenvalue
@@ -143,7 +159,7 @@ struct RSmem {                 // dynamic shared memory carve-up
 // Draws of iteration itn that do not depend on the data: the normals of my coefficient columns, the chi-squares
 // and the normal of the intercept that follows itn.  Stored under parity itn & 1.  (One copy of this code: the
 // kernel is instruction-fetch sensitive, every phase runs once per iteration.)
-__device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, int ndraw, int ngroups, int nk, long long n,
+__device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, int ndraw, int ngroups, int nk, int q, long long n,
                                        long long itn, bool normals, bool scalars) {
   RShared& sh = *shp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -164,8 +180,13 @@ __device__ __noinline__ void draws_for(DrawCfg dc, RShared* shp, double* zbuf, i
   // scalar draws, one per warp from the last warp down: the kernels' chi-squares go with the normals (first
   // barrier of an iteration), the residual chi-square and the intercept normal with the second
   if (lane == 0) {
-    for (int d = R_WARPS - 1 - warp; d <= nk + 1; d += R_WARPS) {
+    for (int d = R_WARPS - 1 - warp; d <= nk + 1 + q; d += R_WARPS) {
       if (!(d < nk ? normals : scalars)) continue;
+      if (d > nk + 1) {   // fixed-effect normals of the iteration that follows itn (R/BGGE.R:107)
+        const int k = d - nk - 2;
+        sh.zxf[par][k] = draw_normal(dc, itn + 1, STREAM_XF, (unsigned long long)k, dc.z_init + itn * dc.z_per_it + dc.z_off_xf + k);
+        continue;
+      }
       if (d < nk)
         sh.chi[par][d] = draw_chisq(dc, itn, STREAM_CHI_K + (uint32_t)d, (double)sh.nrk[d] + NU, (itn - 1) * dc.c_per_it + d);
       else if (d == nk)
@@ -194,20 +215,41 @@ __device__ __forceinline__ void column_constants(RShared* shp, const double* svs
   }
 }
 
-// Row phase of step j (update = true), or only the gather of the next step's etil0 (update = false: prologue
-// of a launch and after the imputation of missing phenotypes).
+// b = tXX (XF' r_s - shift XF'1) + sqrt(sigsq) L z  (R/BGGE.R:286-288, 106-109); every thread calls, result in sh.bet
+__device__ __forceinline__ void xf_draw(RShared& sh, int q, const double* xr, double shift, double sigsq, const double* z) {
+  const int k = threadIdx.x;
+  double bn = 0.0;
+  if (k < q) {
+    double media = 0.0, lz = 0.0;
+    for (int k2 = 0; k2 < q; ++k2) media += sh.txx[k + k2 * q] * (xr[k2] - shift * sh.x1[k2]);
+    for (int k2 = 0; k2 <= k; ++k2) lz += sh.lch[k + k2 * q] * z[k2];
+    bn = media + sqrt(sigsq) * lz;
+  }
+  __syncthreads();
+  if (k < q) sh.bet[k] = bn;
+  __syncthreads();
+}
+
+// Row phase of step j.  mode 0: update (u_i from the partial sums, r, Welford) and the next step's etil0;
+// mode 1: only the gather of the next step's etil0 (after the imputation of missing phenotypes);
+// mode 2: launch prologue: as 1 and r -> r_s = r + XF b;  mode 3: launch epilogue: r_s -> r = r_s - XF b.
+// last (mode 0 on the last step, always for modes 1-2): the etil0 produced is for step 0 of the NEXT iteration, whose
+// fixed effects are not known yet, so it carries no XF term (P1 of step 0 subtracts it) and the per-CTA pieces of
+// XF' r_s are formed; other steps get etil0 with the current XF b removed.
 template <bool TIMED>
-__device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const RSmem& m, int j, bool update, bool last,
+__device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const RSmem& m, int j, int mode, bool last,
                                            double shift, bool keep, double kcount, unsigned long long* tacc = nullptr,
                                            unsigned long long* tlast_p = nullptr) {
   const bool timed = TIMED && tacc != nullptr;
   unsigned long long tlast = timed ? *tlast_p : 0ull;
+  const bool update = mode == 0;
   const int cta = blockIdx.x, tid = threadIdx.x;
   const int sub = tid / R_SUB, sl = tid % R_SUB;
   const int ne = sh.nent[j], nu = sh.nun[j];
   const REntry* ent = m.sent + (size_t)j * p.max_entries;
   const RUnit* units = m.sunit + (size_t)j * p.max_units;
   const int jn = sh.steps[j].next;
+  const int q = p.q;
   double sse = 0.0, sr = 0.0;
   for (int k0 = 0; k0 < ne; k0 += R_THREADS / R_SUB) {
     const int k = k0 + sub;
@@ -219,7 +261,7 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
     // kn: the kernel whose u enters the next step's residual for this row (-1: none)
     const bool upd = update && E.kj >= 0;
     double* ujp = p.u + (size_t)(upd ? E.kj : 0) * p.n + E.row;
-    double rold = 0.0, uold = 0.0, ujn = 0.0, mm = 0.0, m2 = 0.0;
+    double rold = 0.0, uold = 0.0, ujn = 0.0, mm = 0.0, m2 = 0.0, xfb = 0.0;
     if (valid && sl == 0) {
       rold = __ldcg(p.r + E.row);
       if (upd) uold = __ldcg(ujp);
@@ -228,6 +270,8 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
         mm = __ldcg(p.umean + (size_t)E.kj * p.n + E.row);
         m2 = __ldcg(p.um2 + (size_t)E.kj * p.n + E.row);
       }
+      if (q > 0 && mode != 1)
+        for (int kk = 0; kk < q; ++kk) xfb = fma(__ldg(p.xf + (size_t)kk * p.n + E.row), sh.bet[kk], xfb);
     }
     double v;
     if (update) {
@@ -237,8 +281,8 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
       const size_t pstep = (size_t)R_SUB * p.pstride;
       const int nq = live ? (p.ncta - sl + R_SUB - 1) / R_SUB : 0;   // partials this lane reads
 #pragma unroll
-      for (int q = 0; q < R_NPL; ++q) {
-        x[q] = q < nq ? __ldcg(pp) : 0.0;
+      for (int qq = 0; qq < R_NPL; ++qq) {
+        x[qq] = qq < nq ? __ldcg(pp) : 0.0;
         pp += pstep;
       }
       R_TICK(14)
@@ -264,20 +308,30 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
           }
         }
         if (last) {
-          const double e = rn - shift;
+          const double e = (rn - shift) - xfb;
           sse = fma(e, e, sse);
           sr += rn;
+          if (q > 0) m.rvals[E.vpos] = rn;
         }
       }
-      v = E.w * (rn + (upd && E.kn == E.kj ? un : ujn));
+      v = E.w * ((last ? rn : rn - xfb) + (upd && E.kn == E.kj ? un : ujn));
+    } else if (mode == 3) {
+      if (valid && sl == 0) p.r[E.row] = rold - xfb;
+      v = 0.0;
     } else {
-      v = E.w * (rold + ujn);
+      const double rs = mode == 2 ? rold + xfb : rold;
+      if (valid && sl == 0 && q > 0) {
+        if (mode == 2) p.r[E.row] = rs;
+        m.rvals[E.vpos] = rs;
+      }
+      v = E.w * (rs + ujn);
     }
     if (valid && sl == 0) m.vals[E.vpos] = v;
   }
   R_TICK(11)
   __syncthreads();
   R_TICK(12)
+  if (mode == 3) return;
   double* etil0 = sh.steps[jn].etil0;
   for (int un = tid; un < nu; un += R_THREADS) {
     const RUnit U = units[un];
@@ -287,19 +341,33 @@ __device__ __forceinline__ void rows_phase(const RParams& p, RShared& sh, const 
     etil0[U.eoff] = acc;
   }
   R_TICK(13)
-  if (last) {   // per-CTA pieces of sum e^2 and sum r (fixed order)
+  if (last && update) {   // per-CTA pieces of sum e^2 and sum r (fixed order)
     sse = warp_sum(sse);
     sr = warp_sum(sr);
     if ((tid & 31) == 0) {
       sh.red[0][tid >> 5] = sse;
       sh.red[1][tid >> 5] = sr;
     }
+  }
+  if (last && q > 0) {    // per-CTA pieces of XF' r_s: 64 threads per column, rows in storage order
+    const int kk = tid >> 6, t = tid & 63;
+    double acc = 0.0;
+    if (kk < q)
+      for (int e = t; e < ne; e += 64) acc = fma(__ldg(p.xf + (size_t)kk * p.n + ent[e].row), m.rvals[ent[e].vpos], acc);
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) sh.red[2 + (tid >> 6)][(tid >> 5) & 1] = acc;
+  }
+  if (last) {
     __syncthreads();
-    if (tid < 2) {
+    if (update && tid < 2) {
       double t = 0.0;
 #pragma unroll
       for (int w = 0; w < R_WARPS; ++w) t += sh.red[tid][w];
       p.sspart[(size_t)tid * p.ncta + cta] = t;
+    }
+    if (tid >= 32 && tid < 32 + q) {
+      const int kk = tid - 32;
+      p.xrpart[(size_t)kk * p.ncta + cta] = sh.red[2 + kk][0] + sh.red[2 + kk][1];
     }
   }
   if (timed) *tlast_p = tlast;
@@ -315,7 +383,8 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
   m.wsm = reinterpret_cast<double*>(rsm);
   m.etil = m.wsm + p.smem_w;
   m.vals = m.etil + 4 * p.etp;
-  m.zbuf = m.vals + p.max_entries;
+  m.rvals = m.vals + p.max_entries;
+  m.zbuf = m.rvals + p.max_entries;
   m.svs = m.zbuf + 2 * p.ndraw;
   m.isv = m.svs + p.ncolc;
   m.tv = m.isv + p.ncolc;
@@ -384,13 +453,33 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
     sh.Sc[j] = sc->Sc[j];
     sh.nrk[j] = p.nr_k[j];
   }
+  for (int k = tid; k < p.q; k += R_THREADS) {
+    sh.bet[k] = p.bet[k];
+    sh.x1[k] = p.x1[k];
+  }
+  for (int k = tid; k < p.q * p.q; k += R_THREADS) {
+    sh.txx[k] = p.txx[k];
+    sh.lch[k] = p.lchol[k];
+  }
   __syncthreads();
   column_constants(&sh, m.svs, m.tv, m.sd, p.ndraw, p.ngroups, tau);
-  draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it, true, true);
+  draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.q, p.n, it, true, true);
   // first kernel's etil0 from the state in memory
-  rows_phase<false>(p, sh, m, p.nsteps - 1, false, false, 0.0, false, 1.0);
+  rows_phase<false>(p, sh, m, p.nsteps - 1, p.q > 0 ? 2 : 1, true, 0.0, false, 1.0);
   bar_arrive(gb);
   bar_wait(gb);
+  if (p.q > 0) {   // fixed effects of the first iteration of this launch (later ones are drawn at the end of the one before)
+    for (int v = warp; v < p.q; v += R_WARPS) {
+      double x = 0.0;
+      for (int c = lane; c < p.ncta; c += 32) x += __ldcg(p.xrpart + (size_t)v * p.ncta + c);
+      x = warp_sum(x);
+      if (lane == 0) sh.tot[v] = x;
+    }
+    if (tid < p.q)
+      sh.betn[tid] = draw_normal(dc, it, STREAM_XF, (unsigned long long)tid, dc.z_init + (it - 1) * dc.z_per_it + dc.z_off_xf + tid);
+    __syncthreads();
+    xf_draw(sh, p.q, sh.tot, shift, sigsq, sh.betn);
+  }
 
   const bool timed = p.timing && cta == 0 && tid == 0;
   unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -426,7 +515,12 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int idx = i0 + q * R_THREADS;
-              if (idx < tot) et[idx] = v[q] - shift * ws[idx];
+              if (idx < tot) {
+                double e = v[q] - shift * ws[idx];
+                if (j == 0 && p.q > 0)   // step 0: etil0 was formed before this iteration's fixed effects were drawn
+                  for (int kk = 0; kk < p.q; ++kk) e -= __ldg(p.mx0 + (size_t)kk * p.ps0 + po + idx) * sh.bet[kk];
+                et[idx] = e;
+              }
             }
           }
         }
@@ -511,27 +605,29 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       R_TICK(0)
       bar_arrive(gb);
       R_TICK(9)
-      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it + 1, true, false);   // hidden behind the barrier
+      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.q, p.n, it + 1, true, false);   // hidden behind the barrier
       R_TICK(10)
       bar_wait(gb);
       R_TICK(1)
-      rows_phase<TIMED>(p, sh, m, j, true, j == p.nsteps - 1, shift, keep, kcount, timed ? tacc : nullptr, &tlast);
+      rows_phase<TIMED>(p, sh, m, j, 0, j == p.nsteps - 1, shift, keep, kcount, timed ? tacc : nullptr, &tlast);
       R_TICK(2)
       bar_arrive(gb);
-      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.n, it + 1, false, true);
+      if (j == 0 && step + 1 < p.iters) draws_for(dc, &sh, m.zbuf, p.ndraw, p.ngroups, p.nk, p.q, p.n, it + 1, false, true);
       bar_wait(gb);
       R_TICK(3)
     }
     // ---- scalars, identically in every CTA: sum the per-CTA pieces (R/BGGE.R:360-367)
-    for (int v = warp; v < p.nk + 2; v += R_WARPS) {
-      const double* src = v < p.nk ? p.zqpart + ((size_t)par * p.nk + v) * p.ncta : p.sspart + (size_t)(v - p.nk) * p.ncta;
+    for (int v = warp; v < p.nk + 2 + p.q; v += R_WARPS) {
+      const double* src = v < p.nk       ? p.zqpart + ((size_t)par * p.nk + v) * p.ncta
+                          : v < p.nk + 2 ? p.sspart + (size_t)(v - p.nk) * p.ncta
+                                         : p.xrpart + (size_t)(v - p.nk - 2) * p.ncta;
       double x = 0.0;
       for (int c = lane; c < p.ncta; c += 32) x += __ldcg(src + c);
       x = warp_sum(x);
       if (lane == 0) sh.tot[v] = x;
     }
     __syncthreads();
-    double sr = sh.tot[p.nk + 1];
+    double sr = sh.tot[p.nk + 1];   // sum of r_s; the fixed-effect part comes off below
     sigsq = (sh.tot[p.nk] + Sce) / sh.chi[par][p.nk];
     tau = 1.0 / sigsq;
     if (tid < p.nk) sh.sigb[tid] = (sh.tot[tid] + NU * sh.Sc[tid]) / sh.chi[par][tid];
@@ -544,10 +640,12 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
         const long long i = p.na_idx[k];
         double uhat = 0.0;
         for (int j = 0; j < p.nk; ++j) uhat = (j == 0) ? __ldcg(p.u + i) : uhat + __ldcg(p.u + (size_t)j * p.n + i);
+        double aux = 0.0;
+        for (int kk = 0; kk < p.q; ++kk) aux += __ldg(p.xf + (size_t)kk * p.n + i) * sh.bet[kk];
         const double z = draw_normal(dc, it, STREAM_NA, (unsigned long long)k, dc.z_init + (it - 1) * dc.z_per_it + dc.z_off_na + k);
-        const double yv = ((0.0 + mu) + uhat) + sd * z;
+        const double yv = ((aux + mu) + uhat) + sd * z;
         p.y[i] = yv;
-        const double rn = (((yv - uhat) - 0.0) - mu) + shift;
+        const double rn = ((((yv - uhat) - aux) - mu) + shift) + aux;   // r_s keeps the fixed-effect part
         dsum += rn - __ldcg(p.r + i);
         p.r[i] = rn;
       }
@@ -562,25 +660,38 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
       }
       bar_arrive(gb);
       bar_wait(gb);
-      rows_phase<false>(p, sh, m, p.nsteps - 1, false, false, 0.0, false, 1.0);
+      rows_phase<false>(p, sh, m, p.nsteps - 1, 1, true, 0.0, false, 1.0);   // also renews the XF' r_s pieces
       bar_arrive(gb);
       bar_wait(gb);
       double x = 0.0;
       for (int c = lane; c < p.ncta; c += 32) x += __ldcg(p.sspart + (size_t)2 * p.ncta + c);
       sr += warp_sum(x);   // every warp computes the same sum
+      for (int v = warp; v < p.q; v += R_WARPS) {
+        double xx = 0.0;
+        for (int c = lane; c < p.ncta; c += 32) xx += __ldcg(p.xrpart + (size_t)v * p.ncta + c);
+        xx = warp_sum(xx);
+        if (lane == 0) sh.tot[p.nk + 2 + v] = xx;
+      }
+      __syncthreads();
     }
+    for (int kk = 0; kk < p.q; ++kk) sr -= sh.x1[kk] * sh.bet[kk];   // sum r = sum r_s - 1'XF b
     if (cta == 0 && tid == 0 && tmod == 0) {   // thinned chain (R/BGGE.R:384-395)
       const long long slot = qit - 1;
       if (slot < p.ncum) {
         p.chain_varE[slot] = sigsq;
         p.chain_mu[slot] = mu;
         for (int j = 0; j < p.nk; ++j) p.chain_varU[(long long)j * p.ncum + slot] = sh.sigb[j];
+        for (int kk = 0; kk < p.q; ++kk) p.chain_bet[slot * p.q + kk] = sh.bet[kk];
       }
     }
     // next intercept (R/BGGE.R:278-281): mean(temp + mu) = mean(r) + mu0
     mu_done = mu;
     mu = (sr / (double)p.n + mu0) + sqrt(sigsq / (double)p.n) * sh.zmu[par];
     shift = mu - mu0;
+    if (p.q > 0 && step + 1 < p.iters) {   // fixed effects of the next iteration (R/BGGE.R:284-290)
+      __syncthreads();                     // sh.bet was read above (chain record, sum r)
+      xf_draw(sh, p.q, sh.tot + p.nk + 2, shift, sigsq, sh.zxf[par]);
+    }
     if (++tmod == p.thin) {
       tmod = 0;
       ++qit;
@@ -590,6 +701,11 @@ resident_sweep_kernel(const RParams p, DrawCfg dc) {
   if (TIMED && timed) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) p.timing[k] = tacc[k];
+  }
+  if (p.q > 0) {   // back to the streaming path's convention: r without the fixed-effect part
+    __syncthreads();
+    rows_phase<false>(p, sh, m, p.nsteps - 1, 3, false, 0.0, false, 1.0);
+    if (cta == 0 && tid < p.q) p.bet[tid] = sh.bet[tid];
   }
   if (cta == 0 && tid == 0) {   // hand the chain state back (fetch functions, streaming path)
     sc->mu = mu;
@@ -616,8 +732,8 @@ int plan_resident(Gibbs* g) {
   ResidentPlan& rp = g->resident;
   rp.enabled = false;
   rp.has_merged = false;
-  if (g->q > 0 || g->mode != 1 || getenv("BGGE_NO_RESIDENT")) return OK;
-  if (g->n > 32768 || g->nk > R_MAXKR) return OK;
+  if (g->mode != 1 || getenv("BGGE_NO_RESIDENT")) return OK;
+  if (g->n > 32768 || g->nk > R_MAXKR || g->q > R_MAXQ) return OK;
   cudaStream_t st = g->stream;
   const int sms = sm_count();
   const int64_t n = g->n;
@@ -844,7 +960,7 @@ int plan_resident(Gibbs* g) {
     off = (off + 1) & ~1ll;
     smem_w = off;
     max_entries = entries_of(ncta);
-    smem = ((size_t)off + 4 * (size_t)etp + (size_t)max_entries + 4 * (size_t)ndraw + 2 * (size_t)ncolc + (size_t)nwsum) *
+    smem = ((size_t)off + 4 * (size_t)etp + 2 * (size_t)max_entries + 4 * (size_t)ndraw + 2 * (size_t)ncolc + (size_t)nwsum) *
                sizeof(double) +
            (size_t)nsteps * ((size_t)max_entries * sizeof(REntry) + (size_t)max_units * sizeof(RUnit));
     if (ok && smem <= 200 * 1024) break;
@@ -926,6 +1042,24 @@ int plan_resident(Gibbs* g) {
   BGGE_CUDA(rp.part.alloc((size_t)ncta * pstride));
   BGGE_CUDA(rp.zqpart.alloc((size_t)2 * nk * ncta));
   BGGE_CUDA(rp.sspart.alloc((size_t)3 * ncta));
+  if (g->q > 0) {   // XF'1 and, for step 0, C^-1/2 Z' XF per virtual row
+    const int q = g->q;
+    std::vector<double> x1((size_t)q, 0.0), mx0((size_t)q * (size_t)std::max<long long>(1, sstride[0]), 0.0);
+    for (int k = 0; k < q; ++k) {
+      long double a1 = 0.0L;
+      for (int64_t i = 0; i < n; ++i) {
+        const double x = g->xf_host[(size_t)(i + (int64_t)k * n)];
+        a1 += x;
+        const int po = row_poff[0][(size_t)i];
+        if (po >= 0) mx0[(size_t)k * (size_t)sstride[0] + (size_t)po] += row_isq[0][(size_t)i] * x;
+      }
+      x1[(size_t)k] = (double)a1;
+    }
+    BGGE_TRY(upload_vec(rp.x1, x1, st));
+    BGGE_TRY(upload_vec(rp.mx0, mx0, st));
+    BGGE_CUDA(rp.xrpart.alloc((size_t)q * ncta));
+    rp.ps0 = sstride[0];
+  }
   BGGE_CUDA(cudaStreamSynchronize(st));
   rp.enabled = true;
   if (getenv("BGGE_DEBUG"))
@@ -972,6 +1106,16 @@ int launch_resident(Gibbs* g, int64_t iters) {
   p.ncolc = rp.ncolc;
   p.nwsum = rp.nwsum;
   p.ngroups = rp.ngroups;
+  p.q = g->q;
+  p.xf = g->xf.p;
+  p.txx = g->txx.p;
+  p.lchol = g->lchol.p;
+  p.x1 = rp.x1.p;
+  p.mx0 = rp.mx0.p;
+  p.ps0 = rp.ps0;
+  p.bet = g->bet.p;
+  p.chain_bet = g->chain_bet.p;
+  p.xrpart = rp.xrpart.p;
   p.bar = rp.bar.p;
   BGGE_CUDA(cudaMemsetAsync(rp.bar.p, 0, sizeof(unsigned long long), g->stream));
   DrawCfg dc = g->draw;

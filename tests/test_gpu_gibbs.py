@@ -78,6 +78,32 @@ def test_per_iteration_parity(L, E, p, model, kernel, n_na, q, mode):
     assert list(got.keys()) == ["yHat", "varE", "varE.sd", "K", "chain", "ite", "burn", "thin", "y"]
 
 
+@pytest.mark.parametrize("model,q,n_na", [("MDs", 3, 6), ("MM", 1, 0), ("MDe", 2, 5)])
+def test_fixed_effects_in_the_resident_kernel_and_chunked_runs(model, q, n_na, capsys):
+    """XF models run in the resident kernel too (r kept without the fixed-effect part, the XF step is scalar work).
+    One run, a run cut into chunks of 4 iterations (verbose = 4: state handed back and converted each time), the
+    streaming path and the oracle agree per iteration; the chain of fixed effects enters yHat."""
+    import bgge_b200
+    K, y, XF, ne = _problem(22, 3, 30, model, kernel="GB", n_na=n_na, q=q, seed=2)
+    n = y.shape[0]
+    ite = 18
+    Ei = bgge_b200.setDEC(K, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in blocks) for blocks in Ei]
+    z, c = _tape(n, nrs, ite, q, n_na, 5)
+    ref = oracle.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=3, thin=2, draws=oracle.TapeDraws(z, c), eig=Ei)
+    runs = {"resident": dict(mode=1), "resident, chunks of 4": dict(mode=1, verbose=4), "streaming": dict(mode=2)}
+    for label, kw in runs.items():
+        got = bgge_b200.BGGE(y, K, XF=XF, ne=ne, ite=ite, burn=3, thin=2, draws=(z, c), eig=Ei, **kw)
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= TOL_IT, label
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= TOL_IT, label
+        for nm in ref["K"]:
+            assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= TOL_IT, (label, nm)
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= TOL_IT, (label, nm)
+        assert relmax(np.asarray(got["yHat"]).ravel(), np.asarray(ref["yHat"]).ravel()) <= TOL_IT, label
+        assert relmax(got["y"], ref["y"]) <= TOL_IT, label
+    capsys.readouterr()
+
+
 def test_state_after_each_iteration(lib):
     """Step the handle one sweep at a time and compare u, e (R's temp), sigb, sigsq, mu."""
     import bgge_b200
