@@ -1083,6 +1083,9 @@ int bgge_gibbs_kernel_bytes(bgge_gibbs* h, int j, int64_t* basis_bytes, int* fac
       }
     }
   }
+  // member of a merged unit (kernels sharing one matrix on disjoint rows, swept by one launch): the matrix is
+  // streamed once per unit, accounted to the unit's first kernel
+  if (!g.units.empty() && g.unit_of[(size_t)j] >= 0 && g.units[(size_t)g.unit_of[(size_t)j]].members[0] != j) bytes = 0;
   if (basis_bytes) *basis_bytes = bytes;
   if (factored_blocks) *factored_blocks = nv;
   return OK;

@@ -489,7 +489,7 @@ int launch_proj(Gibbs* g, HostKernel& hk, int j) {
   return OK;
 }
 
-int launch_scalar(Gibbs* g) {
+int launch_scalar(Gibbs* g, bool merged = false) {
   ScalarArgs a{};
   a.n = g->n;
   a.nk = g->nk;
@@ -511,6 +511,7 @@ int launch_scalar(Gibbs* g) {
   for (int j = 0; j < g->nk; ++j) {
     a.bpart[j] = g->kernels[j].bpart.p;
     a.n_bpart[j] = g->kernels[j].fused ? g->kernels[j].fused_clusters : g->kernels[j].n_atasks;
+    if (merged && g->unit_of[(size_t)j] >= 0) a.n_bpart[j] = g->units[(size_t)g->unit_of[(size_t)j]].fused_clusters;
     a.nr[j] = g->kernels[j].nr_total;
   }
   cudaLaunchConfig_t cfg{};
@@ -529,7 +530,7 @@ int launch_scalar(Gibbs* g) {
   return OK;
 }
 
-int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
+int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr, bool merged = false) {
   int ne = 0;
   auto mark = [&]() {
     if (ev) cudaEventRecord(ev[ne++], g->stream);
@@ -547,6 +548,14 @@ int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
     mark();
   }
   for (int j = 0; j < g->nk; ++j) {
+    if (merged && g->unit_of[(size_t)j] >= 0) {   // one launch for the whole unit, at its first kernel
+      HostKernel& uk = g->units[(size_t)g->unit_of[(size_t)j]];
+      if (uk.members[0] == j) {
+        BGGE_TRY(launch_fused(g, uk, -1));
+        BGGE_TRY(launch_fused_finalize(g, uk, -1));
+      }
+      continue;
+    }
     HostKernel& hk = g->kernels[j];
     if (hk.fused) {
       BGGE_TRY(launch_fused(g, hk, j));   // proj + back in one pass over U (sweep_fused.cu)
@@ -560,7 +569,7 @@ int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr) {
       mark();
     }
   }
-  BGGE_TRY(launch_scalar(g));
+  BGGE_TRY(launch_scalar(g, merged));
   mark();
   return OK;
 }
@@ -695,7 +704,10 @@ int gibbs_init(Gibbs* g) {
     BGGE_REQUIRE((int64_t)hk.s_host.size() == hk.nr_total, "gibbs: kernel %d eigenvalue count mismatch", j);
     BGGE_TRY(upload(hk.s, hk.s_host, st));
     BGGE_CUDA(hk.b.alloc((size_t)hk.nr_total));
-    if (g->mode >= 1) BGGE_TRY(plan_fused(g, hk, st));
+    hk.z_off = z_off;                                        // the fused panels carry these
+    BGGE_CUDA(hk.bpart.alloc((size_t)std::max(1, sms)));
+    BGGE_CUDA(cudaMemsetAsync(hk.bpart.p, 0, (size_t)std::max(1, sms) * sizeof(double), st));
+    if (g->mode >= 1) BGGE_TRY(plan_fused(g, hk, j, st));
     hk.n_atasks = hk.n_btasks = 0;
     if (!hk.fused) {
       // two-pass kernels work on dense U: materialise factorised blocks
@@ -754,10 +766,59 @@ int gibbs_init(Gibbs* g) {
     }
     max_clusters = std::max(max_clusters, hk.fused ? hk.fused_clusters : 0);
     max_vpart = std::max<int64_t>(max_vpart, hk.fused ? hk.vtotal * hk.fused_clusters : 0);
-    BGGE_CUDA(hk.bpart.alloc((size_t)std::max(std::max(1, hk.n_atasks), hk.fused_clusters)));
-    hk.z_off = z_off;
+    if (std::max(hk.n_atasks, hk.fused_clusters) > std::max(1, sms))
+      BGGE_CUDA(hk.bpart.alloc((size_t)std::max(hk.n_atasks, hk.fused_clusters)));   // two-pass task lists only
     z_off += hk.nr_total;
     sum_nr += hk.nr_total;
+  }
+
+  // ---- merged units: consecutive single-block kernels sharing one matrix on disjoint rows (the environment kernels
+  // of MDe) are conditionally independent and are swept by one multi-right-hand-side launch from iteration 2 on
+  g->units.clear();
+  g->unit_of.assign((size_t)g->nk, -1);
+  if (g->mode >= 1 && !getenv("BGGE_NO_MERGED_STEPS")) {
+    for (int j = 0; j < g->nk;) {
+      std::vector<int> set{j};
+      const HostKernel& h0 = g->kernels[(size_t)j];
+      if (h0.fused && h0.blocks.size() == 1) {
+        const HostBlock& b0 = h0.blocks[0];
+        while ((int)set.size() < 4) {
+          const int jn = j + (int)set.size();
+          if (jn >= g->nk || !g->kernels[(size_t)jn].fused || g->kernels[(size_t)jn].blocks.size() != 1) break;
+          const HostBlock& bn = g->kernels[(size_t)jn].blocks[0];
+          if (bn.dU != b0.dU || bn.nr != b0.nr || bn.rows != b0.rows || bn.vrows != b0.vrows || bn.ldu != b0.ldu) break;
+          if (g->kernels[(size_t)jn].s_host != h0.s_host) break;   // same matrix, same eigenvalues
+          bool disjoint = true;
+          for (int kk : set) {
+            const HostBlock& bk = g->kernels[(size_t)kk].blocks[0];
+            if (bn.pos0 < bk.pos0 + bk.rows && bk.pos0 < bn.pos0 + bn.rows) disjoint = false;
+          }
+          if (!disjoint) break;
+          set.push_back(jn);
+        }
+      }
+      if (set.size() > 1) {
+        HostKernel uk;
+        uk.merged = true;
+        uk.members = set;
+        for (int kk : set) {
+          HostBlock bl = g->kernels[(size_t)kk].blocks[0];
+          bl.owns = bl.owns_map = bl.owns_dense = false;
+          bl.dU_dense = nullptr;
+          bl.kid = kk;
+          uk.blocks.push_back(bl);
+        }
+        std::sort(uk.blocks.begin(), uk.blocks.end(), [](const HostBlock& a, const HostBlock& b) { return a.pos0 < b.pos0; });
+        BGGE_TRY(plan_fused(g, uk, -1, st));
+        if (uk.fused && uk.fused_clusters <= std::max(1, sms)) {
+          for (int kk : set) g->unit_of[(size_t)kk] = (int)g->units.size();
+          max_clusters = std::max(max_clusters, uk.fused_clusters);
+          max_vpart = std::max<int64_t>(max_vpart, uk.vtotal * uk.fused_clusters);
+          g->units.push_back(std::move(uk));
+        }
+      }
+      j += (int)set.size();
+    }
   }
 
   // ---- draw configuration / tape bookkeeping
@@ -852,9 +913,16 @@ int gibbs_run(Gibbs* g, int64_t iters) {
     g->done += iters;
     return OK;
   }
+  const bool merged = !g->units.empty();
+  if (merged && g->done == 0 && iters > 0) {
+    // merged units rely on u_k = 0 outside kernel k's block, true once every kernel has been swept once
+    BGGE_TRY(launch_iteration(g));
+    g->done += 1;
+    iters -= 1;
+  }
   if (g->use_graph && !g->graph_exec) {
     BGGE_CUDA(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
-    int s = launch_iteration(g);
+    int s = launch_iteration(g, nullptr, merged);
     cudaError_t ce = cudaStreamEndCapture(g->stream, &g->graph);
     if (s != OK) return s;
     BGGE_CUDA(ce);
@@ -864,7 +932,7 @@ int gibbs_run(Gibbs* g, int64_t iters) {
     if (g->use_graph) {
       BGGE_CUDA(cudaGraphLaunch(g->graph_exec, g->stream));
     } else {
-      BGGE_TRY(launch_iteration(g));
+      BGGE_TRY(launch_iteration(g, nullptr, merged));
     }
   }
   g->done += iters;

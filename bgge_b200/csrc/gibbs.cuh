@@ -69,6 +69,15 @@ struct FPanel {                  // fused path: columns [c0, c1) of one block, h
   int nb;
   long long voffs[4];
   int col_offs[4];
+  // per member: the kernel it belongs to (sigb, draw stream, u), first row of a dense member, the kernel's
+  // coefficient-normal offset in a tape iteration, its eigenvalues (from the block's first column) and where the
+  // cluster's sum of b^2/s goes.  All members belong to one kernel unless the launch is a merged unit
+  // (kernels sharing one matrix on disjoint rows, e.g. the environment kernels of MDe).
+  int kids[4];
+  int pos0s[4];
+  long long zoffs[4];
+  const double* ss[4];
+  double* bps[4];
 };
 
 struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo, qhi] contributed (qlo > qhi: none)
@@ -76,6 +85,7 @@ struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo
   const int* loc;                // factorised block: row -> virtual row (already offset to row0), else nullptr
   const double* isq;             // 1/sqrt(count) per row (offset to row0)
   long long voff;
+  int kid, pad;                  // kernel whose u / Welford arrays the rows belong to (-1: none, merged units)
 };
 
 struct VDesc {                   // one factorised block for virt_gather_kernel
@@ -84,6 +94,7 @@ struct VDesc {                   // one factorised block for virt_gather_kernel
   const int* rowptr;
   const int* rowidx;
   const double* isq;
+  int kid, pad;                  // kernel whose u enters the gathered residual
 };
 
 // An eigen block.  Dense: U (rows x nr).  Factorised (bgge_gibbs_add_expanded_kernel, repeated genotypes):
@@ -102,6 +113,7 @@ struct HostBlock {
   int64_t ldu_dense = 0;
   bool owns_dense = false;
   bool owns_map = false;         // loc / isq / CSR arrays (dU may be shared with an identical block)
+  int kid = -1;                  // merged units only: the kernel this block belongs to
   int64_t stream_rows() const { return vrows > 0 ? vrows : rows; }
 };
 
@@ -129,6 +141,10 @@ struct HostKernel {
   int fused_nb = 1;              // right-hand sides per panel the fused kernel is instantiated for (1, 2 or 4)
   DevBuf<VDesc> vdesc;           // factorised blocks of this kernel (one gather launch for all of them)
   int n_vdesc = 0, vgrid = 0;
+  // merged unit (streaming path): up to 4 single-block kernels sharing one matrix on disjoint rows, swept by one
+  // launch; `members` lists them, the blocks above are copies tagged with their kernel
+  bool merged = false;
+  std::vector<int> members;
 };
 
 // Resident path (resident.cu): small models whose whole basis fits the shared memory of the chip.
@@ -203,6 +219,8 @@ struct Gibbs {
   bool own_stream = false;
   std::vector<HostKernel> kernels;
   std::vector<SharedDecomp> decomps;
+  std::vector<HostKernel> units;      // merged units of the streaming path
+  std::vector<int> unit_of;           // per kernel: index into units, or -1
   // data
   std::vector<double> y_host;
   std::vector<unsigned char> na_host;
@@ -234,7 +252,7 @@ struct Gibbs {
 int gibbs_init(Gibbs* g);
 int gibbs_run(Gibbs* g, int64_t iters);
 int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
-int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st);
+int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st);
 int launch_fused(Gibbs* g, HostKernel& hk, int j);
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j);
 int plan_resident(Gibbs* g);

@@ -101,10 +101,10 @@ __device__ __forceinline__ double warp_multi_reduce(double (&a)[P], int lane, in
 template <int RPT, int G, int NB>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cluster_panels,
-                   const double* __restrict__ r, const double* __restrict__ u_old, const double* __restrict__ s,
-                   double* __restrict__ upart, double* __restrict__ bpart, long long n,
+                   const double* __restrict__ r, const double* __restrict__ u_all,
+                   double* __restrict__ upart, long long n,
                    const double* __restrict__ ve, double* __restrict__ vupart, long long vtotal,
-                   const Scal* __restrict__ sc, int j, DrawCfg dc, long long z_off, int ns, int npx) {
+                   const Scal* __restrict__ sc, int merged, DrawCfg dc, int ns, int npx) {
   pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
@@ -125,8 +125,9 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   double* parts = ring + (size_t)ns * slot_doubles;
   double* red = parts + (size_t)npx * F_MAXCS * NG;
   double* bsm = red + 2 * 8 * NG;                // NB > 1: coefficients of the current group (double buffered)
-  double* tvb = bsm + 2 * NG;                    // tau * v       per column of a draw batch (same for all members)
-  double* isb = tvb + 2 * ZB;                    // 1 / s
+  const int tvm = merged ? NB : 1;               // merged unit: every member has its own sigb, hence its own tau * v
+  double* tvb = bsm + 2 * NG;                    // tau * v       per column of a draw batch, [tvm][2][ZB]
+  double* isb = tvb + (size_t)tvm * 2 * ZB;      // 1 / s         (members share the matrix, hence s)
   double* zsb = isb + 2 * ZB;                    // sqrt(v) * z,  [NB][2][ZB]
   uint64_t* full = reinterpret_cast<uint64_t*>(zsb + (size_t)NB * 2 * ZB);
   uint64_t* empty = full + F_MAX_NS;
@@ -152,7 +153,6 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   // (gather / finalize / scalars of the step before) is still finishing; everybody else needs its results.
   if (warp != 2 * (F_ROLE / 32)) pdl_wait();
   const double shift = sc->shift;
-  const double lam = sc->sigb[j];
   const double tau = sc->tau;
   const long long it = sc->it;
 
@@ -208,7 +208,8 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
               e[m][k].x = row < my_rows ? ve[gi] : 0.0;
               e[m][k].y = row + 1 < my_rows ? ve[gi + 1] : 0.0;
             } else {
-              const long long gi = (long long)pn.pos0 + row0 + row;
+              const long long gi = (long long)pn.pos0s[m] + row0 + row;
+              const double* u_old = u_all + (size_t)pn.kids[m] * n;
               e[m][k].x = row < my_rows ? (r[gi] - shift) + u_old[gi] : 0.0;
               e[m][k].y = row + 1 < my_rows ? (r[gi + 1] - shift) + u_old[gi + 1] : 0.0;
             }
@@ -303,17 +304,20 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
           // draw batch for panel columns [rel0, rel0 + ZB): the normal draw does not depend on d
           const int rel = rel0 + tid;
           if (tid < ZB && rel < ncols) {
-            const long long col = (long long)pn.col_offs[0] + pn.c0 + rel;   // members share s (same matrix)
-            const double sv = s[col];
-            const double vari = sv * lam / (1.0 + sv * lam * tau);                 // R/BGGE.R:302
+            const double sv = pn.ss[0][pn.c0 + rel];                               // members share s (same matrix)
             const int zb = ((rel0 / ZB) & 1) * ZB + tid;
-            tvb[zb] = tau * vari;
             isb[zb] = 1.0 / sv;
-            const double sq = sqrt(vari);
+            double sq = 0.0;
             for (int m = 0; m < pn.nb; ++m) {
+              if (m == 0 || merged) {                                              // one sigb per kernel
+                const double lam = sc->sigb[pn.kids[m]];
+                const double vari = sv * lam / (1.0 + sv * lam * tau);             // R/BGGE.R:302
+                tvb[(size_t)m * 2 * ZB + zb] = tau * vari;
+                sq = sqrt(vari);
+              }
               const long long cm = (long long)pn.col_offs[m] + pn.c0 + rel;
-              const double z = draw_normal(dc, it, (uint32_t)j, (unsigned long long)cm,
-                                           dc.z_init + (it - 1) * dc.z_per_it + z_off + cm);
+              const double z = draw_normal(dc, it, (uint32_t)pn.kids[m], (unsigned long long)cm,
+                                           dc.z_init + (it - 1) * dc.z_per_it + pn.zoffs[m] + cm);
               zsb[(size_t)m * 2 * ZB + zb] = sq * z;
             }
           }
@@ -351,7 +355,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
               double d = 0.0;
               for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * NG];
               const int zb = (((rel0 + g) / ZB) & 1) * ZB + (rel0 + g) % ZB;
-              bcoef = tvb[zb] * d + zsb[(size_t)m * 2 * ZB + zb];
+              bcoef = tvb[(size_t)(merged ? m : 0) * 2 * ZB + zb] * d + zsb[(size_t)m * 2 * ZB + zb];
               zq += bcoef * bcoef * isb[zb];
             }
             bsm[(cc & 1u) * NG + m * G + g] = bcoef;
@@ -386,7 +390,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
       for (int m = 0; m < NB; ++m) {
         if (m < pn.nb) {
           double* up = pn.virt ? vupart + (size_t)pn.slot * vtotal + pn.voffs[m] + row0
-                               : upart + (size_t)pn.slot * n + pn.pos0 + row0;
+                               : upart + (size_t)pn.slot * n + pn.pos0s[m] + row0;
 #pragma unroll
           for (int k = 0; k < RPT; ++k) {
             const int row = k * F_ROWS_PER_STEP + 2 * tid;
@@ -397,10 +401,20 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
       }
       role_barrier(2);   // batch buffers are reused by the next panel
     }
+    // all panels of a launch belong to one kernel, or to one merged unit (one group): a cluster without panels
+    // finds the destination of its (zero) sum in panel 0
+    const FPanel& p0 = panels[cp.y > 0 ? cp.x : 0];
     if constexpr (NB > 1) {   // the (member, column) lanes of warp 0 of this role hold the pieces of sum b^2/s
-      zq = warp_sum(tid < 32 ? zq : 0.0);
+      if (merged) {           // one sum per member kernel
+        for (int m = 0; m < p0.nb; ++m) {
+          const double zm = warp_sum(tid < 32 && tid / G == m ? zq : 0.0);
+          if (rank == 0 && tid == 0) p0.bps[m][cid] = zm;
+        }
+      } else {
+        zq = warp_sum(tid < 32 ? zq : 0.0);
+      }
     }
-    if (rank == 0 && tid == 0) bpart[cid] = zq;
+    if (!merged && rank == 0 && tid == 0) p0.bps[0][cid] = zq;
   }
   cluster.sync();      // nobody leaves while a peer may still write into its shared memory
 }
@@ -412,11 +426,16 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
 constexpr int FIN_ROWS = 32, FIN_Q = 8;
 __global__ void __launch_bounds__(FIN_ROWS * FIN_Q)
 fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict__ upart, long long n,
-                      const double* __restrict__ vupart, long long vtotal, double* __restrict__ r, double* __restrict__ u, double* __restrict__ umean,
-                      double* __restrict__ um2, const Scal* __restrict__ sc, long long thin, long long burn) {
+                      const double* __restrict__ vupart, long long vtotal, double* __restrict__ r, double* __restrict__ u_all,
+                      double* __restrict__ umean_all, double* __restrict__ um2_all, const Scal* __restrict__ sc, long long thin,
+                      long long burn) {
   __shared__ double part[FIN_Q][FIN_ROWS];
   pdl_trigger();
   const FTile t = tiles[blockIdx.x];
+  if (t.kid < 0) return;   // merged unit: rows none of its kernels covers (their u is zero there already)
+  double* u = u_all + (size_t)t.kid * n;
+  double* umean = umean_all + (size_t)t.kid * n;
+  double* um2 = um2_all + (size_t)t.kid * n;
   const int lane = threadIdx.x, ql = threadIdx.y;
   pdl_wait();
   const long long it = sc->it;
@@ -458,7 +477,7 @@ fused_finalize_kernel(const FTile* __restrict__ tiles, const double* __restrict_
 // CSR order (deterministic); one launch covers every factorised block of the kernel
 __global__ void __launch_bounds__(256)
 virt_gather_kernel(const VDesc* __restrict__ desc, int ndesc, const double* __restrict__ r,
-                   const double* __restrict__ u_old, const Scal* __restrict__ sc, double* __restrict__ ve) {
+                   const double* __restrict__ u_all, long long n, const Scal* __restrict__ sc, double* __restrict__ ve) {
   pdl_trigger();
   int d = 0;
   while (d + 1 < ndesc && (int)blockIdx.x >= desc[d + 1].cta0) ++d;
@@ -469,7 +488,7 @@ virt_gather_kernel(const VDesc* __restrict__ desc, int ndesc, const double* __re
   if (a >= vd.vrows) return;
   const double shift = sc->shift;
   const double* rp = r + vd.pos0;
-  const double* up = u_old + vd.pos0;
+  const double* up = u_all + (size_t)vd.kid * n + vd.pos0;
   double acc = 0.0;
   for (int k = k0; k < k1; ++k) {
     const int i = vd.rowidx[k];
@@ -495,11 +514,11 @@ int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  (void)j;
   BGGE_CUDA(cudaLaunchKernelEx(&cfg, kfn, (const FPanel*)hk.fpanels.p, (const int2*)hk.fcluster.p,
-                               (const double*)g->r.p, (const double*)(g->u.p + (size_t)j * g->n),
-                               (const double*)hk.s.p, g->upart.p, hk.bpart.p, (long long)g->n,
+                               (const double*)g->r.p, (const double*)g->u.p, g->upart.p, (long long)g->n,
                                (const double*)hk.ve.p, g->vupart.p, (long long)hk.vtotal,
-                               (const Scal*)g->scal.p, j, g->draw, hk.z_off, hk.fused_ns, 2 * hk.fused_ns + 4));
+                               (const Scal*)g->scal.p, hk.merged ? 1 : 0, g->draw, hk.fused_ns, 2 * hk.fused_ns + 4));
   return OK;
 }
 
@@ -576,7 +595,7 @@ int launch_fused(Gibbs* g, HostKernel& hk, int j) {
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     BGGE_CUDA(cudaLaunchKernelEx(&cfg, virt_gather_kernel, (const VDesc*)hk.vdesc.p, hk.n_vdesc, (const double*)g->r.p,
-                                 (const double*)(g->u.p + (size_t)j * g->n), (const Scal*)g->scal.p, hk.ve.p));
+                                 (const double*)g->u.p, (long long)g->n, (const Scal*)g->scal.p, hk.ve.p));
   }
   auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
   return run();
@@ -592,16 +611,16 @@ int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)j;
   BGGE_CUDA(cudaLaunchKernelEx(&cfg, fused_finalize_kernel, (const FTile*)hk.ftiles.p, (const double*)g->upart.p, (long long)g->n,
-                               (const double*)g->vupart.p, (long long)hk.vtotal, g->r.p, g->u.p + (size_t)j * g->n,
-                               g->umean.p + (size_t)j * g->n, g->um2.p + (size_t)j * g->n, (const Scal*)g->scal.p,
-                               (long long)g->thin, (long long)g->burn));
+                               (const double*)g->vupart.p, (long long)hk.vtotal, g->r.p, g->u.p, g->umean.p, g->um2.p,
+                               (const Scal*)g->scal.p, (long long)g->thin, (long long)g->burn));
   return OK;
 }
 
 // Decide whether kernel j can use the fused path and build its panel / tile tables.
 // Returns OK with hk.fused == false when the shape does not fit (caller keeps the two-pass kernels).
-int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
+int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   hk.fused = false;
   // groups of blocks that stream the same matrix: a dense / unshared block alone, or up to 4 factorised
   // blocks sharing one W (identical diagonal blocks) swept as one multi-RHS panel
@@ -621,10 +640,11 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
     }
     max_rows = std::max(max_rows, bl.stream_rows());
     bool placed = false;
-    if (bl.vrows > 0)
+    if (bl.vrows > 0 || hk.merged)   // a merged unit also shares a matrix between dense blocks (U = W)
       for (auto& gr : groups) {
         const HostBlock& b0 = hk.blocks[(size_t)gr.members[0]];
-        if (b0.vrows > 0 && b0.dU == bl.dU && b0.vrows == bl.vrows && b0.nr == bl.nr && gr.members.size() < 4) {
+        if ((b0.vrows > 0) == (bl.vrows > 0) && b0.dU == bl.dU && b0.vrows == bl.vrows && b0.rows == bl.rows &&
+            b0.nr == bl.nr && gr.members.size() < 4) {
           gr.members.push_back((int)bi);
           nbmax = std::max(nbmax, (int)gr.members.size());
           placed = true;
@@ -660,8 +680,9 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   int dev = 0, optin = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
   BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t tvm = hk.merged ? (size_t)nb_t : 1;   // tau * v per member kernel in a merged unit
   auto fixed_bytes = [&](int nsv) {   // exchange ring depth 2 ns + 4 (protocol note) -> grows with the data ring
-    return ((size_t)(2 * nsv + 4) * F_MAXCS * ng + 2 * 8 * ng + 2 * ng + 4 * zb + (size_t)nb_t * 2 * zb) * sizeof(double) +
+    return ((size_t)(2 * nsv + 4) * F_MAXCS * ng + 2 * 8 * ng + 2 * ng + (2 * tvm + 2) * zb + (size_t)nb_t * 2 * zb) * sizeof(double) +
            (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
   };
   int ns = 0;
@@ -718,8 +739,15 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
         p.nb = (int)gr.members.size();
         for (size_t m = 0; m < gr.members.size(); ++m) {
           const HostBlock& bm = hk.blocks[(size_t)gr.members[m]];
+          const int kid = bm.kid >= 0 ? bm.kid : j;
+          HostKernel& owner = g->kernels[(size_t)kid];
           p.voffs[m] = bm.voff;
           p.col_offs[m] = (int)bm.col_off;
+          p.kids[m] = kid;
+          p.pos0s[m] = (int)bm.pos0;
+          p.zoffs[m] = owner.z_off;
+          p.ss[m] = owner.s.p + bm.col_off;
+          p.bps[m] = owner.bpart.p;
           block_q[(size_t)gr.members[m]].first = std::min(block_q[(size_t)gr.members[m]].first, q);
           block_q[(size_t)gr.members[m]].second = std::max(block_q[(size_t)gr.members[m]].second, q);
         }
@@ -749,6 +777,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
         d.rowptr = bl.d_rowptr;
         d.rowidx = bl.d_rowidx;
         d.isq = bl.d_isq;
+        d.kid = bl.kid >= 0 ? bl.kid : j;
         vd.push_back(d);
         cta += (int)((bl.vrows + 255) / 256);
       }
@@ -763,13 +792,14 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   // finalize tiles: every row of y, gaps included (qlo > qhi -> zero)
   std::vector<FTile> tiles;
   int64_t cursor = 0;
-  auto add_rows = [&](int64_t pos0, int64_t rows, int qlo, int qhi, const HostBlock* vb = nullptr) {
+  auto add_rows = [&](int64_t pos0, int64_t rows, int qlo, int qhi, int kid, const HostBlock* vb = nullptr) {
     for (int64_t r0 = 0; r0 < rows; r0 += 64) {
       FTile t{};
       t.row0 = (int)(pos0 + r0);
       t.rows = (int)std::min<int64_t>(64, rows - r0);
       t.qlo = qlo;
       t.qhi = qhi;
+      t.kid = kid;
       if (vb) {
         t.loc = vb->d_loc + r0;
         t.isq = vb->d_isq + r0;
@@ -780,11 +810,12 @@ int plan_fused(Gibbs* g, HostKernel& hk, cudaStream_t st) {
   };
   for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
     HostBlock& bl = hk.blocks[bi];
-    if (bl.pos0 > cursor) add_rows(cursor, bl.pos0 - cursor, 1, 0);
-    add_rows(bl.pos0, bl.rows, block_q[bi].first, block_q[bi].second, bl.vrows > 0 ? &bl : nullptr);
+    // rows no block covers: u_j = 0 there (R/BGGE.R:334); a merged unit leaves them alone (kid -1)
+    if (bl.pos0 > cursor) add_rows(cursor, bl.pos0 - cursor, 1, 0, hk.merged ? -1 : j);
+    add_rows(bl.pos0, bl.rows, block_q[bi].first, block_q[bi].second, bl.kid >= 0 ? bl.kid : j, bl.vrows > 0 ? &bl : nullptr);
     cursor = bl.pos0 + bl.rows;
   }
-  if (cursor < g->n) add_rows(cursor, g->n - cursor, 1, 0);
+  if (cursor < g->n) add_rows(cursor, g->n - cursor, 1, 0, hk.merged ? -1 : j);
   hk.fused_clusters = ncl;
   hk.n_ftiles = (int)tiles.size();
   if (hk.vtotal > 0) {
