@@ -584,6 +584,11 @@ def main():
         res_en, res_ctas, res_smem = C.c_int(), C.c_int(), C.c_int64()
         lib.call("bgge_gibbs_resident_info", h, C.byref(res_en), C.byref(res_ctas), C.byref(res_smem))
         resident = {"enabled": bool(res_en.value), "ctas": res_ctas.value, "smem_bytes_per_cta": res_smem.value}
+        mu_n, mu_k = C.c_int(), C.c_int()
+        lib.call("bgge_gibbs_merged_info", h, C.byref(mu_n), C.byref(mu_k))
+        merged_units = {"units": mu_n.value, "kernels_in_units": mu_k.value,
+                        "note": "kernels sharing one matrix on disjoint rows are swept by one launch in the timed run; "
+                                "the per-kernel list below times the unmerged launches" if mu_n.value else ""}
         for _ in range(args.warmup):
             lib.call("bgge_gibbs_run", h, iters)
         torch.cuda.synchronize()
@@ -794,7 +799,7 @@ def main():
                       "two_pass_equivalent_gbs_per_gpu": (16 * sum(b[1] * b[2] for blk in blocks for b in blk)
                                                           + 8 * n * (4 * nk + 3) + 40 * sum_nr)
                                                          * (args.steps * iters) / (ms_total * 1e-3) / 1e9,
-                      "resident": resident, "kernel_paths": kinfo,
+                      "resident": resident, "merged_units": merged_units, "kernel_paths": kinfo,
                       "kernels": kern, "last_mu": mu_c.value, "last_varE": s2_c.value,
                       "dense_basis_reference": dense_ref,
                       "dense_single_pass_equivalent_gbs": (8 * sum(b[1] * b[2] for blk in blocks for b in blk)

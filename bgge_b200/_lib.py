@@ -81,6 +81,7 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int64]),
     "bgge_gibbs_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "bgge_gibbs_resident_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bgge_gibbs_merged_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgge_gibbs_kernel_bytes": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.POINTER(C.c_int)]),

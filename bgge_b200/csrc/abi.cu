@@ -1034,7 +1034,9 @@ int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, 
   if (launches) {
     int nv = 0;
     for (auto& b : hk.blocks) nv += b.vrows > 0 ? 1 : 0;
-    *launches = 2 + (hk.fused ? nv : 0);
+    *launches = 2 + (hk.fused && nv > 0 ? 1 : 0);   // [gather] + sweep + finalize
+    // a merged unit is launched once, accounted to its first kernel
+    if (!g.units.empty() && g.unit_of[(size_t)j] >= 0 && g.units[(size_t)g.unit_of[(size_t)j]].members[0] != j) *launches = 0;
   }
   return OK;
 }
@@ -1047,6 +1049,18 @@ int bgge_gibbs_resident_info(bgge_gibbs* h, int* enabled, int* ctas, int64_t* sm
   if (enabled) *enabled = g.resident.enabled ? 1 : 0;
   if (ctas) *ctas = g.resident.enabled ? g.resident.ncta : 0;
   if (smem_bytes) *smem_bytes = g.resident.enabled ? (int64_t)g.resident.smem : 0;
+  return OK;
+}
+
+// after init: merged units of the streaming path (kernels sharing one matrix on disjoint rows, one launch each)
+int bgge_gibbs_merged_info(bgge_gibbs* h, int* units, int* kernels_in_units) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised, "gibbs_merged_info: handle not initialised");
+  int nk = 0;
+  for (auto& u : g.units) nk += (int)u.members.size();
+  if (units) *units = (int)g.units.size();
+  if (kernels_in_units) *kernels_in_units = nk;
   return OK;
 }
 

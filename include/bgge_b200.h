@@ -181,6 +181,10 @@ int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int6
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode);
 /* after init: whether bgge_gibbs_run uses the resident kernel, its grid size and shared memory per CTA */
 int bgge_gibbs_resident_info(bgge_gibbs* h, int* enabled, int* ctas, int64_t* smem_bytes);
+/* after init: merged units of the streaming path -- consecutive single-block kernels that share one decomposed
+ * matrix on disjoint rows (the environment kernels of MDe, R/getK.R:207-218) are swept by one launch from the second
+ * iteration on; how many units there are and how many kernels they contain */
+int bgge_gibbs_merged_info(bgge_gibbs* h, int* units, int* kernels_in_units);
 /* after init: which path kernel j uses, its cluster size / cluster (or tile) count, launches per step */
 int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches);
 /* after init: bytes of eigen basis one step of kernel j streams (W, not U, for blocks kept factorised; twice
