@@ -81,6 +81,10 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int64]),
     "bgge_gibbs_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "bgge_gibbs_resident_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bgge_gibbs_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bgge_gibbs_shard_begin": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "bgge_gibbs_shard_end": (C.c_int, [C.c_void_p, C.c_int]),
+    "bgge_gibbs_shard_iteration_end": (C.c_int, [C.c_void_p]),
     "bgge_gibbs_merged_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),

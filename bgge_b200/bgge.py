@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from .getk import factor_matches
+from .multigpu import run_sharded
 from .rrng import r_tapes
 
 
@@ -104,7 +105,7 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
 
 
 def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=1e-10, R2=0.5, *, seed=0, chain=0,
-         draws=None, eig=None, device=None, mode=None, rng="philox"):
+         draws=None, eig=None, device=None, mode=None, rng="philox", shard=None):
     """Fit the G x E model by Gibbs sampling (signature of R/BGGE.R:84 plus keyword-only extras).
 
     draws : optional (normals, chisq) tapes -> injected-draw mode.
@@ -115,6 +116,10 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     rng   : "philox" (default) = counter-based device draws keyed by (seed, chain); "R" = the stream of R's
             `set.seed(seed)` (Mersenne-Twister, inversion normals, Ahrens-Dieter gammas) consumed in the
             reference's call order and injected as tapes (bgge_b200.rrng).
+    shard : None, or (rank, world, reduce): this process sweeps its slice of the eigen-columns of a single chain and
+            reduce(ptr, count) adds the per-step partial vectors of all processes in place (bgge_b200.multigpu.
+            nccl_allreduce() for torch.distributed over NCCL).  Every process must call BGGE() with the same
+            arguments; all return the same fit.  No XF in this mode.
     """
     if rng not in ("philox", "R"):
         raise ValueError("rng must be 'philox' or 'R'")
@@ -149,6 +154,10 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
             _lib.call("bgge_gibbs_set_xf", h, _lib.ptr(XF))
         if mode is not None:
             _lib.call("bgge_gibbs_set_mode", h, int(mode))
+        if shard is not None and int(shard[1]) > 1:
+            if q:
+                raise ValueError("a column-sharded chain does not support XF")
+            _lib.call("bgge_gibbs_set_shard", h, int(shard[0]), int(shard[1]))
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
             if eig is None and "factor" in k and factor_matches(k):
@@ -199,7 +208,10 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
         while done < ite:                                                    # R/BGGE.R:274, 398-401
             t0 = time.perf_counter()
             k = min(step, ite - done)
-            _lib.call("bgge_gibbs_run", h, k)
+            if shard is not None and int(shard[1]) > 1:
+                run_sharded(h, nk, k, shard[2])
+            else:
+                _lib.call("bgge_gibbs_run", h, k)
             _lib.call("bgge_gibbs_sync", h)
             done += k
             if int(verbose) != 0 and done % int(verbose) == 0:

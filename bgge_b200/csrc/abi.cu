@@ -989,6 +989,53 @@ int bgge_gibbs_run(bgge_gibbs* h, int64_t iters) {
   return gibbs_run(&h->g, iters);
 }
 
+// ---------------------------------------------------------------------- column-sharded single chain
+// Every process holds the full state (r, u, scalars: a few n-vectors) and sweeps only its slice of the eigen-columns
+// of every basis matrix; draws are keyed by the global column, so the chain does not depend on the number of
+// processes except for the order of the sums.  Per kernel step the partial W b and sum b^2/s of all processes are
+// added up by the caller (NCCL all-reduce in the Python mirror) between shard_begin and shard_end.
+int bgge_gibbs_set_shard(bgge_gibbs* h, int rank, int world) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(!h->g.initialised, "gibbs_set_shard: handle already initialised");
+  BGGE_REQUIRE(world >= 1 && rank >= 0 && rank < world, "gibbs_set_shard: rank %d of %d", rank, world);
+  h->g.shard_rank = rank;
+  h->g.shard_world = world;
+  return OK;
+}
+
+int bgge_gibbs_shard_begin(bgge_gibbs* h, int j, double** d_vector, int64_t* count) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && g.shard_world > 1, "gibbs_shard_begin: handle is not a column shard");
+  BGGE_REQUIRE(g.shard_step == -1 && j >= 0 && j < g.nk, "gibbs_shard_begin: step %d out of order", j);
+  BGGE_REQUIRE(g.done < g.ite, "gibbs_shard_begin: all %lld iterations are done", (long long)g.ite);
+  HostKernel& hk = g.kernels[(size_t)j];
+  BGGE_TRY(launch_fused(&g, hk, j));
+  BGGE_TRY(launch_shard_sum(&g, hk));
+  g.shard_step = j;
+  if (d_vector) *d_vector = hk.xbuf.p;
+  if (count) *count = g.n + hk.vtotal + 1;
+  return OK;
+}
+
+int bgge_gibbs_shard_end(bgge_gibbs* h, int j) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && g.shard_step == j, "gibbs_shard_end: step %d was not begun", j);
+  BGGE_TRY(launch_shard_apply(&g, g.kernels[(size_t)j]));
+  g.shard_step = -1;
+  return OK;
+}
+
+int bgge_gibbs_shard_iteration_end(bgge_gibbs* h) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && g.shard_world > 1 && g.shard_step == -1, "gibbs_shard_iteration_end: a step is still open");
+  BGGE_TRY(launch_scalar_sharded(&g));
+  g.done += 1;
+  return OK;
+}
+
 int bgge_gibbs_set_mode(bgge_gibbs* h, int mode) {
   BGGE_HANDLE(h);
   BGGE_REQUIRE(!h->g.initialised, "gibbs_set_mode: handle already initialised");

@@ -512,6 +512,10 @@ int launch_scalar(Gibbs* g, bool merged = false) {
     a.bpart[j] = g->kernels[j].bpart.p;
     a.n_bpart[j] = g->kernels[j].fused ? g->kernels[j].fused_clusters : g->kernels[j].n_atasks;
     if (merged && g->unit_of[(size_t)j] >= 0) a.n_bpart[j] = g->units[(size_t)g->unit_of[(size_t)j]].fused_clusters;
+    if (g->shard_world > 1) {   // the all-reduced sum of b^2/s sits behind the reduced vector
+      a.bpart[j] = g->kernels[j].xbuf.p + g->n + g->kernels[j].vtotal;
+      a.n_bpart[j] = 1;
+    }
     a.nr[j] = g->kernels[j].nr_total;
   }
   cudaLaunchConfig_t cfg{};
@@ -529,6 +533,12 @@ int launch_scalar(Gibbs* g, bool merged = false) {
   BGGE_CUDA(cudaLaunchKernelEx(&cfg, scalar_kernel, a, g->draw));
   return OK;
 }
+
+}  // namespace
+
+int launch_scalar_sharded(Gibbs* g) { return launch_scalar(g, false); }
+
+namespace {
 
 int launch_iteration(Gibbs* g, cudaEvent_t* ev = nullptr, bool merged = false) {
   int ne = 0;
@@ -709,6 +719,7 @@ int gibbs_init(Gibbs* g) {
     BGGE_CUDA(cudaMemsetAsync(hk.bpart.p, 0, (size_t)std::max(1, sms) * sizeof(double), st));
     if (g->mode >= 1) BGGE_TRY(plan_fused(g, hk, j, st));
     hk.n_atasks = hk.n_btasks = 0;
+    BGGE_REQUIRE(g->shard_world == 1 || hk.fused, "column-sharded chain: kernel %d does not fit the fused sweep", j);
     if (!hk.fused) {
       // two-pass kernels work on dense U: materialise factorised blocks
       for (auto& bl : hk.blocks) BGGE_TRY(ensure_dense(bl, st));
@@ -776,7 +787,7 @@ int gibbs_init(Gibbs* g) {
   // of MDe) are conditionally independent and are swept by one multi-right-hand-side launch from iteration 2 on
   g->units.clear();
   g->unit_of.assign((size_t)g->nk, -1);
-  if (g->mode >= 1 && !getenv("BGGE_NO_MERGED_STEPS")) {
+  if (g->mode >= 1 && g->shard_world == 1 && !getenv("BGGE_NO_MERGED_STEPS")) {
     for (int j = 0; j < g->nk;) {
       std::vector<int> set{j};
       const HostKernel& h0 = g->kernels[(size_t)j];
@@ -845,6 +856,10 @@ int gibbs_init(Gibbs* g) {
   BGGE_CUDA(g->r.alloc((size_t)n));
   if (max_clusters > 0) BGGE_CUDA(g->upart.alloc((size_t)n * max_clusters));
   if (max_vpart > 0) BGGE_CUDA(g->vupart.alloc((size_t)max_vpart));
+  if (g->shard_world > 1) {
+    BGGE_REQUIRE(q == 0, "column-sharded chain: fixed effects are not supported");
+    for (int j = 0; j < g->nk; ++j) BGGE_TRY(plan_shard(g, g->kernels[(size_t)j], st));
+  }
   BGGE_CUDA(g->u.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->umean.alloc((size_t)n * g->nk));
   BGGE_CUDA(g->um2.alloc((size_t)n * g->nk));
@@ -902,6 +917,7 @@ int gibbs_run(Gibbs* g, int64_t iters) {
   }
   BGGE_REQUIRE(iters >= 0 && g->done + iters <= g->ite, "gibbs: asked for %lld iterations, %lld of %lld already done",
                (long long)iters, (long long)g->done, (long long)g->ite);
+  BGGE_REQUIRE(g->shard_world == 1, "gibbs: a column-sharded chain is driven step by step (bgge_gibbs_shard_begin / _end)");
   if (g->resident.enabled) {   // the whole run is one cooperative launch
     if (g->resident.has_merged && g->done == 0 && iters > 0) {
       // merged steps rely on u_k = 0 outside kernel k's block, true once every kernel has been swept once
@@ -948,6 +964,7 @@ int gibbs_profile(Gibbs* g, int64_t iters, double* ms) {
   }
   BGGE_REQUIRE(iters >= 0 && g->done + iters <= g->ite, "gibbs: asked for %lld iterations, %lld of %lld already done",
                (long long)iters, (long long)g->done, (long long)g->ite);
+  BGGE_REQUIRE(g->shard_world == 1, "gibbs: profile is not available for a column-sharded chain");
   const int nslots = 2 * g->nk + 2;
   for (int i = 0; i < nslots; ++i) ms[i] = 0.0;
   const int nev = 2 * g->nk + 3 + (g->q > 0 ? 1 : 0);

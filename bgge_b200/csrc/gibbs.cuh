@@ -88,6 +88,12 @@ struct FTile {                   // fused finalize: up to 64 rows, clusters [qlo
   int kid, pad;                  // kernel whose u / Welford arrays the rows belong to (-1: none, merged units)
 };
 
+struct SSeg {                    // shard_sum_kernel: dst[doff + i] = sum_{q = qlo..qhi} src[q * stride + off + i], i < len
+  const double* src;
+  long long stride, off, doff;
+  int len, qlo, qhi, pad;
+};
+
 struct VDesc {                   // one factorised block for virt_gather_kernel
   int vrows, pos0, cta0;         // CTAs [cta0, cta0 + ceil(vrows/256)) of the gather launch belong to it
   long long voff;
@@ -114,6 +120,7 @@ struct HostBlock {
   bool owns_dense = false;
   bool owns_map = false;         // loc / isq / CSR arrays (dU may be shared with an identical block)
   int kid = -1;                  // merged units only: the kernel this block belongs to
+  int fq_lo = 1 << 30, fq_hi = -1;   // fused plan: clusters that sweep columns of this block (lo > hi: none)
   int64_t stream_rows() const { return vrows > 0 ? vrows : rows; }
 };
 
@@ -141,6 +148,13 @@ struct HostKernel {
   int fused_nb = 1;              // right-hand sides per panel the fused kernel is instantiated for (1, 2 or 4)
   DevBuf<VDesc> vdesc;           // factorised blocks of this kernel (one gather launch for all of them)
   int n_vdesc = 0, vgrid = 0;
+  // column-sharded chain (bgge_gibbs_set_shard): this process' partial W b and sum b^2/s of the kernel step, in one
+  // vector [ rows of y : n | virtual rows : vtotal | sum b^2/s : 1 ] that the host all-reduces between
+  // bgge_gibbs_shard_begin and bgge_gibbs_shard_end
+  DevBuf<double> xbuf;
+  DevBuf<SSeg> ssegs;
+  int n_ssegs = 0;
+  DevBuf<FTile> atiles;          // the finalize tiles reading the reduced vector (one "cluster")
   // merged unit (streaming path): up to 4 single-block kernels sharing one matrix on disjoint rows, swept by one
   // launch; `members` lists them, the blocks above are copies tagged with their kernel
   bool merged = false;
@@ -228,6 +242,8 @@ struct Gibbs {
   int64_t n_na = 0;
   // device state
   DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart, vupart;
+  int shard_rank = 0, shard_world = 1;   // column shard of a single chain across processes / GPUs
+  int shard_step = -1;           // kernel step between shard_begin and shard_end (-1: none)
   int mode = 1;                  // 0: two-pass kernels only, 1: resident kernel if the model fits on chip, else
                                  // fused single-pass where the shape fits, 2: as 1 without the resident kernel
   ResidentPlan resident;
@@ -255,6 +271,10 @@ int gibbs_profile(Gibbs* g, int64_t iters, double* ms);
 int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st);
 int launch_fused(Gibbs* g, HostKernel& hk, int j);
 int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j);
+int plan_shard(Gibbs* g, HostKernel& hk, cudaStream_t st);
+int launch_shard_sum(Gibbs* g, HostKernel& hk);
+int launch_shard_apply(Gibbs* g, HostKernel& hk);
+int launch_scalar_sharded(Gibbs* g);
 int plan_resident(Gibbs* g);
 int launch_resident(Gibbs* g, int64_t iters);
 int ensure_dense(HostBlock& bl, cudaStream_t st);   // materialise U = Z C^{-1/2} W of a factorised block

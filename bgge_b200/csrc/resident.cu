@@ -732,7 +732,7 @@ int plan_resident(Gibbs* g) {
   ResidentPlan& rp = g->resident;
   rp.enabled = false;
   rp.has_merged = false;
-  if (g->mode != 1 || getenv("BGGE_NO_RESIDENT")) return OK;
+  if (g->mode != 1 || g->shard_world > 1 || getenv("BGGE_NO_RESIDENT")) return OK;
   if (g->n > 32768 || g->nk > R_MAXKR || g->q > R_MAXQ) return OK;
   cudaStream_t st = g->stream;
   const int sms = sm_count();

@@ -497,6 +497,29 @@ virt_gather_kernel(const VDesc* __restrict__ desc, int ndesc, const double* __re
   ve[vd.voff + a] = acc;
 }
 
+// Column-sharded chain: the cluster partials of this process, summed in fixed order, -> one vector the host
+// all-reduces.  Segments are <= 1024 entries; the extra last CTA adds up the clusters' sum b^2/s.
+__global__ void __launch_bounds__(256)
+shard_sum_kernel(const SSeg* __restrict__ segs, int nsegs, const double* __restrict__ bpart, int nclusters,
+                 double* __restrict__ xbuf, long long zq_index) {
+  pdl_trigger();
+  pdl_wait();
+  if ((int)blockIdx.x == nsegs) {
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int c = 0; c < nclusters; ++c) t += bpart[c];
+      xbuf[zq_index] = t;
+    }
+    return;
+  }
+  const SSeg sg = segs[blockIdx.x];
+  for (int i = threadIdx.x; i < sg.len; i += blockDim.x) {
+    double a = 0.0;
+    for (int q = sg.qlo; q <= sg.qhi; ++q) a += sg.src[(size_t)q * sg.stride + sg.off + i];
+    xbuf[sg.doff + i] = a;
+  }
+}
+
 template <int RPT, int G, int NB>
 int launch_fused_t(Gibbs* g, HostKernel& hk, int j) {
   auto kfn = sweep_fused_kernel<RPT, G, NB>;
@@ -618,6 +641,42 @@ int launch_fused_finalize(Gibbs* g, HostKernel& hk, int j) {
   return OK;
 }
 
+namespace {
+int launch_pdl(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return OK;
+}
+}  // namespace
+
+int launch_shard_sum(Gibbs* g, HostKernel& hk) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)hk.n_ssegs + 1, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = g->stream;
+  cudaLaunchAttribute attr[1];
+  launch_pdl(cfg, attr);
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, shard_sum_kernel, (const SSeg*)hk.ssegs.p, hk.n_ssegs, (const double*)hk.bpart.p,
+                               hk.fused_clusters, hk.xbuf.p, (long long)(g->n + hk.vtotal)));
+  return OK;
+}
+
+// u, r, Welford from the all-reduced vector: the finalize kernel with one "cluster" whose partials are the sums
+int launch_shard_apply(Gibbs* g, HostKernel& hk) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)hk.n_ftiles, 1, 1);
+  cfg.blockDim = dim3(FIN_ROWS, FIN_Q, 1);
+  cfg.stream = g->stream;
+  cudaLaunchAttribute attr[1];
+  launch_pdl(cfg, attr);
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, fused_finalize_kernel, (const FTile*)hk.atiles.p, (const double*)hk.xbuf.p, (long long)g->n,
+                               (const double*)(hk.xbuf.p + g->n), (long long)hk.vtotal, g->r.p, g->u.p, g->umean.p, g->um2.p,
+                               (const Scal*)g->scal.p, (long long)g->thin, (long long)g->burn));
+  return OK;
+}
+
 // Decide whether kernel j can use the fused path and build its panel / tile tables.
 // Returns OK with hk.fused == false when the shape does not fit (caller keeps the two-pass kernels).
 int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
@@ -627,6 +686,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   struct Group {
     std::vector<int> members;
     int64_t rows, nr;
+    int64_t c_lo = 0, c_hi = 0;   // columns this process sweeps (all of them unless the chain is column-sharded)
   };
   std::vector<Group> groups;
   hk.vtotal = 0;
@@ -695,12 +755,20 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   int ncl = 0;
   BGGE_TRY(occupancy_dispatch(hk, cs, hk.fused_smem, &ncl));
   if (ncl < 1) return OK;
+  // column shard (bgge_gibbs_set_shard): rank r of w sweeps columns [nr r / w, nr (r + 1) / w) of every matrix,
+  // boundaries on multiples of the column-group size
+  for (auto& gr : groups) {
+    const int64_t gc = combo->gcols;
+    gr.c_lo = g->shard_world > 1 ? gr.nr * g->shard_rank / g->shard_world / gc * gc : 0;
+    gr.c_hi = g->shard_world > 1 && g->shard_rank + 1 < g->shard_world ? gr.nr * (g->shard_rank + 1) / g->shard_world / gc * gc
+                                                                      : gr.nr;
+  }
   // work-balanced contiguous split of the (group, column) space over the clusters
   double total = 0.0;
   int64_t total_cols = 0;
   for (auto& gr : groups) {
-    total += (double)gr.rows * (double)gr.nr;
-    total_cols += gr.nr;
+    total += (double)gr.rows * (double)(gr.c_hi - gr.c_lo);
+    total_cols += gr.c_hi - gr.c_lo;
   }
   ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, combo->gcols)));
   std::vector<FPanel> panels;
@@ -709,20 +777,21 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   {
     const double quota = total / (double)ncl;
     size_t gi = 0;
-    int64_t col = 0;   // next unassigned column of group gi
+    while (total_cols > 0 && gi < groups.size() && groups[gi].c_lo >= groups[gi].c_hi) ++gi;
+    int64_t col = gi < groups.size() ? groups[gi].c_lo : 0;   // next unassigned column of group gi
     for (int q = 0; q < ncl; ++q) {
       const bool last = q == ncl - 1;
       double need = quota;
       cpan[(size_t)q].x = (int)panels.size();
       while (gi < groups.size() && (last || need > 0.02 * quota)) {
         Group& gr = groups[gi];
-        const int64_t avail = gr.nr - col;
+        const int64_t avail = gr.c_hi - col;
         int64_t take = avail;
         if (!last) {
           const int64_t want = (int64_t)std::ceil(need / (double)gr.rows);
           take = std::min<int64_t>(avail, (want + combo->gcols - 1) / combo->gcols * combo->gcols);
         }
-        if (take <= 0) break;
+        if (take <= 0 && total_cols > 0) break;   // (a shard without any column gets one empty panel, below)
         const HostBlock& b0 = hk.blocks[(size_t)gr.members[0]];
         FPanel p{};
         p.U = b0.dU;
@@ -754,9 +823,14 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
         panels.push_back(p);
         need -= (double)gr.rows * (double)take;
         col += take;
-        if (col >= gr.nr) {
+        if (total_cols == 0) {   // empty shard: the panel has no columns, the launch only zeroes its partial sums
+          gi = groups.size();
+          break;
+        }
+        if (col >= gr.c_hi) {
           ++gi;
-          col = 0;
+          while (gi < groups.size() && groups[gi].c_lo >= groups[gi].c_hi) ++gi;
+          col = gi < groups.size() ? groups[gi].c_lo : 0;
         }
       }
       cpan[(size_t)q].y = (int)panels.size() - cpan[(size_t)q].x;
@@ -828,12 +902,61 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   BGGE_CUDA(cudaMemcpyAsync(hk.fcluster.p, cpan.data(), cpan.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
   BGGE_CUDA(hk.ftiles.alloc(tiles.size()));
   BGGE_CUDA(cudaMemcpyAsync(hk.ftiles.p, tiles.data(), tiles.size() * sizeof(FTile), cudaMemcpyHostToDevice, st));
+  for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
+    hk.blocks[bi].fq_lo = block_q[bi].first;
+    hk.blocks[bi].fq_hi = block_q[bi].second;
+  }
   BGGE_CUDA(cudaStreamSynchronize(st));
   hk.fused = true;
   if (getenv("BGGE_DEBUG"))
     fprintf(stderr, "[bgge] fused plan: cs=%d clusters=%d rpt=%d g=%d nb=%d ns=%d smem=%zu groups=%zu panels=%zu vtotal=%lld\n",
             hk.fused_cs, hk.fused_clusters, hk.fused_rpt, hk.fused_g, hk.fused_nb, hk.fused_ns, hk.fused_smem,
             groups.size(), panels.size(), (long long)hk.vtotal);
+  return OK;
+}
+
+// Column-sharded chain: tables of shard_sum_kernel and of the apply pass.  Called from gibbs_init once the partial-sum
+// buffers exist.
+int plan_shard(Gibbs* g, HostKernel& hk, cudaStream_t st) {
+  std::vector<SSeg> segs;
+  auto add_seg = [&](const double* src, long long stride, long long off, long long doff, int64_t len, int qlo, int qhi) {
+    if (qlo > qhi) return;   // no cluster of this process touches the block: its part of the vector stays zero
+    for (int64_t i0 = 0; i0 < len; i0 += 1024) {
+      SSeg sg{};
+      sg.src = src;
+      sg.stride = stride;
+      sg.off = off + i0;
+      sg.doff = doff + i0;
+      sg.len = (int)std::min<int64_t>(1024, len - i0);
+      sg.qlo = qlo;
+      sg.qhi = qhi;
+      segs.push_back(sg);
+    }
+  };
+  BGGE_CUDA(hk.xbuf.alloc((size_t)(g->n + hk.vtotal + 1)));
+  BGGE_CUDA(cudaMemsetAsync(hk.xbuf.p, 0, (size_t)(g->n + hk.vtotal + 1) * sizeof(double), st));
+  for (const HostBlock& bl : hk.blocks) {
+    if (bl.vrows > 0)
+      add_seg(g->vupart.p, hk.vtotal, bl.voff, g->n + bl.voff, bl.vrows, bl.fq_lo, bl.fq_hi);
+    else
+      add_seg(g->upart.p, g->n, bl.pos0, bl.pos0, bl.rows, bl.fq_lo, bl.fq_hi);
+  }
+  hk.n_ssegs = (int)segs.size();
+  BGGE_CUDA(hk.ssegs.alloc(std::max<size_t>(1, segs.size())));
+  if (!segs.empty()) BGGE_CUDA(cudaMemcpyAsync(hk.ssegs.p, segs.data(), segs.size() * sizeof(SSeg), cudaMemcpyHostToDevice, st));
+  // every block tile reads slot 0 of the reduced vector (a block without local columns still receives the other
+  // processes' contributions); tiles of rows no block covers keep qlo > qhi (u = 0 there)
+  std::vector<FTile> at((size_t)hk.n_ftiles);
+  BGGE_CUDA(cudaMemcpyAsync(at.data(), hk.ftiles.p, at.size() * sizeof(FTile), cudaMemcpyDeviceToHost, st));
+  BGGE_CUDA(cudaStreamSynchronize(st));
+  for (auto& t : at) {
+    bool in_block = false;
+    for (auto& bl : hk.blocks) in_block = in_block || (t.row0 >= bl.pos0 && t.row0 < bl.pos0 + bl.rows);
+    if (in_block) t.qlo = t.qhi = 0;
+  }
+  BGGE_CUDA(hk.atiles.alloc(std::max<size_t>(1, at.size())));
+  BGGE_CUDA(cudaMemcpyAsync(hk.atiles.p, at.data(), at.size() * sizeof(FTile), cudaMemcpyHostToDevice, st));
+  BGGE_CUDA(cudaStreamSynchronize(st));
   return OK;
 }
 

@@ -58,3 +58,53 @@ def assemble_panels(S, gathered, L: int, world: int):
             if r1 > r0:
                 S[:, r0:r1] = gathered[r][k][:, :r1 - r0]
     return S
+
+
+# ----------------------------------------------------------------------------------------------------------
+# column-sharded single chain: host loop around bgge_gibbs_shard_begin / _end
+# ----------------------------------------------------------------------------------------------------------
+def column_range(nr: int, world: int, rank: int, group: int = 1):
+    """Eigen-columns [lo, hi) of a matrix with nr columns that rank sweeps; boundaries on multiples of `group`
+    (the column-group size of the sweep kernel).  Mirrors the planner in csrc/sweep_fused.cu."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    lo = nr * rank // world // group * group if world > 1 else 0
+    hi = nr * (rank + 1) // world // group * group if (world > 1 and rank + 1 < world) else nr
+    return lo, hi
+
+
+class DeviceVector:
+    """A device buffer owned by libbgge_b200, exposed through __cuda_array_interface__ so that torch can wrap it
+    without a copy (torch.as_tensor(DeviceVector(ptr, count), device="cuda"))."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def nccl_allreduce(group=None):
+    """reduce(ptr, count): in-place sum over the ranks of `group` with torch.distributed (NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    cache = {}
+
+    def reduce(ptr, count):
+        t = cache.get((ptr, count))
+        if t is None:
+            t = cache[(ptr, count)] = torch.as_tensor(DeviceVector(ptr, count), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    return reduce
+
+
+def run_sharded(h, nk: int, iters: int, reduce):
+    """`iters` iterations of a column-sharded chain: per kernel step sweep the local columns, add the partial
+    W b and sum b^2/s of all processes (reduce(ptr, count), in place, on the handle's stream), finish the step."""
+    import ctypes as C
+    from . import _lib
+    vec, cnt = C.c_void_p(), C.c_int64()
+    for _ in range(int(iters)):
+        for j in range(nk):
+            _lib.call("bgge_gibbs_shard_begin", h, j, C.byref(vec), C.byref(cnt))
+            reduce(vec.value, cnt.value)
+            _lib.call("bgge_gibbs_shard_end", h, j)
+        _lib.call("bgge_gibbs_shard_iteration_end", h)

@@ -174,6 +174,19 @@ int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* 
 /* device pointer / leading dimension of a block's U (owned by handle h; other handles may borrow it with
  * bgge_gibbs_add_block(..., on_device = 1) while h is alive: one decomposition, many chains) */
 int bgge_gibbs_block_device(bgge_gibbs* h, int j, int b, const double** dU, int64_t* ldu);
+/* Column-sharded single chain (the sweep of R/BGGE.R:296-339 spread over processes / GPUs).
+ * bgge_gibbs_set_shard (before init): this handle sweeps eigen-columns [nr rank / world, nr (rank + 1) / world) of every
+ * basis matrix; the state is replicated.  Then, instead of bgge_gibbs_run, per iteration and per kernel j:
+ *   bgge_gibbs_shard_begin(h, j, &vec, &count)   launches the sweep; vec (device, count doubles) holds this process'
+ *                                                partial W b and sum b^2/s
+ *   <all-reduce (sum) vec over the processes, on the handle's stream>
+ *   bgge_gibbs_shard_end(h, j)                   u_j, residual, running means from the reduced vector
+ * and after the last kernel bgge_gibbs_shard_iteration_end(h) (variances, imputation, next intercept).  Draws are
+ * keyed by the global column: every process holds the same chain.  No fixed effects in this mode. */
+int bgge_gibbs_set_shard(bgge_gibbs* h, int rank, int world);
+int bgge_gibbs_shard_begin(bgge_gibbs* h, int j, double** d_vector, int64_t* count);
+int bgge_gibbs_shard_end(bgge_gibbs* h, int j);
+int bgge_gibbs_shard_iteration_end(bgge_gibbs* h);
 /* sweep implementation: 1 (default) = resident kernel when the whole eigen basis fits the chip's shared memory
  * (small models: one cooperative launch runs all iterations), else the fused single-pass kernel step where
  * the block shapes fit (U read once per kernel per iteration); 2 = as 1 but never resident; 0 = two-pass

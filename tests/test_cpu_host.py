@@ -121,6 +121,23 @@ def test_shard_units_partitions():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_column_shards_partition_the_columns():
+    """column_range (the host mirror of the sharded sweep's planner): disjoint, covering, on column-group boundaries."""
+    from bgge_b200.multigpu import column_range
+    for nr in (1, 7, 599, 2999, 10000):
+        for world in (1, 2, 3, 4, 8):
+            for group in (1, 2, 4, 6):
+                cur = 0
+                for r in range(world):
+                    lo, hi = column_range(nr, world, r, group)
+                    assert lo == cur and hi >= lo
+                    assert r == world - 1 or hi % group == 0
+                    cur = hi
+                assert cur == nr
+    with pytest.raises(ValueError):
+        column_range(10, 2, 2)
+
+
 def test_panel_plan_is_balanced_and_covers():
     from bgge_b200 import multigpu
     for L, world in [(10000, 8), (10000, 2), (599, 4), (3000, 8), (130, 2)]:
