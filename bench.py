@@ -427,6 +427,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-ref", action="store_true", help="skip the extra dense-basis measurement")
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass proj/back kernels (no fused sweep)")
+    ap.add_argument("--shard-chain", action="store_true",
+                    help="N > 1: ONE chain, its eigen-columns sharded over the GPUs (strong scaling, SURVEY 8 f-4) "
+                         "instead of one independent chain per GPU")
     ap.add_argument("--full-eigen", action="store_true", help="decompose the expanded n x n kernels directly")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -566,6 +569,7 @@ def main():
         y_np = y_pinned.numpy()
         del Ub, root
 
+        sharded = bool(args.shard_chain) and world > 1
         total_iters = (args.warmup + args.steps) * iters + args.prof_iters + 8
 
         def make_handle(ite, src=None):
@@ -576,8 +580,21 @@ def main():
                 lib.call("bgge_gibbs_share_kernel", h, j, src or h0, j)   # borrow the decomposition (dense or factorised)
             if args.two_pass:
                 lib.call("bgge_gibbs_set_mode", h, 0)
-            lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + rank, rank)
+            if sharded:
+                lib.call("bgge_gibbs_set_shard", h, rank, world)
+            lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + (0 if sharded else rank),
+                     0 if sharded else rank)
             return h
+
+        if sharded:
+            from bgge_b200 import multigpu
+            reduce_fn = multigpu.nccl_allreduce()
+
+        def run(hh, k, graph=True):
+            if sharded:
+                multigpu.run_sharded(hh, nk, k, reduce_fn)
+            else:
+                lib.call("bgge_gibbs_run", hh, k)
 
         # ------------------------------------------------------------- timed region: device-resident sweep
         h = make_handle(total_iters)
@@ -590,7 +607,7 @@ def main():
                         "note": "kernels sharing one matrix on disjoint rows are swept by one launch in the timed run; "
                                 "the per-kernel list below times the unmerged launches" if mu_n.value else ""}
         for _ in range(args.warmup):
-            lib.call("bgge_gibbs_run", h, iters)
+            run(h, iters)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -601,7 +618,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
-            lib.call("bgge_gibbs_run", h, iters)
+            run(h, iters)
         ev1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -612,11 +629,12 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms_total = float(ms.item())
-        value = world * args.steps * iters / (ms_total * 1e-3)
+        value = (1 if sharded else world) * args.steps * iters / (ms_total * 1e-3)
 
         # ------------------------------------------------------------- per-kernel times (instrumented sweeps)
         prof = np.zeros(2 * nk + 2)
-        lib.call("bgge_gibbs_profile", h, args.prof_iters, lib.ptr(prof))
+        if not sharded:
+            lib.call("bgge_gibbs_profile", h, args.prof_iters, lib.ptr(prof))
         prof_ms = prof / max(1, args.prof_iters)
         mu_c, s2_c = C.c_double(), C.c_double()
         lib.call("bgge_gibbs_state", h, C.byref(mu_c), C.byref(s2_c), None, None, None, None)
@@ -644,7 +662,7 @@ def main():
             t = [time.perf_counter()]
             hh = make_handle(iters)                       # uploads y from pinned host memory, initialises the chain
             t.append(time.perf_counter())
-            lib.call("bgge_gibbs_run", hh, iters)
+            run(hh, iters, graph=False)   # a fresh handle per call: no graph to reuse
             t.append(time.perf_counter())
             lib.call("bgge_gibbs_summary", hh, lib.ptr(yHat), C.byref(ve), C.byref(vesd), lib.ptr(u_m), lib.ptr(u_sd),
                      lib.ptr(vu), lib.ptr(vusd), lib.ptr(yout))
@@ -668,13 +686,13 @@ def main():
         if world > 1:
             dist.barrier()
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_val = world * args.steps * iters / float(te.item())
+        e2e_val = (1 if sharded else world) * args.steps * iters / float(te.item())
 
         # ------------------------------------------------------------- the same sweep on the dense eigen basis
         # (no factorisation, no sharing of identical blocks): the plain single-pass HBM-streaming regime, for
         # the roofline reading of the kernel when the structure above is not available (unbalanced designs)
         dense_ref = None
-        if any(k["factored_blocks"] for k in kinfo) and not args.no_dense_ref and not args.two_pass:
+        if any(k["factored_blocks"] for k in kinfo) and not args.no_dense_ref and not args.two_pass and not sharded:
             os.environ["BGGE_NO_FACTORED_SWEEP"] = "1"
             hd0 = C.c_void_p()
             lib.call("bgge_gibbs_create", n, nk, 0, stream, C.byref(hd0))
@@ -729,6 +747,8 @@ def main():
             kern.append({"name": f"back_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": basis // 2 + 32 * n + 8 * nrj})
     bytes_iter = u_bytes + 8 * n * (4 * nk + 3) + 40 * sum_nr
     sweep_gbs = bytes_iter * (world * args.steps * iters) / (ms_total * 1e-3) / 1e9 / world
+    if sharded:   # one chain: every GPU streams 1 / world of the basis
+        sweep_gbs /= world
     kern.append({"name": "scalar_kernel", "ms": prof_ms[2 * nk], "bytes": 16 * n})
     for k in kern:
         k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
@@ -775,10 +795,13 @@ def main():
         line = {
             "metric": METRIC if args.workload == "c5" else f"Gibbs iterations/sec ({args.workload})",
             "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "iters_per_step": iters, "kernels": nk, "n": n, "L": L, "p": p, "E": E,
-                       "parallelism": f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain",
+                       "parallelism": (f"1 chain, eigen-columns sharded over {world} GPUs, one NCCL all-reduce of n + 1 "
+                                       "doubles per kernel step" if sharded else
+                                       f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain"),
                        "l2": "inputs larger than L2 (U streamed from HBM every iteration)" if u_bytes > 256e6
                              else "working set fits in L2; latency-bound, HBM roofline not binding",
                        "eigen": "factorised setDEC in the library: L x L syevd per block, n x n kernels never built"},

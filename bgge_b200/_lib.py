@@ -85,6 +85,7 @@ SIGNATURES = {
     "bgge_gibbs_shard_begin": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "bgge_gibbs_shard_end": (C.c_int, [C.c_void_p, C.c_int]),
     "bgge_gibbs_shard_iteration_end": (C.c_int, [C.c_void_p]),
+    "bgge_gibbs_shard_advance": (C.c_int, [C.c_void_p, C.c_int64]),
     "bgge_gibbs_merged_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgge_gibbs_kernel_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),

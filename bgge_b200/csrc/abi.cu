@@ -1013,8 +1013,11 @@ int bgge_gibbs_shard_begin(bgge_gibbs* h, int j, double** d_vector, int64_t* cou
   BGGE_TRY(launch_fused(&g, hk, j));
   BGGE_TRY(launch_shard_sum(&g, hk));
   g.shard_step = j;
-  if (d_vector) *d_vector = hk.xbuf.p;
-  if (count) *count = g.n + hk.vtotal + 1;
+  // a kernel whose blocks are all factorised exchanges only the genotype-space part (+ the sum b^2/s behind it)
+  bool all_virtual = true;
+  for (auto& bl : hk.blocks) all_virtual = all_virtual && bl.vrows > 0;
+  if (d_vector) *d_vector = hk.xbuf.p + (all_virtual ? g.n : 0);
+  if (count) *count = (all_virtual ? 0 : g.n) + hk.vtotal + 1;
   return OK;
 }
 
@@ -1033,6 +1036,18 @@ int bgge_gibbs_shard_iteration_end(bgge_gibbs* h) {
   BGGE_REQUIRE(g.initialised && g.shard_world > 1 && g.shard_step == -1, "gibbs_shard_iteration_end: a step is still open");
   BGGE_TRY(launch_scalar_sharded(&g));
   g.done += 1;
+  return OK;
+}
+
+// Iteration bookkeeping for callers that capture one sharded iteration into a CUDA graph (NCCL collective
+// included) and replay it: the captured calls are not executed, the replays are not seen by the library.
+int bgge_gibbs_shard_advance(bgge_gibbs* h, int64_t iterations) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && g.shard_world > 1 && g.shard_step == -1, "gibbs_shard_advance: not a column shard at an iteration boundary");
+  BGGE_REQUIRE(g.done + iterations >= 0 && g.done + iterations <= g.ite, "gibbs_shard_advance: %lld + %lld outside [0, %lld]",
+               (long long)g.done, (long long)iterations, (long long)g.ite);
+  g.done += iterations;
   return OK;
 }
 

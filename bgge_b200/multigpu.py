@@ -108,3 +108,4 @@ def run_sharded(h, nk: int, iters: int, reduce):
             reduce(vec.value, cnt.value)
             _lib.call("bgge_gibbs_shard_end", h, j)
         _lib.call("bgge_gibbs_shard_iteration_end", h)
+

@@ -187,6 +187,10 @@ int bgge_gibbs_set_shard(bgge_gibbs* h, int rank, int world);
 int bgge_gibbs_shard_begin(bgge_gibbs* h, int j, double** d_vector, int64_t* count);
 int bgge_gibbs_shard_end(bgge_gibbs* h, int j);
 int bgge_gibbs_shard_iteration_end(bgge_gibbs* h);
+/* adds `iterations` (may be negative) to the handle's count of finished iterations: for callers that capture one
+ * sharded iteration, collective included, into a CUDA graph and replay it (captured calls do not execute, replays
+ * do not pass through the library) */
+int bgge_gibbs_shard_advance(bgge_gibbs* h, int64_t iterations);
 /* sweep implementation: 1 (default) = resident kernel when the whole eigen basis fits the chip's shared memory
  * (small models: one cooperative launch runs all iterations), else the fused single-pass kernel step where
  * the block shapes fit (U read once per kernel per iteration); 2 = as 1 but never resident; 0 = two-pass
