@@ -282,10 +282,12 @@ scalar_kernel(const ScalarArgs a, DrawCfg dc) {
   __shared__ double sh_a[33], sh_b[33];
   __shared__ double sh_chi[MAXK + 1];
   __shared__ double sh_zmu, sh_sigsq;
-  pdl_trigger();
+  // No early pdl_trigger() here: the launches of the next iteration start only when this kernel has completed.
+  // That is what makes the reads below safe before pdl_wait(): it / shift / mu were written by the previous
+  // scalar_kernel, and none of the launches since then (hence this one) could start before that kernel was done.
+  // (With an early trigger a single-kernel model could cascade scalar -> gather -> sweep -> finalize -> scalar
+  // while the first scalar kernel is still running.)
   Scal* sc = a.sc;
-  // it / shift / mu were written by the previous scalar_kernel, at least two launches upstream: every launch
-  // in between passed its own pdl_wait(), so that kernel has completed and the values are visible here
   const long long it = sc->it;        // iteration that just finished (0 right after init)
   const double shift = sc->shift;
   const double mu = sc->mu;
