@@ -17,7 +17,8 @@ enum Status : int {
   ERR_STATE = 4,     // call out of order (e.g. run before init)
   ERR_NODEVICE = 5,  // no usable sm_100 device
   ERR_TAPE = 6,      // injected tape exhausted
-  ERR_UNSUPPORTED = 7
+  ERR_UNSUPPORTED = 7,
+  ERR_RETRY_STREAMING = 100   // internal: the resident kernel could not be launched, use the streaming kernels
 };
 
 void set_error(const char* fmt, ...);

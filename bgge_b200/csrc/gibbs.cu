@@ -927,9 +927,17 @@ int gibbs_run(Gibbs* g, int64_t iters) {
       g->done += 1;
       iters -= 1;
     }
-    if (iters > 0) BGGE_TRY(launch_resident(g, iters));
-    g->done += iters;
-    return OK;
+    if (iters > 0) {
+      const int rs = launch_resident(g, iters);
+      if (rs != ERR_RETRY_STREAMING) {
+        if (rs != OK) return rs;
+        g->done += iters;
+        return OK;
+      }
+      // fall through to the streaming path with the remaining iterations
+    } else {
+      return OK;
+    }
   }
   const bool merged = !g->units.empty();
   if (merged && g->done == 0 && iters > 0) {

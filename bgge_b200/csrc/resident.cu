@@ -1126,8 +1126,15 @@ int launch_resident(Gibbs* g, int64_t iters) {
     p.timing = timing.p;
   }
   void* args[] = {&p, &dc};
-  BGGE_CUDA(cudaLaunchCooperativeKernel(p.timing ? (void*)resident_sweep_kernel<true> : (void*)resident_sweep_kernel<false>,
-                                        dim3((unsigned)rp.ncta), dim3(R_THREADS), args, rp.smem, g->stream));
+  const cudaError_t le = cudaLaunchCooperativeKernel(p.timing ? (void*)resident_sweep_kernel<true> : (void*)resident_sweep_kernel<false>,
+                                                     dim3((unsigned)rp.ncta), dim3(R_THREADS), args, rp.smem, g->stream);
+  if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+    // the grid cannot be co-resident right now (GPU shared with other work): the streaming kernels take over
+    (void)cudaGetLastError();
+    rp.enabled = false;
+    return ERR_RETRY_STREAMING;
+  }
+  BGGE_CUDA(le);
   if (p.timing) {
     unsigned long long t[16];
     BGGE_CUDA(cudaMemcpyAsync(t, timing.p, sizeof(t), cudaMemcpyDeviceToHost, g->stream));
