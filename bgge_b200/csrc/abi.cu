@@ -811,7 +811,7 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         BGGE_CUDA(cudaStreamSynchronize(st));
         const SharedDecomp* hit = nullptr;
         for (auto& d : g.decomps)
-          if (d.h1 == hh[0] && d.h2 == hh[1] && d.T == T && d.cnt == cntT) hit = &d;
+          if (d.h1 == hh[0] && d.h2 == hh[1] && d.tol == tol && d.canonical == canonical_sign && d.T == T && d.cnt == cntT) hit = &d;
         if (hit) {   // this matrix was decomposed already: share its W and eigenvalues
           if (hit->nr == 0) continue;
           if (env_mode && identity && !duplicated) {
@@ -827,7 +827,7 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       int64_t nr = 0;
       BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
       if (nr == 0) {                                                // R/BGGE.R:162
-        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, nullptr, 0, 0, {}});
+        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, nullptr, 0, 0, {}});
         continue;
       }
       bl.nr = nr;
@@ -856,10 +856,10 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       if (keep_factored) {   // fewer rows to stream (repeated genotypes) or W shared with identical blocks
         BGGE_TRY(upload_map());
         BGGE_TRY(make_virtual(dWfinal, ldw, nr, true));
-        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, dWfinal, ldw, nr, s_host});
+        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, dWfinal, ldw, nr, s_host});
       } else if (shareable && identity) {   // U = W: the block streams W itself, later identical kernels share it
         BGGE_TRY(add_dense_shared(dWfinal, ldw, nr, true));
-        g.decomps.push_back(SharedDecomp{hh[0], hh[1], T, cntT, dWfinal, ldw, nr, s_host});
+        g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, dWfinal, ldw, nr, s_host});
       } else {
         BGGE_TRY(upload_map());
         BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));

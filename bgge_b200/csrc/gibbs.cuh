@@ -219,6 +219,8 @@ struct ResidentPlan {
 // blocks of different kernels (the environment kernels of MDe) share W and the eigenvalues.
 struct SharedDecomp {
   unsigned long long h1, h2;     // content hash of the matrix that was decomposed
+  double tol;                    // eigenvalue threshold it was truncated with
+  int canonical;                 // sign convention applied
   std::vector<int> T, cnt;
   double* W;
   int64_t ldw, nr;
