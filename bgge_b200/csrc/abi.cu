@@ -706,8 +706,22 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       }
     return std::make_pair(T, c);
   };
+  auto block_is_live = [&](int64_t pos, int64_t m) {   // uniform all-ones mask: the block will be decomposed
+    if (mode == BGGE_EXPAND_GE) {
+      for (int64_t i = 1; i < m; ++i)
+        if (env[pos + i] != env[pos]) return false;
+      return true;
+    }
+    if (mode == BGGE_EXPAND_ENV) {
+      for (int64_t i = 0; i < m; ++i)
+        if (env[pos + i] != env_k) return false;
+      return true;
+    }
+    return true;
+  };
   if (share_blocks && spans.size() > 1)
-    for (auto& sp : spans) ++key_count[block_key(sp.first, sp.second)];
+    for (auto& sp : spans)
+      if (block_is_live(sp.first, sp.second)) ++key_count[block_key(sp.first, sp.second)];
   for (auto& sp : spans) {
     const int64_t pos = sp.first, m = sp.second;
     // is the mask constant on this block?  (first row decides; every pair is checked through the row classes)
