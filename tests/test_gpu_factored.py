@@ -162,6 +162,40 @@ def test_mde_environment_kernels_share_one_decomposition_and_sweep_together(E, d
             assert relmax(got["y"], ref["y"]) <= 1e-9, mode
 
 
+def test_mde_merged_sweeps_with_fixed_effects():
+    """Merged environment kernels together with XF (environment means) and missing phenotypes: resident kernel
+    (merged steps + the scalar XF step), streaming path (xf kernels + merged units), two-pass, against the oracle."""
+    import bgge_b200
+    L, E, p = 30, 4, 40
+    X = markers(L, p, 8)
+    Y, names = design(L, E)
+    ne = [L] * E
+    n = L * E
+    Kf = bgge_b200.getK(Y, X, kernel="GB", model="MDe", rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel="GB", model="MDe", rownames=names)
+    rng = np.random.default_rng(21)
+    y = rng.standard_normal(n)
+    y[rng.choice(n, 6, replace=False)] = np.nan
+    XF = np.zeros((n, E))
+    for e in range(E):
+        XF[e * L:(e + 1) * L, e] = 1.0
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    ite = 16
+    nz, nc = oracle.tape_sizes(n, nrs, ite, q=E, n_na=6)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    ref = oracle.BGGE(y, Kd, XF=XF, ne=ne, ite=ite, burn=2, thin=2, draws=oracle.TapeDraws(z, c), eig=Ei)
+    for mode in (1, 2, 0):
+        got = bgge_b200.BGGE(y, Kf, XF=XF, ne=ne, ite=ite, burn=2, thin=2, draws=(z, c), mode=mode)
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, mode
+        for nm in ref["K"]:
+            assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9, (mode, nm)
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (mode, nm)
+        assert relmax(np.asarray(got["yHat"]).ravel(), np.asarray(ref["yHat"]).ravel()) <= 1e-9, mode
+
+
 def test_shared_kernel_handles_reproduce_owner(lib):
     """bgge_gibbs_share_kernel: chains that borrow a decomposition (factorised + shared blocks included) give
     the same chain as a handle that built it itself."""
