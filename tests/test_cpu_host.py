@@ -33,6 +33,18 @@ def test_library_exports_every_declared_symbol(built):
     assert isinstance(lib.bgge_last_error(), bytes)
 
 
+def test_ctypes_prototypes_have_the_header_arity(built):
+    """Every prototype in include/bgge_b200.h has as many parameters as its ctypes signature (ABI drift guard)."""
+    hdr = open(os.path.join(ROOT, "include", "bgge_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"^\s*(?:int|void|const char\*)\s+(bgge_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.M | re.S)
+    assert len(protos) >= 36
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([x for x in params.split(",") if x.strip()])
+        assert n == len(built.SIGNATURES[name][1]), (name, n, len(built.SIGNATURES[name][1]))
+
+
 def test_no_cpu_fallback(built):
     """Without a CUDA device every compute entry point must fail loudly (never compute on the host)."""
     import torch
