@@ -38,6 +38,24 @@ def _factor_mean_diag(f):
     return float(v.mean())
 
 
+def _plan_info(h, nk):
+    """Execution plan of an initialised handle (which kernels run, how they are tiled)."""
+    en, ct, sm = C.c_int(), C.c_int(), C.c_int64()
+    _lib.call("bgge_gibbs_resident_info", h, C.byref(en), C.byref(ct), C.byref(sm))
+    un, ku = C.c_int(), C.c_int()
+    _lib.call("bgge_gibbs_merged_info", h, C.byref(un), C.byref(ku))
+    ks = []
+    for j in range(nk):
+        f_, cs_, ncl_, nl_ = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.call("bgge_gibbs_kernel_info", h, j, C.byref(f_), C.byref(cs_), C.byref(ncl_), C.byref(nl_))
+        bb_, nf_ = C.c_int64(), C.c_int()
+        _lib.call("bgge_gibbs_kernel_bytes", h, j, C.byref(bb_), C.byref(nf_))
+        ks.append({"path": f_.value, "cluster_size": cs_.value, "clusters": ncl_.value, "launches": nl_.value,
+                   "basis_bytes": bb_.value, "factored_blocks": nf_.value})
+    return {"resident": bool(en.value), "resident_ctas": ct.value, "merged_units": un.value,
+            "kernels_in_units": ku.value, "kernels": ks}
+
+
 def _add_factored(h, j, k, ne_arr, tol, canonical_sign):
     f = k["factor"]
     tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
@@ -105,7 +123,7 @@ def setDEC(K, ne=None, tol=1e-10, canonical_sign=True):
 
 
 def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=1e-10, R2=0.5, *, seed=0, chain=0,
-         draws=None, eig=None, device=None, mode=None, rng="philox", shard=None):
+         draws=None, eig=None, device=None, mode=None, rng="philox", shard=None, info=None):
     """Fit the G x E model by Gibbs sampling (signature of R/BGGE.R:84 plus keyword-only extras).
 
     draws : optional (normals, chisq) tapes -> injected-draw mode.
@@ -116,6 +134,9 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     rng   : "philox" (default) = counter-based device draws keyed by (seed, chain); "R" = the stream of R's
             `set.seed(seed)` (Mersenne-Twister, inversion normals, Ahrens-Dieter gammas) consumed in the
             reference's call order and injected as tapes (bgge_b200.rrng).
+    info  : optional dict, filled after initialisation with the execution plan: "resident" (bool), "merged_units",
+            and per kernel "path" (0 two-pass, 1 sweep_fused_kernel, 2 sweep_mrhs_kernel), "cluster_size", "clusters",
+            "launches", "basis_bytes", "factored_blocks" (bgge_gibbs_kernel_info / _kernel_bytes).
     shard : None, or (rank, world, reduce): this process sweeps its slice of the eigen-columns of a single chain and
             reduce(ptr, count) adds the per-step partial vectors of all processes in place (bgge_b200.multigpu.
             nccl_allreduce() for torch.distributed over NCCL).  Every process must call BGGE() with the same
@@ -203,6 +224,8 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
             _lib.call("bgge_gibbs_set_tape", h, _lib.ptr(z), z.shape[0], _lib.ptr(c), c.shape[0])
             mode = _lib.RNG_TAPE
         _lib.call("bgge_gibbs_init", h, int(ite), int(burn), int(thin), float(R2), mode, int(seed), int(chain))
+        if info is not None:
+            info.update(_plan_info(h, nk))
         step = int(verbose) if int(verbose) != 0 else int(ite)
         done = 0
         while done < ite:                                                    # R/BGGE.R:274, 398-401

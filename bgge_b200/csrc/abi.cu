@@ -1104,7 +1104,7 @@ int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, 
   Gibbs& g = h->g;
   BGGE_REQUIRE(g.initialised && j >= 0 && j < g.nk, "gibbs_kernel_info: bad kernel index or handle not initialised");
   HostKernel& hk = g.kernels[(size_t)j];
-  if (fused) *fused = hk.fused ? 1 : 0;
+  if (fused) *fused = hk.fused ? (hk.fused_engine == 1 ? 2 : 1) : 0;
   if (cluster_size) *cluster_size = hk.fused ? hk.fused_cs : hk.cs;
   if (clusters) *clusters = hk.fused ? hk.fused_clusters : hk.n_btasks;
   if (launches) {

@@ -18,6 +18,7 @@
 #include "gibbs.cuh"
 #include "kernels.h"
 #include "rng.cuh"
+#include "sweep_mrhs.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
@@ -620,6 +621,7 @@ int launch_fused(Gibbs* g, HostKernel& hk, int j) {
     BGGE_CUDA(cudaLaunchKernelEx(&cfg, virt_gather_kernel, (const VDesc*)hk.vdesc.p, hk.n_vdesc, (const double*)g->r.p,
                                  (const double*)g->u.p, (long long)g->n, (const Scal*)g->scal.p, hk.ve.p));
   }
+  if (hk.fused_engine == 1) return mrhs_launch(g, hk);
   auto run = [&]() -> int { BGGE_FUSED_DISPATCH(launch_fused_t, g, hk, j) };
   return run();
 }
@@ -715,50 +717,75 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   }
   if (max_rows <= 0) return OK;
   const int nb_t = nbmax > 2 ? 4 : nbmax;            // instantiated right-hand-side counts: 1, 2, 4
-  const int rpt_cap = 12 / nb_t;                     // register budget: NB * RPT <= 12 row pairs per thread
-  // smallest cluster whose row slice fits the register budget: long contiguous column slices (~40 KB)
-  // stream best and small clusters leave no SM idle
-  int cs = 1;
-  while (cs < 8 && max_rows > (int64_t)cs * rpt_cap * F_ROWS_PER_STEP) cs *= 2;
-  if (const char* ev = getenv("BGGE_FUSED_CS")) {   // tuning hook
-    const int v = atoi(ev);
-    if (v == 1 || v == 2 || v == 4 || v == 8) cs = std::max(cs, v);
+  int cs = 1, gcols = 1, ncl = 0;
+  hk.fused_engine = 0;
+  // multi-RHS panels go to sweep_mrhs_kernel (register-resident e and u at 4-CTA clusters, helper warps for the
+  // exchange); BGGE_MRHS=0 keeps them on sweep_fused_kernel
+  if (nb_t >= 2 && !(getenv("BGGE_MRHS") && atoi(getenv("BGGE_MRHS")) == 0) &&
+      (max_rows >= mrhs_min_rows() || (getenv("BGGE_MRHS") && atoi(getenv("BGGE_MRHS")) == 2))) {
+    MrhsCfg mc;
+    BGGE_TRY(mrhs_configure(max_rows, nb_t, hk.merged, &mc));
+    if (mc.ok) {
+      hk.fused_engine = 1;
+      cs = mc.cs;
+      gcols = MRHS_G;
+      ncl = mc.clusters;
+      hk.fused_cs = cs;
+      hk.fused_rpt = 0;
+      hk.fused_g = gcols;
+      hk.fused_nb = nb_t;
+      hk.fused_ns = mc.ns;
+      hk.fused_kr = mc.kr;
+      hk.fused_lag = mc.lag;
+      hk.fused_smem = mc.smem;
+    }
   }
-  const int64_t rs_max = round_up((max_rows + cs - 1) / cs, 16);
-  const int rpt_need = (int)((rs_max + F_ROWS_PER_STEP - 1) / F_ROWS_PER_STEP);
-  const Combo* combo = nullptr;
-  for (const Combo& c : kCombos)
-    if (c.rpt >= rpt_need && c.rpt <= rpt_cap) { combo = &c; break; }
-  if (!combo) return OK;   // slices too long for the register budget: two-pass path
-  hk.fused_cs = cs;
-  hk.fused_rpt = combo->rpt;
-  hk.fused_g = combo->gcols;
-  hk.fused_nb = nb_t;
-  const size_t slot_bytes = (size_t)combo->gcols * rs_max * sizeof(double);
-  const size_t zb = (size_t)combo->gcols * (F_ROLE / combo->gcols);
-  const size_t ng = (size_t)nb_t * combo->gcols;
-  int dev = 0, optin = 0;
-  BGGE_CUDA(cudaGetDevice(&dev));
-  BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t tvm = hk.merged ? (size_t)nb_t : 1;   // tau * v per member kernel in a merged unit
-  auto fixed_bytes = [&](int nsv) {   // exchange ring depth 2 ns + 4 (protocol note) -> grows with the data ring
-    return ((size_t)(2 * nsv + 4) * F_MAXCS * ng + 2 * 8 * ng + 2 * ng + (2 * tvm + 2) * zb + (size_t)nb_t * 2 * zb) * sizeof(double) +
-           (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
-  };
-  int ns = 0;
-  for (int c = F_MAX_NS; c >= 3; --c)
-    if ((size_t)c * slot_bytes + fixed_bytes(c) + 1024 <= (size_t)optin) { ns = c; break; }
-  if (ns < 3) return OK;
-  const size_t fixed = fixed_bytes(ns);
-  hk.fused_ns = ns;
-  hk.fused_smem = ns * slot_bytes + fixed;
-  int ncl = 0;
-  BGGE_TRY(occupancy_dispatch(hk, cs, hk.fused_smem, &ncl));
+  if (hk.fused_engine == 0) {
+    const int rpt_cap = 12 / nb_t;                     // register budget: NB * RPT <= 12 row pairs per thread
+    // smallest cluster whose row slice fits the register budget: long contiguous column slices (~40 KB)
+    // stream best and small clusters leave no SM idle
+    while (cs < 8 && max_rows > (int64_t)cs * rpt_cap * F_ROWS_PER_STEP) cs *= 2;
+    if (const char* ev = getenv("BGGE_FUSED_CS")) {   // tuning hook
+      const int v = atoi(ev);
+      if (v == 1 || v == 2 || v == 4 || v == 8) cs = std::max(cs, v);
+    }
+    const int64_t rs_max = round_up((max_rows + cs - 1) / cs, 16);
+    const int rpt_need = (int)((rs_max + F_ROWS_PER_STEP - 1) / F_ROWS_PER_STEP);
+    const Combo* combo = nullptr;
+    for (const Combo& c : kCombos)
+      if (c.rpt >= rpt_need && c.rpt <= rpt_cap) { combo = &c; break; }
+    if (!combo) return OK;   // slices too long for the register budget: two-pass path
+    gcols = combo->gcols;
+    hk.fused_cs = cs;
+    hk.fused_rpt = combo->rpt;
+    hk.fused_g = combo->gcols;
+    hk.fused_nb = nb_t;
+    const size_t slot_bytes = (size_t)combo->gcols * rs_max * sizeof(double);
+    const size_t zb = (size_t)combo->gcols * (F_ROLE / combo->gcols);
+    const size_t ng = (size_t)nb_t * combo->gcols;
+    int dev = 0, optin = 0;
+    BGGE_CUDA(cudaGetDevice(&dev));
+    BGGE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t tvm = hk.merged ? (size_t)nb_t : 1;   // tau * v per member kernel in a merged unit
+    auto fixed_bytes = [&](int nsv) {   // exchange ring depth 2 ns + 4 (protocol note) -> grows with the data ring
+      return ((size_t)(2 * nsv + 4) * F_MAXCS * ng + 2 * 8 * ng + 2 * ng + (2 * tvm + 2) * zb + (size_t)nb_t * 2 * zb) * sizeof(double) +
+             (2 * F_MAX_NS + NPX) * sizeof(uint64_t) + 128;
+    };
+    int ns = 0;
+    for (int c = F_MAX_NS; c >= 3; --c)
+      if ((size_t)c * slot_bytes + fixed_bytes(c) + 1024 <= (size_t)optin) { ns = c; break; }
+    if (ns < 3) return OK;
+    const size_t fixed = fixed_bytes(ns);
+    hk.fused_ns = ns;
+    hk.fused_smem = ns * slot_bytes + fixed;
+    BGGE_TRY(occupancy_dispatch(hk, cs, hk.fused_smem, &ncl));
+  }
   if (ncl < 1) return OK;
+  if (const char* ev = getenv("BGGE_FUSED_MAX_CLUSTERS")) ncl = std::max(1, std::min(ncl, atoi(ev)));   // test / tuning hook
   // column shard (bgge_gibbs_set_shard): rank r of w sweeps columns [nr r / w, nr (r + 1) / w) of every matrix,
   // boundaries on multiples of the column-group size
   for (auto& gr : groups) {
-    const int64_t gc = combo->gcols;
+    const int64_t gc = gcols;
     gr.c_lo = g->shard_world > 1 ? gr.nr * g->shard_rank / g->shard_world / gc * gc : 0;
     gr.c_hi = g->shard_world > 1 && g->shard_rank + 1 < g->shard_world ? gr.nr * (g->shard_rank + 1) / g->shard_world / gc * gc
                                                                       : gr.nr;
@@ -770,7 +797,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
     total += (double)gr.rows * (double)(gr.c_hi - gr.c_lo);
     total_cols += gr.c_hi - gr.c_lo;
   }
-  ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, combo->gcols)));
+  ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, total_cols / std::max(1, gcols)));
   std::vector<FPanel> panels;
   std::vector<int2> cpan((size_t)ncl, make_int2(0, 0));
   std::vector<std::pair<int, int>> block_q(hk.blocks.size(), {1 << 30, -1});
@@ -789,7 +816,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
         int64_t take = avail;
         if (!last) {
           const int64_t want = (int64_t)std::ceil(need / (double)gr.rows);
-          take = std::min<int64_t>(avail, (want + combo->gcols - 1) / combo->gcols * combo->gcols);
+          take = std::min<int64_t>(avail, (want + gcols - 1) / gcols * gcols);
         }
         if (take <= 0 && total_cols > 0) break;   // (a shard without any column gets one empty panel, below)
         const HostBlock& b0 = hk.blocks[(size_t)gr.members[0]];
@@ -909,8 +936,8 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   BGGE_CUDA(cudaStreamSynchronize(st));
   hk.fused = true;
   if (getenv("BGGE_DEBUG"))
-    fprintf(stderr, "[bgge] fused plan: cs=%d clusters=%d rpt=%d g=%d nb=%d ns=%d smem=%zu groups=%zu panels=%zu vtotal=%lld\n",
-            hk.fused_cs, hk.fused_clusters, hk.fused_rpt, hk.fused_g, hk.fused_nb, hk.fused_ns, hk.fused_smem,
+    fprintf(stderr, "[bgge] fused plan: engine=%d cs=%d clusters=%d rpt=%d kr=%d g=%d nb=%d ns=%d smem=%zu groups=%zu panels=%zu vtotal=%lld\n",
+            hk.fused_engine, hk.fused_cs, hk.fused_clusters, hk.fused_rpt, hk.fused_kr, hk.fused_g, hk.fused_nb, hk.fused_ns, hk.fused_smem,
             groups.size(), panels.size(), (long long)hk.vtotal);
   return OK;
 }

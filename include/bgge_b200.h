@@ -202,7 +202,8 @@ int bgge_gibbs_resident_info(bgge_gibbs* h, int* enabled, int* ctas, int64_t* sm
  * matrix on disjoint rows (the environment kernels of MDe, R/getK.R:207-218) are swept by one launch from the second
  * iteration on; how many units there are and how many kernels they contain */
 int bgge_gibbs_merged_info(bgge_gibbs* h, int* units, int* kernels_in_units);
-/* after init: which path kernel j uses, its cluster size / cluster (or tile) count, launches per step */
+/* after init: which path kernel j uses (*fused: 0 two-pass proj/back, 1 single-pass sweep_fused_kernel, 2 single-pass
+ * multi-right-hand-side sweep_mrhs_kernel), its cluster size / cluster (or tile) count, launches per step */
 int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, int* clusters, int* launches);
 /* after init: bytes of eigen basis one step of kernel j streams (W, not U, for blocks kept factorised; twice
  * for two-pass steps) and the number of its blocks kept factorised */
