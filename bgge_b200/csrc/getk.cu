@@ -12,12 +12,13 @@ namespace bgge {
 namespace {
 
 // ------------------------------------------------------------------ symmetrize
-__global__ void symmetrize_kernel(double* __restrict__ S, int64_t lds, int64_t L) {
+__global__ void symmetrize_kernel(double* __restrict__ S, int64_t lds, int64_t L, int from_upper) {
   // 32x32 tile transpose through shared memory; only tiles strictly below the diagonal are
-  // read, diagonal tiles mirror in place.
+  // read, diagonal tiles mirror in place.  from_upper: the same with the roles of the triangles swapped
+  // (block (bi, bj) then is the source tile in the UPPER triangle: rows i0.., columns j0.., bj >= bi).
   __shared__ double t[32][33];
-  const int bi = blockIdx.x, bj = blockIdx.y;
-  if (bj > bi) return;
+  const int bi = from_upper ? blockIdx.y : blockIdx.x, bj = from_upper ? blockIdx.x : blockIdx.y;
+  if (from_upper ? (bj < bi) : (bj > bi)) return;
   const int64_t i0 = (int64_t)bi * 32, j0 = (int64_t)bj * 32;
   for (int c = threadIdx.y; c < 32; c += blockDim.y) {
     const int64_t i = i0 + threadIdx.x, j = j0 + c;
@@ -27,7 +28,7 @@ __global__ void symmetrize_kernel(double* __restrict__ S, int64_t lds, int64_t L
   for (int c = threadIdx.y; c < 32; c += blockDim.y) {
     // write S[j0 + x, i0 + c] = S[i0 + c, j0 + x] = t[x][c]
     const int64_t r = j0 + threadIdx.x, q = i0 + c;
-    if (r < L && q < L && (bi != bj || r < q)) S[r + q * lds] = t[threadIdx.x][c];
+    if (r < L && q < L && (bi != bj || (from_upper ? r > q : r < q))) S[r + q * lds] = t[threadIdx.x][c];
   }
 }
 
@@ -163,10 +164,10 @@ __global__ void expand_kernel(const double* __restrict__ K0, int64_t ldk, const 
 }  // namespace
 
 // ====================================================================== launchers
-int symmetrize_launch(double* dS, int64_t lds, int64_t L, cudaStream_t st) {
+int symmetrize_launch(double* dS, int64_t lds, int64_t L, cudaStream_t st, int from_upper) {
   if (L <= 0) return OK;
   const unsigned nb = (unsigned)((L + 31) / 32);
-  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, st>>>(dS, lds, L);
+  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, st>>>(dS, lds, L, from_upper);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }

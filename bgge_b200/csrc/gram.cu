@@ -38,8 +38,8 @@ constexpr size_t GRAM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __restrict__ tiles,
-                 int ntiles, double* __restrict__ S, double* __restrict__ Spart, int64_t part_stride, int64_t lds,
-                 int64_t L, int64_t row_off, double divisor, int mirror) {
+                 int ntiles, double* __restrict__ S, double* __restrict__ Spart, int64_t part_stride, int64_t pld,
+                 int64_t prow_off, int64_t lds, int64_t L, int64_t row_off, double divisor, int mirror) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)STAGES * STAGE_DOUBLES);
@@ -122,9 +122,13 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __re
     // (with the mirror); K-split tiles store their raw partial, gram_reduce_kernel finishes them.
     const int64_t gi0 = (int64_t)tc.ti * TM + wm * 64 + fr;
     const int64_t gj0 = (int64_t)tc.tj * TN + wn * 32 + 2 * fk;
+    // mirror: 0 = the tile itself (lower triangle), 1 = tile + transposed tile, 2 = transposed tile only (row-panel
+    // builds store S[:, panel rows], which is contiguous in column-major memory: one in-place exchange, no staging)
     const bool direct = Spart == nullptr;
-    const bool offdiag = direct && mirror && (tc.ti != tc.tj);
+    const bool lower = !direct || mirror != 2;
+    const bool upper = direct && (mirror == 2 || (mirror == 1 && tc.ti != tc.tj));
     double* out = direct ? S : Spart + (int64_t)tc.split * part_stride;
+    const int64_t old = direct ? lds : pld, oro = direct ? row_off : prow_off;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t gi = gi0 + i * 8;
@@ -136,8 +140,8 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __re
           const int64_t gj = gj0 + j * 8 + h;
           if (gj >= L) continue;
           const double v = direct ? acc[i][j][h] / divisor : acc[i][j][h];
-          out[(gi - row_off) + gj * lds] = v;
-          if (offdiag) S[gj + gi * lds] = v;
+          if (lower) out[(gi - oro) + gj * old] = v;
+          if (upper) S[gj + gi * lds] = v;
         }
       }
     }
@@ -147,20 +151,20 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __re
 // sums the K-split partials of every tile in fixed order, scales, stores (+ mirror)
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const GramItem* __restrict__ tiles, int nsplit, const double* __restrict__ Spart,
-                   int64_t part_stride, double* __restrict__ S, int64_t lds, int64_t L, int64_t row_off, double divisor,
-                   int mirror) {
+                   int64_t part_stride, int64_t pld, int64_t prow_off, double* __restrict__ S, int64_t lds, int64_t L,
+                   int64_t row_off, double divisor, int mirror) {
   const GramItem tc = tiles[blockIdx.x];   // the split-0 item of each tile
   const int64_t i = (int64_t)tc.ti * TM + (threadIdx.x & 127);
   if (i >= L) return;
   for (int c = threadIdx.x >> 7; c < TN; c += 2) {
     const int64_t jx = (int64_t)tc.tj * TN + c;
     if (jx >= L) break;
-    const int64_t off = (i - row_off) + jx * lds;
+    const int64_t poff = (i - prow_off) + jx * pld;
     double v = 0.0;
-    for (int sp = 0; sp < nsplit; ++sp) v += Spart[(int64_t)sp * part_stride + off];
+    for (int sp = 0; sp < nsplit; ++sp) v += Spart[(int64_t)sp * part_stride + poff];
     v /= divisor;
-    S[off] = v;
-    if (mirror && tc.ti != tc.tj) S[jx + i * lds] = v;
+    if (mirror != 2) S[(i - row_off) + jx * lds] = v;
+    if (mirror == 2 || (mirror == 1 && tc.ti != tc.tj)) S[jx + i * lds] = v;
   }
 }
 
@@ -170,11 +174,16 @@ gram_reduce_kernel(const GramItem* __restrict__ tiles, int nsplit, const double*
 // persistent grid (mid-size L), the marker dimension is split so that the items spread evenly; partials go
 // to a workspace and are summed in fixed order by gram_reduce_kernel (deterministic).
 int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tr0, int64_t tr1, double* dS,
-                int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st) {
+                int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st, int split_on_panel,
+                int64_t tr0b, int64_t tr1b) {
   BGGE_REQUIRE(ldx % TM == 0 && ldx >= round_up(L, TM), "gram: ldx=%lld must be a multiple of 128 >= L", (long long)ldx);
   BGGE_REQUIRE(p_pad % BK == 0 && p_pad > 0, "gram: padded marker count %lld must be a positive multiple of 16", (long long)p_pad);
   BGGE_REQUIRE(!(mirror && row_off != 0), "gram: mirror store needs the full square output");
+  BGGE_REQUIRE(mirror >= 0 && mirror <= 2, "gram: store mode %d", mirror);
   std::vector<int2> tl;
+  // (a second tile-row range [tr0b, tr1b) lets a rank build both of its row panels with one launch)
+  for (int64_t ti = tr1b - 1; ti >= tr0b; --ti)
+    for (int64_t tj = 0; tj <= ti; ++tj) tl.push_back(make_int2((int)ti, (int)tj));
   for (int64_t ti = tr1 - 1; ti >= tr0; --ti)   // longest tile rows first
     for (int64_t tj = 0; tj <= ti; ++tj) tl.push_back(make_int2((int)ti, (int)tj));
   const int64_t ntiles = (int64_t)tl.size();
@@ -185,15 +194,16 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   {
     // the split is a function of (L, p) only -- computed on the full triangle, not on this panel -- so that
     // a row-panel build (multi-GPU) stays bit-identical to the one-shot build
+    // (split_on_panel: the collective row-panel build balances its own tile list instead)
     const int64_t Tfull = (L + TM - 1) / TM;
-    const int64_t nfull = Tfull * (Tfull + 1) / 2;
+    const int64_t nfull = split_on_panel ? ntiles : Tfull * (Tfull + 1) / 2;
     auto cost = [&](int sp) {
       const double waves = (double)((nfull * sp + sms - 1) / sms);
       return waves * ((double)kblocks / sp + 8.0) + (sp > 1 ? 0.03 * sp * kblocks / std::max<int64_t>(1, nfull / sms + 1) : 0.0);
     };
     double best = cost(1);
     for (int sp = 2; sp <= 16 && kblocks / sp >= 64; ++sp)
-      if (cost(sp) < 0.95 * best && cost(sp) < cost(nsplit)) nsplit = sp;
+      if (cost(sp) < (split_on_panel ? 0.98 : 0.95) * best && cost(sp) < cost(nsplit)) nsplit = sp;
   }
   if (const char* ev = getenv("BGGE_GRAM_SPLIT")) {
     const int v = atoi(ev);
@@ -214,7 +224,10 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   DevBuf<double> part;
   BGGE_CUDA(d_items.alloc(items.size()));
   BGGE_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(GramItem), cudaMemcpyHostToDevice, st));
-  const int64_t part_stride = lds * L;
+  // K-split partials: compact workspace over the tile rows of this launch (rows [prow_off, prow_off + pld))
+  const int64_t trlo = tr1b > tr0b ? std::min(tr0, tr0b) : tr0, trhi = tr1b > tr0b ? std::max(tr1, tr1b) : tr1;
+  const int64_t prow_off = trlo * TM, pld = (trhi - trlo) * TM;
+  const int64_t part_stride = pld * std::min<int64_t>(L, trhi * TM);
   if (nsplit > 1) BGGE_CUDA(part.alloc((size_t)part_stride * nsplit));
   static bool attr_set = false;
   if (!attr_set) {
@@ -224,11 +237,11 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   const int nitems = (int)items.size();
   const int grid = nitems < sms ? nitems : sms;
   gram_dmma_kernel<<<grid, NTHREADS, GRAM_SMEM, st>>>(dX, ldx, d_items.p, nitems, dS, nsplit > 1 ? part.p : nullptr,
-                                                       part_stride, lds, L, row_off, divisor, mirror);
+                                                       part_stride, pld, prow_off, lds, L, row_off, divisor, mirror);
   BGGE_CUDA(cudaGetLastError());
   if (nsplit > 1) {
-    gram_reduce_kernel<<<(unsigned)ntiles, 256, 0, st>>>(d_items.p, nsplit, part.p, part_stride, dS, lds, L, row_off,
-                                                        divisor, mirror);
+    gram_reduce_kernel<<<(unsigned)ntiles, 256, 0, st>>>(d_items.p, nsplit, part.p, part_stride, pld, prow_off, dS, lds, L,
+                                                        row_off, divisor, mirror);
     BGGE_CUDA(cudaGetLastError());
   }
   BGGE_CUDA(cudaStreamSynchronize(st));   // the item list and the workspace die here

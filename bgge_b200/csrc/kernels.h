@@ -6,11 +6,15 @@
 namespace bgge {
 
 // gram.cu
+// mirror: 0 lower-triangle tiles only, 1 tiles + transposes (full symmetric S), 2 transposes only (S[:, panel rows]).
+// split_on_panel: choose the K split from this launch's tile count (collective row-panel builds) instead of from the
+// full triangle (which keeps a panel build bit-identical to the one-shot build).  [tr0b, tr1b): optional second panel.
 int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t tile_row0, int64_t tile_row1,
-                double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st);
+                double* dS, int64_t lds, int64_t row_off, double divisor, int mirror, cudaStream_t st,
+                int split_on_panel = 0, int64_t tr0b = 0, int64_t tr1b = 0);
 
 // getk.cu
-int symmetrize_launch(double* dS, int64_t lds, int64_t L, cudaStream_t st);
+int symmetrize_launch(double* dS, int64_t lds, int64_t L, cudaStream_t st, int from_upper = 0);   // lower -> upper (or the reverse)
 int gk_distance_launch(double* dS, int64_t lds, int64_t L, double* d_diag_scratch, cudaStream_t st);
 size_t quantile_scratch_bytes();
 int quantile7_launch(const double* dD, int64_t ldd, int64_t L, double prob, void* d_scratch, double* d_q,

@@ -60,6 +60,12 @@ __device__ __forceinline__ void wait_relaxed(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
     if (++polls > 4) __nanosleep(40);
 }
+// pusher / coefficient warps sit on the exchange's critical path: mbarrier.try_wait already suspends the warp in
+// hardware for a while, no extra sleep
+__device__ __forceinline__ void wait_tight(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
 
 // see sweep_fused.cu: P values summed over the warp with P - 1 + (5 - log2 P) shuffles; value idx = (lane * P) >> 5
 template <int P>
@@ -190,16 +196,18 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           e[k][m] = v;
         }
       }
-      // row steps that reach past the slot's columns (KR * 384 >= rs) are skipped: bit k <=> row k * 384 + tid exists
-      uint32_t inmask = 0;
-#pragma unroll
-      for (int k = 0; k < KR; ++k) inmask |= (k * M_T + tid < max_rs ? 1u : 0u) << k;
+      // Row steps that reach past the CTA's slice (KR * 384 >= rs) read on into the next column / the next ring slot /
+      // the small arrays behind the ring: always finite doubles (everything up to the barriers is zeroed at start and
+      // only ever receives W, partial sums and coefficients), and they meet e = 0 in the dots while their u
+      // accumulators are never stored.  So the hot loops carry no row predicates.  mrhs_configure() checks that
+      // the overshoot stays inside those arrays.
       const int ngroups = (pn.c1 - pn.c0 + G - 1) / G;
       for (int h = 0; h < ngroups + lag; ++h) {
         if (h < ngroups) {
           // ---------------------------------------------------------- dots of group h
           wait_relaxed(&s.full[dslot], dphase);
-          const double* src = s.ring + (size_t)dslot * slot_doubles + tid;
+          const double* src0 = s.ring + (size_t)dslot * slot_doubles + tid;
+          const double* src1 = src0 + max_rs;
           if (++dslot == ns) {
             dslot = 0;
             dphase ^= 1u;
@@ -209,14 +217,13 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           for (int v = 0; v < NG; ++v) a[v] = 0.0;
 #pragma unroll
           for (int k = 0; k < KR; ++k) {
-            double x[G];
+            static_assert(G == 2, "two columns per group");
+            const double x0 = src0[k * M_T], x1 = src1[k * M_T];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
-              x[g] = ((inmask >> k) & 1u) ? src[(size_t)g * max_rs + k * M_T] : 0.0;
-#pragma unroll
-            for (int m = 0; m < NB; ++m)
-#pragma unroll
-              for (int g = 0; g < G; ++g) a[m * G + g] = fma(x[g], e[k][m], a[m * G + g]);
+            for (int m = 0; m < NB; ++m) {
+              a[m * G] = fma(x0, e[k][m], a[m * G]);
+              a[m * G + 1] = fma(x1, e[k][m], a[m * G + 1]);
+            }
           }
           int vi;
           const double tot = multi_reduce<NG>(a, lane, vi);
@@ -238,17 +245,13 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
             b[v] = t.x;
             b[v + 1] = t.y;
           }
-          const double* src = s.ring + (size_t)aslot * slot_doubles + tid;
+          const double* src0 = s.ring + (size_t)aslot * slot_doubles + tid;
+          const double* src1 = src0 + max_rs;
 #pragma unroll
           for (int k = 0; k < KR; ++k) {
-            double x[G];
+            const double x0 = src0[k * M_T], x1 = src1[k * M_T];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
-              x[g] = ((inmask >> k) & 1u) ? src[(size_t)g * max_rs + k * M_T] : 0.0;
-#pragma unroll
-            for (int m = 0; m < NB; ++m)
-#pragma unroll
-              for (int g = 0; g < G; ++g) uacc[k][m] = fma(x[g], b[m * G + g], uacc[k][m]);
+            for (int m = 0; m < NB; ++m) uacc[k][m] = fma(x1, b[m * G + 1], fma(x0, b[m * G], uacc[k][m]));
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&s.empty[aslot]);
@@ -311,7 +314,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
         for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cnt) {
           const int gc = min(G, pn.c1 - c0);
           const uint32_t pw = cnt & (M_NP - 1), px = cnt & (M_NPX - 1);
-          wait_relaxed(&s.dotdone[pw], (cnt / M_NP) & 1u);
+          wait_tight(&s.dotdone[pw], (cnt / M_NP) & 1u);
           if (lane == 0) mbar_expect_tx(&s.pbar[px], cs * (uint32_t)(gc * pn.nb) * (uint32_t)sizeof(double));
           __syncwarp();
           if (m < pn.nb && gq < gc) {
@@ -338,7 +341,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           const int gc = min(G, ncols - rel0);
           if (rel0 % M_ZB == 0) wait_relaxed(&s.zready[batch & 1u], (batch >> 1) & 1u);
           const uint32_t px = cnt & (M_NPX - 1);
-          wait_relaxed(&s.pbar[px], (cnt / M_NPX) & 1u);
+          wait_tight(&s.pbar[px], (cnt / M_NPX) & 1u);
           if (v < NG) {
             double bcoef = 0.0;
             if (m < pn.nb && gq < gc) {
@@ -428,9 +431,10 @@ struct Inst {
   MrhsFn fn;
 };
 const Inst kInst[] = {
-    {4, 3, sweep_mrhs_kernel<3, 4>},  {4, 5, sweep_mrhs_kernel<5, 4>},   {4, 7, sweep_mrhs_kernel<7, 4>},
-    {2, 4, sweep_mrhs_kernel<4, 2>},  {2, 7, sweep_mrhs_kernel<7, 2>},   {2, 10, sweep_mrhs_kernel<10, 2>},
-    {2, 14, sweep_mrhs_kernel<14, 2>},
+    {4, 2, sweep_mrhs_kernel<2, 4>},   {4, 3, sweep_mrhs_kernel<3, 4>},   {4, 4, sweep_mrhs_kernel<4, 4>},
+    {4, 5, sweep_mrhs_kernel<5, 4>},   {4, 6, sweep_mrhs_kernel<6, 4>},   {4, 7, sweep_mrhs_kernel<7, 4>},
+    {2, 4, sweep_mrhs_kernel<4, 2>},   {2, 6, sweep_mrhs_kernel<6, 2>},   {2, 8, sweep_mrhs_kernel<8, 2>},
+    {2, 10, sweep_mrhs_kernel<10, 2>}, {2, 12, sweep_mrhs_kernel<12, 2>}, {2, 14, sweep_mrhs_kernel<14, 2>},
 };
 
 const Inst* find_inst(int nb, int kr_need) {
@@ -466,6 +470,10 @@ int mrhs_configure(int64_t max_rows, int nb, bool merged, MrhsCfg* cfg) {
     if (!inst) continue;
     const size_t slot_bytes = (size_t)M_G * rs * sizeof(double);
     const size_t fixed = fixed_bytes(nb, merged);
+    // unpredicated row steps may read (kr * 384 - rs) doubles past the last ring slot: they must stay in the zeroed
+    // arrays in front of the mbarriers
+    const size_t tail = fixed - ((2 * M_MAXNS + M_NP + 2 * M_NPX + 4) * sizeof(uint64_t) + 128);
+    if ((size_t)(inst->kr * (int64_t)M_T - rs) * sizeof(double) > tail) continue;
     int ns = (int)std::min<size_t>(M_MAXNS, ((size_t)optin - fixed - 1024) / slot_bytes);
     if (ns < 3) continue;
     int lag = 2;
