@@ -286,7 +286,7 @@ def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
         lib.call("bgge_gibbs_create", n, 1, 0, stream, C.byref(h0))
         torch.cuda.synchronize()
         t_eig = time.perf_counter()
-        lib.call("bgge_gibbs_add_expanded_kernel", h0, 0, 0, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), 0, 0, None, 0,
+        lib.call("bgge_gibbs_add_expanded_kernel", h0, 0, 0, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), n, 0, 0, None, 0,
                  1e-10, 1)
         torch.cuda.synchronize()
         t_eig = time.perf_counter() - t_eig
@@ -521,7 +521,7 @@ def main():
         torch.cuda.synchronize()
         t_eig = time.perf_counter()
         for j, (tp, mode, k) in enumerate(kspec):
-            lib.call("bgge_gibbs_add_expanded_kernel", h0, j, tp, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), mode, k,
+            lib.call("bgge_gibbs_add_expanded_kernel", h0, j, tp, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), n, mode, k,
                      lib.ptr(ne_h), E, 1e-10, 1)
         torch.cuda.synchronize()
         t_eig = time.perf_counter() - t_eig
@@ -697,7 +697,7 @@ def main():
             hd0 = C.c_void_p()
             lib.call("bgge_gibbs_create", n, nk, 0, stream, C.byref(hd0))
             for j, (tp, mode, k) in enumerate(kspec):
-                lib.call("bgge_gibbs_add_expanded_kernel", hd0, j, tp, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), mode, k,
+                lib.call("bgge_gibbs_add_expanded_kernel", hd0, j, tp, vp(K0), L, L, 1, lib.ptr(gid_h), lib.ptr(env_h), n, mode, k,
                          lib.ptr(ne_h), E, 1e-10, 1)
             del os.environ["BGGE_NO_FACTORED_SWEEP"]
             hd = make_handle((args.warmup + args.steps) * iters + 4, hd0)

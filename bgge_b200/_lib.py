@@ -73,7 +73,7 @@ SIGNATURES = {
     "bgge_gibbs_add_kernel_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                                C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "bgge_gibbs_add_expanded_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
-                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                                  C.c_double, C.c_int]),
     "bgge_gibbs_block_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "bgge_gibbs_block_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_int64_p]),
@@ -121,6 +121,18 @@ SIGNATURES = {
                            C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, c_double_p,
                            c_double_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    "bgge_comm_init_all": (C.c_int, [C.c_int, C.c_void_p, c_void_pp]),
+    "bgge_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "bgge_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp]),
+    "bgge_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgge_comm_destroy": (None, [C.c_void_p]),
+    "bgge_dev_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bgge_dev_gram_panels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
+                                       C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "bgge_getk_base_multi": (C.c_int, [c_void_pp, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_double, C.c_void_p, c_double_p]),
+    "bgge_gibbs_set_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bgge_gibbs_run_sharded": (C.c_int, [C.c_void_p, C.c_int64]),
     "bgge_test_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgge_test_draws": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p]),
 }
@@ -146,6 +158,36 @@ def load():
     return lib
 
 
+_nccl_preloaded = False
+_NCCL_ENTRY = ("bgge_comm_init_all", "bgge_comm_unique_id", "bgge_comm_init_rank")
+
+
+def preload_nccl():
+    """libbgge_b200 binds NCCL at run time (dlopen "libnccl.so.2"; a copy the process already holds is reused).  A
+    Python process that will ALSO import torch must end up with torch's own (newer) NCCL under that soname, otherwise
+    `import torch` fails on symbols the system copy lacks -- so before the first communicator is made, load the copy
+    bundled with the Python environment if there is one (BGGE_NCCL_LIB overrides the path).  Without such a copy the
+    library falls back to the system NCCL by itself."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    path = os.environ.get("BGGE_NCCL_LIB")
+    if not path:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations if spec is not None else []):
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    path = cand
+                    break
+        except (ImportError, ValueError, AttributeError):
+            path = None
+    if path and os.path.exists(path):
+        C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
 def check(code):
     if code != 0:
         raise BGGEError(code, load().bgge_last_error().decode("utf-8", "replace"))
@@ -153,6 +195,8 @@ def check(code):
 
 def call(name, *args):
     lib = load()
+    if name in _NCCL_ENTRY:
+        preload_nccl()
     check(getattr(lib, name)(*args))
 
 

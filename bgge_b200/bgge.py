@@ -56,12 +56,20 @@ def _plan_info(h, nk):
             "kernels_in_units": ku.value, "kernels": ks}
 
 
+def _check_factor_rows(k, n, name):
+    """The factored description must describe exactly the n rows of y (the reference fails with non-conformable
+    arguments when K and y disagree)."""
+    f = k["factor"]
+    if f["gid"].shape[0] != n or f["env"].shape[0] != n:
+        raise ValueError(f"kernel {name} describes {f['gid'].shape[0]} rows, expected {n} (non-conformable arguments)")
+
+
 def _add_factored(h, j, k, ne_arr, tol, canonical_sign):
     f = k["factor"]
     tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
     K0 = None if f["K0"] is None else _lib.f64(f["K0"])
     _lib.call("bgge_gibbs_add_expanded_kernel", h, j, tcode, _lib.ptr(K0), f["L"], f["L"], 0, _lib.ptr(f["gid"]),
-              _lib.ptr(f["env"]), f["mode"], f["env_k"], None if ne_arr is None else _lib.ptr(ne_arr),
+              _lib.ptr(f["env"]), int(f["gid"].shape[0]), f["mode"], f["env_k"], None if ne_arr is None else _lib.ptr(ne_arr),
               0 if ne_arr is None else ne_arr.shape[0], float(tol), int(canonical_sign))
 
 
@@ -137,10 +145,11 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     info  : optional dict, filled after initialisation with the execution plan: "resident" (bool), "merged_units",
             and per kernel "path" (0 two-pass, 1 sweep_fused_kernel, 2 sweep_mrhs_kernel), "cluster_size", "clusters",
             "launches", "basis_bytes", "factored_blocks" (bgge_gibbs_kernel_info / _kernel_bytes).
-    shard : None, or (rank, world, reduce): this process sweeps its slice of the eigen-columns of a single chain and
-            reduce(ptr, count) adds the per-step partial vectors of all processes in place (bgge_b200.multigpu.
-            nccl_allreduce() for torch.distributed over NCCL).  Every process must call BGGE() with the same
-            arguments; all return the same fit.  No XF in this mode.
+    shard : None, or (rank, world, comm_or_reduce): this process sweeps its slice of the eigen-columns of a single
+            chain.  Third element a bgge_b200.multigpu.Comm: the per-step all-reduce runs inside the library on the
+            handle's own stream (fast path).  A callable reduce(ptr, count): it must add the per-step partial vectors
+            of all processes in place and return when done (multigpu.nccl_allreduce(); the handle's stream is drained
+            before each call).  Every process calls BGGE() with the same arguments; all return the same fit.  No XF.
     """
     if rng not in ("philox", "R"):
         raise ValueError("rng must be 'philox' or 'R'")
@@ -178,11 +187,15 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
         if shard is not None and int(shard[1]) > 1:
             if q:
                 raise ValueError("a column-sharded chain does not support XF")
-            _lib.call("bgge_gibbs_set_shard", h, int(shard[0]), int(shard[1]))
+            if hasattr(shard[2], "handle"):
+                _lib.call("bgge_gibbs_set_comm", h, shard[2].handle)
+            else:
+                _lib.call("bgge_gibbs_set_shard", h, int(shard[0]), int(shard[1]))
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
             if eig is None and "factor" in k and factor_matches(k):
                 # getK() output: decompose through the L x L problem instead of the n x n matrix
+                _check_factor_rows(k, n, names[j])
                 _add_factored(h, j, k, ne_arr, tol, True)
                 continue
             if eig is not None and ("mean_diag" in k or "factor" in k):
@@ -232,7 +245,10 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
             t0 = time.perf_counter()
             k = min(step, ite - done)
             if shard is not None and int(shard[1]) > 1:
-                run_sharded(h, nk, k, shard[2])
+                if hasattr(shard[2], "handle"):
+                    _lib.call("bgge_gibbs_run_sharded", h, k)
+                else:
+                    run_sharded(h, nk, k, shard[2])
             else:
                 _lib.call("bgge_gibbs_run", h, k)
             _lib.call("bgge_gibbs_sync", h)
@@ -306,6 +322,7 @@ def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, 
                     _lib.call("bgge_gibbs_add_block", h0, j, pos0, U.shape[0], U.shape[1], _lib.ptr(s), _lib.ptr(U),
                               U.shape[0], 0)
             elif "factor" in k and factor_matches(k):
+                _check_factor_rows(k, n, names[j])
                 md = _factor_mean_diag(k["factor"])
                 _add_factored(h0, j, k, ne_arr, tol, True)
             else:

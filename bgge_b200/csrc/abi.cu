@@ -5,6 +5,7 @@
 #include "gibbs.cuh"
 #include "batch.cuh"
 #include "kernels.h"
+#include "multi.cuh"
 #include "rng.cuh"
 #include <cmath>
 #include <cstring>
@@ -636,11 +637,13 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
 // U = Z C^{-1/2} W (orthonormal columns), so the |T| x |T| problem gives the same eigenpairs (> tol) as
 // eigen(K_S) (R/BGGE.R:112-116, 144-171).  Blocks whose mask is not constant fall back to the direct route.
 int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double* K0, int64_t L, int64_t ldk,
-                                   int on_device, const int32_t* gid, const int32_t* env, int mode, int env_k,
-                                   const int64_t* ne, int n_ne, double tol, int canonical_sign) {
+                                   int on_device, const int32_t* gid, const int32_t* env, int64_t n_codes, int mode,
+                                   int env_k, const int64_t* ne, int n_ne, double tol, int canonical_sign) {
   BGGE_HANDLE(h);
   Gibbs& g = h->g;
   BGGE_REQUIRE(!g.initialised, "gibbs_add_expanded_kernel: handle already initialised");
+  BGGE_REQUIRE(n_codes == g.n, "gibbs_add_expanded_kernel: %lld genotype / environment codes for a model with n = %lld rows "
+               "(non-conformable arguments)", (long long)n_codes, (long long)g.n);
   BGGE_REQUIRE(j >= 0 && j < g.nk && gid != nullptr && L > 0, "gibbs_add_expanded_kernel: bad arguments");
   BGGE_REQUIRE(type == BGGE_TYPE_D || type == BGGE_TYPE_BD, "Matrix should be of types BD or D");
   BGGE_REQUIRE(mode >= BGGE_EXPAND_G && mode <= BGGE_EXPAND_GI, "gibbs_add_expanded_kernel: unknown expansion mode %d", mode);
@@ -797,7 +800,16 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       const bool duplicated = share_blocks && spans.size() > 1 && key_count[std::make_pair(T, cntT)] > 1;
       // the environment kernels of MDe are one block each and, in a balanced trial, the same matrix: shared through
       // the handle-level cache (bgge::SharedDecomp) like the identical blocks of one BD kernel
-      const bool shareable = share_blocks && (duplicated || env_mode);
+      // Uniform counts (every genotype of T occurs c times: any balanced design): C^{1/2} K0[T,T] C^{1/2} = c K0[T,T].
+      // Decompose K0[T,T] itself with the threshold tol / c and scale the eigenvalues by c afterwards; blocks and
+      // KERNELS that differ only in c -- the G kernel (c = E) and the GE blocks (c = 1) of a balanced MDs model --
+      // then share ONE decomposition (C5: one 10000^2 syevd instead of two).
+      int ucount = cntT.empty() ? 0 : cntT[0];
+      for (int64_t a = 1; a < t && ucount; ++a)
+        if (cntT[(size_t)a] != ucount) ucount = 0;
+      if (!share_blocks || getenv("BGGE_NO_SCALED_SHARING")) ucount = 0;
+      const double eff_tol = ucount ? tol / (double)ucount : tol;
+      const bool shareable = share_blocks && (duplicated || env_mode || ucount > 0);
       auto add_dense_shared = [&](double* W, int64_t ldw, int64_t nr, bool owns_w) -> int {
         bl.dU = W;
         bl.ldu = ldw;
@@ -815,7 +827,8 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       BGGE_CUDA(dM.alloc((size_t)t * t));
       BGGE_CUDA(dW.alloc((size_t)t));
       BGGE_CUDA(cudaMemcpyAsync(dT.p, T.data(), (size_t)t * sizeof(int), cudaMemcpyHostToDevice, st));
-      BGGE_CUDA(cudaMemcpyAsync(dsqc.p, sqc.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
+      std::vector<double> sqc_gather = ucount ? std::vector<double>((size_t)t, 1.0) : sqc;
+      BGGE_CUDA(cudaMemcpyAsync(dsqc.p, sqc_gather.data(), (size_t)t * sizeof(double), cudaMemcpyHostToDevice, st));
       BGGE_TRY(gather_scale_launch(dK0, ld0, dT.p, dsqc.p, t, dM.p, st));
       unsigned long long hh[2] = {0, 0};
       if (shareable) {
@@ -824,24 +837,45 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         BGGE_CUDA(cudaMemcpyAsync(hh, dhash.p, sizeof(hh), cudaMemcpyDeviceToHost, st));
         BGGE_CUDA(cudaStreamSynchronize(st));
         const SharedDecomp* hit = nullptr;
-        for (auto& d : g.decomps)
-          if (d.h1 == hh[0] && d.h2 == hh[1] && d.tol == tol && d.canonical == canonical_sign && d.T == T && d.cnt == cntT) hit = &d;
+        for (auto& d : g.decomps) {
+          if (d.h1 != hh[0] || d.h2 != hh[1] || d.canonical != canonical_sign || d.T != T) continue;
+          if (ucount > 0 && d.ucount > 0) {
+            // the cached pairs are those above d.tol: enough if this block's threshold is not lower, or if
+            // nothing between the two thresholds was truncated
+            if (eff_tol >= d.tol || d.max_dropped <= eff_tol) hit = &d;
+          } else if (ucount == 0 && d.ucount == 0 && d.tol == tol && d.cnt == cntT) {
+            hit = &d;
+          }
+        }
         if (hit) {   // this matrix was decomposed already: share its W and eigenvalues
-          if (hit->nr == 0) continue;
+          int64_t nr_use = hit->nr;
+          if (ucount > 0) {
+            nr_use = 0;
+            while (nr_use < hit->nr && hit->s[(size_t)nr_use] > eff_tol) ++nr_use;   // descending: a prefix
+          }
+          if (nr_use == 0) continue;
           if (env_mode && identity && !duplicated) {
-            BGGE_TRY(add_dense_shared(hit->W, hit->ldw, hit->nr, false));
+            BGGE_TRY(add_dense_shared(hit->W, hit->ldw, nr_use, false));
           } else {
             BGGE_TRY(upload_map());
-            BGGE_TRY(make_virtual(hit->W, hit->ldw, hit->nr, false));
+            BGGE_TRY(make_virtual(hit->W, hit->ldw, nr_use, false));
           }
-          hk.s_host.insert(hk.s_host.end(), hit->s.begin(), hit->s.end());
+          for (int64_t c = 0; c < nr_use; ++c) hk.s_host.push_back(ucount > 0 ? hit->s[(size_t)c] * (double)ucount : hit->s[(size_t)c]);
           continue;
         }
       }
       int64_t nr = 0;
-      BGGE_TRY(eig_decompose(dM.p, t, t, tol, dW.p, &nr, st));
+      BGGE_TRY(eig_decompose(dM.p, t, t, eff_tol, dW.p, &nr, st));
+      double max_dropped = -INFINITY;                               // syevd order is ascending: the value below the kept ones
+      if (ucount > 0 && nr < t)
+        BGGE_CUDA(cudaMemcpy(&max_dropped, dW.p + (t - nr - 1), sizeof(double), cudaMemcpyDeviceToHost));
+      auto remember = [&](double* W, int64_t ldw_, int64_t nr_, const std::vector<double>& s_unscaled) {
+        g.decomps.push_back(SharedDecomp{hh[0], hh[1], eff_tol, canonical_sign, T, cntT, W, ldw_, nr_, s_unscaled});
+        g.decomps.back().ucount = ucount;
+        g.decomps.back().max_dropped = max_dropped;
+      };
       if (nr == 0) {                                                // R/BGGE.R:162
-        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, nullptr, 0, 0, {}});
+        if (shareable) remember(nullptr, 0, 0, {});
         continue;
       }
       bl.nr = nr;
@@ -865,15 +899,18 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       s_host.resize((size_t)nr);
       BGGE_CUDA(cudaMemcpyAsync(s_host.data(), dS.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, st));
       BGGE_CUDA(cudaStreamSynchronize(st));
+      const std::vector<double> s_unscaled = s_host;
+      if (ucount > 1)
+        for (auto& v : s_host) v *= (double)ucount;
       const bool no_fact = getenv("BGGE_NO_FACTORED_SWEEP") != nullptr;
       const bool keep_factored = (duplicated || 3 * t <= 2 * m) && !no_fact;
       if (keep_factored) {   // fewer rows to stream (repeated genotypes) or W shared with identical blocks
         BGGE_TRY(upload_map());
         BGGE_TRY(make_virtual(dWfinal, ldw, nr, true));
-        if (shareable) g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, dWfinal, ldw, nr, s_host});
+        if (shareable) remember(dWfinal, ldw, nr, s_unscaled);
       } else if (shareable && identity) {   // U = W: the block streams W itself, later identical kernels share it
         BGGE_TRY(add_dense_shared(dWfinal, ldw, nr, true));
-        g.decomps.push_back(SharedDecomp{hh[0], hh[1], tol, canonical_sign, T, cntT, dWfinal, ldw, nr, s_host});
+        remember(dWfinal, ldw, nr, s_unscaled);
       } else {
         BGGE_TRY(upload_map());
         BGGE_CUDA(pool_alloc((void**)&bl.dU, (size_t)bl.ldu * nr * sizeof(double)));
@@ -1062,6 +1099,40 @@ int bgge_gibbs_shard_advance(bgge_gibbs* h, int64_t iterations) {
   BGGE_REQUIRE(g.done + iterations >= 0 && g.done + iterations <= g.ite, "gibbs_shard_advance: %lld + %lld outside [0, %lld]",
                (long long)g.done, (long long)iterations, (long long)g.ite);
   g.done += iterations;
+  return OK;
+}
+
+// The same chain with the collective inside the library: NCCL all-reduce of the step vector on the handle's stream
+// (stream-ordered between the shard_sum and the apply kernels, no host synchronisation anywhere in the loop).
+int bgge_gibbs_set_comm(bgge_gibbs* h, bgge_comm* c) {
+  BGGE_HANDLE(h);
+  BGGE_REQUIRE(c != nullptr, "gibbs_set_comm: NULL communicator");
+  BGGE_REQUIRE(!h->g.initialised, "gibbs_set_comm: handle already initialised");
+  BGGE_REQUIRE(c->device == h->g.device, "gibbs_set_comm: communicator lives on device %d, the handle on %d", c->device,
+               h->g.device);
+  h->g.shard_rank = c->rank;
+  h->g.shard_world = c->world;
+  h->g.comm = c;
+  return OK;
+}
+
+int bgge_gibbs_run_sharded(bgge_gibbs* h, int64_t iters) {
+  BGGE_HANDLE(h);
+  Gibbs& g = h->g;
+  BGGE_REQUIRE(g.initialised && g.comm != nullptr, "gibbs_run_sharded: call bgge_gibbs_set_comm before bgge_gibbs_init");
+  BGGE_REQUIRE(iters >= 0 && g.done + iters <= g.ite, "gibbs_run_sharded: %lld + %lld iterations exceed ite = %lld",
+               (long long)g.done, (long long)iters, (long long)g.ite);
+  if (g.shard_world == 1) return gibbs_run(&g, iters);
+  for (int64_t i = 0; i < iters; ++i) {
+    for (int j = 0; j < g.nk; ++j) {
+      double* vec = nullptr;
+      int64_t cnt = 0;
+      BGGE_TRY(bgge_gibbs_shard_begin(h, j, &vec, &cnt));
+      BGGE_TRY(comm_allreduce_sum(static_cast<bgge_comm*>(g.comm), vec, cnt, g.stream));
+      BGGE_TRY(bgge_gibbs_shard_end(h, j));
+    }
+    BGGE_TRY(bgge_gibbs_shard_iteration_end(h));
+  }
   return OK;
 }
 

@@ -143,7 +143,12 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
   if (nitems <= 0) return OK;
   const int grid = nitems < sm_count() ? nitems : sm_count();
-  static bool attr64 = false, attr128 = false;
+  static bool attr64s[64] = {false}, attr128s[64] = {false};   // function attributes are per device
+  int dev = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  dev = dev >= 0 && dev < 64 ? dev : 0;
+  bool& attr64 = attr64s[dev];
+  bool& attr128 = attr128s[dev];
   if (tn == 64) {
     if (!attr64) {
       BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64>::BYTES));

@@ -226,7 +226,10 @@ struct SharedDecomp {
   std::vector<int> T, cnt;
   double* W;
   int64_t ldw, nr;
-  std::vector<double> s;
+  std::vector<double> s;         // eigenvalues (of the UNSCALED K0[T,T] when ucount > 0)
+  int ucount = 0;                // > 0: every genotype of T occurs equally often in the first user's block; the matrix
+                                 // decomposed is K0[T,T] itself, users scale the eigenvalues by their own count
+  double max_dropped = 0.0;      // largest eigenvalue that was truncated (-inf: none), ucount > 0 only
 };
 
 struct Gibbs {
@@ -248,6 +251,7 @@ struct Gibbs {
   DevBuf<double> r, u, y, xf, umean, um2, bet, xf_part, txx, lchol, betmean, upart, vupart;
   int shard_rank = 0, shard_world = 1;   // column shard of a single chain across processes / GPUs
   int shard_step = -1;           // kernel step between shard_begin and shard_end (-1: none)
+  void* comm = nullptr;          // bgge_comm* when the library runs the all-reduce itself (bgge_gibbs_set_comm)
   int mode = 1;                  // 0: two-pass kernels only, 1: resident kernel if the model fits on chip, else
                                  // fused single-pass where the shape fits, 2: as 1 without the resident kernel
   ResidentPlan resident;

@@ -229,10 +229,12 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   const int64_t prow_off = trlo * TM, pld = (trhi - trlo) * TM;
   const int64_t part_stride = pld * std::min<int64_t>(L, trhi * TM);
   if (nsplit > 1) BGGE_CUDA(part.alloc((size_t)part_stride * nsplit));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};   // function attributes are per device
+  int dev = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     BGGE_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int nitems = (int)items.size();
   const int grid = nitems < sms ? nitems : sms;

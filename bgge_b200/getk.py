@@ -22,7 +22,14 @@ def _factor(col):
     """factor(): sorted unique levels, 0-based codes (R/getK.R:101-104)."""
     col = np.asarray(col)
     if col.dtype == object:
-        col = np.array([str(v) for v in col])
+        # factor() on a numeric column sorts numerically; only genuinely non-numeric columns are compared as strings
+        # (codepoint order -- R collates by locale; only the order of the MDe environment kernels could differ)
+        if all(isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, bool) for v in col):
+            col = np.array([float(v) for v in col])
+            if np.all(col == np.round(col)):
+                col = col.astype(np.int64)
+        else:
+            col = np.array([str(v) for v in col])
     levels, codes = np.unique(col, return_inverse=True)
     return [v.item() if hasattr(v, "item") else v for v in levels], np.ascontiguousarray(codes, dtype=np.int32)
 
@@ -45,25 +52,31 @@ def _named_matrix(km):
     return None, None
 
 
-def factor_matches(entry, samples=256, seed=0):
-    """Cheap check that entry["Kernel"] still is the expansion its "factor" describes (a caller may have
-    edited the matrix after getK): a few hundred sampled entries and the full diagonal must agree exactly."""
+def factor_matches(entry, chunk=1 << 24):
+    """True when entry["Kernel"] still IS the expansion its "factor" describes (or when there is no dense matrix).
+    A caller may have edited the matrix after getK() -- the reference always decomposes the matrix it is given
+    (R/BGGE.R:144,160) -- so EVERY entry is compared, bit for bit, in column chunks (an n^2 pass over host memory,
+    negligible next to the eigendecomposition it gates).  Any difference sends BGGE()/setDEC() to the dense route."""
     f, K = entry.get("factor"), entry.get("Kernel")
     if f is None or K is None:
         return f is not None
     gid, env, mode, k = f["gid"], f["env"], f["mode"], f["env_k"]
     n = gid.shape[0]
+    K = np.asarray(K)
     if K.shape != (n, n):
         return False
-    rng = np.random.default_rng(seed)
-    i = np.concatenate([rng.integers(0, n, samples), np.arange(n)])
-    j = np.concatenate([rng.integers(0, n, samples), np.arange(n)])
-    base = (gid[i] == gid[j]).astype(np.float64) if f["K0"] is None else f["K0"][gid[i], gid[j]]
-    if mode == _lib.EXPAND_GE:
-        base = base * (env[i] == env[j])
-    elif mode == _lib.EXPAND_ENV:
-        base = base * ((env[i] == k) & (env[j] == k))
-    return bool(np.array_equal(np.asarray(K)[i, j], base))
+    cols = max(1, min(n, chunk // max(1, n)))
+    for c0 in range(0, n, cols):
+        c1 = min(n, c0 + cols)
+        gj = gid[c0:c1]
+        base = (gid[:, None] == gj[None, :]).astype(np.float64) if f["K0"] is None else f["K0"][np.ix_(gid, gj)]
+        if mode == _lib.EXPAND_GE:
+            base = base * (env[:, None] == env[None, c0:c1])
+        elif mode == _lib.EXPAND_ENV:
+            base = base * ((env == k)[:, None] & (env[c0:c1] == k)[None, :])
+        if not np.array_equal(K[:, c0:c1], base):
+            return False
+    return True
 
 
 def materialize(entry):

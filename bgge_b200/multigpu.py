@@ -82,7 +82,11 @@ class DeviceVector:
 
 
 def nccl_allreduce(group=None):
-    """reduce(ptr, count): in-place sum over the ranks of `group` with torch.distributed (NCCL over NVLink)."""
+    """reduce(ptr, count): in-place sum over the ranks of `group` with torch.distributed (NCCL over NVLink).  The
+    collective is ordered against torch's current stream, which knows nothing about the handle's own stream: the
+    callback therefore returns only when the reduction has finished (run_sharded drains the handle's stream before it
+    calls).  Correct but latency-bound -- the fast path is a library communicator (Comm below, BGGE(shard=(rank,
+    world, comm))): the all-reduce is then issued on the handle's stream inside libbgge_b200, no host sync at all."""
     import torch
     import torch.distributed as dist
     cache = {}
@@ -92,20 +96,67 @@ def nccl_allreduce(group=None):
         if t is None:
             t = cache[(ptr, count)] = torch.as_tensor(DeviceVector(ptr, count), device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream().synchronize()
 
     return reduce
 
 
 def run_sharded(h, nk: int, iters: int, reduce):
-    """`iters` iterations of a column-sharded chain: per kernel step sweep the local columns, add the partial
-    W b and sum b^2/s of all processes (reduce(ptr, count), in place, on the handle's stream), finish the step."""
+    """`iters` iterations of a column-sharded chain with a caller-supplied collective: per kernel step sweep the local
+    columns, wait for them (the callback's stream is not the handle's), add the partial W b and sum b^2/s of all
+    processes (reduce(ptr, count): in place, complete on return), finish the step."""
     import ctypes as C
     from . import _lib
     vec, cnt = C.c_void_p(), C.c_int64()
     for _ in range(int(iters)):
         for j in range(nk):
             _lib.call("bgge_gibbs_shard_begin", h, j, C.byref(vec), C.byref(cnt))
+            _lib.call("bgge_gibbs_sync", h)
             reduce(vec.value, cnt.value)
             _lib.call("bgge_gibbs_shard_end", h, j)
         _lib.call("bgge_gibbs_shard_iteration_end", h)
+
+
+class Comm:
+    """A communicator owned by libbgge_b200 (NCCL inside the library, include/bgge_b200.h "multi-GPU inside the
+    library").  Comm.local(ndev) -> one per GPU of this process; Comm.from_torch_distributed() -> this process' rank
+    of the default torch.distributed group (torch only ships the 128-byte id; the collectives are the library's)."""
+
+    def __init__(self, handle, rank, world, device):
+        self.handle, self.rank, self.world, self.device = handle, rank, world, device
+
+    @staticmethod
+    def local(ndev, devices=None):
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        arr = (C.c_void_p * ndev)()
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _lib.call("bgge_comm_init_all", int(ndev), _lib.ptr(dv), C.cast(arr, C.POINTER(C.c_void_p)))
+        return [Comm(C.c_void_p(arr[d]), d, ndev, d if devices is None else int(devices[d])) for d in range(ndev)]
+
+    @staticmethod
+    def from_torch_distributed(device):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idbuf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.call("bgge_comm_unique_id", idbuf)
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device=device)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(raw)
+        _lib.call("bgge_set_device", int(device.index if hasattr(device, "index") else device))
+        h = C.c_void_p()
+        _lib.call("bgge_comm_init_rank", idbuf, world, rank, C.byref(h))
+        return Comm(h, rank, world, int(device.index if hasattr(device, "index") else device))
+
+    def destroy(self):
+        from . import _lib
+        if self.handle:
+            _lib.load().bgge_comm_destroy(self.handle)
+            self.handle = None
 

@@ -159,14 +159,15 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
  * genotype / environment codes of the n rows (host pointers) and the expansion mode of bgge_getk_expand.
  * Each block is decomposed through the |T| x |T| matrix C^{1/2} K0[T,T] C^{1/2} (T = genotypes present,
  * C = their counts), which has the same eigenpairs > tol as the block itself; blocks whose mask is not
- * constant fall back to the direct m x m decomposition.  Sets mean(diag(K)) as well.
+ * constant fall back to the direct m x m decomposition.  Sets mean(diag(K)) as well.  n_codes = length of the gid /
+ * env arrays; it must equal the handle's n (the reference fails with "non-conformable arguments" otherwise).
  * When genotypes repeat inside a block (|T| <= 2/3 of its rows, e.g. the G kernel of a multi-environment
  * trial) the block stays factorised: the sweep streams W (|T| x nr) and applies Z C^{-1/2} on the fly, so
  * that kernel step moves |T|/rows of the bytes.  bgge_gibbs_fetch_block / block_device expand it on demand.
  */
 int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double* K0, int64_t L, int64_t ldk,
-                                   int on_device, const int32_t* gid, const int32_t* env, int mode, int env_k,
-                                   const int64_t* ne, int n_ne, double tol, int canonical_sign);
+                                   int on_device, const int32_t* gid, const int32_t* env, int64_t n_codes, int mode,
+                                   int env_k, const int64_t* ne, int n_ne, double tol, int canonical_sign);
 /* eigen blocks currently attached to kernel j (valid before bgge_gibbs_init; U is rows x nr, leading dimension ldu) */
 int bgge_gibbs_block_count(bgge_gibbs* h, int j, int* n_blocks);
 int bgge_gibbs_fetch_block(bgge_gibbs* h, int j, int b, int64_t* pos0, int64_t* rows, int64_t* nr, double* s, double* U,
@@ -284,6 +285,43 @@ int bgge_fit(const double* y, const uint8_t* na_mask, int64_t n, const double* c
 int bgge_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* n standard normals / chi-squares from the device generator: stream = kernel index semantics */
 int bgge_test_draws(uint64_t seed, uint32_t chain, int64_t n, double* normals, double df, double* chisq);
+
+/* ------------------------------------------------------------------ multi-GPU inside the library
+ * SURVEY.md 8b "Threading" / 8e: the reference is one R process, so the fan-out over the GPUs of a box has to live
+ * below the .Call boundary.  Communicators wrap NCCL (bound at run time with dlopen, an already loaded libnccl is
+ * reused); no torch, MPI or other launcher is needed for the single-process forms.
+ */
+typedef struct bgge_comm bgge_comm;
+#define BGGE_COMM_ID_BYTES 128
+/* one communicator per GPU of this process (devices == NULL: 0..ndev-1); out receives ndev handles, rank d = out[d] */
+int bgge_comm_init_all(int ndev, const int* devices, bgge_comm** out);
+/* multi-process form: rank 0 creates an id, ships the 128 bytes to the other processes by any channel, then every
+ * process calls init_rank with its rank on its current device */
+int bgge_comm_unique_id(void* id);
+int bgge_comm_init_rank(const void* id, int world, int rank, bgge_comm** out);
+int bgge_comm_info(const bgge_comm* c, int* rank, int* world, int* device);
+void bgge_comm_destroy(bgge_comm* c);
+/* in-place sum of d_buf[0..count) over the ranks, ordered on `stream` */
+int bgge_dev_allreduce(bgge_comm* c, double* d_buf, int64_t count, void* stream);
+/*
+ * Row-panel build of S = X X' / divisor (R/getK.R:136; the O(L^2 p) part of :142) over the ranks of c: every rank
+ * holds the padded markers dX (bgge_marker_ld / _cols layout), builds the lower-triangle tiles of its two tile-row
+ * panels on the FP64 tensor cores, stores them transposed (contiguous column panels of dS) and the panels are
+ * exchanged in place; on return dS (L x L, leading dimension L) is complete and symmetric on every rank.
+ * ms_compute / ms_exchange (optional): device time of the contraction and of exchange + mirror pass.
+ */
+int bgge_dev_gram_panels(bgge_comm* c, const double* dX, int64_t ldx, int64_t L, int64_t p_pad, double* dS,
+                         double divisor, void* stream, float* ms_compute, float* ms_exchange);
+/* bgge_getk_base (R/getK.R:131-149) over the ndev GPUs of this process, host buffers in and out: one host thread per
+ * device, marker columns uploaded 1/ndev per device and all-gathered over NVLink, row-panel contraction, device 0
+ * runs the L x L epilogue.  comms = the handles of bgge_comm_init_all. */
+int bgge_getk_base_multi(bgge_comm* const* comms, int ndev, const double* X, int64_t L, int64_t p, int kind,
+                         const double* bandwidth, int nb, double quantil, double* out_K0, double* out_q);
+/* Column-sharded chain without a host-side collective: the handle becomes shard `rank of world` of c (call before
+ * bgge_gibbs_init, instead of bgge_gibbs_set_shard) and bgge_gibbs_run_sharded sweeps `iters` iterations with the
+ * per-step all-reduce issued on the handle's own stream.  Every rank calls it with the same arguments. */
+int bgge_gibbs_set_comm(bgge_gibbs* h, bgge_comm* c);
+int bgge_gibbs_run_sharded(bgge_gibbs* h, int64_t iters);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -214,3 +214,55 @@ def test_row_panel_plan_over_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_factor_matches_compares_every_entry():
+    """an edited off-diagonal entry must send BGGE()/setDEC() to the dense route (the reference always
+    decomposes the matrix it is given, R/BGGE.R:144,160); the check is exact, not sampled."""
+    from bgge_b200 import _lib
+    from bgge_b200.getk import factor_matches
+    rng = np.random.default_rng(0)
+    L, E = 23, 3
+    A = rng.standard_normal((L, L))
+    K0 = A @ A.T
+    gid = np.tile(np.arange(L, dtype=np.int32), E)
+    env = np.repeat(np.arange(E, dtype=np.int32), L)
+    for mode, k in ((_lib.EXPAND_G, 0), (_lib.EXPAND_GE, 0), (_lib.EXPAND_ENV, 1), (_lib.EXPAND_GI, 0)):
+        base = (gid[:, None] == gid[None, :]).astype(float) if mode == _lib.EXPAND_GI else K0[np.ix_(gid, gid)]
+        if mode == _lib.EXPAND_GE:
+            base = base * (env[:, None] == env[None, :])
+        if mode == _lib.EXPAND_ENV:
+            base = base * ((env == k)[:, None] & (env == k)[None, :])
+        ent = {"Type": "D", "Kernel": np.asfortranarray(base),
+               "factor": {"K0": None if mode == _lib.EXPAND_GI else K0, "gid": gid, "env": env, "mode": mode, "env_k": k, "L": L}}
+        for chunk in (1 << 24, 97):               # one chunk, and many ragged column chunks
+            assert factor_matches(ent, chunk=chunk)
+        for (i, j) in ((5, 40), (L * E - 1, 0), (L + 2, L + 3)):
+            old = ent["Kernel"][i, j]
+            ent["Kernel"][i, j] = old + 1e-9
+            assert not factor_matches(ent, chunk=97), (mode, i, j)
+            ent["Kernel"][i, j] = old
+        assert factor_matches(ent)
+    assert factor_matches({"Type": "D", "factor": ent["factor"]})          # factored-only entry
+    assert not factor_matches({"Type": "D", "Kernel": base})               # no description to match
+
+
+def test_numeric_factor_levels_sort_numerically():
+    """factor() on a numeric column sorts numerically ('10' must not come before '2')."""
+    from bgge_b200.getk import _factor
+    lev, codes = _factor(np.array([10, 2, 33, 2, 10], dtype=object))
+    assert lev == [2, 10, 33] and codes.tolist() == [1, 0, 2, 0, 1]
+    lev, codes = _factor(np.array(["e10", "e2", "e2"], dtype=object))
+    assert lev == ["e10", "e2"] and codes.tolist() == [0, 1, 1]
+    lev, codes = _factor(np.array([1.5, 0.25, 1.5], dtype=object))
+    assert lev == [0.25, 1.5] and codes.tolist() == [1, 0, 1]
+
+
+def test_factored_kernel_must_describe_the_rows_of_y():
+    """a factored description with a different row count than y is an error, not a truncation."""
+    from bgge_b200.bgge import _check_factor_rows
+    f = {"gid": np.zeros(12, dtype=np.int32), "env": np.zeros(12, dtype=np.int32)}
+    _check_factor_rows({"factor": f}, 12, "G")
+    for n in (11, 13):
+        with pytest.raises(ValueError, match="non-conformable"):
+            _check_factor_rows({"factor": f}, n, "G")

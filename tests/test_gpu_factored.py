@@ -214,7 +214,7 @@ def test_shared_kernel_handles_reproduce_owner(lib):
     for j, k in enumerate(Kf.values()):
         f = k["factor"]
         lib.call("bgge_gibbs_add_expanded_kernel", h0, j, 0 if k["Type"] == "D" else 1, lib.ptr(lib.f64(f["K0"])), L, L, 0,
-                 lib.ptr(f["gid"]), lib.ptr(f["env"]), f["mode"], f["env_k"], lib.ptr(ne), E, 1e-10, 1)
+                 lib.ptr(f["gid"]), lib.ptr(f["env"]), n, f["mode"], f["env_k"], lib.ptr(ne), E, 1e-10, 1)
     for rep in range(2):
         h = C.c_void_p()
         lib.call("bgge_gibbs_create", n, 2, 0, None, C.byref(h))
