@@ -28,6 +28,18 @@ TYPE_D, TYPE_BD = 0, 1
 RNG_PHILOX, RNG_TAPE = 0, 1
 
 
+KERNEL_DENSE = -1
+
+
+class KernelDesc(C.Structure):
+    """struct bgge_kernel_desc (include/bgge_b200.h)."""
+    _fields_ = [("type", C.c_int), ("mode", C.c_int), ("env_k", C.c_int), ("reserved", C.c_int), ("L", C.c_int64),
+                ("K0", C.c_void_p), ("dense", C.c_void_p)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_int64, C.c_double, C.c_void_p)
+
+
 class BGGEError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libbgge_b200 error {code}: {msg}")
@@ -133,6 +145,12 @@ SIGNATURES = {
                                        C.c_double, C.c_void_p, c_double_p]),
     "bgge_gibbs_set_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bgge_gibbs_run_sharded": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bgge_fit_kernels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double,
+                                   C.c_int, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_int)]),
     "bgge_test_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgge_test_draws": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p]),
 }

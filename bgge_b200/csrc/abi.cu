@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "multi.cuh"
 #include "rng.cuh"
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -1630,6 +1631,90 @@ int bgge_fit(const double* y, const uint8_t* na_mask, int64_t n, const double* c
   BGGE_TRY(bgge_gibbs_run(h, ite));
   BGGE_TRY(bgge_gibbs_summary(h, yHat, varE, varE_sd, u, u_sd, varu, varu_sd, y_out));
   BGGE_TRY(bgge_gibbs_chain(h, chain_mu, chain_varE, chain_varU, nullptr));
+  return OK;
+}
+
+// BGGE() with the K list as getK() builds it: factored descriptions go through the L x L setDEC route and stay
+// factorised in the sweep, dense entries through the n x n route.  See include/bgge_b200.h.
+int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const bgge_kernel_desc* kernels, int nk,
+                     const int32_t* gid, const int32_t* env, const double* XF, int q, const int64_t* ne, int n_ne,
+                     int64_t ite, int64_t burn, int64_t thin, double tol, double R2, int rng_mode, uint64_t seed,
+                     const double* normals, int64_t n_normals, const double* chisq, int64_t n_chisq, int64_t chunk,
+                     bgge_progress_fn progress, void* user, double* yHat, double* varE, double* varE_sd, double* u,
+                     double* u_sd, double* varu, double* varu_sd, double* y_out, double* chain_mu, double* chain_varE,
+                     double* chain_varU, double* chain_bet, int* factored_kernels) {
+  BGGE_TRY(ensure_device());
+  BGGE_REQUIRE(y && kernels && nk >= 1 && n > 1, "fit_kernels: NULL pointer or empty model");
+  BGGE_REQUIRE(ite >= 1 && thin >= 1 && burn >= 0, "fit_kernels: ite=%lld burn=%lld thin=%lld", (long long)ite, (long long)burn,
+               (long long)thin);
+  bool any_bd = false, any_fact = false;
+  for (int j = 0; j < nk; ++j) {
+    const bgge_kernel_desc& kd = kernels[j];
+    BGGE_REQUIRE(kd.type == BGGE_TYPE_D || kd.type == BGGE_TYPE_BD, "Matrix should be of types BD or D");       // R/BGGE.R:220
+    BGGE_REQUIRE(kd.mode == BGGE_KERNEL_DENSE || (kd.mode >= BGGE_EXPAND_G && kd.mode <= BGGE_EXPAND_GI),
+                 "fit_kernels: kernel %d has unknown mode %d", j, kd.mode);
+    BGGE_REQUIRE(kd.mode != BGGE_KERNEL_DENSE || kd.dense != nullptr, "fit_kernels: kernel %d: dense matrix missing", j);
+    any_bd |= kd.type == BGGE_TYPE_BD;
+    any_fact |= kd.mode != BGGE_KERNEL_DENSE;
+  }
+  BGGE_REQUIRE(!any_bd || ne != nullptr, "For type BD, number of subjects in each sub matrices should be provided");  // R/BGGE.R:129
+  BGGE_REQUIRE(!(any_bd && n_ne <= 1), "Type BD should be used only for block diagonal matrices");              // R/BGGE.R:223
+  BGGE_REQUIRE(!any_fact || gid != nullptr, "fit_kernels: genotype codes missing");
+  bgge_gibbs* h = nullptr;
+  BGGE_TRY(bgge_gibbs_create(n, nk, q, nullptr, &h));
+  std::unique_ptr<bgge_gibbs, void (*)(bgge_gibbs*)> guard(h, bgge_gibbs_destroy);
+  BGGE_TRY(bgge_gibbs_set_y(h, y, na_mask));
+  if (q > 0) BGGE_TRY(bgge_gibbs_set_xf(h, XF));
+  {
+    // every distinct base kernel is uploaded once and shared by the kernels that expand it (G and GE of MDs, G and
+    // the E environment kernels of MDe)
+    std::vector<std::pair<const double*, std::unique_ptr<DevBuf<double>>>> up;
+    int nfact = 0;
+    for (int j = 0; j < nk; ++j) {
+      const bgge_kernel_desc& kd = kernels[j];
+      if (kd.mode == BGGE_KERNEL_DENSE) {
+        BGGE_TRY(bgge_gibbs_add_kernel_matrix(h, j, kd.type, kd.dense, n, 0, ne, n_ne, tol, 1));
+        continue;
+      }
+      const double* dK0 = nullptr;
+      if (kd.mode != BGGE_EXPAND_GI) {
+        BGGE_REQUIRE(kd.K0 != nullptr && kd.L > 0, "fit_kernels: kernel %d: base kernel missing", j);
+        for (auto& e : up)
+          if (e.first == kd.K0 && (int64_t)e.second->n == kd.L * kd.L) dK0 = e.second->p;
+        if (!dK0) {
+          std::unique_ptr<DevBuf<double>> b(new DevBuf<double>());
+          BGGE_CUDA(b->alloc((size_t)kd.L * kd.L));
+          BGGE_CUDA(cudaMemcpy(b->p, kd.K0, (size_t)kd.L * kd.L * sizeof(double), cudaMemcpyHostToDevice));
+          dK0 = b->p;
+          up.emplace_back(kd.K0, std::move(b));
+        }
+      }
+      BGGE_TRY(bgge_gibbs_add_expanded_kernel(h, j, kd.type, dK0, kd.L, kd.L, 1, gid, env, n, kd.mode, kd.env_k, ne, n_ne, tol,
+                                              1));
+      ++nfact;
+    }
+    if (factored_kernels) *factored_kernels = nfact;
+    BGGE_CUDA(cudaStreamSynchronize(h->g.stream));   // the base kernels die here; the eigen blocks are what the chain keeps
+  }
+  if (rng_mode == BGGE_RNG_TAPE) BGGE_TRY(bgge_gibbs_set_tape(h, normals, n_normals, chisq, n_chisq));
+  BGGE_TRY(bgge_gibbs_init(h, ite, burn, thin, R2, rng_mode, seed, 0));
+  const int64_t piece = (chunk > 0 && progress) ? chunk : ite;
+  for (int64_t done = 0; done < ite;) {                                                                          // R/BGGE.R:274
+    const int64_t k = std::min(piece, ite - done);
+    const auto t0 = std::chrono::steady_clock::now();
+    BGGE_TRY(bgge_gibbs_run(h, k));
+    done += k;
+    if (progress) {
+      BGGE_CUDA(cudaStreamSynchronize(h->g.stream));
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (progress(done, dt / (double)k, user) != 0) {                                                         // R/BGGE.R:398-401
+        set_error("interrupted after %lld of %lld iterations", (long long)done, (long long)ite);
+        return ERR_STATE;
+      }
+    }
+  }
+  BGGE_TRY(bgge_gibbs_summary(h, yHat, varE, varE_sd, u, u_sd, varu, varu_sd, y_out));
+  BGGE_TRY(bgge_gibbs_chain(h, chain_mu, chain_varE, chain_varU, chain_bet));
   return OK;
 }
 

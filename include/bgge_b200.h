@@ -286,6 +286,37 @@ int bgge_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[
 /* n standard normals / chi-squares from the device generator: stream = kernel index semantics */
 int bgge_test_draws(uint64_t seed, uint32_t chain, int64_t n, double* normals, double df, double* chisq);
 
+/*
+ * The same with the K list in the form getK() builds it (R/getK.R:138,148,173,201,216,232): every kernel is either an
+ * expansion of an L x L base kernel through the row codes gid / env (mode = a bgge_expand_mode; the n x n matrix is
+ * never formed, setDEC runs through bgge_gibbs_add_expanded_kernel and the sweep streams the factorised basis) or a
+ * dense n x n matrix (mode = BGGE_KERNEL_DENSE: hand-built K lists, R/BGGE.R:55-58; kernels a caller edited).
+ * Base kernels with the same K0 pointer are uploaded once.  This is the entry the .Call shim under BGGE() binds.
+ *   chunk     > 0: the sweeps run in pieces of `chunk` iterations (BGGE(verbose = chunk), R/BGGE.R:398-401) and
+ *             progress(done, seconds_per_iteration, user) is called after each piece on the calling thread -- the R
+ *             shim prints the "Iter: ... time: ..." line and calls R_CheckUserInterrupt() there; a non-zero return
+ *             stops the run (BGGE_ERR_STATE, message "interrupted").  chunk <= 0 or progress == NULL: one piece.
+ *   chain_bet optional n_cum x max(q, 1) (column-major) recorded fixed effects.
+ */
+#define BGGE_KERNEL_DENSE (-1)
+typedef struct bgge_kernel_desc {
+  int type;              /* BGGE_TYPE_D / BGGE_TYPE_BD */
+  int mode;              /* bgge_expand_mode, or BGGE_KERNEL_DENSE */
+  int env_k;             /* environment of an MDe kernel (mode BGGE_EXPAND_ENV) */
+  int reserved;
+  int64_t L;             /* order of K0 */
+  const double* K0;      /* L x L, column-major, host; NULL for BGGE_EXPAND_GI */
+  const double* dense;   /* n x n, column-major, host; mode BGGE_KERNEL_DENSE only */
+} bgge_kernel_desc;
+typedef int (*bgge_progress_fn)(int64_t done, double seconds_per_iteration, void* user);
+int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const bgge_kernel_desc* kernels, int nk,
+                     const int32_t* gid, const int32_t* env, const double* XF, int q, const int64_t* ne, int n_ne,
+                     int64_t ite, int64_t burn, int64_t thin, double tol, double R2, int rng_mode, uint64_t seed,
+                     const double* normals, int64_t n_normals, const double* chisq, int64_t n_chisq, int64_t chunk,
+                     bgge_progress_fn progress, void* user, double* yHat, double* varE, double* varE_sd, double* u,
+                     double* u_sd, double* varu, double* varu_sd, double* y_out, double* chain_mu, double* chain_varE,
+                     double* chain_varU, double* chain_bet, int* factored_kernels);
+
 /* ------------------------------------------------------------------ multi-GPU inside the library
  * SURVEY.md 8b "Threading" / 8e: the reference is one R process, so the fan-out over the GPUs of a box has to live
  * below the .Call boundary.  Communicators wrap NCCL (bound at run time with dlopen, an already loaded libnccl is

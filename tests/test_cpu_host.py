@@ -266,3 +266,26 @@ def test_factored_kernel_must_describe_the_rows_of_y():
     for n in (11, 13):
         with pytest.raises(ValueError, match="non-conformable"):
             _check_factor_rows({"factor": f}, n, "G")
+
+
+def test_r_shim_type_checks_against_the_header():
+    """R is not in the image, so the .Call shim cannot be built; it is at least type-checked: every libbgge_b200 call
+    in r-shim/src/bgge_shim.c must match include/bgge_b200.h (arity, pointer types, struct fields) and every R API
+    call a mock of Rinternals.h with R 4.x's prototypes (tests/mock_r).  Catches ABI drift without R."""
+    cmd = ["gcc", "-fsyntax-only", "-std=c11", "-Wall", "-Wextra", "-Wno-cast-function-type", "-Werror",
+           "-I", os.path.join(ROOT, "tests", "mock_r"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "r-shim", "src", "bgge_shim.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the routines the R code calls are the ones the shim registers, with the registered arities
+    shim = open(os.path.join(ROOT, "r-shim", "src", "bgge_shim.c")).read()
+    rsrc = open(os.path.join(ROOT, "r-shim", "R", "native.R")).read()
+    reg = dict(re.findall(r'\{"(bgge_R_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim))
+    assert set(re.findall(r'\.Call\("(bgge_R_\w+)"', rsrc)) == set(reg)
+    for name, nargs in reg.items():
+        sig = re.search(r"SEXP %s\(([^)]*)\)" % name, shim).group(1)
+        assert sig.count("SEXP") == int(nargs), name
+    # the header is plain C (the shim includes it from a C translation unit)
+    r = subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Werror", "-x", "c", os.path.join(ROOT, "include", "bgge_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

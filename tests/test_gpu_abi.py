@@ -155,3 +155,119 @@ def test_default_getk_output_takes_the_factorised_route():
     assert not factor_matches(K["GE"])
     c = bgge_b200.BGGE(y, K, ne=[L] * E, ite=10, burn=2, thin=2, seed=3)
     assert np.isfinite(c["yHat"]).all()
+
+
+def _fit_kernels(lib, y, descs, gid, env, ne, ite, burn, thin, z, c, XF=None, chunk=0, progress=None):
+    n, nk = y.shape[0], len(descs)
+    arr = (lib.KernelDesc * nk)(*descs)
+    q = 0 if XF is None else XF.shape[1]
+    ncum = ite // thin
+    out = {"yHat": np.empty(n), "u": np.empty((nk, n)), "usd": np.empty((nk, n)), "y": np.empty(n), "varu": np.empty(nk),
+           "varusd": np.empty(nk), "cmu": np.empty(ncum), "cve": np.empty(ncum), "cvu": np.empty((nk, ncum)),
+           "cbet": np.empty((max(q, 1), ncum)).T}
+    cbet = np.empty((ncum, max(q, 1)), order="F")
+    varE, varEsd, nfact = C.c_double(), C.c_double(), C.c_int()
+    na = np.isnan(y).astype(np.uint8)
+    yy = np.where(np.isnan(y), 0.0, y)
+    cb = lib.PROGRESS_FN(progress) if progress is not None else None
+    lib.call("bgge_fit_kernels", lib.ptr(yy), lib.ptr(na), n, C.cast(arr, C.c_void_p), nk, lib.ptr(gid), lib.ptr(env),
+             None if XF is None else lib.ptr(lib.f64(XF)), q, lib.ptr(ne), ne.shape[0], ite, burn, thin, 1e-10, 0.5,
+             lib.RNG_TAPE, 0, lib.ptr(z), z.shape[0], lib.ptr(c), c.shape[0], chunk, cb, None, lib.ptr(out["yHat"]),
+             C.byref(varE), C.byref(varEsd), lib.ptr(out["u"]), lib.ptr(out["usd"]), lib.ptr(out["varu"]),
+             lib.ptr(out["varusd"]), lib.ptr(out["y"]), lib.ptr(out["cmu"]), lib.ptr(out["cve"]), lib.ptr(out["cvu"]),
+             lib.ptr(cbet), C.byref(nfact))
+    out.update(varE=varE.value, varEsd=varEsd.value, nfact=nfact.value, cbet=cbet)
+    return out
+
+
+@pytest.mark.parametrize("model,kernel,with_xf", [("MDs", "GK", False), ("MDe", "GB", True), ("MM", "GB", False)])
+def test_fit_kernels_one_shot_from_factor_descriptions_matches_oracle(lib, model, kernel, with_xf):
+    """bgge_fit_kernels -- what the .Call shim under BGGE() binds -- fed with getK()'s factor descriptions (base kernel
+    + codes, the n x n matrices are never built), against the oracle on the dense kernels with the same tapes;
+    verbose chunks call the progress hook after every piece and the chain does not depend on the chunking."""
+    import bgge_b200
+    L, E, p = 60, 4, 80
+    X = markers(L, p, 11)
+    Y, names = design(L, E)
+    n = L * E
+    ne = np.array([L] * E, dtype=np.int64)
+    Kf = bgge_b200.getK(Y, X, kernel=kernel, model=model, rownames=names, factored=True, intercept_random=(model == "MM"))
+    Kd = oracle.getK(Y, X, kernel=kernel, model=model, rownames=names, intercept_random=(model == "MM"))
+    rng = np.random.default_rng(12)
+    y = rng.standard_normal(n)
+    y[rng.choice(n, 7, replace=False)] = np.nan
+    XF = None
+    if with_xf:
+        XF = np.zeros((n, E))
+        for e in range(E):
+            XF[e * L:(e + 1) * L, e] = 1.0
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    ite, burn, thin = 24, 6, 2
+    nz, nc = oracle.tape_sizes(n, nrs, ite, q=(E if with_xf else 0), n_na=7)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    ref = oracle.BGGE(y, Kd, XF=XF, ne=ne, ite=ite, burn=burn, thin=thin, draws=oracle.TapeDraws(z, c), eig=Ei)
+    f0 = next(iter(Kf.values()))["factor"]
+    keep = []
+    descs = []
+    for k in Kf.values():
+        f = k["factor"]
+        K0 = None if f["K0"] is None else lib.f64(f["K0"])
+        keep.append(K0)
+        descs.append(lib.KernelDesc(0 if k["Type"] == "D" else 1, f["mode"], f["env_k"], 0, f["L"],
+                                    None if K0 is None else K0.ctypes.data, None))
+    seen = []
+    got = _fit_kernels(lib, y, descs, f0["gid"], f0["env"], ne, ite, burn, thin, z, c, XF=XF, chunk=5,
+                       progress=lambda done, spi, user: seen.append((done, spi)) or 0)
+    assert [d for d, _ in seen] == [5, 10, 15, 20, 24] and all(s > 0 for _, s in seen)
+    assert got["nfact"] == len(Kf)
+    one = _fit_kernels(lib, y, descs, f0["gid"], f0["env"], ne, ite, burn, thin, z, c, XF=XF)
+    for key in ("yHat", "cmu", "cve", "cvu", "u", "y"):
+        assert np.array_equal(got[key], one[key]), key                  # chunked == one piece, bit for bit
+    assert relmax(got["cve"], ref["chain"]["varE"]) <= 1e-9
+    assert relmax(got["cmu"], ref["chain"]["mu"]) <= 1e-9
+    for j, nm in enumerate(ref["K"]):
+        assert relmax(got["cvu"][j], ref["chain"]["K"][nm]["varU"]) <= 1e-9, nm
+        assert relmax(got["u"][j], ref["K"][nm]["u"]) <= 1e-9, nm
+    assert relmax(got["yHat"], np.asarray(ref["yHat"]).ravel()) <= 1e-9
+    assert relmax(got["y"], ref["y"]) <= 1e-9
+    if with_xf:
+        assert relmax(got["cbet"], ref["_Bet_chain"]) <= 1e-9
+
+
+def test_fit_kernels_mixes_dense_and_factored_kernels_and_can_be_interrupted(lib):
+    """A K list whose second kernel was edited by the caller (so it must be decomposed as the dense n x n matrix it is,
+    R/BGGE.R:144) next to a factored first kernel; and a progress hook that asks to stop."""
+    import bgge_b200
+    L, E, p = 40, 3, 50
+    X = markers(L, p, 4)
+    Y, names = design(L, E)
+    n = L * E
+    ne = np.array([L] * E, dtype=np.int64)
+    Kf = bgge_b200.getK(Y, X, kernel="GB", model="MDs", rownames=names)      # dense + factor descriptions
+    Kd = oracle.getK(Y, X, kernel="GB", model="MDs", rownames=names)
+    for K in (Kf, Kd):                                                       # the caller shrinks GE's first environment block
+        K["GE"]["Kernel"][:L, :L] *= 0.5
+    assert not bgge_b200.getk.factor_matches(Kf["GE"]) and bgge_b200.getk.factor_matches(Kf["G"])
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(n)
+    ite = 10
+    Ei = [bgge_b200.setDEC({"G": Kf["G"]}, ne, 1e-10)[0], bgge_b200.setDEC({"GE": {"Type": "BD", "Kernel": Kf["GE"]["Kernel"]}}, ne, 1e-10)[0]]
+    nrs = [sum(b["s"].shape[0] for b in bl) for bl in Ei]
+    nz, nc = oracle.tape_sizes(n, nrs, ite)
+    z = rng.standard_normal(nz)
+    c = rng.chisquare(np.tile(np.array([nr + 3 for nr in nrs] + [n + 3], dtype=float), ite))
+    ref = oracle.BGGE(y, Kd, ne=ne, ite=ite, burn=0, thin=1, draws=oracle.TapeDraws(z, c), eig=Ei)
+    f = Kf["G"]["factor"]
+    K0 = lib.f64(f["K0"])
+    dense = lib.f64(Kf["GE"]["Kernel"])
+    descs = [lib.KernelDesc(0, f["mode"], 0, 0, L, K0.ctypes.data, None),
+             lib.KernelDesc(1, lib.KERNEL_DENSE, 0, 0, 0, None, dense.ctypes.data)]
+    got = _fit_kernels(lib, y, descs, f["gid"], f["env"], ne, ite, 0, 1, z, c)
+    assert got["nfact"] == 1
+    assert relmax(got["cve"], ref["chain"]["varE"]) <= 1e-9
+    assert relmax(got["cvu"][1], ref["chain"]["K"]["GE"]["varU"]) <= 1e-9
+    assert relmax(got["yHat"], ref["yHat"]) <= 1e-9
+    with pytest.raises(lib.BGGEError, match="interrupted after 4 of 10"):
+        _fit_kernels(lib, y, descs, f["gid"], f["env"], ne, ite, 0, 1, z, c, chunk=2, progress=lambda d, s, u: int(d >= 4))
