@@ -52,6 +52,12 @@ WORKLOADS = {
 METRIC = "Gibbs iterations/sec at n=40k (MDs GK)"
 
 
+def workload_config(name):
+    """The `config` object of the JSON line: the workload and nothing run-specific, so that both arms print the same."""
+    L, p, E, kernel, model, desc = WORKLOADS[name]
+    return {"workload": desc, "n": L * E, "L": L, "p": p, "E": E, "kernel": kernel, "model": model}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,7 +182,8 @@ def run_reference(args):
         "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "iters_per_step": iters, "kind": "reference-algorithm CPU restatement (R not installed)"},
+        "config": workload_config(args.workload),
+        "run": {"iters_per_step": iters, "kind": "reference-algorithm CPU restatement (R not installed)"},
         "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -228,42 +235,44 @@ def dgemm_peak(torch, device):
     """cuBLAS DGEMM 8192^3: the measured FP64 tensor-core denominator (burst and sustained)."""
     a = torch.randn((8192, 8192), dtype=torch.float64, device=device)
     b = torch.randn((8192, 8192), dtype=torch.float64, device=device)
-    torch.matmul(a, b)
-    best = min(timed(torch, lambda: torch.matmul(a, b)) for _ in range(5))
+    for _ in range(6):          # module load, cuBLAS heuristics, clock ramp-up: none of it belongs in either figure
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = min(timed(torch, lambda: torch.matmul(a, b)) for _ in range(6))
     fl = 2.0 * 8192 ** 3
-    t0 = time.perf_counter()
-    k = 0
-    s = timed(torch, lambda: [torch.matmul(a, b) for _ in range(12)])
-    k = 12
+    k = 48                      # ~1.5 s back to back: the power-capped steady state
+    s = timed(torch, lambda: [torch.matmul(a, b) for _ in range(k)])
     del a, b
     return fl / best / 1e12, fl * k / s / 1e12
 
 
-def gram_build(torch, dist, lib, Xp, ldx, L, pp, divisor, world, rank, stream):
-    """S = X X'/divisor (L x L, both triangles).  world == 1: one launch.  world > 1: row-panel
-    build -- 2*world equal tile-row chunks, rank r owns chunks r and 2*world-1-r (balanced lower
-    triangle), panels exchanged with one NCCL all-gather, mirrored locally."""
+def gram_build(torch, dist, lib, Xp, ldx, L, pp, divisor, world, rank, stream, comm=None, S=None, split=None):
+    """S = X X'/divisor (L x L, both triangles).  world == 1: one launch.  world > 1: the library's row-panel build
+    (bgge_dev_gram_panels): 2*world equal tile-row chunks, rank r owns chunks r and 2*world-1-r (balanced lower
+    triangle), stored transposed so that every panel is one contiguous column range of S, exchanged IN PLACE by the
+    library's own NCCL communicator, mirrored locally.  No staging tensors, no torch collective."""
     T = (L + 127) // 128
-    S = torch.empty((L, L), dtype=torch.float64, device=Xp.device)
-    if world == 1:
+    if S is None:
+        S = torch.empty((L, L), dtype=torch.float64, device=Xp.device)
+    if world == 1 or comm is None:
         lib.call("bgge_dev_gram", vp(Xp), ldx, L, pp, 0, T, vp(S), L, 0, float(divisor), 1, stream)
         return S
-    from bgge_b200 import multigpu
-    ch, R, owners = multigpu.panel_plan(L, world)
-    mine = torch.zeros((2, L, R), dtype=torch.float64, device=Xp.device)    # [panel][col j][local row]
-    for k, c in enumerate(owners[rank]):
-        t0, t1 = multigpu.chunk_tile_rows(L, world, c)
-        if t1 > t0:
-            lib.call("bgge_dev_gram", vp(Xp), ldx, L, pp, t0, t1, vp(mine[k]), R, t0 * 128, float(divisor), 0, stream)
-    allp = torch.empty((world, 2, L, R), dtype=torch.float64, device=Xp.device)
-    dist.all_gather_into_tensor(allp, mine)
-    S.zero_()
-    multigpu.assemble_panels(S, allp, L, world)
-    lib.call("bgge_dev_symmetrize", vp(S), L, L, stream)
+    msc, msx = C.c_float(), C.c_float()
+    lib.call("bgge_dev_gram_panels", comm.handle, vp(Xp), ldx, L, pp, vp(S), float(divisor), stream,
+             C.byref(msc) if split is not None else None, C.byref(msx) if split is not None else None)
+    if split is not None:
+        split.append((msc.value * 1e-3, msx.value * 1e-3))
     return S
 
 
-def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
+def pk_hbm_it_s(n, nr):
+    """Iterations/s at which ONE pass pair over U and t(U) (16 n nr bytes) would saturate the measured HBM copy rate:
+    the ceiling of the batched sampler once the per-GPU chain count drops below the ridge."""
+    pk, _ = peaks()
+    return pk["hbm_gbs"] * 1e9 / (16.0 * n * nr)
+
+
+def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t, emit=True):
     """Config C4: B chains x folds sharing one decomposition; the chains are sharded over the ranks (no
     data-path collective) and each rank runs its share as one batched sampler (skinny DMMA GEMMs)."""
     from bgge_b200 import multigpu
@@ -352,6 +361,14 @@ def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
         value = n_total * args.steps * iters / (ms_total * 1e-3)                     # chain-iterations / s, whole job
         it_s = args.steps * iters / (ms_total * 1e-3)
         tflops = fl.value * it_s / 1e12
+        if not emit:   # sub-record of the default line: device-timed value only
+            lib.load().bgge_gibbs_destroy(h0)
+            return {"metric": "chain-iterations/sec, 320 chains x folds (C4)", "value": value, "unit": "chain-it/s",
+                    "scaling": "strong", "n_gpus": world, "chains_total": n_total, "chains_per_gpu": B,
+                    "padded_chains_per_gpu": bp.value, "iters_per_step": iters, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms_total / args.steps, "tflops_per_gpu": tflops, "frac_of_dgemm_burst": tflops / dg_burst,
+                    "regime": ("FP64 tensor pipe (above ~23 chains per GPU)" if B >= 23 else "HBM (below ~23 chains per GPU)"),
+                    "hbm_bound_it_s": pk_hbm_it_s(n, int(nr_b.value)), "contraction_s": t_contr, "setdec_s": t_eig}
         # e2e: host Y -> batch handle -> sweeps -> per-chain summaries back on the host
         yHat = np.empty((B, n))
         vE, vEs, vu, vus = np.empty(B), np.empty(B), np.empty((1, B)), np.empty((1, B))
@@ -392,10 +409,11 @@ def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
             "metric": "chain-iterations/sec, 320 chains x folds (C4)", "value": value, "unit": "chain-it/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "iters_per_step": iters, "chains_total": n_total, "chains_per_gpu": B,
-                       "padded_chains_per_gpu": bp.value, "n": n, "L": L, "p": p, "E": E, "kept_eigen": int(nr_b.value),
-                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
-                       "l2": "U and t(U) (2 x 160 MB) exceed L2; compute-bound above ~23 chains"},
+            "config": workload_config(args.workload),
+            "run": {"iters_per_step": iters, "chains_total": n_total, "chains_per_gpu": B,
+                    "padded_chains_per_gpu": bp.value, "kept_eigen": int(nr_b.value),
+                    "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+                    "l2": "U and t(U) (2 x 160 MB) exceed L2; compute-bound above ~23 chains"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "chain-it/s", "h2d_bytes_per_step": 8 * n * B, "d2h_bytes_per_step": 8 * (n * B + 4 * B + 3 * B * ncum),
                     "covers": "bgge_batch_create + set_y (host) + add_block (resident eigen) + init + sweeps + summaries/chains"},
@@ -403,7 +421,7 @@ def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t):
             "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel (d = U'E and u = U b over all chains)",
                          "achieved": tflops, "peak": dg_burst, "unit": "TFLOP/s", "frac": tflops / dg_burst, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst)",
-                         "note": "flops counted on the padded chain count; whole-iteration time (GEMMs + elementwise)"},
+                         "note": "flops counted on the real chains (padding columns are not credited); whole-iteration time (GEMMs + elementwise)"},
             "cpu_baseline": cpu_base,
             "getk": {"contraction_s": t_contr, "contraction_tflops": float(L) * (L + 1) * p / t_contr / 1e12,
                      "dgemm_peak_tflops_burst": dg_burst, "dgemm_peak_tflops_sustained": dg_sust},
@@ -426,6 +444,7 @@ def main():
     ap.add_argument("--prof-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-ref", action="store_true", help="skip the extra dense-basis measurement")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (320 chains x folds) sub-record of the default line")
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass proj/back kernels (no fused sweep)")
     ap.add_argument("--shard-chain", action="store_true",
                     help="N > 1: ONE chain, its eigen-columns sharded over the GPUs (strong scaling, SURVEY 8 f-4) "
@@ -466,15 +485,23 @@ def main():
         t_gen = time.perf_counter() - t_gen
         dg_burst, dg_sust = dgemm_peak(torch, device)
         gram_build(torch, dist, lib, Xp, ldx, min(L, 512), pp, 1.0, 1, 0, stream)   # warm the kernel (module load)
-        holder = {}
-        t_contr_all = []
-        for _ in range(3):          # first repetition also absorbs clock ramp-up after the marker generation
-            holder.clear()
-            t_contr_all.append(timed(torch, lambda: holder.__setitem__(
-                "S", gram_build(torch, dist, lib, Xp, ldx, L, pp, 1.0 if kernel == "GK" else float(p), world, rank,
-                                stream))))
+        comm = None
+        if world > 1:
+            from bgge_b200 import multigpu
+            comm = multigpu.Comm.from_torch_distributed(device)      # NCCL inside libbgge_b200; torch only ships the id
+        S = torch.empty((L, L), dtype=torch.float64, device=device)
+        t_contr_all, contr_split = [], []
+        for _ in range(4 if world > 1 else 3):   # first repetition also absorbs clock ramp-up / NCCL channel set-up
+            if world > 1:
+                dist.barrier()
+            tt = timed(torch, lambda: gram_build(torch, dist, lib, Xp, ldx, L, pp, 1.0 if kernel == "GK" else float(p),
+                                                 world, rank, stream, comm=comm, S=S, split=contr_split))
+            if world > 1:   # the build is a collective: its time is the slowest rank's
+                tmax = torch.tensor([tt], dtype=torch.float64, device=device)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                tt = float(tmax.item())
+            t_contr_all.append(tt)
         t_contr = min(t_contr_all)
-        S = holder["S"]
         flops = float(L) * (L + 1) * p
         t_q = 0.0
         if kernel == "GK":
@@ -644,7 +671,7 @@ def main():
             lib.call("bgge_gibbs_kernel_info", h, j, C.byref(f_), C.byref(cs_), C.byref(ncl_), C.byref(nl_))
             bb_, nf_ = C.c_int64(), C.c_int()
             lib.call("bgge_gibbs_kernel_bytes", h, j, C.byref(bb_), C.byref(nf_))
-            kinfo.append({"fused": bool(f_.value), "cluster_size": cs_.value, "clusters": ncl_.value,
+            kinfo.append({"fused": bool(f_.value), "path": f_.value, "cluster_size": cs_.value, "clusters": ncl_.value,
                           "basis_bytes": bb_.value, "factored_blocks": nf_.value, "launches": nl_.value})
         lib.load().bgge_gibbs_destroy(h)
 
@@ -686,7 +713,50 @@ def main():
         if world > 1:
             dist.barrier()
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_val = (1 if sharded else world) * args.steps * iters / float(te.item())
+        e2e_sweep_val = (1 if sharded else world) * args.steps * iters / float(te.item())
+
+        # ------------------------------------------------------------- e2e (headline): one BGGE()-equivalent CALL
+        # through the one-shot entry the R shim binds (bgge_fit_kernels), everything from HOST buffers: y, the L x L
+        # base kernel and the row codes go up, setDEC (cuSOLVER syevd through the factorised route) runs INSIDE the
+        # timed region, then the reference's default ite = 1000 / burn = 200 / thin = 3 sweeps, summaries and chains
+        # come back.  it/s = ite / wall time of the call.
+        e2e_ite = max(1000, iters) if n >= 10000 else max(2000, iters)
+        K0_pinned = torch.empty((L, L), dtype=torch.float64).pin_memory()
+        K0_pinned.copy_(K0)
+        torch.cuda.synchronize()
+        K0_np = K0_pinned.numpy()
+        descs = (lib.KernelDesc * nk)(*[lib.KernelDesc(tp, mode, k, 0, L, K0_np.ctypes.data, None) for (tp, mode, k) in kspec])
+        ncum_c = e2e_ite // 3
+        c_yHat, c_u, c_usd, c_y = np.empty(n), np.empty((nk, n)), np.empty((nk, n)), np.empty(n)
+        c_vu, c_vusd = np.empty(nk), np.empty(nk)
+        c_cm, c_cv, c_cu = np.empty(ncum_c), np.empty(ncum_c), np.empty((nk, ncum_c))
+        c_ve, c_vesd, c_nf = C.c_double(), C.c_double(), C.c_int()
+        call_s = []
+
+        def fit_call():
+            t0c = time.perf_counter()
+            lib.call("bgge_fit_kernels", lib.ptr(y_np), None, n, C.cast(descs, C.c_void_p), nk, lib.ptr(gid_h), lib.ptr(env_h),
+                     None, 0, lib.ptr(ne_h), E, e2e_ite, 200, 3, 1e-10, 0.5, lib.RNG_PHILOX, 1000 + rank, None, 0, None, 0, 0,
+                     None, None, lib.ptr(c_yHat), C.byref(c_ve), C.byref(c_vesd), lib.ptr(c_u), lib.ptr(c_usd), lib.ptr(c_vu),
+                     lib.ptr(c_vusd), lib.ptr(c_y), lib.ptr(c_cm), lib.ptr(c_cv), lib.ptr(c_cu), None, C.byref(c_nf))
+            call_s.append(time.perf_counter() - t0c)
+        if sharded:
+            e2e_val, call_s = e2e_sweep_val, []
+        else:
+            fit_call()                                   # warm-up: cuSOLVER handle / workspace, module load
+            call_s.clear()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(2, min(args.steps, 3))):
+                fit_call()
+            tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.barrier()
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            e2e_val = world * len(call_s) * e2e_ite / float(tc.item())
+        h2d_call = 8 * n + 8 * L * L + 8 * n
+        d2h_call = 8 * (n * (2 + 2 * nk) + 2 * nk + 2 + ncum_c * (2 + nk))
 
         # ------------------------------------------------------------- the same sweep on the dense eigen basis
         # (no factorisation, no sharing of identical blocks): the plain single-pass HBM-streaming regime, for
@@ -739,7 +809,7 @@ def main():
         u_bytes += basis
         if kinfo[j]["fused"]:
             ncl = kinfo[j]["clusters"]
-            kern.append({"name": f"sweep_fused_kernel[{j}]", "ms": prof_ms[2 * j],
+            kern.append({"name": f"{'sweep_mrhs_kernel' if kinfo[j]['path'] == 2 else 'sweep_fused_kernel'}[{j}]", "ms": prof_ms[2 * j],
                          "bytes": basis + 24 * cov + 8 * nrj})
             kern.append({"name": f"fused_finalize_kernel[{j}]", "ms": prof_ms[2 * j + 1], "bytes": 8 * cov * ncl + 32 * n})
         else:
@@ -776,9 +846,17 @@ def main():
                             "bound by grid-barrier latency (2 per kernel step), not by HBM"}
     jtop = int(top["name"].split("[")[1].rstrip("]")) if "[" in top["name"] else -1
     if jtop >= 0 and kinfo[jtop]["factored_blocks"] > 1:
-        roofline["note"] = ("identical diagonal blocks share one W and are swept as a multi-right-hand-side panel: 4x fewer "
-                            "bytes than the dense basis, 4x the FP64 work per byte; ncu: issue slots ~48 % busy, FP64 pipe "
-                            "23 %, so this launch is issue/latency-bound, not HBM-bound (see sweep.dense_basis_reference)")
+        roofline["note"] = ("identical diagonal blocks share one W and are swept as a multi-right-hand-side panel "
+                            "(sweep_mrhs_kernel, 4-CTA clusters, 33 clusters = 132 of 148 SMs co-resident): 4x fewer bytes "
+                            "than the dense basis, 4x the FP64 work per byte; ncu (profiles/r02_ncu_mrhs_summary.csv): "
+                            "800.5 MB read per launch, FP64 pipe 36 % of active cycles, issue slots 60 %")
+
+    # ----------------------------------------------------------------- C4 (chains x folds, strong scaling) sub-record
+    c4 = None
+    if args.workload == "c5" and not args.no_c4 and not sharded:
+        a4 = argparse.Namespace(**vars(args))
+        a4.workload, a4.iters, a4.steps, a4.warmup = "c4", 100, 2, 3
+        c4 = run_c4(a4, torch, dist, lib, world, rank, local, device, stream_t, emit=False)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -798,20 +876,30 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "iters_per_step": iters, "kernels": nk, "n": n, "L": L, "p": p, "E": E,
-                       "parallelism": (f"1 chain, eigen-columns sharded over {world} GPUs, one NCCL all-reduce of n + 1 "
-                                       "doubles per kernel step" if sharded else
-                                       f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain"),
-                       "l2": "inputs larger than L2 (U streamed from HBM every iteration)" if u_bytes > 256e6
-                             else "working set fits in L2; latency-bound, HBM roofline not binding",
-                       "eigen": "factorised setDEC in the library: L x L syevd per block, n x n kernels never built"},
+            "config": workload_config(args.workload),
+            "run": {"iters_per_step": iters, "kernels": nk,
+                    "parallelism": (f"1 chain, eigen-columns sharded over {world} GPUs, one NCCL all-reduce of n + 1 "
+                                    "doubles per kernel step" if sharded else
+                                    f"{world} independent chain(s), one per GPU" if world > 1 else "1 chain"),
+                    "l2": "inputs larger than L2 (U streamed from HBM every iteration)" if u_bytes > 256e6
+                          else "working set fits in L2; latency-bound, HBM roofline not binding",
+                    "eigen": "factorised setDEC in the library: L x L syevd per block, n x n kernels never built"},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "step_s": e2e_steps, "phase_s_create_run_fetch_destroy": e2e_phase[1:],
-                    "covers": "bgge_gibbs_create + set_y (pinned host) + add_block (device-resident eigen) + init + "
-                              f"{iters} sweeps + summary/chain download; eigen and getK are one-off setup below"},
+            "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d_call, "d2h_bytes_per_step": d2h_call,
+                    "call_s": call_s, "iterations_per_call": e2e_ite, "factored_kernels": c_nf.value,
+                    "covers": "ONE BGGE()-equivalent call per step through bgge_fit_kernels (the entry the .Call shim binds) "
+                              "from host buffers: upload of y, the L x L base kernel and the row codes, setDEC (syevd, "
+                              f"factorised route) INSIDE the timed region, ite = {e2e_ite} / burn = 200 / thin = 3 sweeps "
+                              "(the reference's defaults), summaries + chains downloaded; it/s = ite / call time"},
+            "e2e_sweep": {"value": e2e_sweep_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                          "step_s": e2e_steps, "phase_s_create_run_fetch_destroy": e2e_phase[1:],
+                          "covers": "round-1 definition, kept for continuity: handle API with a borrowed decomposition -- "
+                                    f"create + set_y (pinned host) + init + {iters} sweeps + summary/chain download, setDEC "
+                                    "NOT included"},
             "gpu_launches": args.steps if resident["enabled"] else args.steps * iters * (sum(k["launches"] for k in kinfo) + 1),
             "roofline": roofline,
             "cpu_baseline": cpu_base,
+            "c4": c4,
             "sweep": {"algorithmic_bytes_per_iter": bytes_iter, "achieved_gbs_per_gpu": sweep_gbs,
                       "frac_of_hbm_peak": sweep_gbs / pk["hbm_gbs"], "accounting": (("1-pass: eigen basis read from HBM once per kernel step (fused proj+draw+back kernel)"
                                       + ("; expanded kernels stay factorised (U = Z C^-1/2 W): the sweep streams W"
@@ -832,11 +920,16 @@ def main():
                      "frac_of_dgemm_burst": flops / t_contr / 1e12 / dg_burst,
                      "frac_of_dgemm_sustained": flops / t_contr / 1e12 / dg_sust,
                      "quantile_exp_s": t_q, "expansion_s": t_exp, "expansion_gbs": 8.0 * n * n * len(modes) / t_exp / 1e9,
-                     "n_gpus_in_contraction": world, "marker_gen_s": t_gen},
+                     "n_gpus_in_contraction": world, "marker_gen_s": t_gen,
+                     "row_panel_compute_exchange_s": contr_split[-1] if contr_split else None,
+                     "exchange": ("in-place grouped NCCL broadcasts of contiguous column panels inside libbgge_b200 "
+                                  "(bgge_dev_gram_panels)" if world > 1 else None)},
             "eigen": {"setdec_s": t_eig, "problems": n_eig_problems, "L": L, "kept_per_block": nr,
                       "route": "bgge_gibbs_add_expanded_kernel: one L x L syevd per block (factorised, SURVEY 8f-1)"},
         }
         print(json.dumps(line))
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbgge_b200.so")
+# BGGE_LIB selects another build of the same library (e.g. libbgge_b200_checks.so from `make CHECKS=1`)
+LIB_PATH = os.environ.get("BGGE_LIB") or os.path.join(_HERE, "libbgge_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -302,11 +302,11 @@ int launch_iteration(Batch* g) {
     BatchKernel& bk = g->kernels[j];
     double* Uj = g->U.p + (size_t)j * total;
     b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p);
-    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, 64, st));
+    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st));
     b_draw_kernel<<<dim3((unsigned)bk.n_ctiles, (unsigned)((g->Bp + 63) / 64)), 64, 0, st>>>(
         (int)bk.nr_total, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
         g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw);
-    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, 64, st));
+    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st));
     b_update_kernel<<<eg, BT, 0, st>>>(total, g->Bp, bk.ksplit_back, g->Upart.p, total, bk.cover.p, g->R.p, Uj,
                                       g->Um.p + (size_t)j * total, g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn);
     BGGE_CUDA(cudaGetLastError());
@@ -336,8 +336,28 @@ int batch_init(Batch* g) {
   cudaStream_t st = g->stream;
   const int64_t n = g->n;
   const int B = g->B;
-  g->Bp = (int)round_up(B, 64);
+  // chains are padded to a multiple of 8 (one DMMA fragment) only; the N tile width is the instantiated width that
+  // covers Bp with the fewest padded columns, wider tiles first on ties (80 chains -> one 80-wide tile, 320 -> 4 x 80)
+  g->Bp = (int)round_up(B, 8);
   const int Bp = g->Bp;
+  {
+    int best_tn = 128;
+    long best_cols = 1L << 40;
+    for (int k = kGemmTileNCount - 1; k >= 0; --k) {
+      const int tn = kGemmTileN[k];
+      const long cols = (long)((Bp + tn - 1) / tn) * tn;
+      if (cols < best_cols) {
+        best_cols = cols;
+        best_tn = tn;
+      }
+    }
+    if (const char* ev = getenv("BGGE_BATCH_TN")) {   // tuning hook
+      const int v = atoi(ev);
+      for (int k = 0; k < kGemmTileNCount; ++k)
+        if (kGemmTileN[k] == v) best_tn = v;
+    }
+    g->tn = best_tn;
+  }
   const int sms = sm_count();
   g->ncum = g->ite / g->thin;
 
@@ -454,7 +474,7 @@ int batch_init(Batch* g) {
     std::vector<unsigned char> cover((size_t)n, 0);
     for (auto& bl : bk.blocks) std::fill(cover.begin() + bl.pos0, cover.begin() + bl.pos0 + bl.rows, (unsigned char)1);
     BGGE_TRY(up(bk.cover, cover, st));
-    const int ntile_n = Bp / 64;
+    const int ntile_n = (Bp + g->tn - 1) / g->tn;
     // K splits: enough work items that the persistent CTAs end within a few percent of each other
     // (>= 6 items per SM), but at least 24 k-blocks per item so the 4-stage ring fill stays amortised
     auto pick_split = [&](int64_t tiles, int64_t kmax) {
@@ -491,7 +511,7 @@ int batch_init(Batch* g) {
       for (int sp = 0; sp < bk.ksplit_proj; ++sp) {
         const int k0 = (int)((int64_t)kbp * sp / bk.ksplit_proj), k1 = (int)((int64_t)kbp * (sp + 1) / bk.ksplit_proj);
         for (int64_t m0 = 0; m0 < bl.nr; m0 += 128)
-          for (int n0 = 0; n0 < Bp; n0 += 64) {
+          for (int n0 = 0; n0 < Bp; n0 += g->tn) {
             GemmItem t{};
             t.A = bl.dT;
             t.lda = bl.ldt;
@@ -512,7 +532,7 @@ int batch_init(Batch* g) {
       for (int sp = 0; sp < bk.ksplit_back; ++sp) {
         const int k0 = (int)((int64_t)kbb * sp / bk.ksplit_back), k1 = (int)((int64_t)kbb * (sp + 1) / bk.ksplit_back);
         for (int64_t m0 = 0; m0 < bl.rows; m0 += 128)
-          for (int n0 = 0; n0 < Bp; n0 += 64) {
+          for (int n0 = 0; n0 < Bp; n0 += g->tn) {
             GemmItem t{};
             t.A = bl.dU;
             t.lda = bl.ldu;

@@ -26,6 +26,7 @@ struct BatchKernel {
 struct Batch {
   int64_t n = 0;
   int nk = 0, B = 0, Bp = 0, device = 0;
+  int tn = 64;                   // N tile width of the skinny GEMMs (dgemm.cu instantiation)
   cudaStream_t stream = nullptr;
   bool own_stream = false, initialised = false, any_na = false;
   std::vector<BatchKernel> kernels;

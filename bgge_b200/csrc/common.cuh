@@ -100,6 +100,27 @@ struct DevBuf {
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// `make CHECKS=1` builds libbgge_b200_checks.so with device-side assertions in the hand-synchronised kernels (ring
+// indices, shared-memory carve, row ranges): the stand-in for compute-sanitizer, which is closed on this pool
+// (profiles/r02_sanitizer.md).  A failed assertion prints its location and traps (the launch fails loudly).
+#ifdef BGGE_CHECKS
+#define BGGE_DEVASSERT(cond)                                                                                        \
+  do {                                                                                                              \
+    if (!(cond)) {                                                                                                  \
+      printf("[bgge] device assertion failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__,          \
+             (int)blockIdx.x, (int)threadIdx.x);                                                                    \
+      __trap();                                                                                                     \
+    }                                                                                                               \
+  } while (0)
+#else
+#define BGGE_DEVASSERT(cond) ((void)0)
+#endif
+__device__ __forceinline__ uint32_t dynamic_smem_bytes() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+  return v;
+}
+
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
 // while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and
 // its writes are visible (no-op otherwise).  Everything before it may only touch data no earlier launch of the

@@ -140,33 +140,44 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
 
 }  // namespace
 
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
-  if (nitems <= 0) return OK;
-  const int grid = nitems < sm_count() ? nitems : sm_count();
-  static bool attr64s[64] = {false}, attr128s[64] = {false};   // function attributes are per device
+namespace {
+template <int TN>
+int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st) {
+  static bool attr[64] = {false};   // function attributes are per device
   int dev = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
   dev = dev >= 0 && dev < 64 ? dev : 0;
-  bool& attr64 = attr64s[dev];
-  bool& attr128 = attr128s[dev];
-  if (tn == 64) {
-    if (!attr64) {
-      BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64>::BYTES));
-      attr64 = true;
-    }
-    dgemm_dmma_kernel<64><<<grid, GTHREADS, GemmSmem<64>::BYTES, st>>>(d_items, nitems);
-  } else if (tn == 128) {
-    if (!attr128) {
-      BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<128>::BYTES));
-      attr128 = true;
-    }
-    dgemm_dmma_kernel<128><<<grid, GTHREADS, GemmSmem<128>::BYTES, st>>>(d_items, nitems);
-  } else {
-    set_error("dgemm: unsupported N tile %d", tn);
-    return ERR_INVALID;
+  if (!attr[dev]) {
+    BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<TN>::BYTES));
+    attr[dev] = true;
   }
+  const int grid = nitems < sm_count() ? nitems : sm_count();
+  dgemm_dmma_kernel<TN><<<grid, GTHREADS, GemmSmem<TN>::BYTES, st>>>(d_items, nitems);
   BGGE_CUDA(cudaGetLastError());
   return OK;
+}
+}  // namespace
+
+// N tile widths the kernel is instantiated for: the batched sampler picks the one that covers its chain count with
+// the fewest padded columns (80 chains per GPU run as one 80-wide tile, not as two 64-wide ones)
+const int kGemmTileN[] = {16, 32, 40, 48, 64, 80, 96, 128};
+const int kGemmTileNCount = 8;
+
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
+  if (nitems <= 0) return OK;
+  switch (tn) {
+    case 16: return dgemm_launch_t<16>(d_items, nitems, st);
+    case 32: return dgemm_launch_t<32>(d_items, nitems, st);
+    case 40: return dgemm_launch_t<40>(d_items, nitems, st);
+    case 48: return dgemm_launch_t<48>(d_items, nitems, st);
+    case 64: return dgemm_launch_t<64>(d_items, nitems, st);
+    case 80: return dgemm_launch_t<80>(d_items, nitems, st);
+    case 96: return dgemm_launch_t<96>(d_items, nitems, st);
+    case 128: return dgemm_launch_t<128>(d_items, nitems, st);
+    default: break;
+  }
+  set_error("dgemm: unsupported N tile %d", tn);
+  return ERR_INVALID;
 }
 
 }  // namespace bgge

@@ -48,5 +48,7 @@ struct GemmItem {
   int kb0, kb1;         // 16-deep k-blocks [kb0, kb1)
 };
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st);
+extern const int kGemmTileN[];     // instantiated N tile widths, ascending
+extern const int kGemmTileNCount;
 
 }  // namespace bgge

@@ -133,6 +133,8 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
   uint64_t* full = reinterpret_cast<uint64_t*>(zsb + (size_t)NB * 2 * ZB);
   uint64_t* empty = full + F_MAX_NS;
   uint64_t* pbar = empty + F_MAX_NS;
+  BGGE_DEVASSERT(reinterpret_cast<unsigned char*>(pbar + NPX) <= fsm + dynamic_smem_bytes() && ns >= 3 && ns <= F_MAX_NS &&
+                 cs <= F_MAXCS);
 
   // Rows of a ring slot beyond this CTA's slice are never written by the TMA copies; zero the ring once so
   // they stay finite: the hot loops then need no per-row predicates (such rows meet e = 0 in the dots and
@@ -171,6 +173,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
         for (int c0 = pn.c0; c0 < pn.c1; c0 += G) {
           const int slot = pslot;
           const int gc = min(G, pn.c1 - c0);
+          BGGE_DEVASSERT(slot < ns && slice_bytes % 16 == 0 && my_rows <= max_rs && gc * max_rs <= (int)slot_doubles);
           mbar_wait_relaxed(&empty[slot], pphase ^ 1u);
           if (++pslot == ns) {
             pslot = 0;
@@ -220,6 +223,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
       for (int c0 = pn.c0; c0 < pn.c1; c0 += G, ++cc) {
         const int slot = dslot;
         const int gc = min(G, pn.c1 - c0);
+        BGGE_DEVASSERT(slot >= 0 && slot < ns && dpg >= 0 && dpg < npx && npx <= NPX);
         mbar_wait_relaxed(&full[slot], dphase);
         if (++dslot == ns) {
           dslot = 0;

@@ -141,6 +141,11 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
   const size_t slot_doubles = (size_t)G * max_rs;
   const int tvm = merged ? NB : 1;
   const MSmem s = carve<NB>(msm, ns, slot_doubles, tvm);
+  BGGE_DEVASSERT(reinterpret_cast<unsigned char*>(s.zfree + 2) <= msm + dynamic_smem_bytes());
+  BGGE_DEVASSERT(ns >= 3 && ns <= M_MAXNS && lag >= 1 && lag + 1 <= M_NP && ns + lag + 1 <= M_NPX && cs <= M_MAXCS);
+  // unpredicated row steps: the furthest read of the last ring slot stays in front of the mbarriers
+  BGGE_DEVASSERT(s.ring + (size_t)(ns - 1) * slot_doubles + max_rs + (size_t)(KR - 1) * M_T + M_T <= reinterpret_cast<double*>(s.full) ||
+                 cp.y == 0);
 
   // rows of a slot beyond the CTA's slice are never written by the bulk copies: zero everything once so they are
   // finite (they meet e = 0 in the dots and their u accumulators are never stored)
@@ -205,6 +210,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
       for (int h = 0; h < ngroups + lag; ++h) {
         if (h < ngroups) {
           // ---------------------------------------------------------- dots of group h
+          BGGE_DEVASSERT(dslot >= 0 && dslot < ns && (int)(dcnt - acnt) <= lag + 1);
           wait_relaxed(&s.full[dslot], dphase);
           const double* src0 = s.ring + (size_t)dslot * slot_doubles + tid;
           const double* src1 = src0 + max_rs;
@@ -236,6 +242,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
         if (h >= lag) {
           // ---------------------------------------------------------- u += W[:, group h - lag] b
           const uint32_t px = acnt & (M_NPX - 1);
+          BGGE_DEVASSERT(aslot >= 0 && aslot < ns && acnt < dcnt + (h >= ngroups ? lag : 0) + 1);
           wait_relaxed(&s.bready[px], (acnt / M_NPX) & 1u);
           double b[NG];
           const double* bs = s.bsm + (size_t)px * NG;
@@ -289,6 +296,8 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           const double* Ubase = pn.U + row0;
           for (int c0 = pn.c0; c0 < pn.c1; c0 += G) {
             const int gc = min(G, pn.c1 - c0);
+            BGGE_DEVASSERT(pslot < ns && slice_bytes % 16 == 0 && (size_t)my_rows <= (size_t)max_rs &&
+                           ((size_t)(Ubase + (long long)c0 * pn.ldu) & 15) == 0);
             wait_relaxed(&s.empty[pslot], pphase ^ 1u);
             mbar_expect_tx(&s.full[pslot], slice_bytes * (uint32_t)gc);
             if (slice_bytes > 0) {
@@ -349,6 +358,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
               double d = 0.0;
               for (uint32_t q = 0; q < cs; ++q) d += pp[(size_t)q * NG];          // rank order
               const int zb = (int)(batch & 1u) * M_ZB + (rel0 + gq) % M_ZB;
+              BGGE_DEVASSERT(zb >= 0 && zb < 2 * M_ZB && isfinite(d));
               bcoef = s.tvb[(size_t)(merged ? m : 0) * 2 * M_ZB + zb] * d + s.zsb[(size_t)m * 2 * M_ZB + zb];   // R/BGGE.R:303, 89-92
               zq = fma(bcoef * bcoef, s.isb[zb], zq);                              // R/BGGE.R:96
             }

@@ -259,6 +259,7 @@ int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64
 int bgge_batch_init(bgge_batch* h, int64_t ite, int64_t burn, int64_t thin, double R2, uint64_t seed, uint32_t chain0);
 int bgge_batch_run(bgge_batch* h, int64_t iters);
 int bgge_batch_sync(bgge_batch* h);
+/* padded_chains: chain columns the GEMM tiles compute (>= n_chains); gemm_flops_per_iter: 4 rows nr per real chain */
 int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_iter, int* launches_per_iter);
 /* mu[B x n_cum], varE[B x n_cum], varU[nk x B x n_cum] */
 int bgge_batch_chain(bgge_batch* h, double* mu, double* varE, double* varU);

@@ -224,7 +224,10 @@ def test_fit_kernels_one_shot_from_factor_descriptions_matches_oracle(lib, model
     assert got["nfact"] == len(Kf)
     one = _fit_kernels(lib, y, descs, f0["gid"], f0["env"], ne, ite, burn, thin, z, c, XF=XF)
     for key in ("yHat", "cmu", "cve", "cvu", "u", "y"):
-        assert np.array_equal(got[key], one[key]), key                  # chunked == one piece, bit for bit
+        if with_xf:   # the resident kernel converts r <-> r + XF beta at every launch boundary: rounding-level differences
+            assert relmax(got[key], one[key]) <= 1e-12, key
+        else:
+            assert np.array_equal(got[key], one[key]), key              # chunked == one piece, bit for bit
     assert relmax(got["cve"], ref["chain"]["varE"]) <= 1e-9
     assert relmax(got["cmu"], ref["chain"]["mu"]) <= 1e-9
     for j, nm in enumerate(ref["K"]):

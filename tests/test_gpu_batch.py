@@ -71,3 +71,70 @@ def test_batch_large_blocks_split_k():
         for nm in ref["K"]:
             assert relmax(fits[b]["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (b, nm)
         assert relmax(fits[b]["yHat"], ref["yHat"]) <= 1e-9, b
+
+
+@pytest.mark.parametrize("model,B", [("MM", 5), ("MDs", 9)])
+def test_batched_chains_match_the_oracle_draw_for_draw(model, B):
+    """the batched sampler against the ORACLE, not against the single-chain CUDA sampler.  Chain b draws from
+    the Philox stream (seed, chain0 + b); helpers.PhiloxDraws regenerates exactly that stream on the host and feeds it
+    to the oracle in the reference's call order.  Folds (different NA masks per chain), D and BD kernels."""
+    import bgge_b200
+    from helpers import PhiloxDraws
+    L, E, p = 50, 3, 70
+    X = markers(L, p, 13)
+    Y, names = design(L, E)
+    n = L * E
+    ne = [L] * E
+    Kf = bgge_b200.getK(Y, X, kernel="GB", model=model, rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel="GB", model=model, rownames=names)
+    rng = np.random.default_rng(14)
+    y = rng.standard_normal(n)
+    perm = rng.permutation(L)
+    Yb = np.empty((B, n))
+    for b in range(B):
+        Yb[b] = y
+        Yb[b, np.tile(perm % 5 == b % 5, E)] = np.nan      # fold b % 5 masked in every environment
+    Yb[0] = y                                              # one chain without missing values
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(bk["s"].shape[0] for bk in bl) for bl in Ei]
+    ite, burn, thin, seed, chain0 = 12, 2, 2, 77, 3
+    fits = bgge_b200.BGGE_batch(Yb, Kf, ne=ne, ite=ite, burn=burn, thin=thin, seed=seed, chain0=chain0, eig=Ei)
+    for b in range(B):
+        draws = PhiloxDraws(seed, chain0 + b, n, nrs, n_na=int(np.isnan(Yb[b]).sum()))
+        ref = oracle.BGGE(Yb[b], Kd, ne=ne, ite=ite, burn=burn, thin=thin, draws=draws, eig=Ei)
+        got = fits[b]
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, b
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, b
+        for nm in ref["K"]:
+            assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9, (b, nm)
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (b, nm)
+        assert relmax(got["yHat"], ref["yHat"]) <= 1e-9, b
+        assert relmax(got["y"], ref["y"]) <= 1e-9, b
+
+
+def test_single_chain_device_rng_matches_the_oracle_draw_for_draw():
+    """The same for the single-chain sampler with XF: device Philox draws == the host mirror, so a device-RNG run can be
+    checked against the oracle exactly, not only statistically."""
+    import bgge_b200
+    from helpers import PhiloxDraws
+    L, E, p = 40, 3, 60
+    X = markers(L, p, 2)
+    Y, names = design(L, E)
+    n = L * E
+    ne = [L] * E
+    Kf = bgge_b200.getK(Y, X, kernel="GK", model="MDs", rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel="GK", model="MDs", rownames=names)
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(n)
+    y[rng.choice(n, 6, replace=False)] = np.nan
+    XF = np.zeros((n, E))
+    for e in range(E):
+        XF[e * L:(e + 1) * L, e] = 1.0
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(bk["s"].shape[0] for bk in bl) for bl in Ei]
+    for mode in (1, 2):
+        got = bgge_b200.BGGE(y, Kf, XF=XF, ne=ne, ite=15, burn=3, thin=2, seed=9, chain=4, eig=Ei, mode=mode)
+        ref = oracle.BGGE(y, Kd, XF=XF, ne=ne, ite=15, burn=3, thin=2, draws=PhiloxDraws(9, 4, n, nrs, q=E, n_na=6), eig=Ei)
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, mode
+        assert relmax(np.asarray(got["yHat"]).ravel(), np.asarray(ref["yHat"]).ravel()) <= 1e-9, mode
