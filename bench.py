@@ -807,6 +807,11 @@ def main():
         nrj = sum(b[2] for b in blocks[j])
         basis = kinfo[j]["basis_bytes"]                   # W (not U) for blocks the sweep keeps factorised
         u_bytes += basis
+        if merged_units["units"] and blocks[j] and len(blocks[j]) == 1 and basis != 8 * blocks[j][0][1] * nrj and j > 0:
+            # member of a merged unit: the timed graph streams the shared W once per unit (accounted to the unit's
+            # first kernel in `basis_bytes`), but the per-kernel times below come from the UNMERGED instrumented
+            # launches, each of which streams the whole matrix -- credit those launches with what they move
+            basis = 8 * blocks[j][0][1] * nrj
         if kinfo[j]["fused"]:
             ncl = kinfo[j]["clusters"]
             kern.append({"name": f"{'sweep_mrhs_kernel' if kinfo[j]['path'] == 2 else 'sweep_fused_kernel'}[{j}]", "ms": prof_ms[2 * j],
