@@ -278,7 +278,7 @@ def run_c4(args, torch, dist, lib, world, rank, local, device, stream_t, emit=Tr
     from bgge_b200 import multigpu
     L, p, E, kernel, model, desc = WORKLOADS[args.workload]
     n = L * E
-    n_total = 320 if args.workload == "c4" else 12
+    n_total = args.chains or (320 if args.workload == "c4" else 12)
     units = list(multigpu.shard_units(n_total, world, rank))
     B = len(units)
     iters = args.iters or (200 if args.workload == "c4" else 20)
@@ -444,6 +444,7 @@ def main():
     ap.add_argument("--prof-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-ref", action="store_true", help="skip the extra dense-basis measurement")
+    ap.add_argument("--chains", type=int, default=0, help="c4: total number of chains x folds (default 320)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (320 chains x folds) sub-record of the default line")
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass proj/back kernels (no fused sweep)")
     ap.add_argument("--shard-chain", action="store_true",

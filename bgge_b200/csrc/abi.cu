@@ -40,8 +40,8 @@ std::mutex g_pool_mu;
 std::map<void*, PoolBlock> g_pool_live;                          // blocks handed out
 std::multimap<std::pair<int, size_t>, void*> g_pool_free;        // (device, bytes) -> cached block
 size_t g_pool_cached = 0;
-constexpr size_t POOL_MAX_BLOCK = 512ull << 20;                  // larger blocks go straight back to the driver
-constexpr size_t POOL_MAX_CACHED = 2048ull << 20;
+constexpr size_t POOL_MAX_BLOCK = 2048ull << 20;                 // larger blocks go straight back to the driver
+constexpr size_t POOL_MAX_CACHED = 4096ull << 20;                // (syevd and K-split workspaces of the C5 shapes are 1-2 GB)
 
 size_t pool_round(size_t b) {
   if (b <= (1u << 20)) {

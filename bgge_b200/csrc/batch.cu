@@ -70,19 +70,23 @@ __global__ void b_eprime_kernel(long long total, int Bp, const double* __restric
 }
 
 // d = sum of K-split partials; b = tau v d + sqrt(v) z; partial sums of b^2/s        (R/BGGE.R:302-305, 96)
-__global__ void b_draw_kernel(int nr, int B, int Bp, int nsplit, const double* __restrict__ Dpart, long long dstride,
-                              const double* __restrict__ s, const double* __restrict__ sigb, const double* __restrict__ tau,
-                              double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp,
-                              int j, DrawCfg dc) {
-  const int b = blockIdx.y * blockDim.x + threadIdx.x;
-  if (b >= Bp) return;
-  const int c0 = blockIdx.x * 32;
+// Small kernels of the batched sampler are tiled as (32 chains) x (8 row / column lanes): with few chains per GPU
+// (40 at 8 GPUs) a thread-per-chain layout leaves the chip idle behind long serial loops (r02: b_draw 79 us at B = 40).
+constexpr int TX = 32, TY = 8;
+
+__global__ void __launch_bounds__(TX * TY)
+b_draw_kernel(int nr, int B, int Bp, int nsplit, const double* __restrict__ Dpart, long long dstride,
+              const double* __restrict__ s, const double* __restrict__ sigb, const double* __restrict__ tau,
+              double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp, int j, DrawCfg dc) {
+  __shared__ double zs[TY][TX];
+  const int b = blockIdx.y * TX + threadIdx.x, cy = threadIdx.y;
+  const int c0 = blockIdx.x * 32, c1 = min(nr, c0 + 32);
   const long long it = *itp;
   double zq = 0.0;
   if (b < B) {
     const DrawCfg c = chain_cfg(dc, b);
     const double lam = sigb[b], tb = tau[b];
-    for (int cc = c0; cc < min(nr, c0 + 32); ++cc) {
+    for (int cc = c0 + cy; cc < c1; cc += TY) {
       double d = 0.0;
       for (int sp = 0; sp < nsplit; ++sp) d += Dpart[(long long)sp * dstride + (long long)cc * Bp + b];
       const double sv = s[cc];
@@ -93,10 +97,17 @@ __global__ void b_draw_kernel(int nr, int B, int Bp, int nsplit, const double* _
       Bm[(long long)cc * Bp + b] = bv;
       zq += bv * bv * (1.0 / sv);
     }
-  } else {
-    for (int cc = c0; cc < min(nr, c0 + 32); ++cc) Bm[(long long)cc * Bp + b] = 0.0;
+  } else if (b < Bp) {
+    for (int cc = c0 + cy; cc < c1; cc += TY) Bm[(long long)cc * Bp + b] = 0.0;
   }
-  zqpart[(long long)blockIdx.x * Bp + b] = zq;
+  zs[cy][threadIdx.x] = zq;
+  __syncthreads();
+  if (cy == 0 && b < Bp) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];   // fixed order
+    zqpart[(long long)blockIdx.x * Bp + b] = t;
+  }
 }
 
 // u_new = sum of K-split partials; R = (R + u_old) - u_new; Welford of kept draws     (R/BGGE.R:306-307, 392)
@@ -122,19 +133,36 @@ __global__ void b_update_kernel(long long total, int Bp, int nsplit, const doubl
 }
 
 // partial[chunk][b] = sum over a row chunk of (R - shift)^2   (mode 0)  or of R (mode 1)
-__global__ void b_colsum_kernel(long long n, int Bp, int rows_per_chunk, const double* __restrict__ R,
-                                const double* __restrict__ shift, int mode, double* __restrict__ part) {
-  const int b = blockIdx.y * blockDim.x + threadIdx.x;
-  if (b >= Bp) return;
+__global__ void __launch_bounds__(TX * TY)
+b_colsum_kernel(long long n, int Bp, int rows_per_chunk, const double* __restrict__ R, const double* __restrict__ shift,
+                int mode, double* __restrict__ part) {
+  __shared__ double zs[TY][TX];
+  const int b = blockIdx.y * TX + threadIdx.x, ry = threadIdx.y;
   const long long i0 = (long long)blockIdx.x * rows_per_chunk;
   const long long i1 = min(n, i0 + rows_per_chunk);
-  const double sh = mode == 0 ? shift[b] : 0.0;
   double a = 0.0;
-  for (long long i = i0; i < i1; ++i) {
-    const double v = R[i * Bp + b] - sh;
-    a = mode == 0 ? fma(v, v, a) : a + v;
+  if (b < Bp) {
+    const double sh = mode == 0 ? shift[b] : 0.0;
+    for (long long i = i0 + ry; i < i1; i += TY) {
+      const double v = R[i * Bp + b] - sh;
+      a = mode == 0 ? fma(v, v, a) : a + v;
+    }
   }
-  part[(long long)blockIdx.x * Bp + b] = a;
+  zs[ry][threadIdx.x] = a;
+  __syncthreads();
+  if (ry == 0 && b < Bp) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];
+    part[(long long)blockIdx.x * Bp + b] = t;
+  }
+}
+
+// sum of count values p[k * stride] by one warp in a fixed order: lane-strided partial sums, then a xor tree
+__device__ __forceinline__ double warp_sum_strided(const double* __restrict__ p, int count, long long stride, int lane) {
+  double a = 0.0;
+  for (int k = lane; k < count; k += 32) a += p[(long long)k * stride];
+  return warp_sum(a);
 }
 
 struct ChainArgs {
@@ -159,34 +187,44 @@ struct ChainArgs {
   double* chain_varU;
 };
 
-// per chain: sigb_j, sigsq, tau        (R/BGGE.R:95-103, 360-367)
-__global__ void b_chain_var_kernel(const ChainArgs a, DrawCfg dc) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// per chain (one warp each): sigb_j, sigsq, tau        (R/BGGE.R:95-103, 360-367)
+// the sums are formed by the whole warp; then lane j draws the chi-square of kernel j and lane nk the residual one, so
+// the Marsaglia-Tsang rejection loops run side by side instead of one after the other
+__global__ void __launch_bounds__(128) b_chain_var_kernel(const ChainArgs a, DrawCfg dc) {
+  __shared__ double ss[4][MAXK + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + w;
   if (b >= a.B) return;
   const long long it = *a.it;
   const DrawCfg c = chain_cfg(dc, b);
   for (int j = 0; j < a.nk; ++j) {
-    double zq = 0.0;
-    for (int k = 0; k < a.n_zq[j]; ++k) zq += a.zqpart[j][(long long)k * a.Bp + b];
-    const double chi = draw_chisq(c, it, STREAM_CHI_K + (uint32_t)j, (double)a.nr[j] + NU, 0);
-    a.sigb[(long long)j * a.Bp + b] = (zq + NU * a.Sc[(long long)j * a.Bp + b]) / chi;
+    const double zq = warp_sum_strided(a.zqpart[j] + b, a.n_zq[j], a.Bp, lane);   // sum b^2/s
+    if (lane == 0) ss[w][j] = zq;
   }
-  double sse = 0.0;
-  for (int k = 0; k < a.nchunks; ++k) sse += a.part[(long long)k * a.Bp + b];
-  const double chi = draw_chisq(c, it, STREAM_CHI_E, (double)a.n + NU, 0);
-  const double s2 = (sse + a.Sce[b]) / chi;
-  a.sigsq[b] = s2;
-  a.tau[b] = 1.0 / s2;
+  const double sse = warp_sum_strided(a.part + b, a.nchunks, a.Bp, lane);         // e'e
+  if (lane == 0) ss[w][a.nk] = sse;
+  __syncwarp();
+  for (int j = lane; j <= a.nk; j += 32) {
+    if (j < a.nk) {
+      const double chi = draw_chisq(c, it, STREAM_CHI_K + (uint32_t)j, (double)a.nr[j] + NU, 0);
+      a.sigb[(long long)j * a.Bp + b] = (ss[w][j] + NU * a.Sc[(long long)j * a.Bp + b]) / chi;
+    } else {
+      const double chi = draw_chisq(c, it, STREAM_CHI_E, (double)a.n + NU, 0);
+      const double s2 = (ss[w][j] + a.Sce[b]) / chi;
+      a.sigsq[b] = s2;
+      a.tau[b] = 1.0 / s2;
+    }
+  }
 }
 
 // NA imputation (R/BGGE.R:370-381) fused with the column sums of r for the next intercept
-__global__ void b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double* __restrict__ R,
-                                 const double* __restrict__ U, double* __restrict__ Y, const int* __restrict__ narank,
-                                 const double* __restrict__ mu, const double* __restrict__ shift,
-                                 const double* __restrict__ sigsq, const long long* __restrict__ itp, int do_na,
-                                 double* __restrict__ part, DrawCfg dc) {
-  const int b = blockIdx.y * blockDim.x + threadIdx.x;
-  if (b >= Bp) return;
+__global__ void __launch_bounds__(TX * TY)
+b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double* __restrict__ R,
+                 const double* __restrict__ U, double* __restrict__ Y, const int* __restrict__ narank,
+                 const double* __restrict__ mu, const double* __restrict__ shift, const double* __restrict__ sigsq,
+                 const long long* __restrict__ itp, int do_na, double* __restrict__ part, DrawCfg dc) {
+  __shared__ double zs[TY][TX];
+  const int b = blockIdx.y * TX + threadIdx.x, ry = threadIdx.y;
   const long long i0 = (long long)blockIdx.x * rows_per_chunk;
   const long long i1 = min(n, i0 + rows_per_chunk);
   const long long it = *itp;
@@ -194,7 +232,7 @@ __global__ void b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_pe
   if (b < B) {
     const DrawCfg c = chain_cfg(dc, b);
     const double mub = mu[b], shb = shift[b], sd = sqrt(sigsq[b]);
-    for (long long i = i0; i < i1; ++i) {
+    for (long long i = i0 + ry; i < i1; i += TY) {
       const long long idx = i * Bp + b;
       double rv = R[idx];
       if (do_na) {
@@ -212,32 +250,38 @@ __global__ void b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_pe
       a += rv;
     }
   }
-  part[(long long)blockIdx.x * Bp + b] = a;
+  zs[ry][threadIdx.x] = a;
+  __syncthreads();
+  if (ry == 0 && b < Bp) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];
+    part[(long long)blockIdx.x * Bp + b] = t;
+  }
 }
 
 // per chain: record the thinned chain (R/BGGE.R:384-395), draw the next intercept (R/BGGE.R:278-281)
 __global__ void b_advance_kernel(long long* it) { *it += 1; }
 
-__global__ void b_chain_mu_kernel(const ChainArgs a, DrawCfg dc) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, DrawCfg dc) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= a.B) return;
   const long long it = *a.it;
-  if (b < a.B) {
-    const DrawCfg c = chain_cfg(dc, b);
-    if (it > 0 && it % a.thin == 0) {
-      const long long slot = it / a.thin - 1;
-      if (slot < a.ncum) {
-        a.chain_mu[slot * a.Bp + b] = a.mu[b];
-        a.chain_varE[slot * a.Bp + b] = a.sigsq[b];
-        for (int j = 0; j < a.nk; ++j) a.chain_varU[((long long)j * a.ncum + slot) * a.Bp + b] = a.sigb[(long long)j * a.Bp + b];
-      }
+  const double sr = warp_sum_strided(a.part + b, a.nchunks, a.Bp, lane);
+  if (lane != 0) return;
+  const DrawCfg c = chain_cfg(dc, b);
+  if (it > 0 && it % a.thin == 0) {
+    const long long slot = it / a.thin - 1;
+    if (slot < a.ncum) {
+      a.chain_mu[slot * a.Bp + b] = a.mu[b];
+      a.chain_varE[slot * a.Bp + b] = a.sigsq[b];
+      for (int j = 0; j < a.nk; ++j) a.chain_varU[((long long)j * a.ncum + slot) * a.Bp + b] = a.sigb[(long long)j * a.Bp + b];
     }
-    double sr = 0.0;
-    for (int k = 0; k < a.nchunks; ++k) sr += a.part[(long long)k * a.Bp + b];
-    const double z = draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
-    const double nmu = (sr / (double)a.n + a.mu0[b]) + sqrt(a.sigsq[b] / (double)a.n) * z;
-    a.mu[b] = nmu;
-    a.shift[b] = nmu - a.mu0[b];
   }
+  const double z = draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
+  const double nmu = (sr / (double)a.n + a.mu0[b]) + sqrt(a.sigsq[b] / (double)a.n) * z;
+  a.mu[b] = nmu;
+  a.shift[b] = nmu - a.mu0[b];
 }
 
 template <typename T>
@@ -279,13 +323,14 @@ ChainArgs chain_args(Batch* g, const double* part) {
 
 int launch_tail(Batch* g, bool init) {
   cudaStream_t st = g->stream;
-  const dim3 cgrid((unsigned)g->nchunks, (unsigned)((g->Bp + BT - 1) / BT));
-  const unsigned cb = (unsigned)((g->B + 127) / 128);
+  const dim3 cgrid((unsigned)g->nchunks, (unsigned)((g->Bp + TX - 1) / TX));
+  const dim3 cblock(TX, TY);
+  const unsigned cb = (unsigned)((g->B + 3) / 4);   // one warp per chain
   if (!init) {
-    b_colsum_kernel<<<cgrid, BT, 0, st>>>(g->n, g->Bp, g->rows_per_chunk, g->R.p, g->shift.p, 0, g->part.p);
+    b_colsum_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->Bp, g->rows_per_chunk, g->R.p, g->shift.p, 0, g->part.p);
     b_chain_var_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part.p), g->draw);
   }
-  b_na_sumr_kernel<<<cgrid, BT, 0, st>>>(g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p, g->narank.p,
+  b_na_sumr_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p, g->narank.p,
                                         g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p,
                                         g->draw);
   b_chain_mu_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part2.p), g->draw);
@@ -303,7 +348,7 @@ int launch_iteration(Batch* g) {
     double* Uj = g->U.p + (size_t)j * total;
     b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p);
     BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st));
-    b_draw_kernel<<<dim3((unsigned)bk.n_ctiles, (unsigned)((g->Bp + 63) / 64)), 64, 0, st>>>(
+    b_draw_kernel<<<dim3((unsigned)bk.n_ctiles, (unsigned)((g->Bp + TX - 1) / TX)), dim3(TX, TY), 0, st>>>(
         (int)bk.nr_total, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
         g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw);
     BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st));
@@ -430,7 +475,8 @@ int batch_init(Batch* g) {
   BGGE_CUDA(cudaMemsetAsync(g->Ep.p, 0, (total + 64) * sizeof(double), st));
   BGGE_CUDA(g->it.alloc(1));
   BGGE_CUDA(cudaMemsetAsync(g->it.p, 0, sizeof(long long), st));
-  g->rows_per_chunk = (int)std::max<int64_t>(32, (n + 2 * sms - 1) / (2 * sms));
+  // row chunks of the column sums / the imputation pass: >= 4 blocks per SM and chain tile, a multiple of the 8 row lanes
+  g->rows_per_chunk = (int)std::max<int64_t>(16, round_up((n + 4 * sms - 1) / (4 * sms), TY));
   g->nchunks = (int)((n + g->rows_per_chunk - 1) / g->rows_per_chunk);
   BGGE_CUDA(g->part.alloc((size_t)g->nchunks * Bp));
   BGGE_CUDA(g->part2.alloc((size_t)g->nchunks * Bp));
@@ -475,23 +521,36 @@ int batch_init(Batch* g) {
     for (auto& bl : bk.blocks) std::fill(cover.begin() + bl.pos0, cover.begin() + bl.pos0 + bl.rows, (unsigned char)1);
     BGGE_TRY(up(bk.cover, cover, st));
     const int ntile_n = (Bp + g->tn - 1) / g->tn;
-    // K splits: enough work items that the persistent CTAs end within a few percent of each other
-    // (>= 6 items per SM), but at least 24 k-blocks per item so the 4-stage ring fill stays amortised
-    auto pick_split = [&](int64_t tiles, int64_t kmax) {
+    // K splits: a cost model in microseconds -- waves of persistent CTAs x (k-blocks per item at the FP64 tensor
+    // rate + ring fill / epilogue) + the traffic of the per-split partial outputs.  (r01's model charged the partial
+    // sums as if the output were as large as at 320 chains; at 40 chains per GPU it picked too few splits and left
+    // a quarter of the SMs idle.)
+    auto pick_split = [&](int64_t tiles, int64_t kmax, int64_t mtot) {
       const int64_t kblocks = (kmax + 15) / 16;
+      const double t_kb = 32.0 * g->tn / 1.9e3;                       // 128 x tn x 16 FMAs at 64 FMA / clk / SM, ~1.9 GHz
+      const double t_fix = 3.0;
+      const double t_part = 2.0 * 8.0 * (double)mtot * Bp / 3.0e6;    // write + re-read of one split's partial C at ~3 TB/s
       int best = 1;
       double best_cost = 1e300;
-      for (int sp = 1; sp <= 32 && kblocks / sp >= 24; ++sp) {
+      for (int sp = 1; sp <= 32 && (sp == 1 || kblocks / sp >= 12); ++sp) {
         const int64_t items = tiles * ntile_n * sp;
         const double waves = (double)((items + sms - 1) / sms);
-        const double per_item = (double)kblocks / sp + 6.0;          // + ring fill / epilogue, in k-block units
-        const double cost = waves * per_item + 0.02 * sp * kblocks;  // + partial-sum traffic
+        const double cost = waves * ((double)((kblocks + sp - 1) / sp) * t_kb + t_fix) + sp * t_part;
         if (cost < best_cost) { best_cost = cost; best = sp; }
       }
       return best;
     };
-    bk.ksplit_proj = pick_split(proj_tiles, max_rows);
-    bk.ksplit_back = pick_split(back_tiles, max_nr);
+    int64_t rows_tot = 0;
+    for (auto& bl : bk.blocks) rows_tot += bl.rows;
+    bk.ksplit_proj = pick_split(proj_tiles, max_rows, bk.nr_total);
+    bk.ksplit_back = pick_split(back_tiles, max_nr, rows_tot);
+    if (const char* ev = getenv("BGGE_BATCH_KSPLIT")) {   // tuning hook: "proj,back"
+      int a1 = 0, a2 = 0;
+      if (sscanf(ev, "%d,%d", &a1, &a2) == 2 && a1 >= 1 && a1 <= 32 && a2 >= 1 && a2 <= 32) {
+        bk.ksplit_proj = a1;
+        bk.ksplit_back = a2;
+      }
+    }
     max_ksplit_back = std::max(max_ksplit_back, bk.ksplit_back);
     bk.nr_pad = round_up(bk.nr_total, 32);
     bk.n_ctiles = (int)((bk.nr_total + 31) / 32);

@@ -148,6 +148,7 @@ struct HostKernel {
   int fused_nb = 1;              // right-hand sides per panel the fused kernel is instantiated for (1, 2 or 4)
   int fused_engine = 0;          // 0: sweep_fused_kernel, 1: sweep_mrhs_kernel (multi-RHS panels, sweep_mrhs.cu)
   int fused_kr = 0, fused_lag = 0;   // engine 1: row steps per compute thread, groups between dots and axpy
+  int fused_tmem = 0;            // engine 1: residual slices kept in tensor memory (2-CTA clusters for 4 members)
   DevBuf<VDesc> vdesc;           // factorised blocks of this kernel (one gather launch for all of them)
   int n_vdesc = 0, vgrid = 0;
   // column-sharded chain (bgge_gibbs_set_shard): this process' partial W b and sum b^2/s of the kernel step, in one

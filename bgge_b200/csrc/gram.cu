@@ -39,7 +39,8 @@ constexpr size_t GRAM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __restrict__ tiles,
                  int ntiles, double* __restrict__ S, double* __restrict__ Spart, int64_t part_stride, int64_t pld,
-                 int64_t prow_off, int64_t lds, int64_t L, int64_t row_off, double divisor, int mirror) {
+                 int64_t prow_off, int64_t prow_thr, int64_t prow_off2, int64_t lds, int64_t L, int64_t row_off,
+                 double divisor, int mirror) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)STAGES * STAGE_DOUBLES);
@@ -128,7 +129,8 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __re
     const bool lower = !direct || mirror != 2;
     const bool upper = direct && (mirror == 2 || (mirror == 1 && tc.ti != tc.tj));
     double* out = direct ? S : Spart + (int64_t)tc.split * part_stride;
-    const int64_t old = direct ? lds : pld, oro = direct ? row_off : prow_off;
+    // K-split partials live in a compact workspace over the rows of this launch's (one or two) tile-row panels
+    const int64_t old = direct ? lds : pld, oro = direct ? row_off : ((int64_t)tc.ti * TM >= prow_thr ? prow_off2 : prow_off);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t gi = gi0 + i * 8;
@@ -151,15 +153,15 @@ gram_dmma_kernel(const double* __restrict__ X, int64_t ldx, const GramItem* __re
 // sums the K-split partials of every tile in fixed order, scales, stores (+ mirror)
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const GramItem* __restrict__ tiles, int nsplit, const double* __restrict__ Spart,
-                   int64_t part_stride, int64_t pld, int64_t prow_off, double* __restrict__ S, int64_t lds, int64_t L,
-                   int64_t row_off, double divisor, int mirror) {
+                   int64_t part_stride, int64_t pld, int64_t prow_off, int64_t prow_thr, int64_t prow_off2,
+                   double* __restrict__ S, int64_t lds, int64_t L, int64_t row_off, double divisor, int mirror) {
   const GramItem tc = tiles[blockIdx.x];   // the split-0 item of each tile
   const int64_t i = (int64_t)tc.ti * TM + (threadIdx.x & 127);
   if (i >= L) return;
   for (int c = threadIdx.x >> 7; c < TN; c += 2) {
     const int64_t jx = (int64_t)tc.tj * TN + c;
     if (jx >= L) break;
-    const int64_t poff = (i - prow_off) + jx * pld;
+    const int64_t poff = (i - (i >= prow_thr ? prow_off2 : prow_off)) + jx * pld;
     double v = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) v += Spart[(int64_t)sp * part_stride + poff];
     v /= divisor;
@@ -224,10 +226,19 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   DevBuf<double> part;
   BGGE_CUDA(d_items.alloc(items.size()));
   BGGE_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(GramItem), cudaMemcpyHostToDevice, st));
-  // K-split partials: compact workspace over the tile rows of this launch (rows [prow_off, prow_off + pld))
-  const int64_t trlo = tr1b > tr0b ? std::min(tr0, tr0b) : tr0, trhi = tr1b > tr0b ? std::max(tr1, tr1b) : tr1;
-  const int64_t prow_off = trlo * TM, pld = (trhi - trlo) * TM;
-  const int64_t part_stride = pld * std::min<int64_t>(L, trhi * TM);
+  // K-split partials: compact workspace over the rows of this launch's panels -- panel A = the lower tile-row range,
+  // panel B (if any) right behind it: workspace row = i - prow_off for i < prow_thr, else i - prow_off2
+  int64_t a0 = tr0, a1 = tr1, b0 = tr0b, b1 = tr1b;
+  if (b1 > b0 && b0 < a0) {
+    std::swap(a0, b0);
+    std::swap(a1, b1);
+  }
+  const bool two = b1 > b0;
+  BGGE_REQUIRE(!two || a1 <= b0, "gram: the two tile-row panels overlap");
+  const int64_t rowsA = (a1 - a0) * TM, rowsB = two ? (b1 - b0) * TM : 0;
+  const int64_t prow_off = a0 * TM, prow_thr = two ? b0 * TM : (int64_t)1 << 60, prow_off2 = two ? b0 * TM - rowsA : 0;
+  const int64_t pld = rowsA + rowsB;
+  const int64_t part_stride = pld * std::min<int64_t>(L, (two ? b1 : a1) * TM);
   if (nsplit > 1) BGGE_CUDA(part.alloc((size_t)part_stride * nsplit));
   static bool attr_set[64] = {false};   // function attributes are per device
   int dev = 0;
@@ -239,11 +250,12 @@ int gram_launch(const double* dX, int64_t ldx, int64_t L, int64_t p_pad, int64_t
   const int nitems = (int)items.size();
   const int grid = nitems < sms ? nitems : sms;
   gram_dmma_kernel<<<grid, NTHREADS, GRAM_SMEM, st>>>(dX, ldx, d_items.p, nitems, dS, nsplit > 1 ? part.p : nullptr,
-                                                       part_stride, pld, prow_off, lds, L, row_off, divisor, mirror);
+                                                       part_stride, pld, prow_off, prow_thr, prow_off2, lds, L, row_off,
+                                                       divisor, mirror);
   BGGE_CUDA(cudaGetLastError());
   if (nsplit > 1) {
-    gram_reduce_kernel<<<(unsigned)ntiles, 256, 0, st>>>(d_items.p, nsplit, part.p, part_stride, pld, prow_off, dS, lds, L,
-                                                        row_off, divisor, mirror);
+    gram_reduce_kernel<<<(unsigned)ntiles, 256, 0, st>>>(d_items.p, nsplit, part.p, part_stride, pld, prow_off, prow_thr,
+                                                        prow_off2, dS, lds, L, row_off, divisor, mirror);
     BGGE_CUDA(cudaGetLastError());
   }
   BGGE_CUDA(cudaStreamSynchronize(st));   // the item list and the workspace die here

@@ -732,7 +732,8 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
     if (mc.ok) {
       hk.fused_engine = 1;
       cs = mc.cs;
-      gcols = MRHS_G;
+      gcols = mc.g;
+      hk.fused_tmem = mc.tmem;
       ncl = mc.clusters;
       hk.fused_cs = cs;
       hk.fused_rpt = 0;

@@ -38,7 +38,6 @@ namespace {
 constexpr int M_NCW = 12;                  // compute warps
 constexpr int M_T = M_NCW * 32;            // compute threads
 constexpr int M_THREADS = M_T + 128;       // + helper warpgroup (producer, pusher, coefficient, draw)
-constexpr int M_G = MRHS_G;                // columns per exchange group
 constexpr int M_NP = 4;                    // warp-partial ring (>= lag + 1)
 constexpr int M_NPX = 16;                  // exchange / coefficient ring (>= ns + lag + 1)
 constexpr int M_ZB = 64;                   // columns per draw batch
@@ -96,11 +95,12 @@ __device__ __forceinline__ double multi_reduce(double (&a)[P], int lane, int& id
 struct MSmem {            // carve of the dynamic shared memory (all offsets in doubles from the base)
   double *ring, *wp, *parts, *bsm, *tvb, *isb, *zsb;
   uint64_t *full, *empty, *dotdone, *pbar, *bready, *zready, *zfree;
+  uint32_t* tmem;   // tensor-memory base address (TM variant)
 };
 
-template <int NB>
+template <int NB, int G>
 __device__ __forceinline__ MSmem carve(unsigned char* base, int ns, size_t slot_doubles, int tvm) {
-  constexpr int NG = NB * M_G;
+  constexpr int NG = NB * G;
   MSmem s;
   s.ring = reinterpret_cast<double*>(base);
   s.wp = s.ring + (size_t)ns * slot_doubles;
@@ -116,10 +116,48 @@ __device__ __forceinline__ MSmem carve(unsigned char* base, int ns, size_t slot_
   s.bready = s.pbar + M_NPX;
   s.zready = s.bready + M_NPX;
   s.zfree = s.zready + 2;
+  s.tmem = reinterpret_cast<uint32_t*>(s.zfree + 2);
   return s;
 }
 
-template <int KR, int NB>
+// ---- tensor memory (TMEM, 256 KB per SM) as a per-thread scratchpad: tcgen05.st / tcgen05.ld in the 32x32b shape move
+// N consecutive 32-bit columns of the calling thread's own lane (lane quarter = warp % 4), SASS STTM / LDTM.
+template <int NB>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const double (&v)[NB]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  if constexpr (NB == 4) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+  }
+}
+template <int NB>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&r)[2 * NB]) {
+  if constexpr (NB == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+
+// G = eigen-columns per exchange group (= per ring slot).  TM = false: e_m and u in registers (KR * NB <= 28).
+// TM = true: e_m lives in tensor memory (written once per panel with tcgen05.st, read back one row step at a time with
+// tcgen05.ld), only u stays in registers, so twice the rows fit a CTA: 2-CTA clusters hold a 10000-row, 4-member
+// panel and 74 clusters cover all 148 SMs.
+template <int KR, int NB, int G, bool TM>
 __global__ void __launch_bounds__(M_THREADS, 1)
 sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cluster_panels,
                   const double* __restrict__ r, const double* __restrict__ u_all, double* __restrict__ upart,
@@ -131,8 +169,8 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
   const uint32_t cs = cluster.num_blocks();
   const int cid = blockIdx.x / cs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NG = NB * M_G;
-  constexpr int G = M_G;
+  constexpr int NG = NB * G;
+  static_assert(G == 1 || G == 2, "one or two columns per group");
 
   extern __shared__ __align__(128) unsigned char msm[];
   const int2 cp = cluster_panels[cid];
@@ -140,8 +178,8 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
   for (int pi = 0; pi < cp.y; ++pi) max_rs = max(max_rs, panels[cp.x + pi].rs);
   const size_t slot_doubles = (size_t)G * max_rs;
   const int tvm = merged ? NB : 1;
-  const MSmem s = carve<NB>(msm, ns, slot_doubles, tvm);
-  BGGE_DEVASSERT(reinterpret_cast<unsigned char*>(s.zfree + 2) <= msm + dynamic_smem_bytes());
+  const MSmem s = carve<NB, G>(msm, ns, slot_doubles, tvm);
+  BGGE_DEVASSERT(reinterpret_cast<unsigned char*>(s.tmem + 4) <= msm + dynamic_smem_bytes());
   BGGE_DEVASSERT(ns >= 3 && ns <= M_MAXNS && lag >= 1 && lag + 1 <= M_NP && ns + lag + 1 <= M_NPX && cs <= M_MAXCS);
   // unpredicated row steps: the furthest read of the last ring slot stays in front of the mbarriers
   BGGE_DEVASSERT(s.ring + (size_t)(ns - 1) * slot_doubles + max_rs + (size_t)(KR - 1) * M_T + M_T <= reinterpret_cast<double*>(s.full) ||
@@ -167,7 +205,19 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
     }
     mbar_fence_init();
   }
+  if constexpr (TM) {
+    if (warp == M_NCW) {   // the producer warp owns the allocation (all 512 columns: one CTA per SM)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   cluster.sync();   // every CTA's barriers exist (and its shared memory is zeroed) before anybody sends
+  uint32_t tbase = 0;
+  if constexpr (TM) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tbase = *s.tmem;
+  }
 
   if (warp < M_NCW) {
     // ================================================================== compute warps
@@ -182,10 +232,13 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
       const FPanel& pn = panels[cp.x + pi];
       const int row0 = (int)rank * pn.rs;
       const int my_rows = max(0, min(pn.rs, pn.rows - row0));
-      double e[KR][NB], uacc[KR][NB];
+      // this thread's tensor-memory window: lane quarter warp % 4, 2 * KR * NB columns per warp slot (3 slots)
+      const uint32_t taddr0 = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (2 * KR * NB));
+      double e[TM ? 1 : KR][NB], uacc[KR][NB];
 #pragma unroll
       for (int k = 0; k < KR; ++k) {
         const int row = k * M_T + tid;
+        double ek[NB];
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
           uacc[k][m] = 0.0;
@@ -198,9 +251,16 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
               v = (r[gi] - shift) + u_all[(size_t)pn.kids[m] * n + gi];
             }
           }
-          e[k][m] = v;
+          ek[m] = v;
+        }
+        if constexpr (TM) {
+          tmem_store<NB>(taddr0 + (uint32_t)(k * 2 * NB), ek);
+        } else {
+#pragma unroll
+          for (int m = 0; m < NB; ++m) e[k][m] = ek[m];
         }
       }
+      if constexpr (TM) tmem_wait_st();
       // Row steps that reach past the CTA's slice (KR * 384 >= rs) read on into the next column / the next ring slot /
       // the small arrays behind the ring: always finite doubles (everything up to the barriers is zeroed at start and
       // only ever receives W, partial sums and coefficients), and they meet e = 0 in the dots while their u
@@ -213,7 +273,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           BGGE_DEVASSERT(dslot >= 0 && dslot < ns && (int)(dcnt - acnt) <= lag + 1);
           wait_relaxed(&s.full[dslot], dphase);
           const double* src0 = s.ring + (size_t)dslot * slot_doubles + tid;
-          const double* src1 = src0 + max_rs;
+          const double* src1 = src0 + (G == 2 ? max_rs : 0);
           if (++dslot == ns) {
             dslot = 0;
             dphase ^= 1u;
@@ -221,14 +281,40 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           double a[NG];
 #pragma unroll
           for (int v = 0; v < NG; ++v) a[v] = 0.0;
+          if constexpr (TM) {
+            // e comes back from tensor memory two row steps at a time (one wait per pair)
 #pragma unroll
-          for (int k = 0; k < KR; ++k) {
-            static_assert(G == 2, "two columns per group");
-            const double x0 = src0[k * M_T], x1 = src1[k * M_T];
+            for (int k = 0; k < KR; k += 2) {
+              uint32_t w0[2 * NB], w1[2 * NB];
+              tmem_load<NB>(taddr0 + (uint32_t)(k * 2 * NB), w0);
+              if (k + 1 < KR) tmem_load<NB>(taddr0 + (uint32_t)((k + 1) * 2 * NB), w1);
+              const double x00 = src0[k * M_T], x01 = G == 2 ? src1[k * M_T] : 0.0;
+              const double x10 = k + 1 < KR ? src0[(k + 1) * M_T] : 0.0, x11 = (G == 2 && k + 1 < KR) ? src1[(k + 1) * M_T] : 0.0;
+              tmem_wait_ld();
 #pragma unroll
-            for (int m = 0; m < NB; ++m) {
-              a[m * G] = fma(x0, e[k][m], a[m * G]);
-              a[m * G + 1] = fma(x1, e[k][m], a[m * G + 1]);
+              for (int m = 0; m < NB; ++m) {
+                const double e0 = u2d(w0[2 * m], w0[2 * m + 1]);
+                a[m * G] = fma(x00, e0, a[m * G]);
+                if constexpr (G == 2) a[m * G + 1] = fma(x01, e0, a[m * G + 1]);
+              }
+              if (k + 1 < KR) {
+#pragma unroll
+                for (int m = 0; m < NB; ++m) {
+                  const double e1 = u2d(w1[2 * m], w1[2 * m + 1]);
+                  a[m * G] = fma(x10, e1, a[m * G]);
+                  if constexpr (G == 2) a[m * G + 1] = fma(x11, e1, a[m * G + 1]);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+              const double x0 = src0[k * M_T], x1 = G == 2 ? src1[k * M_T] : 0.0;
+#pragma unroll
+              for (int m = 0; m < NB; ++m) {
+                a[m * G] = fma(x0, e[k][m], a[m * G]);
+                if constexpr (G == 2) a[m * G + 1] = fma(x1, e[k][m], a[m * G + 1]);
+              }
             }
           }
           int vi;
@@ -253,12 +339,18 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
             b[v + 1] = t.y;
           }
           const double* src0 = s.ring + (size_t)aslot * slot_doubles + tid;
-          const double* src1 = src0 + max_rs;
+          const double* src1 = src0 + (G == 2 ? max_rs : 0);
 #pragma unroll
           for (int k = 0; k < KR; ++k) {
-            const double x0 = src0[k * M_T], x1 = src1[k * M_T];
+            const double x0 = src0[k * M_T];
+            if constexpr (G == 2) {
+              const double x1 = src1[k * M_T];
 #pragma unroll
-            for (int m = 0; m < NB; ++m) uacc[k][m] = fma(x1, b[m * G + 1], fma(x0, b[m * G], uacc[k][m]));
+              for (int m = 0; m < NB; ++m) uacc[k][m] = fma(x1, b[m * G + 1], fma(x0, b[m * G], uacc[k][m]));
+            } else {
+#pragma unroll
+              for (int m = 0; m < NB; ++m) uacc[k][m] = fma(x0, b[m], uacc[k][m]);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&s.empty[aslot]);
@@ -422,35 +514,51 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
       }
     }
   }
+  if constexpr (TM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster.sync();      // nobody leaves while a peer may still write into its shared memory
+  if constexpr (TM) {
+    if (warp == M_NCW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+  }
 }
 
-size_t fixed_bytes(int nb, bool merged) {
-  const size_t ng = (size_t)nb * M_G;
+size_t fixed_bytes(int nb, int g, bool merged) {
+  const size_t ng = (size_t)nb * g;
   const size_t tvm = merged ? (size_t)nb : 1;
   return ((size_t)M_NP * M_NCW * ng + (size_t)M_NPX * M_MAXCS * ng + (size_t)M_NPX * ng + (2 * tvm + 2 + 2 * (size_t)nb) * M_ZB) *
              sizeof(double) +
-         (2 * M_MAXNS + M_NP + 2 * M_NPX + 4) * sizeof(uint64_t) + 128;
+         (2 * M_MAXNS + M_NP + 2 * M_NPX + 4) * sizeof(uint64_t) + 16 + 128;
 }
+size_t barrier_bytes() { return (2 * M_MAXNS + M_NP + 2 * M_NPX + 4) * sizeof(uint64_t) + 16 + 128; }
 
 typedef void (*MrhsFn)(const FPanel*, const int2*, const double*, const double*, double*, long long, const double*, double*,
                        long long, const Scal*, int, DrawCfg, int, int);
 
 struct Inst {
-  int nb, kr;
+  int nb, kr, g, tm;
   MrhsFn fn;
 };
 const Inst kInst[] = {
-    {4, 2, sweep_mrhs_kernel<2, 4>},   {4, 3, sweep_mrhs_kernel<3, 4>},   {4, 4, sweep_mrhs_kernel<4, 4>},
-    {4, 5, sweep_mrhs_kernel<5, 4>},   {4, 6, sweep_mrhs_kernel<6, 4>},   {4, 7, sweep_mrhs_kernel<7, 4>},
-    {2, 4, sweep_mrhs_kernel<4, 2>},   {2, 6, sweep_mrhs_kernel<6, 2>},   {2, 8, sweep_mrhs_kernel<8, 2>},
-    {2, 10, sweep_mrhs_kernel<10, 2>}, {2, 12, sweep_mrhs_kernel<12, 2>}, {2, 14, sweep_mrhs_kernel<14, 2>},
+    // e and u in registers, two columns per group
+    {4, 2, 2, 0, sweep_mrhs_kernel<2, 4, 2, false>},   {4, 3, 2, 0, sweep_mrhs_kernel<3, 4, 2, false>},
+    {4, 4, 2, 0, sweep_mrhs_kernel<4, 4, 2, false>},   {4, 5, 2, 0, sweep_mrhs_kernel<5, 4, 2, false>},
+    {4, 6, 2, 0, sweep_mrhs_kernel<6, 4, 2, false>},   {4, 7, 2, 0, sweep_mrhs_kernel<7, 4, 2, false>},
+    {2, 4, 2, 0, sweep_mrhs_kernel<4, 2, 2, false>},   {2, 6, 2, 0, sweep_mrhs_kernel<6, 2, 2, false>},
+    {2, 8, 2, 0, sweep_mrhs_kernel<8, 2, 2, false>},   {2, 10, 2, 0, sweep_mrhs_kernel<10, 2, 2, false>},
+    {2, 12, 2, 0, sweep_mrhs_kernel<12, 2, 2, false>}, {2, 14, 2, 0, sweep_mrhs_kernel<14, 2, 2, false>},
+    // e in tensor memory, one column per group: four members at twice the rows per CTA (2-CTA clusters at 10000 rows)
+    {4, 8, 1, 1, sweep_mrhs_kernel<8, 4, 1, true>},    {4, 10, 1, 1, sweep_mrhs_kernel<10, 4, 1, true>},
+    {4, 12, 1, 1, sweep_mrhs_kernel<12, 4, 1, true>},  {4, 14, 1, 1, sweep_mrhs_kernel<14, 4, 1, true>},
 };
 
-const Inst* find_inst(int nb, int kr_need) {
+const Inst* find_inst(int nb, int kr_need, int tm) {
   for (const Inst& i : kInst)
-    if (i.nb == nb && i.kr >= kr_need) return &i;
+    if (i.nb == nb && i.tm == tm && i.kr >= kr_need) return &i;
   return nullptr;
+}
+
+int tmem_mode() {   // BGGE_MRHS_TMEM: 0 never, 1 when it lets a smaller cluster hold the panel (default), 2 whenever it fits
+  if (const char* ev = getenv("BGGE_MRHS_TMEM")) return atoi(ev);
+  return MRHS_TMEM_DEFAULT;
 }
 
 }  // namespace
@@ -473,52 +581,61 @@ int mrhs_configure(int64_t max_rows, int nb, bool merged, MrhsCfg* cfg) {
     const int v = atoi(ev);
     if (v == 1 || v == 2 || v == 4 || v == 8) cs_min = v;
   }
+  const int tmode = tmem_mode();
   for (int cs = cs_min; cs <= M_MAXCS; cs *= 2) {
     const int64_t rs = round_up((max_rows + cs - 1) / cs, 16);
     const int kr_need = (int)((rs + M_T - 1) / M_T);
-    const Inst* inst = find_inst(nb, kr_need);
-    if (!inst) continue;
-    const size_t slot_bytes = (size_t)M_G * rs * sizeof(double);
-    const size_t fixed = fixed_bytes(nb, merged);
-    // unpredicated row steps may read (kr * 384 - rs) doubles past the last ring slot: they must stay in the zeroed
-    // arrays in front of the mbarriers
-    const size_t tail = fixed - ((2 * M_MAXNS + M_NP + 2 * M_NPX + 4) * sizeof(uint64_t) + 128);
-    if ((size_t)(inst->kr * (int64_t)M_T - rs) * sizeof(double) > tail) continue;
-    int ns = (int)std::min<size_t>(M_MAXNS, ((size_t)optin - fixed - 1024) / slot_bytes);
-    if (ns < 3) continue;
-    int lag = 2;
-    if (const char* ev = getenv("BGGE_MRHS_LAG")) lag = std::max(1, std::min(3, atoi(ev)));
-    lag = std::min(lag, ns - 2);
-    cfg->cs = cs;
-    cfg->kr = inst->kr;
-    cfg->ns = ns;
-    cfg->lag = lag;
-    cfg->smem = (size_t)ns * slot_bytes + fixed;
-    BGGE_CUDA(cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3((unsigned)(cs * 64), 1, 1);
-    lc.blockDim = dim3(M_THREADS, 1, 1);
-    lc.dynamicSmemBytes = cfg->smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr;
-    lc.numAttrs = 1;
-    int ncl = 0;
-    BGGE_CUDA(cudaOccupancyMaxActiveClusters(&ncl, inst->fn, &lc));
-    if (ncl < 1) continue;
-    cfg->clusters = ncl;
-    cfg->ok = true;
-    return OK;
+    // register variant first; the tensor-memory variant where the registers cannot hold the slice (mode 1) or first
+    // (mode 2).  Each candidate has to pass its own shared-memory checks.
+    const int order[2] = {tmode == 2 ? 1 : 0, tmode == 2 ? 0 : 1};
+    for (int oi = 0; oi < 2; ++oi) {
+      if (order[oi] == 1 && tmode == 0) continue;
+      const Inst* inst = find_inst(nb, kr_need, order[oi]);
+      if (!inst) continue;
+      const size_t slot_bytes = (size_t)inst->g * rs * sizeof(double);
+      const size_t fixed = fixed_bytes(nb, inst->g, merged);
+      // unpredicated row steps may read (kr * 384 - rs) doubles past the last ring slot: they must stay in the zeroed
+      // arrays in front of the mbarriers
+      const size_t tail = fixed - barrier_bytes();
+      if ((size_t)(inst->kr * (int64_t)M_T - rs) * sizeof(double) > tail) continue;
+      int ns = (int)std::min<size_t>(M_MAXNS, ((size_t)optin - fixed - 1024) / slot_bytes);
+      if (ns < 3) continue;
+      int lag = 2;     // groups between the dots and the axpy of a group
+      if (const char* ev = getenv("BGGE_MRHS_LAG")) lag = std::max(1, std::min(3, atoi(ev)));
+      lag = std::min(lag, ns - 2);
+      cfg->cs = cs;
+      cfg->kr = inst->kr;
+      cfg->g = inst->g;
+      cfg->tmem = inst->tm;
+      cfg->ns = ns;
+      cfg->lag = lag;
+      cfg->smem = (size_t)ns * slot_bytes + fixed;
+      BGGE_CUDA(cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+      lc.blockDim = dim3(M_THREADS, 1, 1);
+      lc.dynamicSmemBytes = cfg->smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)cs;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      lc.attrs = attr;
+      lc.numAttrs = 1;
+      int ncl = 0;
+      BGGE_CUDA(cudaOccupancyMaxActiveClusters(&ncl, inst->fn, &lc));
+      if (ncl < 1) continue;
+      cfg->clusters = ncl;
+      cfg->ok = true;
+      return OK;
+    }
   }
   return OK;
 }
 
 int mrhs_launch(Gibbs* g, HostKernel& hk) {
-  const Inst* inst = find_inst(hk.fused_nb, hk.fused_kr);
-  BGGE_REQUIRE(inst && inst->kr == hk.fused_kr, "multi-RHS sweep: no kernel instantiation for kr=%d nb=%d", hk.fused_kr,
+  const Inst* inst = find_inst(hk.fused_nb, hk.fused_kr, hk.fused_tmem);
+  BGGE_REQUIRE(inst && inst->kr == hk.fused_kr && inst->g == hk.fused_g, "multi-RHS sweep: no kernel instantiation for kr=%d nb=%d", hk.fused_kr,
                hk.fused_nb);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(hk.fused_clusters * hk.fused_cs), 1, 1);

@@ -4,13 +4,15 @@
 
 namespace bgge {
 
-constexpr int MRHS_G = 2;        // eigen-columns per exchange group (= per ring slot)
 constexpr int MRHS_MAX_NS = 8;   // ring depth limit (groups)
+constexpr int MRHS_TMEM_DEFAULT = 0;   // BGGE_MRHS_TMEM default (see sweep_mrhs.cu: 0 never, 1 to shrink the cluster, 2 always)
 
 struct MrhsCfg {
   bool ok = false;
   int cs = 1;          // CTAs per cluster (row split)
   int kr = 0;          // row steps per compute thread the kernel is instantiated for
+  int g = 2;           // eigen-columns per exchange group (= per ring slot)
+  int tmem = 0;        // 1: residual slices in tensor memory
   int ns = 0;          // ring depth (groups)
   int lag = 2;         // groups between the dots and the axpy of a group
   int clusters = 0;    // co-resident clusters

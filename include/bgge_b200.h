@@ -52,7 +52,7 @@ int bgge_version(void);
 const char* bgge_last_error(void);
 int bgge_device_count(int* count);
 int bgge_set_device(int device);
-/* the library keeps freed device scratch blocks (<= 2 GB in total) for reuse; this returns them to the driver */
+/* the library keeps freed device scratch blocks (<= 4 GB in total) for reuse; this returns them to the driver */
 int bgge_release_cache(void);
 /* free bytes / total bytes of the current device */
 int bgge_device_memory(uint64_t* free_bytes, uint64_t* total_bytes);
@@ -297,7 +297,7 @@ int bgge_test_draws(uint64_t seed, uint32_t chain, int64_t n, double* normals, d
  *             progress(done, seconds_per_iteration, user) is called after each piece on the calling thread -- the R
  *             shim prints the "Iter: ... time: ..." line and calls R_CheckUserInterrupt() there; a non-zero return
  *             stops the run (BGGE_ERR_STATE, message "interrupted").  chunk <= 0 or progress == NULL: one piece.
- *   chain_bet optional n_cum x max(q, 1) (column-major) recorded fixed effects.
+ *   chain_bet optional recorded fixed effects, n_cum rows of max(q, 1) values (row-major, as bgge_gibbs_chain).
  */
 #define BGGE_KERNEL_DENSE (-1)
 typedef struct bgge_kernel_desc {

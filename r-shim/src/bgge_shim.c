@@ -142,7 +142,7 @@ SEXP bgge_R_fit(SEXP y, SEXP kernels, SEXP types, SEXP gid, SEXP env, SEXP XF, S
   SEXP cmu = Rf_allocVector(REALSXP, ncum);            SET_VECTOR_ELT(out, 8, cmu);
   SEXP cve = Rf_allocVector(REALSXP, ncum);            SET_VECTOR_ELT(out, 9, cve);
   SEXP cvu = Rf_allocMatrix(REALSXP, (int)ncum, nk);   SET_VECTOR_ELT(out, 10, cvu);
-  SEXP cbt = Rf_allocMatrix(REALSXP, (int)ncum, q > 0 ? q : 1); SET_VECTOR_ELT(out, 11, cbt);
+  SEXP cbt = Rf_allocMatrix(REALSXP, q > 0 ? q : 1, (int)ncum); SET_VECTOR_ELT(out, 11, cbt);   /* q x n_cum: the library writes n_cum rows of q */
   int nfact = 0;
   struct progress_state ps;
   ps.verbose = Rf_asInteger(verbose) > 0;

@@ -165,7 +165,7 @@ def _fit_kernels(lib, y, descs, gid, env, ne, ite, burn, thin, z, c, XF=None, ch
     out = {"yHat": np.empty(n), "u": np.empty((nk, n)), "usd": np.empty((nk, n)), "y": np.empty(n), "varu": np.empty(nk),
            "varusd": np.empty(nk), "cmu": np.empty(ncum), "cve": np.empty(ncum), "cvu": np.empty((nk, ncum)),
            "cbet": np.empty((max(q, 1), ncum)).T}
-    cbet = np.empty((ncum, max(q, 1)), order="F")
+    cbet = np.empty((ncum, max(q, 1)))            # row-major n_cum x q, like bgge_gibbs_chain
     varE, varEsd, nfact = C.c_double(), C.c_double(), C.c_int()
     na = np.isnan(y).astype(np.uint8)
     yy = np.where(np.isnan(y), 0.0, y)

@@ -90,11 +90,24 @@ def test_c5_row_shape_shared_blocks_on_4cta_clusters_match_oracle():
     _check(got, ref)
 
 
+def test_c5_row_shape_with_tensor_memory_residuals_on_2cta_clusters():
+    """The same model with the residual slices of the 4-member panel kept in tensor memory (tcgen05.st / tcgen05.ld):
+    2-CTA clusters then hold the 10000-row block (sweep_mrhs_kernel<14, 4, 1, true>, 74 clusters = all 148 SMs)."""
+    got, ref, info, nrs = _fit_both(10000, 4, 192, "GB", "MDs", ite=5, mode=None, n_na=300, seed=31,
+                                    env={"BGGE_MRHS_TMEM": "1" if os.environ.get("BGGE_MRHS_TMEM") is None else os.environ["BGGE_MRHS_TMEM"],
+                                         "BGGE_MRHS_CS": "2"})
+    ge = info["kernels"][1]
+    assert ge["path"] == 2 and ge["cluster_size"] == 2 and ge["factored_blocks"] == 4
+    _check(got, ref)
+
+
 @pytest.mark.parametrize("E,env,want_cs", [
     (4, {"BGGE_MRHS_CS": "4", "BGGE_FUSED_MAX_CLUSTERS": "3"}, 4),   # ~830 columns per cluster: ring, exchange ring and draw batches wrap
     (4, {}, 1),                                                       # single-CTA clusters, 7 row steps
     (2, {"BGGE_FUSED_MAX_CLUSTERS": "5"}, 1),                         # two right-hand sides
     (3, {"BGGE_MRHS_CS": "2"}, 2),                                    # three members in a 4-wide panel (one idle slot)
+    (4, {"BGGE_MRHS_TMEM": "2", "BGGE_FUSED_MAX_CLUSTERS": "3"}, 1),  # residual slices in tensor memory, one column per group
+    (4, {"BGGE_MRHS_TMEM": "2", "BGGE_MRHS_CS": "2"}, 2),             # the same on 2-CTA clusters
 ])
 def test_multi_rhs_kernel_long_pipelines_match_oracle(E, env, want_cs):
     """sweep_mrhs_kernel with hundreds of column groups per cluster (the C5 launch runs ~140 groups per cluster): a
