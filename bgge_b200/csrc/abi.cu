@@ -1508,7 +1508,7 @@ int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_i
   BGGE_HANDLE(h);
   Batch& g = h->g;
   BGGE_REQUIRE(g.initialised, "batch_info: handle not initialised");
-  if (padded_chains) *padded_chains = (g.Bp + g.tn - 1) / g.tn * g.tn;   // chain columns the GEMM tiles compute
+  if (padded_chains) *padded_chains = (g.Bq + g.tn - 1) / g.tn * g.tn;   // chain columns the GEMM tiles compute
   int64_t fl = 0;                                                        // useful flops: the B real chains
   for (auto& k : g.kernels)
     for (auto& b : k.blocks) fl += 4 * b.rows * b.nr * (int64_t)g.B;

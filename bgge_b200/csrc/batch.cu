@@ -21,22 +21,6 @@ __device__ __forceinline__ DrawCfg chain_cfg(const DrawCfg& dc, int b) {
   return c;
 }
 
-// tU[c + i*ldt] = U[i + c*ldu]
-__global__ void transpose_kernel(const double* __restrict__ U, long long ldu, int rows, int nr, double* __restrict__ T,
-                                 long long ldt) {
-  __shared__ double t[32][33];
-  const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
-    const int i = i0 + threadIdx.x, c = c0 + cc;
-    t[cc][threadIdx.x] = (i < rows && c < nr) ? U[i + (long long)c * ldu] : 0.0;
-  }
-  __syncthreads();
-  for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
-    const int c = c0 + threadIdx.x, i = i0 + ii;
-    if (c < nr && i < rows) T[c + (long long)i * ldt] = t[threadIdx.x][ii];
-  }
-}
-
 // u_j = z/(2n), R = (y - mu0) - sum_j u_j          (R/BGGE.R:254, 260-267)
 __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* __restrict__ Y,
                               const double* __restrict__ mu0, double* __restrict__ U, double* __restrict__ R, DrawCfg dc) {
@@ -369,7 +353,8 @@ Batch::~Batch() {
   for (auto& k : kernels)
     for (auto& bl : k.blocks) {
       if (bl.owns && bl.dU) pool_free(bl.dU);
-      if (bl.dT) pool_free(bl.dT);
+      if (bl.dTb) pool_free(bl.dTb);
+      if (bl.dUb) pool_free(bl.dUb);
     }
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -383,14 +368,15 @@ int batch_init(Batch* g) {
   const int B = g->B;
   // chains are padded to a multiple of 8 (one DMMA fragment) only; the N tile width is the instantiated width that
   // covers Bp with the fewest padded columns, wider tiles first on ties (80 chains -> one 80-wide tile, 320 -> 4 x 80)
-  g->Bp = (int)round_up(B, 8);
-  const int Bp = g->Bp;
+  g->Bq = (int)round_up(B, 8);
+  g->Bp = g->Bq + 4;
+  const int Bp = g->Bp, Bq = g->Bq;
   {
     int best_tn = 128;
     long best_cols = 1L << 40;
     for (int k = kGemmTileNCount - 1; k >= 0; --k) {
       const int tn = kGemmTileN[k];
-      const long cols = (long)((Bp + tn - 1) / tn) * tn;
+      const long cols = (long)((Bq + tn - 1) / tn) * tn;
       if (cols < best_cols) {
         best_cols = cols;
         best_tn = tn;
@@ -510,17 +496,19 @@ int batch_init(Batch* g) {
       back_tiles += (bl.rows + 127) / 128;
       max_rows = std::max(max_rows, bl.rows);
       max_nr = std::max(max_nr, bl.nr);
-      bl.ldt = round_up(bl.nr, 2);
-      BGGE_CUDA(pool_alloc((void**)&bl.dT, (size_t)bl.ldt * bl.rows * sizeof(double)));
-      transpose_kernel<<<dim3((unsigned)((bl.rows + 31) / 32), (unsigned)((bl.nr + 31) / 32)), dim3(32, 8), 0, st>>>(
-          bl.dU, bl.ldu, (int)bl.rows, (int)bl.nr, bl.dT, bl.ldt);
-      BGGE_CUDA(cudaGetLastError());
+      // blocked copies of t(U) and U: element (m, k) of t(U) is U[k + m ldu], of U it is U[m + k ldu]
+      const int64_t mtT = (bl.nr + 127) / 128, kbT = (bl.rows + 15) / 16, mtU = (bl.rows + 127) / 128, kbU = (bl.nr + 15) / 16;
+      BGGE_CUDA(pool_alloc((void**)&bl.dTb, (size_t)(mtT * kbT * GEMM_ABLK_DOUBLES) * sizeof(double)));
+      BGGE_CUDA(pool_alloc((void**)&bl.dUb, (size_t)(mtU * kbU * GEMM_ABLK_DOUBLES) * sizeof(double)));
+      BGGE_TRY(gemm_pack_launch(bl.dU, bl.ldu, 1, bl.nr, bl.rows, bl.dTb, st));
+      BGGE_TRY(gemm_pack_launch(bl.dU, 1, bl.ldu, bl.rows, bl.nr, bl.dUb, st));
     }
     BGGE_REQUIRE((int64_t)bk.s_host.size() == bk.nr_total, "batch: kernel %d eigenvalue count mismatch", j);
     std::vector<unsigned char> cover((size_t)n, 0);
     for (auto& bl : bk.blocks) std::fill(cover.begin() + bl.pos0, cover.begin() + bl.pos0 + bl.rows, (unsigned char)1);
     BGGE_TRY(up(bk.cover, cover, st));
-    const int ntile_n = (Bp + g->tn - 1) / g->tn;
+    const int ntile_n = (Bq + g->tn - 1) / g->tn;
+    BGGE_REQUIRE(ntile_n > 1 || Bp <= g->tn + 4, "batch: internal error (B slab pitch %d exceeds the stage)", Bp);
     // K splits: a cost model in microseconds -- waves of persistent CTAs x (k-blocks per item at the FP64 tensor
     // rate + ring fill / epilogue) + the traffic of the per-split partial outputs.  (r01's model charged the partial
     // sums as if the output were as large as at 320 chains; at 40 chains per GPU it picked too few splits and left
@@ -570,16 +558,17 @@ int batch_init(Batch* g) {
       for (int sp = 0; sp < bk.ksplit_proj; ++sp) {
         const int k0 = (int)((int64_t)kbp * sp / bk.ksplit_proj), k1 = (int)((int64_t)kbp * (sp + 1) / bk.ksplit_proj);
         for (int64_t m0 = 0; m0 < bl.nr; m0 += 128)
-          for (int n0 = 0; n0 < Bp; n0 += g->tn) {
+          for (int n0 = 0; n0 < Bq; n0 += g->tn) {
             GemmItem t{};
-            t.A = bl.dT;
-            t.lda = bl.ldt;
+            t.Ablk = bl.dTb;
+            t.ablk_kblocks = kbp;
+            t.bcontig = Bq <= g->tn ? 1 : 0;
             t.B = g->Ep.p + (size_t)bl.pos0 * Bp;
             t.ldb = Bp;
             t.C = bk.Dpart.p + (size_t)sp * bk.nr_pad * Bp + (size_t)bl.col_off * Bp;
             t.ldc = Bp;
             t.M = (int)bl.nr;
-            t.N = Bp;
+            t.N = Bq;
             t.K = (int)bl.rows;
             t.m0 = (int)m0;
             t.n0 = n0;
@@ -591,16 +580,17 @@ int batch_init(Batch* g) {
       for (int sp = 0; sp < bk.ksplit_back; ++sp) {
         const int k0 = (int)((int64_t)kbb * sp / bk.ksplit_back), k1 = (int)((int64_t)kbb * (sp + 1) / bk.ksplit_back);
         for (int64_t m0 = 0; m0 < bl.rows; m0 += 128)
-          for (int n0 = 0; n0 < Bp; n0 += g->tn) {
+          for (int n0 = 0; n0 < Bq; n0 += g->tn) {
             GemmItem t{};
-            t.A = bl.dU;
-            t.lda = bl.ldu;
+            t.Ablk = bl.dUb;
+            t.ablk_kblocks = kbb;
+            t.bcontig = Bq <= g->tn ? 1 : 0;
             t.B = bk.Bm.p + (size_t)bl.col_off * Bp;
             t.ldb = Bp;
             t.C = g->Upart.p + (size_t)sp * total + (size_t)bl.pos0 * Bp;
             t.ldc = Bp;
             t.M = (int)bl.rows;
-            t.N = Bp;
+            t.N = Bq;
             t.K = (int)bl.nr;
             t.m0 = (int)m0;
             t.n0 = n0;

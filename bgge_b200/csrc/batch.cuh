@@ -6,9 +6,11 @@
 namespace bgge {
 
 struct BatchBlock {
-  int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, ldt = 0, col_off = 0;
-  double* dU = nullptr;   // rows x nr, column-major (A operand of u = U b)
-  double* dT = nullptr;   // nr x rows, column-major = t(U) (A operand of d = U'e), owned
+  int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, col_off = 0;
+  double* dU = nullptr;   // rows x nr, column-major (borrowed from the handle that decomposed, or owned)
+  // the A operands of the two skinny GEMMs in the blocked layout of dgemm.cu (one bulk copy per ring stage), owned:
+  double* dTb = nullptr;  // t(U): M = nr, K = rows   (d = U'e)
+  double* dUb = nullptr;  // U:    M = rows, K = nr   (u = U b)
   bool owns = false;
 };
 
@@ -25,7 +27,8 @@ struct BatchKernel {
 
 struct Batch {
   int64_t n = 0;
-  int nk = 0, B = 0, Bp = 0, device = 0;
+  int nk = 0, B = 0, Bp = 0, device = 0;   // Bp = Bq + 4: row pitch of the n x Bp matrices (== 4 mod 8: a B slab that is
+  int Bq = 0;                              // one contiguous copy stays bank-conflict free); Bq = B rounded up to 8 = GEMM N
   int tn = 64;                   // N tile width of the skinny GEMMs (dgemm.cu instantiation)
   cudaStream_t stream = nullptr;
   bool own_stream = false, initialised = false, any_na = false;

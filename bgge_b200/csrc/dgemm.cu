@@ -21,7 +21,7 @@ constexpr int GTHREADS = 384;    // 2 consumer warpgroups + producer warpgroup
 
 template <int TN>
 struct GemmSmem {
-  static constexpr int SLD_B = TN + 4;
+  static constexpr int SLD_B = TN + 4;     // pitch of a B slab row (a contiguous slab brings its own pitch ldb <= TN + 4)
   static constexpr int STAGE_DOUBLES = GK * GSLD_A + GK * SLD_B;
   static constexpr size_t BYTES = (size_t)GSTAGES * STAGE_DOUBLES * sizeof(double) + 2 * GSTAGES * sizeof(uint64_t);
 };
@@ -50,7 +50,8 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
   if (warp >= GCONS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp != GCONS) return;
-    // producer: lane l < 16 copies A slab row l, lane >= 16 copies B slab row l-16
+    // producer: lane l < 16 copies A slab row l, lane >= 16 copies B slab row l-16 -- or, with a blocked A operand /
+    // a contiguous B slab, lane 0 / lane 16 issue ONE copy for the whole slab
     const int row = lane & 15;
     const bool isB = lane >= 16;
     uint32_t it = 0;
@@ -60,22 +61,34 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
       const int ncols = min(TN, gi.N - gi.n0);
       const uint32_t bytesA = (uint32_t)((mrows + 1) & ~1) * 8u;
       const uint32_t bytesB = (uint32_t)((ncols + 1) & ~1) * 8u;
+      const bool ablk = gi.Ablk != nullptr, bcon = gi.bcontig != 0;
+      const double* ablk_base = ablk ? gi.Ablk + (long long)(gi.m0 / GM) * gi.ablk_kblocks * GEMM_ABLK_DOUBLES : nullptr;
       for (int kb = gi.kb0; kb < gi.kb1; ++kb, ++it) {
         const int stage = it % GSTAGES;
         mbar_wait(&empty[stage], ((it / GSTAGES) & 1u) ^ 1u);
         const int k = kb * GK + row;
+        const int klive = min(GK, gi.K - kb * GK);
         const bool live = k < gi.K;
         // every lane announces its own bytes; lane 0 arrives
-        uint32_t mine = live ? (isB ? bytesB : bytesA) : 0u;
+        uint32_t mine;
+        if (isB) mine = bcon ? (row == 0 ? (uint32_t)(klive * gi.ldb) * 8u : 0u) : (live ? bytesB : 0u);
+        else mine = ablk ? (row == 0 ? (uint32_t)(GEMM_ABLK_DOUBLES * 8) : 0u) : (live ? bytesA : 0u);
         uint32_t tot = mine;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) mbar_expect_tx(&full[stage], tot);
         __syncwarp();
-        if (live) {
-          double* dst = sm + (size_t)stage * SM::STAGE_DOUBLES + (isB ? GK * GSLD_A + row * SM::SLD_B : row * GSLD_A);
-          const double* src = isB ? gi.B + gi.n0 + (long long)k * gi.ldb : gi.A + gi.m0 + (long long)k * gi.lda;
-          bulk_g2s(dst, src, mine, &full[stage]);
+        if (mine > 0) {
+          double* stage_base = sm + (size_t)stage * SM::STAGE_DOUBLES;
+          if (isB) {
+            double* dst = stage_base + GK * GSLD_A + (bcon ? 0 : row * SM::SLD_B);
+            const double* src = bcon ? gi.B + (long long)kb * GK * gi.ldb : gi.B + gi.n0 + (long long)k * gi.ldb;
+            bulk_g2s(dst, src, mine, &full[stage]);
+          } else {
+            double* dst = stage_base + (ablk ? 0 : row * GSLD_A);
+            const double* src = ablk ? ablk_base + (long long)kb * GEMM_ABLK_DOUBLES : gi.A + gi.m0 + (long long)k * gi.lda;
+            bulk_g2s(dst, src, mine, &full[stage]);
+          }
         }
       }
     }
@@ -99,6 +112,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
       mbar_wait(&full[stage], (it / GSTAGES) & 1u);
       const double* As = sm + (size_t)stage * SM::STAGE_DOUBLES + m_w + fr;
       const double* Bs = sm + (size_t)stage * SM::STAGE_DOUBLES + GK * GSLD_A + fr;
+      const int sldb = gi.bcontig ? (int)gi.ldb : SM::SLD_B;
       const int klive = min(GK, gi.K - kb * GK);   // rows >= klive hold stale (finite) data: skip them
 #pragma unroll
       for (int kk = 0; kk < GK / 4; ++kk) {
@@ -109,7 +123,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) a[i] = kv ? As[k * GSLD_A + i * 8] : 0.0;
 #pragma unroll
-          for (int j = 0; j < NT8; ++j) b[j] = kv ? Bs[k * SM::SLD_B + j * 8] : 0.0;
+          for (int j = 0; j < NT8; ++j) b[j] = kv ? Bs[k * sldb + j * 8] : 0.0;
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -141,6 +155,29 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
 }  // namespace
 
 namespace {
+// dst[((mt * KB + kb) * 16 + kl) * 132 + ml] = A(mt * 128 + ml, kb * 16 + kl), zero outside M x K and in the pad columns
+__global__ void __launch_bounds__(256)
+gemm_pack_kernel(const double* __restrict__ src, long long sm_, long long sk_, long long M, long long K, long long KB,
+                 double* __restrict__ dst) {
+  const long long chunk = blockIdx.x;             // (mt, kb)
+  const long long mt = chunk / KB, kb = chunk % KB;
+  double* d = dst + chunk * GEMM_ABLK_DOUBLES;
+  for (int e = threadIdx.x; e < GEMM_ABLK_DOUBLES; e += blockDim.x) {
+    // consecutive threads walk the source's fast dimension: m when stride_m == 1, k otherwise
+    int kl, ml;
+    if (sm_ == 1) {
+      kl = e / GSLD_A;
+      ml = e % GSLD_A;
+    } else {
+      ml = e / GK;
+      kl = e % GK;
+    }
+    const long long m = mt * GM + ml, k = kb * GK + kl;
+    const double v = (ml < GM && m < M && k < K) ? src[m * sm_ + k * sk_] : 0.0;
+    d[kl * GSLD_A + ml] = v;
+  }
+}
+
 template <int TN>
 int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st) {
   static bool attr[64] = {false};   // function attributes are per device
@@ -162,6 +199,17 @@ int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st) {
 // the fewest padded columns (80 chains per GPU run as one 80-wide tile, not as two 64-wide ones)
 const int kGemmTileN[] = {16, 32, 40, 48, 64, 80, 96, 128};
 const int kGemmTileNCount = 8;
+
+int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, double* dst,
+                     cudaStream_t st) {
+  static_assert(GEMM_ABLK_DOUBLES == (long long)GK * GSLD_A, "blocked chunk == one A ring stage");
+  const long long MT = (M + GM - 1) / GM, KB = (K + GK - 1) / GK;
+  if (MT * KB <= 0) return OK;
+  BGGE_REQUIRE(MT * KB < (1ll << 31), "gemm_pack: too many chunks");
+  gemm_pack_kernel<<<(unsigned)(MT * KB), 256, 0, st>>>(src, stride_m, stride_k, M, K, KB, dst);
+  BGGE_CUDA(cudaGetLastError());
+  return OK;
+}
 
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
   if (nitems <= 0) return OK;

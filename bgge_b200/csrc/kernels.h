@@ -39,15 +39,28 @@ int expand_rows_launch(const double* dW, int64_t ldw, const int* d_loc, const do
 
 // dgemm.cu -- one work item of the skinny DMMA GEMM: C[m][n] (row-major, ldc) = sum_k A[m + k lda] B[n + k ldb]
 struct GemmItem {
-  const double* A;
+  const double* A;      // plain operand (M-fast), or nullptr when Ablk is set
   const double* B;
   double* C;
+  // Blocked A operand (gemm_pack_launch): for M tile mt and k-block kb one contiguous [16][132] chunk -- exactly a
+  // ring stage of the kernel -- at Ablk + (mt * kblocks_total + kb) * GEMM_ABLK_DOUBLES, so the producer issues ONE
+  // bulk copy per stage instead of 16 (the TMA unit is request-rate bound on 1 KB copies; r02 ncu: consumers waited
+  // on `full` for 30 % of the launch at 40 chains).  bcontig: the B slab of a k-block is contiguous in memory
+  // (single N tile, n0 == 0, ldb == the shared-memory pitch): one more single copy.
+  const double* Ablk;
+  long long ablk_kblocks;
+  int bcontig, pad0;
   long long lda, ldb, ldc;
   int M, N, K;          // full extents (for edge clipping)
   int m0, n0;           // tile origin
   int kb0, kb1;         // 16-deep k-blocks [kb0, kb1)
 };
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st);
+constexpr long long GEMM_ABLK_DOUBLES = 16 * 132;
+// packs A (element (m, k) at src[m * stride_m + k * stride_k], M x K) into the blocked layout; dst holds
+// ceil(M / 128) * ceil(K / 16) * GEMM_ABLK_DOUBLES doubles, padding zero-filled
+int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, double* dst,
+                     cudaStream_t st);
 extern const int kGemmTileN[];     // instantiated N tile widths, ascending
 extern const int kGemmTileNCount;
 

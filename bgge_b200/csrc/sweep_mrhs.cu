@@ -582,15 +582,21 @@ int mrhs_configure(int64_t max_rows, int nb, bool merged, MrhsCfg* cfg) {
     if (v == 1 || v == 2 || v == 4 || v == 8) cs_min = v;
   }
   const int tmode = tmem_mode();
-  for (int cs = cs_min; cs <= M_MAXCS; cs *= 2) {
-    const int64_t rs = round_up((max_rows + cs - 1) / cs, 16);
-    const int kr_need = (int)((rs + M_T - 1) / M_T);
-    // register variant first; the tensor-memory variant where the registers cannot hold the slice (mode 1) or first
-    // (mode 2).  Each candidate has to pass its own shared-memory checks.
-    const int order[2] = {tmode == 2 ? 1 : 0, tmode == 2 ? 0 : 1};
-    for (int oi = 0; oi < 2; ++oi) {
-      if (order[oi] == 1 && tmode == 0) continue;
-      const Inst* inst = find_inst(nb, kr_need, order[oi]);
+  // Candidate order.  Default (mode 1): the register variant while it fits 1- or 2-CTA clusters (C3: 3000 rows on
+  // cs = 2 measured faster than the tensor-memory variant on cs = 1), then the tensor-memory variant at its smallest
+  // cluster (C5: 10000 rows x 4 members on cs = 2 instead of cs = 4), then the register variant on larger clusters.
+  // Mode 0: register variant only.  Mode 2: tensor-memory variant first.
+  struct Cand { int tm, cs_lo, cs_hi; };
+  const Cand only_reg[3] = {{0, 1, M_MAXCS}, {0, 1, 0}, {0, 1, 0}};
+  const Cand tm_first[3] = {{1, 1, M_MAXCS}, {0, 1, M_MAXCS}, {0, 1, 0}};
+  const Cand mixed[3] = {{0, 1, 2}, {1, 1, M_MAXCS}, {0, 4, M_MAXCS}};
+  const Cand* cands = tmode == 0 ? only_reg : tmode == 2 ? tm_first : mixed;
+  for (int ci = 0; ci < 3; ++ci) {
+    const Cand& cd = cands[ci];
+    for (int cs = std::max(cs_min, cd.cs_lo); cs <= cd.cs_hi; cs *= 2) {
+      const int64_t rs = round_up((max_rows + cs - 1) / cs, 16);
+      const int kr_need = (int)((rs + M_T - 1) / M_T);
+      const Inst* inst = find_inst(nb, kr_need, cd.tm);
       if (!inst) continue;
       const size_t slot_bytes = (size_t)inst->g * rs * sizeof(double);
       const size_t fixed = fixed_bytes(nb, inst->g, merged);

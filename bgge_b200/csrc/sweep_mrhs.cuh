@@ -5,7 +5,7 @@
 namespace bgge {
 
 constexpr int MRHS_MAX_NS = 8;   // ring depth limit (groups)
-constexpr int MRHS_TMEM_DEFAULT = 0;   // BGGE_MRHS_TMEM default (see sweep_mrhs.cu: 0 never, 1 to shrink the cluster, 2 always)
+constexpr int MRHS_TMEM_DEFAULT = 1;   // BGGE_MRHS_TMEM default (see sweep_mrhs.cu: 0 never, 1 to shrink the cluster, 2 always)
 
 struct MrhsCfg {
   bool ok = false;

@@ -78,10 +78,11 @@ def _fit_both(L, E, p, kernel, model, ite, mode, n_na, seed, env=None, burn=0, t
 
 
 def test_c5_row_shape_shared_blocks_on_4cta_clusters_match_oracle():
-    """n = 40000 (L = 10000 x E = 4), MDs: exactly the kernel instances the headline number comes from -- G factorised
-    (W 10000 x nr on 2-CTA clusters), GE = four identical blocks swept as one 4-right-hand-side panel by
-    sweep_mrhs_kernel<7, 4> on 4-CTA clusters -- five tape-injected iterations against the oracle."""
-    got, ref, info, nrs = _fit_both(10000, 4, 192, "GB", "MDs", ite=5, mode=None, n_na=300, seed=31)
+    """n = 40000 (L = 10000 x E = 4), MDs: G factorised (W 10000 x nr on 2-CTA clusters), GE = four identical blocks
+    swept as one 4-right-hand-side panel by the register variant sweep_mrhs_kernel<7, 4, 2, false> on 4-CTA clusters
+    (BGGE_MRHS_TMEM=0) -- five tape-injected iterations against the oracle."""
+    got, ref, info, nrs = _fit_both(10000, 4, 192, "GB", "MDs", ite=5, mode=None, n_na=300, seed=31,
+                                    env={"BGGE_MRHS_TMEM": "0"})
     assert not info["resident"]
     g, ge = info["kernels"]
     assert g["path"] == 1 and g["cluster_size"] == 2 and g["factored_blocks"] == 1
@@ -91,12 +92,12 @@ def test_c5_row_shape_shared_blocks_on_4cta_clusters_match_oracle():
 
 
 def test_c5_row_shape_with_tensor_memory_residuals_on_2cta_clusters():
-    """The same model with the residual slices of the 4-member panel kept in tensor memory (tcgen05.st / tcgen05.ld):
-    2-CTA clusters then hold the 10000-row block (sweep_mrhs_kernel<14, 4, 1, true>, 74 clusters = all 148 SMs)."""
-    got, ref, info, nrs = _fit_both(10000, 4, 192, "GB", "MDs", ite=5, mode=None, n_na=300, seed=31,
-                                    env={"BGGE_MRHS_TMEM": "1" if os.environ.get("BGGE_MRHS_TMEM") is None else os.environ["BGGE_MRHS_TMEM"],
-                                         "BGGE_MRHS_CS": "2"})
-    ge = info["kernels"][1]
+    """The same model as the DEFAULT plans it -- exactly the kernel instances the headline number comes from: the
+    residual slices of the 4-member panel live in tensor memory (tcgen05.st / tcgen05.ld), so 2-CTA clusters hold the
+    10000-row block (sweep_mrhs_kernel<14, 4, 1, true>, 74 clusters = all 148 SMs)."""
+    got, ref, info, nrs = _fit_both(10000, 4, 192, "GB", "MDs", ite=5, mode=None, n_na=300, seed=31)
+    g, ge = info["kernels"]
+    assert g["path"] == 1 and g["cluster_size"] == 2 and g["factored_blocks"] == 1
     assert ge["path"] == 2 and ge["cluster_size"] == 2 and ge["factored_blocks"] == 4
     _check(got, ref)
 
