@@ -1513,7 +1513,7 @@ int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_i
   for (auto& k : g.kernels)
     for (auto& b : k.blocks) fl += 4 * b.rows * b.nr * (int64_t)g.B;
   if (gemm_flops_per_iter) *gemm_flops_per_iter = fl;
-  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 5;
+  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 3;   // per kernel: e', GEMM, draw, GEMM, update; tail: variances, imputation, intercept
   return OK;
 }
 

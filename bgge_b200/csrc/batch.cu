@@ -46,9 +46,12 @@ __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* 
 }
 
 // E' = (R - shift_b) + U_j
+// (the first launch of an iteration also advances the iteration counter: nothing in this kernel reads it, everything
+// after it in the stream sees the new value -- one launch less per iteration than a separate increment)
 __global__ void b_eprime_kernel(long long total, int Bp, const double* __restrict__ R, const double* __restrict__ Uj,
-                                const double* __restrict__ shift, double* __restrict__ Ep) {
+                                const double* __restrict__ shift, double* __restrict__ Ep, long long* __restrict__ advance_it) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (advance_it != nullptr && idx == 0) *advance_it += 1;
   if (idx >= total) return;
   Ep[idx] = (R[idx] - shift[idx % Bp]) + Uj[idx];
 }
@@ -56,21 +59,55 @@ __global__ void b_eprime_kernel(long long total, int Bp, const double* __restric
 // d = sum of K-split partials; b = tau v d + sqrt(v) z; partial sums of b^2/s        (R/BGGE.R:302-305, 96)
 // Small kernels of the batched sampler are tiled as (32 chains) x (8 row / column lanes): with few chains per GPU
 // (40 at 8 GPUs) a thread-per-chain layout leaves the chip idle behind long serial loops (r02: b_draw 79 us at B = 40).
-constexpr int TX = 32, TY = 8;
+// Block = tx chains x ty lanes with tx * ty = 256; tx = 16 for <= 48 chain columns (44 columns = 16 + 16 + 12 lanes
+// busy instead of 32 + 12), else 32.
+constexpr int TXY = 256;
+inline int tile_x(int Bp) { return Bp <= 48 ? 16 : 32; }
 
-__global__ void __launch_bounds__(TX * TY)
-b_draw_kernel(int nr, int B, int Bp, int nsplit, const double* __restrict__ Dpart, long long dstride,
+// Blocks [0, n_ctiles): one coefficient draw per thread (ty columns x tx chains per block), partial sums of b^2/s per
+// block.  Blocks >= n_ctiles prepare, off the critical path, the draws later kernels of the iteration would otherwise
+// wait for: block n_ctiles the chi-squares of kernel j (and, for the last kernel, the residual chi-square and the
+// next intercept's normal) per chain, the blocks behind it the imputation normals (last kernel only).  The draws are
+// counter based, so they are the same numbers the consumers used to draw themselves.
+struct PreDraws {
+  double* chiK;     // [nk][Bp]
+  double* chiE;     // [Bp]
+  double* zmu;      // [Bp]
+  double* zna;      // [max_na][Bp]
+  int max_na, last; // last: this launch belongs to the last kernel of the iteration
+  const int* n_na;  // [Bp] missing phenotypes per chain
+  long long n;
+  long long nr_j;
+};
+__global__ void __launch_bounds__(TXY)
+b_draw_kernel(int nr, int n_ctiles, int B, int Bp, int nsplit, const double* __restrict__ Dpart, long long dstride,
               const double* __restrict__ s, const double* __restrict__ sigb, const double* __restrict__ tau,
-              double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp, int j, DrawCfg dc) {
-  __shared__ double zs[TY][TX];
-  const int b = blockIdx.y * TX + threadIdx.x, cy = threadIdx.y;
-  const int c0 = blockIdx.x * 32, c1 = min(nr, c0 + 32);
+              double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp, int j, DrawCfg dc,
+              PreDraws pd) {
+  __shared__ double zs[TXY];
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int b = blockIdx.y * tx + threadIdx.x, cy = threadIdx.y;
   const long long it = *itp;
-  double zq = 0.0;
-  if (b < B) {
+  if ((int)blockIdx.x >= n_ctiles) {
+    const int extra = (int)blockIdx.x - n_ctiles;
+    if (b >= B) return;
     const DrawCfg c = chain_cfg(dc, b);
-    const double lam = sigb[b], tb = tau[b];
-    for (int cc = c0 + cy; cc < c1; cc += TY) {
+    if (extra == 0) {
+      if (cy == 0) pd.chiK[(long long)j * Bp + b] = draw_chisq(c, it, STREAM_CHI_K + (uint32_t)j, (double)pd.nr_j + NU, 0);
+      if (pd.last && cy == 1) pd.chiE[b] = draw_chisq(c, it, STREAM_CHI_E, (double)pd.n + NU, 0);
+      if (pd.last && cy == 2) pd.zmu[b] = draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
+    } else {
+      const int k = (extra - 1) * ty + cy;
+      if (k < pd.n_na[b]) pd.zna[(long long)k * Bp + b] = draw_normal(c, it, STREAM_NA, (unsigned long long)k, 0);
+    }
+    return;
+  }
+  const int cc = blockIdx.x * ty + cy;
+  double zq = 0.0;
+  if (cc < nr) {
+    if (b < B) {
+      const DrawCfg c = chain_cfg(dc, b);
+      const double lam = sigb[b], tb = tau[b];
       double d = 0.0;
       for (int sp = 0; sp < nsplit; ++sp) d += Dpart[(long long)sp * dstride + (long long)cc * Bp + b];
       const double sv = s[cc];
@@ -79,66 +116,66 @@ b_draw_kernel(int nr, int B, int Bp, int nsplit, const double* __restrict__ Dpar
       const double z = draw_normal(c, it, (uint32_t)j, (unsigned long long)cc, 0);
       const double bv = media + sqrt(vari) * z;
       Bm[(long long)cc * Bp + b] = bv;
-      zq += bv * bv * (1.0 / sv);
+      zq = bv * bv * (1.0 / sv);
+    } else if (b < Bp) {
+      Bm[(long long)cc * Bp + b] = 0.0;
     }
-  } else if (b < Bp) {
-    for (int cc = c0 + cy; cc < c1; cc += TY) Bm[(long long)cc * Bp + b] = 0.0;
   }
-  zs[cy][threadIdx.x] = zq;
+  zs[cy * tx + threadIdx.x] = zq;
   __syncthreads();
   if (cy == 0 && b < Bp) {
     double t = 0.0;
-#pragma unroll
-    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];   // fixed order
+    for (int k = 0; k < ty; ++k) t += zs[k * tx + threadIdx.x];   // fixed order
     zqpart[(long long)blockIdx.x * Bp + b] = t;
   }
 }
 
-// u_new = sum of K-split partials; R = (R + u_old) - u_new; Welford of kept draws     (R/BGGE.R:306-307, 392)
-__global__ void b_update_kernel(long long total, int Bp, int nsplit, const double* __restrict__ Upart, long long ustride,
-                                const unsigned char* __restrict__ cover, double* __restrict__ R, double* __restrict__ Uj, double* __restrict__ Um,
-                                double* __restrict__ Um2, const long long* __restrict__ itp, long long thin, long long burn) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  double un = 0.0;   // rows no block of this kernel covers: u = 0 (R/BGGE.R:334); Upart is shared between kernels
-  if (cover[idx / Bp])
-    for (int sp = 0; sp < nsplit; ++sp) un += Upart[(long long)sp * ustride + idx];
-  R[idx] = (R[idx] + Uj[idx]) - un;
-  Uj[idx] = un;
-  const long long it = *itp;
-  if ((it % thin == 0) && (it > burn)) {
-    const double k = (double)(it / thin - burn / thin);
-    const double m = Um[idx];
-    const double dlt = un - m;
-    const double mn = m + dlt / k;
-    Um[idx] = mn;
-    Um2[idx] += dlt * (un - mn);
-  }
-}
-
-// partial[chunk][b] = sum over a row chunk of (R - shift)^2   (mode 0)  or of R (mode 1)
-__global__ void __launch_bounds__(TX * TY)
-b_colsum_kernel(long long n, int Bp, int rows_per_chunk, const double* __restrict__ R, const double* __restrict__ shift,
-                int mode, double* __restrict__ part) {
-  __shared__ double zs[TY][TX];
-  const int b = blockIdx.y * TX + threadIdx.x, ry = threadIdx.y;
+// u_new = sum of the partial planes; R = (R + u_old) - u_new; Welford of kept draws     (R/BGGE.R:306-307, 392)
+// After the last kernel of the iteration R is final for the residual variance: the same pass then leaves the per-chunk
+// sums of (R - shift)^2 in `part` (want_sse), which saves the separate column-sum launch.
+__global__ void __launch_bounds__(TXY)
+b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const double* __restrict__ Upart, long long ustride,
+                const unsigned char* __restrict__ cover, double* __restrict__ R, double* __restrict__ Uj,
+                double* __restrict__ Um, double* __restrict__ Um2, const long long* __restrict__ itp, long long thin,
+                long long burn, const double* __restrict__ shift, double* __restrict__ part, int want_sse) {
+  __shared__ double zs[TXY];
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
   const long long i0 = (long long)blockIdx.x * rows_per_chunk;
   const long long i1 = min(n, i0 + rows_per_chunk);
+  const long long it = *itp;
+  const bool keep = (it % thin == 0) && (it > burn);
+  const double kcount = keep ? (double)(it / thin - burn / thin) : 1.0;
   double a = 0.0;
   if (b < Bp) {
-    const double sh = mode == 0 ? shift[b] : 0.0;
-    for (long long i = i0 + ry; i < i1; i += TY) {
-      const double v = R[i * Bp + b] - sh;
-      a = mode == 0 ? fma(v, v, a) : a + v;
+    const double sh = want_sse ? shift[b] : 0.0;
+    for (long long i = i0 + ry; i < i1; i += ty) {
+      const long long idx = i * Bp + b;
+      double un = 0.0;   // rows no block of this kernel covers: u = 0 (R/BGGE.R:334)
+      if (cover[i])
+        for (int sp = 0; sp < nsplit; ++sp) un += Upart[(long long)sp * ustride + idx];
+      const double rn = (R[idx] + Uj[idx]) - un;
+      R[idx] = rn;
+      Uj[idx] = un;
+      if (keep) {
+        const double m = Um[idx];
+        const double dlt = un - m;
+        const double mn = m + dlt / kcount;
+        Um[idx] = mn;
+        Um2[idx] += dlt * (un - mn);
+      }
+      const double v = rn - sh;
+      a = fma(v, v, a);
     }
   }
-  zs[ry][threadIdx.x] = a;
-  __syncthreads();
-  if (ry == 0 && b < Bp) {
-    double t = 0.0;
-#pragma unroll
-    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];
-    part[(long long)blockIdx.x * Bp + b] = t;
+  if (want_sse) {
+    zs[ry * tx + threadIdx.x] = a;
+    __syncthreads();
+    if (ry == 0 && b < Bp) {
+      double t = 0.0;
+      for (int k = 0; k < ty; ++k) t += zs[k * tx + threadIdx.x];
+      part[(long long)blockIdx.x * Bp + b] = t;
+    }
   }
 }
 
@@ -169,6 +206,9 @@ struct ChainArgs {
   double* chain_mu;
   double* chain_varE;
   double* chain_varU;
+  const double* chiK;   // prepared draws (b_draw_kernel's extra blocks); zmu == nullptr: draw the intercept normal here
+  const double* chiE;
+  const double* zmu;
 };
 
 // per chain (one warp each): sigb_j, sigsq, tau        (R/BGGE.R:95-103, 360-367)
@@ -188,12 +228,14 @@ __global__ void __launch_bounds__(128) b_chain_var_kernel(const ChainArgs a, Dra
   const double sse = warp_sum_strided(a.part + b, a.nchunks, a.Bp, lane);         // e'e
   if (lane == 0) ss[w][a.nk] = sse;
   __syncwarp();
+  (void)c;
+  (void)it;
   for (int j = lane; j <= a.nk; j += 32) {
     if (j < a.nk) {
-      const double chi = draw_chisq(c, it, STREAM_CHI_K + (uint32_t)j, (double)a.nr[j] + NU, 0);
+      const double chi = a.chiK[(long long)j * a.Bp + b];    // drawn by the extra block of kernel j's b_draw launch
       a.sigb[(long long)j * a.Bp + b] = (ss[w][j] + NU * a.Sc[(long long)j * a.Bp + b]) / chi;
     } else {
-      const double chi = draw_chisq(c, it, STREAM_CHI_E, (double)a.n + NU, 0);
+      const double chi = a.chiE[b];
       const double s2 = (ss[w][j] + a.Sce[b]) / chi;
       a.sigsq[b] = s2;
       a.tau[b] = 1.0 / s2;
@@ -202,21 +244,21 @@ __global__ void __launch_bounds__(128) b_chain_var_kernel(const ChainArgs a, Dra
 }
 
 // NA imputation (R/BGGE.R:370-381) fused with the column sums of r for the next intercept
-__global__ void __launch_bounds__(TX * TY)
+__global__ void __launch_bounds__(TXY)
 b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double* __restrict__ R,
                  const double* __restrict__ U, double* __restrict__ Y, const int* __restrict__ narank,
                  const double* __restrict__ mu, const double* __restrict__ shift, const double* __restrict__ sigsq,
-                 const long long* __restrict__ itp, int do_na, double* __restrict__ part, DrawCfg dc) {
-  __shared__ double zs[TY][TX];
-  const int b = blockIdx.y * TX + threadIdx.x, ry = threadIdx.y;
+                 const long long* __restrict__ itp, int do_na, double* __restrict__ part, const double* __restrict__ zna) {
+  __shared__ double zs[TXY];
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
   const long long i0 = (long long)blockIdx.x * rows_per_chunk;
   const long long i1 = min(n, i0 + rows_per_chunk);
-  const long long it = *itp;
+  (void)itp;
   double a = 0.0;
   if (b < B) {
-    const DrawCfg c = chain_cfg(dc, b);
     const double mub = mu[b], shb = shift[b], sd = sqrt(sigsq[b]);
-    for (long long i = i0 + ry; i < i1; i += TY) {
+    for (long long i = i0 + ry; i < i1; i += ty) {
       const long long idx = i * Bp + b;
       double rv = R[idx];
       if (do_na) {
@@ -224,7 +266,7 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
         if (k >= 0) {
           double uhat = 0.0;
           for (int j = 0; j < nk; ++j) uhat = (j == 0) ? U[idx] : uhat + U[(long long)j * n * Bp + idx];
-          const double z = draw_normal(c, it, STREAM_NA, (unsigned long long)k, 0);
+          const double z = zna[(long long)k * Bp + b];   // drawn by the extra blocks of the last b_draw launch
           const double yv = ((0.0 + mub) + uhat) + sd * z;
           Y[idx] = yv;
           rv = (((yv - uhat) - 0.0) - mub) + shb;
@@ -234,19 +276,16 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
       a += rv;
     }
   }
-  zs[ry][threadIdx.x] = a;
+  zs[ry * tx + threadIdx.x] = a;
   __syncthreads();
   if (ry == 0 && b < Bp) {
     double t = 0.0;
-#pragma unroll
-    for (int k = 0; k < TY; ++k) t += zs[k][threadIdx.x];
+    for (int k = 0; k < ty; ++k) t += zs[k * tx + threadIdx.x];
     part[(long long)blockIdx.x * Bp + b] = t;
   }
 }
 
 // per chain: record the thinned chain (R/BGGE.R:384-395), draw the next intercept (R/BGGE.R:278-281)
-__global__ void b_advance_kernel(long long* it) { *it += 1; }
-
 __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, DrawCfg dc) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= a.B) return;
@@ -262,7 +301,7 @@ __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, Draw
       for (int j = 0; j < a.nk; ++j) a.chain_varU[((long long)j * a.ncum + slot) * a.Bp + b] = a.sigb[(long long)j * a.Bp + b];
     }
   }
-  const double z = draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
+  const double z = a.zmu ? a.zmu[b] : draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
   const double nmu = (sr / (double)a.n + a.mu0[b]) + sqrt(a.sigsq[b] / (double)a.n) * z;
   a.mu[b] = nmu;
   a.shift[b] = nmu - a.mu0[b];
@@ -302,23 +341,26 @@ ChainArgs chain_args(Batch* g, const double* part) {
   a.chain_mu = g->chain_mu.p;
   a.chain_varE = g->chain_varE.p;
   a.chain_varU = g->chain_varU.p;
+  a.chiK = g->chiK.p;
+  a.chiE = g->chiE.p;
+  a.zmu = g->zmu.p;
   return a;
 }
 
 int launch_tail(Batch* g, bool init) {
   cudaStream_t st = g->stream;
-  const dim3 cgrid((unsigned)g->nchunks, (unsigned)((g->Bp + TX - 1) / TX));
-  const dim3 cblock(TX, TY);
+  const int tx = tile_x(g->Bp), ty = TXY / tx;
+  const dim3 cgrid((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx));
+  const dim3 cblock(tx, ty);
   const unsigned cb = (unsigned)((g->B + 3) / 4);   // one warp per chain
-  if (!init) {
-    b_colsum_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->Bp, g->rows_per_chunk, g->R.p, g->shift.p, 0, g->part.p);
+  if (!init)   // the per-chunk sums of (R - shift)^2 were left in `part` by the last kernel's update pass
     b_chain_var_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part.p), g->draw);
-  }
   b_na_sumr_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p, g->narank.p,
                                         g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p,
-                                        g->draw);
-  b_chain_mu_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part2.p), g->draw);
-  b_advance_kernel<<<1, 1, 0, st>>>(g->it.p);   // separate launch: other CTAs of the kernel above still read it
+                                        g->zna.p);
+  ChainArgs ca = chain_args(g, g->part2.p);
+  if (init) ca.zmu = nullptr;   // no b_draw launch has run yet: the first intercept's normal is drawn in place
+  b_chain_mu_kernel<<<cb, 128, 0, st>>>(ca, g->draw);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }
@@ -327,17 +369,23 @@ int launch_iteration(Batch* g) {
   cudaStream_t st = g->stream;
   const long long total = g->n * g->Bp;
   const unsigned eg = (unsigned)((total + BT - 1) / BT);
+  const int tx = tile_x(g->Bp), ty = TXY / tx;
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     double* Uj = g->U.p + (size_t)j * total;
-    b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p);
-    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st));
-    b_draw_kernel<<<dim3((unsigned)bk.n_ctiles, (unsigned)((g->Bp + TX - 1) / TX)), dim3(TX, TY), 0, st>>>(
-        (int)bk.nr_total, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
-        g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw);
-    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st));
-    b_update_kernel<<<eg, BT, 0, st>>>(total, g->Bp, bk.ksplit_back, g->Upart.p, total, bk.cover.p, g->R.p, Uj,
-                                      g->Um.p + (size_t)j * total, g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn);
+    b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p, j == 0 ? g->it.p : nullptr);
+    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj));
+    const bool last = j == g->nk - 1;
+    PreDraws pd{g->chiK.p, g->chiE.p, g->zmu.p, g->zna.p, g->max_na, last ? 1 : 0, g->n_na.p, (long long)g->n,
+                (long long)bk.nr_total};
+    const int extra = 1 + (last && g->any_na ? (g->max_na + ty - 1) / ty : 0);   // prepared draws, see b_draw_kernel
+    b_draw_kernel<<<dim3((unsigned)(bk.n_ctiles + extra), (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
+        (int)bk.nr_total, bk.n_ctiles, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
+        g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw, pd);
+    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st, bk.grid_back));
+    b_update_kernel<<<dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
+        g->n, g->Bp, g->rows_per_chunk, bk.ksplit_back, bk.Upart.p, total, bk.cover.p, g->R.p, Uj, g->Um.p + (size_t)j * total,
+        g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn, g->shift.p, g->part.p, j == g->nk - 1 ? 1 : 0);
     BGGE_CUDA(cudaGetLastError());
   }
   return launch_tail(g, false);
@@ -394,7 +442,8 @@ int batch_init(Batch* g) {
 
   // ---- per-chain phenotype statistics (R/BGGE.R:191-200, 245-258), matrices in [i][b] layout
   std::vector<double> Y((size_t)n * Bp, 0.0), mu0((size_t)Bp, 0.0), vy((size_t)Bp, 1.0);
-  std::vector<int> narank((size_t)n * Bp, -1);
+  std::vector<int> narank((size_t)n * Bp, -1), nna_host((size_t)Bp, 0);
+  g->max_na = 0;
   g->any_na = false;
   for (int b = 0; b < B; ++b) {
     const double* yb = g->y_host.data() + (size_t)b * n;
@@ -422,6 +471,8 @@ int batch_init(Batch* g) {
       }
       m1 += v;
     }
+    nna_host[(size_t)b] = rank;
+    g->max_na = std::max(g->max_na, rank);
     const long double ybar = m1 / (long double)n;
     long double ss = 0.0L;
     for (int64_t i = 0; i < n; ++i) {
@@ -443,6 +494,11 @@ int batch_init(Batch* g) {
   const size_t total = (size_t)n * Bp;
   BGGE_TRY(up(g->Y, Y, st));
   BGGE_TRY(up(g->narank, narank, st));
+  BGGE_TRY(up(g->n_na, nna_host, st));
+  BGGE_CUDA(g->chiK.alloc((size_t)g->nk * Bp));
+  BGGE_CUDA(g->chiE.alloc((size_t)Bp));
+  BGGE_CUDA(g->zmu.alloc((size_t)Bp));
+  BGGE_CUDA(g->zna.alloc((size_t)std::max(1, g->max_na) * Bp));
   BGGE_TRY(up(g->mu0, mu0, st));
   BGGE_TRY(up(g->mu, mu0, st));
   BGGE_TRY(up(g->shift, zero, st));
@@ -462,7 +518,7 @@ int batch_init(Batch* g) {
   BGGE_CUDA(g->it.alloc(1));
   BGGE_CUDA(cudaMemsetAsync(g->it.p, 0, sizeof(long long), st));
   // row chunks of the column sums / the imputation pass: >= 4 blocks per SM and chain tile, a multiple of the 8 row lanes
-  g->rows_per_chunk = (int)std::max<int64_t>(16, round_up((n + 4 * sms - 1) / (4 * sms), TY));
+  g->rows_per_chunk = (int)std::max<int64_t>(16, round_up((n + 4 * sms - 1) / (4 * sms), TXY / tile_x(Bp)));
   g->nchunks = (int)((n + g->rows_per_chunk - 1) / g->rows_per_chunk);
   BGGE_CUDA(g->part.alloc((size_t)g->nchunks * Bp));
   BGGE_CUDA(g->part2.alloc((size_t)g->nchunks * Bp));
@@ -472,7 +528,6 @@ int batch_init(Batch* g) {
   BGGE_CUDA(g->chain_varU.alloc(nc * Bp * g->nk));
 
   // ---- per kernel: transposed copies, GEMM work items (split-K so that every launch fills the machine)
-  int max_ksplit_back = 1;
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     BGGE_REQUIRE(!bk.blocks.empty(), "batch: kernel %d has no eigen blocks", j);
@@ -509,103 +564,124 @@ int batch_init(Batch* g) {
     BGGE_TRY(up(bk.cover, cover, st));
     const int ntile_n = (Bq + g->tn - 1) / g->tn;
     BGGE_REQUIRE(ntile_n > 1 || Bp <= g->tn + 4, "batch: internal error (B slab pitch %d exceeds the stage)", Bp);
-    // K splits: a cost model in microseconds -- waves of persistent CTAs x (k-blocks per item at the FP64 tensor
-    // rate + ring fill / epilogue) + the traffic of the per-split partial outputs.  (r01's model charged the partial
-    // sums as if the output were as large as at 320 chains; at 40 chains per GPU it picked too few splits and left
-    // a quarter of the SMs idle.)
-    auto pick_split = [&](int64_t tiles, int64_t kmax, int64_t mtot) {
-      const int64_t kblocks = (kmax + 15) / 16;
-      const double t_kb = 32.0 * g->tn / 1.9e3;                       // 128 x tn x 16 FMAs at 64 FMA / clk / SM, ~1.9 GHz
-      const double t_fix = 3.0;
-      const double t_part = 2.0 * 8.0 * (double)mtot * Bp / 3.0e6;    // write + re-read of one split's partial C at ~3 TB/s
-      int best = 1;
-      double best_cost = 1e300;
-      for (int sp = 1; sp <= 32 && (sp == 1 || kblocks / sp >= 12); ++sp) {
-        const int64_t items = tiles * ntile_n * sp;
-        const double waves = (double)((items + sms - 1) / sms);
-        const double cost = waves * ((double)((kblocks + sp - 1) / sp) * t_kb + t_fix) + sp * t_part;
-        if (cost < best_cost) { best_cost = cost; best = sp; }
-      }
-      return best;
-    };
-    int64_t rows_tot = 0;
-    for (auto& bl : bk.blocks) rows_tot += bl.rows;
-    bk.ksplit_proj = pick_split(proj_tiles, max_rows, bk.nr_total);
-    bk.ksplit_back = pick_split(back_tiles, max_nr, rows_tot);
-    if (const char* ev = getenv("BGGE_BATCH_KSPLIT")) {   // tuning hook: "proj,back"
-      int a1 = 0, a2 = 0;
-      if (sscanf(ev, "%d,%d", &a1, &a2) == 2 && a1 >= 1 && a1 <= 32 && a2 >= 1 && a2 <= 32) {
-        bk.ksplit_proj = a1;
-        bk.ksplit_back = a2;
-      }
-    }
-    max_ksplit_back = std::max(max_ksplit_back, bk.ksplit_back);
     bk.nr_pad = round_up(bk.nr_total, 32);
-    bk.n_ctiles = (int)((bk.nr_total + 31) / 32);
-    BGGE_CUDA(bk.Dpart.alloc((size_t)bk.ksplit_proj * bk.nr_pad * Bp));
+    bk.n_ctiles = (int)((bk.nr_total + (TXY / tile_x(Bp)) - 1) / (TXY / tile_x(Bp)));   // one block per ty eigen-columns
     BGGE_CUDA(bk.Bm.alloc((size_t)bk.nr_pad * Bp));
     BGGE_CUDA(cudaMemsetAsync(bk.Bm.p, 0, (size_t)bk.nr_pad * Bp * sizeof(double), st));
     BGGE_CUDA(bk.zqpart.alloc((size_t)bk.n_ctiles * Bp));
     BGGE_TRY(up(bk.s, bk.s_host, st));
   }
-  BGGE_CUDA(g->Upart.alloc(total * max_ksplit_back));
-  BGGE_CUDA(cudaMemsetAsync(g->Upart.p, 0, total * max_ksplit_back * sizeof(double), st));
-  for (int j = 0; j < g->nk; ++j) {
-    BatchKernel& bk = g->kernels[j];
-    std::vector<GemmItem> pi, bi;
-    for (auto& bl : bk.blocks) {
-      const int kbp = (int)((bl.rows + 15) / 16), kbb = (int)((bl.nr + 15) / 16);
-      for (int sp = 0; sp < bk.ksplit_proj; ++sp) {
-        const int k0 = (int)((int64_t)kbp * sp / bk.ksplit_proj), k1 = (int)((int64_t)kbp * (sp + 1) / bk.ksplit_proj);
-        for (int64_t m0 = 0; m0 < bl.nr; m0 += 128)
-          for (int n0 = 0; n0 < Bq; n0 += g->tn) {
-            GemmItem t{};
-            t.Ablk = bl.dTb;
-            t.ablk_kblocks = kbp;
-            t.bcontig = Bq <= g->tn ? 1 : 0;
-            t.B = g->Ep.p + (size_t)bl.pos0 * Bp;
-            t.ldb = Bp;
-            t.C = bk.Dpart.p + (size_t)sp * bk.nr_pad * Bp + (size_t)bl.col_off * Bp;
-            t.ldc = Bp;
-            t.M = (int)bl.nr;
-            t.N = Bq;
-            t.K = (int)bl.rows;
-            t.m0 = (int)m0;
-            t.n0 = n0;
-            t.kb0 = k0;
-            t.kb1 = k1;
-            pi.push_back(t);
-          }
+  // ---- GEMM work items, stream-K style: the (tile, k-block) space of a GEMM is cut into one contiguous range per
+  // persistent CTA (equal k-block counts), a range that crosses a tile boundary becomes two items.  Every item writes
+  // its partial C into the plane = its position among the pieces of its tile; the consumer kernels add the planes in
+  // order (planes a tile does not use stay zero from initialisation).  Deterministic, no atomics, no wave
+  // quantisation: the 79 row tiles of u = U b at C4 no longer run as 2 waves on 148 SMs.
+  struct TileSpec {
+    GemmItem base;      // everything but kb0 / kb1 / C
+    int kblocks;
+    long long coff;     // offset of the tile's block inside a plane of the output
+  };
+  // (called twice per GEMM: once without an output to learn the plane count, then with the allocated planes)
+  auto streamk = [&](const std::vector<TileSpec>& tiles, double* cbase, long long plane_stride, int* nplanes, int* grid) {
+    std::vector<GemmItem> out;
+    long long total_kb = 0;
+    for (auto& t : tiles) total_kb += t.kblocks;
+    const int min_piece = 6;
+    int P = (int)std::max<long long>(1, std::min<long long>(sms, total_kb / (2 * min_piece)));
+    if (const char* ev = getenv("BGGE_BATCH_CTAS")) P = std::max(1, std::min(sms, atoi(ev)));   // tuning hook
+    std::vector<std::vector<GemmItem>> per_cta((size_t)P);
+    std::vector<int> used(tiles.size(), 0);
+    size_t ti = 0;
+    long long tile_start = 0, pos = 0;     // linear k-block position of the current tile / of the cursor
+    for (int c = 0; c < P; ++c) {
+      long long end = c == P - 1 ? total_kb : total_kb * (c + 1) / P;
+      // snap the cut to a tile edge when it would leave a sliver
+      {
+        size_t tj = ti;
+        long long ts = tile_start;
+        while (tj < tiles.size() && ts + tiles[tj].kblocks <= end) ts += tiles[tj++].kblocks;
+        if (tj < tiles.size()) {
+          if (end - ts > 0 && end - ts < min_piece) end = ts;
+          else if (ts + tiles[tj].kblocks - end < min_piece) end = ts + tiles[tj].kblocks;
+        }
       }
-      for (int sp = 0; sp < bk.ksplit_back; ++sp) {
-        const int k0 = (int)((int64_t)kbb * sp / bk.ksplit_back), k1 = (int)((int64_t)kbb * (sp + 1) / bk.ksplit_back);
-        for (int64_t m0 = 0; m0 < bl.rows; m0 += 128)
-          for (int n0 = 0; n0 < Bq; n0 += g->tn) {
-            GemmItem t{};
-            t.Ablk = bl.dUb;
-            t.ablk_kblocks = kbb;
-            t.bcontig = Bq <= g->tn ? 1 : 0;
-            t.B = bk.Bm.p + (size_t)bl.col_off * Bp;
-            t.ldb = Bp;
-            t.C = g->Upart.p + (size_t)sp * total + (size_t)bl.pos0 * Bp;
-            t.ldc = Bp;
-            t.M = (int)bl.rows;
-            t.N = Bq;
-            t.K = (int)bl.nr;
-            t.m0 = (int)m0;
-            t.n0 = n0;
-            t.kb0 = k0;
-            t.kb1 = k1;
-            bi.push_back(t);
-          }
+      while (pos < end && ti < tiles.size()) {
+        const long long tile_end = tile_start + tiles[ti].kblocks;
+        const long long piece_end = std::min(end, tile_end);
+        GemmItem it = tiles[ti].base;
+        it.kb0 = (int)(pos - tile_start);
+        it.kb1 = (int)(piece_end - tile_start);
+        it.C = cbase ? cbase + (long long)used[ti] * plane_stride + tiles[ti].coff : nullptr;
+        ++used[ti];
+        per_cta[(size_t)c].push_back(it);
+        pos = piece_end;
+        if (pos == tile_end) {
+          tile_start = tile_end;
+          ++ti;
+        }
       }
     }
+    size_t rounds = 0;
+    for (auto& v : per_cta) rounds = std::max(rounds, v.size());
+    GemmItem idle{};   // M = 0, no k-blocks: nothing loaded, nothing stored
+    for (size_t r = 0; r < rounds; ++r)
+      for (int c = 0; c < P; ++c) out.push_back(r < per_cta[(size_t)c].size() ? per_cta[(size_t)c][r] : idle);
+    *nplanes = 1;
+    for (int u : used) *nplanes = std::max(*nplanes, u);
+    *grid = P;
+    return out;
+  };
+  for (int j = 0; j < g->nk; ++j) {
+    BatchKernel& bk = g->kernels[j];
+    std::vector<TileSpec> pt, bt;
+    for (auto& bl : bk.blocks) {
+      const int kbp = (int)((bl.rows + 15) / 16), kbb = (int)((bl.nr + 15) / 16);
+      for (int64_t m0 = 0; m0 < bl.nr; m0 += 128)
+        for (int n0 = 0; n0 < Bq; n0 += g->tn) {
+          GemmItem t{};
+          t.Ablk = bl.dTb;
+          t.ablk_kblocks = kbp;
+          t.bcontig = Bq <= g->tn ? 1 : 0;
+          t.B = g->Ep.p + (size_t)bl.pos0 * Bp;
+          t.ldb = Bp;
+          t.ldc = Bp;
+          t.M = (int)bl.nr;
+          t.N = Bq;
+          t.K = (int)bl.rows;
+          t.m0 = (int)m0;
+          t.n0 = n0;
+          pt.push_back(TileSpec{t, kbp, (long long)bl.col_off * Bp});
+        }
+      for (int64_t m0 = 0; m0 < bl.rows; m0 += 128)
+        for (int n0 = 0; n0 < Bq; n0 += g->tn) {
+          GemmItem t{};
+          t.Ablk = bl.dUb;
+          t.ablk_kblocks = kbb;
+          t.bcontig = Bq <= g->tn ? 1 : 0;
+          t.B = bk.Bm.p + (size_t)bl.col_off * Bp;
+          t.ldb = Bp;
+          t.ldc = Bp;
+          t.M = (int)bl.rows;
+          t.N = Bq;
+          t.K = (int)bl.nr;
+          t.m0 = (int)m0;
+          t.n0 = n0;
+          bt.push_back(TileSpec{t, kbb, (long long)bl.pos0 * Bp});
+        }
+    }
+    streamk(pt, nullptr, 0, &bk.ksplit_proj, &bk.grid_proj);
+    streamk(bt, nullptr, 0, &bk.ksplit_back, &bk.grid_back);
+    BGGE_CUDA(bk.Dpart.alloc((size_t)bk.ksplit_proj * bk.nr_pad * Bp));
+    BGGE_CUDA(cudaMemsetAsync(bk.Dpart.p, 0, (size_t)bk.ksplit_proj * bk.nr_pad * Bp * sizeof(double), st));
+    BGGE_CUDA(bk.Upart.alloc(total * bk.ksplit_back));
+    BGGE_CUDA(cudaMemsetAsync(bk.Upart.p, 0, total * bk.ksplit_back * sizeof(double), st));
+    std::vector<GemmItem> pi = streamk(pt, bk.Dpart.p, bk.nr_pad * Bp, &bk.ksplit_proj, &bk.grid_proj);
+    std::vector<GemmItem> bi = streamk(bt, bk.Upart.p, (long long)total, &bk.ksplit_back, &bk.grid_back);
     bk.n_proj = (int)pi.size();
     bk.n_back = (int)bi.size();
     BGGE_TRY(up(bk.proj_items, pi, st));
     BGGE_TRY(up(bk.back_items, bi, st));
   }
-  // a kernel with fewer K splits than Upart holds must not read stale splits: every kernel uses its own count
   const unsigned ig = (unsigned)((total + BT - 1) / BT);
   b_init_kernel<<<ig, BT, 0, st>>>(n, g->nk, B, Bp, g->Y.p, g->mu0.p, g->U.p, g->R.p, g->draw);
   BGGE_CUDA(cudaGetLastError());

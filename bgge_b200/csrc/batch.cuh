@@ -19,8 +19,9 @@ struct BatchKernel {
   std::vector<double> s_host;
   double mean_diag = 1.0;
   int64_t nr_total = 0, nr_pad = 0;
-  int ksplit_proj = 1, ksplit_back = 1, n_proj = 0, n_back = 0, n_ctiles = 0;
-  DevBuf<double> s, Dpart, Bm, zqpart;
+  int ksplit_proj = 1, ksplit_back = 1, n_proj = 0, n_back = 0, n_ctiles = 0;   // ksplit_* = planes of partial outputs
+  int grid_proj = 0, grid_back = 0;      // persistent CTAs the stream-K item lists were laid out for
+  DevBuf<double> s, Dpart, Upart, Bm, zqpart;
   DevBuf<GemmItem> proj_items, back_items;
   DevBuf<unsigned char> cover;           // 1 for rows some block of this kernel covers
 };
@@ -40,8 +41,10 @@ struct Batch {
   DrawCfg draw{};
   int rows_per_chunk = 0, nchunks = 0;
   // all matrices are row-major n x Bp (chain index fastest)
-  DevBuf<double> Y, R, Ep, U, Um, Um2, Upart, part, part2;
-  DevBuf<int> narank;
+  DevBuf<double> Y, R, Ep, U, Um, Um2, part, part2;
+  DevBuf<int> narank, n_na;              // rank of a missing entry inside its chain (-1: observed); count per chain
+  int max_na = 0;
+  DevBuf<double> chiK, chiE, zmu, zna;   // draws prepared by b_draw_kernel's extra blocks for the tail kernels
   DevBuf<double> mu, mu0, shift, sigsq, tau, Sce, Sc, sigb;
   DevBuf<long long> it;
   DevBuf<double> chain_mu, chain_varE, chain_varU;

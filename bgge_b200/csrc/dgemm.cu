@@ -8,6 +8,7 @@
 // padded 4-stage ring), 8 consumer warps x 16 rows x TN columns of mma.sync.m8n8k4.f64 (DMMA.8x8x4).
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace bgge {
 namespace {
@@ -179,7 +180,7 @@ gemm_pack_kernel(const double* __restrict__ src, long long sm_, long long sk_, l
 }
 
 template <int TN>
-int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st) {
+int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint) {
   static bool attr[64] = {false};   // function attributes are per device
   int dev = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
@@ -188,7 +189,7 @@ int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st) {
     BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<TN>::BYTES));
     attr[dev] = true;
   }
-  const int grid = nitems < sm_count() ? nitems : sm_count();
+  const int grid = grid_hint > 0 ? std::min(grid_hint, nitems) : (nitems < sm_count() ? nitems : sm_count());
   dgemm_dmma_kernel<TN><<<grid, GTHREADS, GemmSmem<TN>::BYTES, st>>>(d_items, nitems);
   BGGE_CUDA(cudaGetLastError());
   return OK;
@@ -211,17 +212,17 @@ int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, 
   return OK;
 }
 
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st) {
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid) {
   if (nitems <= 0) return OK;
   switch (tn) {
-    case 16: return dgemm_launch_t<16>(d_items, nitems, st);
-    case 32: return dgemm_launch_t<32>(d_items, nitems, st);
-    case 40: return dgemm_launch_t<40>(d_items, nitems, st);
-    case 48: return dgemm_launch_t<48>(d_items, nitems, st);
-    case 64: return dgemm_launch_t<64>(d_items, nitems, st);
-    case 80: return dgemm_launch_t<80>(d_items, nitems, st);
-    case 96: return dgemm_launch_t<96>(d_items, nitems, st);
-    case 128: return dgemm_launch_t<128>(d_items, nitems, st);
+    case 16: return dgemm_launch_t<16>(d_items, nitems, st, grid);
+    case 32: return dgemm_launch_t<32>(d_items, nitems, st, grid);
+    case 40: return dgemm_launch_t<40>(d_items, nitems, st, grid);
+    case 48: return dgemm_launch_t<48>(d_items, nitems, st, grid);
+    case 64: return dgemm_launch_t<64>(d_items, nitems, st, grid);
+    case 80: return dgemm_launch_t<80>(d_items, nitems, st, grid);
+    case 96: return dgemm_launch_t<96>(d_items, nitems, st, grid);
+    case 128: return dgemm_launch_t<128>(d_items, nitems, st, grid);
     default: break;
   }
   set_error("dgemm: unsupported N tile %d", tn);

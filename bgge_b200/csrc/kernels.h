@@ -55,7 +55,8 @@ struct GemmItem {
   int m0, n0;           // tile origin
   int kb0, kb1;         // 16-deep k-blocks [kb0, kb1)
 };
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st);
+// grid > 0: number of persistent CTAs the item list was laid out for (item w runs on CTA w % grid)
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid = 0);
 constexpr long long GEMM_ABLK_DOUBLES = 16 * 132;
 // packs A (element (m, k) at src[m * stride_m + k * stride_k], M x K) into the blocked layout; dst holds
 // ceil(M / 128) * ceil(K / 16) * GEMM_ABLK_DOUBLES doubles, padding zero-filled
