@@ -609,18 +609,14 @@ def main():
             if args.two_pass:
                 lib.call("bgge_gibbs_set_mode", h, 0)
             if sharded:
-                lib.call("bgge_gibbs_set_shard", h, rank, world)
+                lib.call("bgge_gibbs_set_comm", h, comm.handle)   # shard = rank of the library communicator
             lib.call("bgge_gibbs_init", h, ite, ite // 5, 3, 0.5, lib.RNG_PHILOX, 1000 + (0 if sharded else rank),
                      0 if sharded else rank)
             return h
 
-        if sharded:
-            from bgge_b200 import multigpu
-            reduce_fn = multigpu.nccl_allreduce()
-
         def run(hh, k, graph=True):
-            if sharded:
-                multigpu.run_sharded(hh, nk, k, reduce_fn)
+            if sharded:   # per-step all-reduce issued inside the library on the handle's stream
+                lib.call("bgge_gibbs_run_sharded", hh, k)
             else:
                 lib.call("bgge_gibbs_run", hh, k)
 
@@ -930,7 +926,7 @@ def main():
                      "row_panel_compute_exchange_s": contr_split[-1] if contr_split else None,
                      "exchange": ("in-place grouped NCCL broadcasts of contiguous column panels inside libbgge_b200 "
                                   "(bgge_dev_gram_panels)" if world > 1 else None)},
-            "eigen": {"setdec_s": t_eig, "problems": n_eig_problems, "L": L, "kept_per_block": nr,
+            "eigen": {"setdec_s": t_eig, "blocks": n_eig_problems, "L": L, "kept_per_block": nr,
                       "route": "bgge_gibbs_add_expanded_kernel: one L x L syevd per block (factorised, SURVEY 8f-1)"},
         }
         print(json.dumps(line))
