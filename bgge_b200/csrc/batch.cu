@@ -552,11 +552,12 @@ int batch_init(Batch* g) {
       max_rows = std::max(max_rows, bl.rows);
       max_nr = std::max(max_nr, bl.nr);
       // blocked copies of t(U) and U: element (m, k) of t(U) is U[k + m ldu], of U it is U[m + k ldu]
-      const int64_t mtT = (bl.nr + 127) / 128, kbT = (bl.rows + 15) / 16, mtU = (bl.rows + 127) / 128, kbU = (bl.nr + 15) / 16;
-      BGGE_CUDA(pool_alloc((void**)&bl.dTb, (size_t)(mtT * kbT * GEMM_ABLK_DOUBLES) * sizeof(double)));
-      BGGE_CUDA(pool_alloc((void**)&bl.dUb, (size_t)(mtU * kbU * GEMM_ABLK_DOUBLES) * sizeof(double)));
-      BGGE_TRY(gemm_pack_launch(bl.dU, bl.ldu, 1, bl.nr, bl.rows, bl.dTb, st));
-      BGGE_TRY(gemm_pack_launch(bl.dU, 1, bl.ldu, bl.rows, bl.nr, bl.dUb, st));
+      const int64_t gm = gemm_tile_m(g->tn), ablk = gemm_ablk_doubles(g->tn);
+      const int64_t mtT = (bl.nr + gm - 1) / gm, kbT = (bl.rows + 15) / 16, mtU = (bl.rows + gm - 1) / gm, kbU = (bl.nr + 15) / 16;
+      BGGE_CUDA(pool_alloc((void**)&bl.dTb, (size_t)(mtT * kbT * ablk) * sizeof(double)));
+      BGGE_CUDA(pool_alloc((void**)&bl.dUb, (size_t)(mtU * kbU * ablk) * sizeof(double)));
+      BGGE_TRY(gemm_pack_launch(bl.dU, bl.ldu, 1, bl.nr, bl.rows, g->tn, bl.dTb, st));
+      BGGE_TRY(gemm_pack_launch(bl.dU, 1, bl.ldu, bl.rows, bl.nr, g->tn, bl.dUb, st));
     }
     BGGE_REQUIRE((int64_t)bk.s_host.size() == bk.nr_total, "batch: kernel %d eigenvalue count mismatch", j);
     std::vector<unsigned char> cover((size_t)n, 0);
@@ -636,7 +637,8 @@ int batch_init(Batch* g) {
     std::vector<TileSpec> pt, bt;
     for (auto& bl : bk.blocks) {
       const int kbp = (int)((bl.rows + 15) / 16), kbb = (int)((bl.nr + 15) / 16);
-      for (int64_t m0 = 0; m0 < bl.nr; m0 += 128)
+      const int64_t gm = gemm_tile_m(g->tn);
+      for (int64_t m0 = 0; m0 < bl.nr; m0 += gm)
         for (int n0 = 0; n0 < Bq; n0 += g->tn) {
           GemmItem t{};
           t.Ablk = bl.dTb;
@@ -652,7 +654,7 @@ int batch_init(Batch* g) {
           t.n0 = n0;
           pt.push_back(TileSpec{t, kbp, (long long)bl.col_off * Bp});
         }
-      for (int64_t m0 = 0; m0 < bl.rows; m0 += 128)
+      for (int64_t m0 = 0; m0 < bl.rows; m0 += gm)
         for (int n0 = 0; n0 < Bq; n0 += g->tn) {
           GemmItem t{};
           t.Ablk = bl.dUb;

@@ -13,24 +13,29 @@
 namespace bgge {
 namespace {
 
-constexpr int GM = 128;          // M tile
 constexpr int GK = 16;           // K slab
-constexpr int GSLD_A = 132;      // padded shared leading dimensions (== 4 mod 16: conflict-free DMMA fragments)
 constexpr int GSTAGES = 4;
 constexpr int GCONS = 8;
 constexpr int GTHREADS = 384;    // 2 consumer warpgroups + producer warpgroup
 
-template <int TN>
+// MI = 8-row fragments per consumer warp: 2 -> 128-row CTA tiles, 4 -> 256-row tiles.  Narrow N tiles (<= 48 chains)
+// use MI = 4: 20 DMMA per 9 fragment loads instead of 10 per 7 (r02 ncu at TN = 40, MI = 2: DMMA pipe 76 %, the rest
+// fixed-latency waits between DMMAs).
+template <int TN, int MI>
 struct GemmSmem {
+  static constexpr int GM = 64 * MI;       // M tile
+  static constexpr int SLD_A = GM + 4;     // padded pitch (== 4 mod 16: conflict-free DMMA fragments)
   static constexpr int SLD_B = TN + 4;     // pitch of a B slab row (a contiguous slab brings its own pitch ldb <= TN + 4)
-  static constexpr int STAGE_DOUBLES = GK * GSLD_A + GK * SLD_B;
+  static constexpr int STAGE_DOUBLES = GK * SLD_A + GK * SLD_B;
   static constexpr size_t BYTES = (size_t)GSTAGES * STAGE_DOUBLES * sizeof(double) + 2 * GSTAGES * sizeof(uint64_t);
 };
 
-template <int TN>
+template <int TN, int MI>
 __global__ void __launch_bounds__(GTHREADS, 1)
 dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
-  using SM = GemmSmem<TN>;
+  using SM = GemmSmem<TN, MI>;
+  constexpr int GM = SM::GM, GSLD_A = SM::SLD_A;
+  constexpr long long ABLK = (long long)GK * GSLD_A;   // doubles of one blocked A chunk == one A ring stage
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)GSTAGES * SM::STAGE_DOUBLES);
@@ -63,7 +68,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
       const uint32_t bytesA = (uint32_t)((mrows + 1) & ~1) * 8u;
       const uint32_t bytesB = (uint32_t)((ncols + 1) & ~1) * 8u;
       const bool ablk = gi.Ablk != nullptr, bcon = gi.bcontig != 0;
-      const double* ablk_base = ablk ? gi.Ablk + (long long)(gi.m0 / GM) * gi.ablk_kblocks * GEMM_ABLK_DOUBLES : nullptr;
+      const double* ablk_base = ablk ? gi.Ablk + (long long)(gi.m0 / GM) * gi.ablk_kblocks * ABLK : nullptr;
       for (int kb = gi.kb0; kb < gi.kb1; ++kb, ++it) {
         const int stage = it % GSTAGES;
         mbar_wait(&empty[stage], ((it / GSTAGES) & 1u) ^ 1u);
@@ -73,7 +78,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
         // every lane announces its own bytes; lane 0 arrives
         uint32_t mine;
         if (isB) mine = bcon ? (row == 0 ? (uint32_t)(klive * gi.ldb) * 8u : 0u) : (live ? bytesB : 0u);
-        else mine = ablk ? (row == 0 ? (uint32_t)(GEMM_ABLK_DOUBLES * 8) : 0u) : (live ? bytesA : 0u);
+        else mine = ablk ? (row == 0 ? (uint32_t)(ABLK * 8) : 0u) : (live ? bytesA : 0u);
         uint32_t tot = mine;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -87,7 +92,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
             bulk_g2s(dst, src, mine, &full[stage]);
           } else {
             double* dst = stage_base + (ablk ? 0 : row * GSLD_A);
-            const double* src = ablk ? ablk_base + (long long)kb * GEMM_ABLK_DOUBLES : gi.A + gi.m0 + (long long)k * gi.lda;
+            const double* src = ablk ? ablk_base + (long long)kb * ABLK : gi.A + gi.m0 + (long long)k * gi.lda;
             bulk_g2s(dst, src, mine, &full[stage]);
           }
         }
@@ -99,13 +104,13 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   constexpr int NT8 = TN / 8;
   const int fr = lane >> 2, fk = lane & 3;
-  const int m_w = warp * 16;
+  const int m_w = warp * 8 * MI;
   uint32_t it = 0;
   for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
     const GemmItem gi = items[w];
-    double acc[2][NT8][2];
+    double acc[MI][NT8][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < NT8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kb = gi.kb0; kb < gi.kb1; ++kb, ++it) {
@@ -120,13 +125,13 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
         if (kk * 4 < klive) {
           const int k = kk * 4 + fk;
           const bool kv = k < klive;
-          double a[2], b[NT8];
+          double a[MI], b[NT8];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) a[i] = kv ? As[k * GSLD_A + i * 8] : 0.0;
+          for (int i = 0; i < MI; ++i) a[i] = kv ? As[k * GSLD_A + i * 8] : 0.0;
 #pragma unroll
           for (int j = 0; j < NT8; ++j) b[j] = kv ? Bs[k * sldb + j * 8] : 0.0;
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int j = 0; j < NT8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -136,7 +141,7 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
     }
     // epilogue: C fragment (row = lane/4, cols 2*(lane%4) + {0,1}) -> this item's partial C
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MI; ++i) {
       const int m = gi.m0 + m_w + i * 8 + fr;
       if (m >= gi.M) continue;
 #pragma unroll
@@ -156,41 +161,42 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
 }  // namespace
 
 namespace {
-// dst[((mt * KB + kb) * 16 + kl) * 132 + ml] = A(mt * 128 + ml, kb * 16 + kl), zero outside M x K and in the pad columns
+// dst[((mt * KB + kb) * 16 + kl) * (gm + 4) + ml] = A(mt * gm + ml, kb * 16 + kl), zero outside M x K and in the pad columns
 __global__ void __launch_bounds__(256)
 gemm_pack_kernel(const double* __restrict__ src, long long sm_, long long sk_, long long M, long long K, long long KB,
-                 double* __restrict__ dst) {
+                 int gm, double* __restrict__ dst) {
   const long long chunk = blockIdx.x;             // (mt, kb)
   const long long mt = chunk / KB, kb = chunk % KB;
-  double* d = dst + chunk * GEMM_ABLK_DOUBLES;
-  for (int e = threadIdx.x; e < GEMM_ABLK_DOUBLES; e += blockDim.x) {
+  const int pitch = gm + 4, ablk = GK * pitch;
+  double* d = dst + chunk * ablk;
+  for (int e = threadIdx.x; e < ablk; e += blockDim.x) {
     // consecutive threads walk the source's fast dimension: m when stride_m == 1, k otherwise
     int kl, ml;
     if (sm_ == 1) {
-      kl = e / GSLD_A;
-      ml = e % GSLD_A;
+      kl = e / pitch;
+      ml = e % pitch;
     } else {
       ml = e / GK;
       kl = e % GK;
     }
-    const long long m = mt * GM + ml, k = kb * GK + kl;
-    const double v = (ml < GM && m < M && k < K) ? src[m * sm_ + k * sk_] : 0.0;
-    d[kl * GSLD_A + ml] = v;
+    const long long m = mt * gm + ml, k = kb * GK + kl;
+    const double v = (ml < gm && m < M && k < K) ? src[m * sm_ + k * sk_] : 0.0;
+    d[kl * pitch + ml] = v;
   }
 }
 
-template <int TN>
+template <int TN, int MI>
 int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint) {
   static bool attr[64] = {false};   // function attributes are per device
   int dev = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
   dev = dev >= 0 && dev < 64 ? dev : 0;
   if (!attr[dev]) {
-    BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<TN>::BYTES));
+    BGGE_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<TN, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<TN, MI>::BYTES));
     attr[dev] = true;
   }
   const int grid = grid_hint > 0 ? std::min(grid_hint, nitems) : (nitems < sm_count() ? nitems : sm_count());
-  dgemm_dmma_kernel<TN><<<grid, GTHREADS, GemmSmem<TN>::BYTES, st>>>(d_items, nitems);
+  dgemm_dmma_kernel<TN, MI><<<grid, GTHREADS, GemmSmem<TN, MI>::BYTES, st>>>(d_items, nitems);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }
@@ -201,13 +207,16 @@ int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int gri
 const int kGemmTileN[] = {16, 32, 40, 48, 64, 80, 96, 128};
 const int kGemmTileNCount = 8;
 
-int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, double* dst,
+int gemm_tile_m(int tn) { return tn <= 48 ? 256 : 128; }
+long long gemm_ablk_doubles(int tn) { return (long long)GK * (gemm_tile_m(tn) + 4); }
+
+int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, int tn, double* dst,
                      cudaStream_t st) {
-  static_assert(GEMM_ABLK_DOUBLES == (long long)GK * GSLD_A, "blocked chunk == one A ring stage");
-  const long long MT = (M + GM - 1) / GM, KB = (K + GK - 1) / GK;
+  const int gm = gemm_tile_m(tn);
+  const long long MT = (M + gm - 1) / gm, KB = (K + GK - 1) / GK;
   if (MT * KB <= 0) return OK;
   BGGE_REQUIRE(MT * KB < (1ll << 31), "gemm_pack: too many chunks");
-  gemm_pack_kernel<<<(unsigned)(MT * KB), 256, 0, st>>>(src, stride_m, stride_k, M, K, KB, dst);
+  gemm_pack_kernel<<<(unsigned)(MT * KB), 256, 0, st>>>(src, stride_m, stride_k, M, K, KB, gm, dst);
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }
@@ -215,14 +224,14 @@ int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, 
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid) {
   if (nitems <= 0) return OK;
   switch (tn) {
-    case 16: return dgemm_launch_t<16>(d_items, nitems, st, grid);
-    case 32: return dgemm_launch_t<32>(d_items, nitems, st, grid);
-    case 40: return dgemm_launch_t<40>(d_items, nitems, st, grid);
-    case 48: return dgemm_launch_t<48>(d_items, nitems, st, grid);
-    case 64: return dgemm_launch_t<64>(d_items, nitems, st, grid);
-    case 80: return dgemm_launch_t<80>(d_items, nitems, st, grid);
-    case 96: return dgemm_launch_t<96>(d_items, nitems, st, grid);
-    case 128: return dgemm_launch_t<128>(d_items, nitems, st, grid);
+    case 16: return dgemm_launch_t<16, 4>(d_items, nitems, st, grid);
+    case 32: return dgemm_launch_t<32, 4>(d_items, nitems, st, grid);
+    case 40: return dgemm_launch_t<40, 4>(d_items, nitems, st, grid);
+    case 48: return dgemm_launch_t<48, 4>(d_items, nitems, st, grid);
+    case 64: return dgemm_launch_t<64, 2>(d_items, nitems, st, grid);
+    case 80: return dgemm_launch_t<80, 2>(d_items, nitems, st, grid);
+    case 96: return dgemm_launch_t<96, 2>(d_items, nitems, st, grid);
+    case 128: return dgemm_launch_t<128, 2>(d_items, nitems, st, grid);
     default: break;
   }
   set_error("dgemm: unsupported N tile %d", tn);

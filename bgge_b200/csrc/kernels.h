@@ -43,7 +43,7 @@ struct GemmItem {
   const double* B;
   double* C;
   // Blocked A operand (gemm_pack_launch): for M tile mt and k-block kb one contiguous [16][132] chunk -- exactly a
-  // ring stage of the kernel -- at Ablk + (mt * kblocks_total + kb) * GEMM_ABLK_DOUBLES, so the producer issues ONE
+  // ring stage of the kernel -- at Ablk + (mt * kblocks_total + kb) * gemm_ablk_doubles(tn), so the producer issues ONE
   // bulk copy per stage instead of 16 (the TMA unit is request-rate bound on 1 KB copies; r02 ncu: consumers waited
   // on `full` for 30 % of the launch at 40 chains).  bcontig: the B slab of a k-block is contiguous in memory
   // (single N tile, n0 == 0, ldb == the shared-memory pitch): one more single copy.
@@ -57,10 +57,13 @@ struct GemmItem {
 };
 // grid > 0: number of persistent CTAs the item list was laid out for (item w runs on CTA w % grid)
 int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid = 0);
-constexpr long long GEMM_ABLK_DOUBLES = 16 * 132;
-// packs A (element (m, k) at src[m * stride_m + k * stride_k], M x K) into the blocked layout; dst holds
-// ceil(M / 128) * ceil(K / 16) * GEMM_ABLK_DOUBLES doubles, padding zero-filled
-int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, double* dst,
+// M tile of the GEMM instantiation for N tile width tn (256 rows for tn <= 48, else 128) and the size of one blocked
+// A chunk ([16][tile_m + 4] doubles)
+int gemm_tile_m(int tn);
+long long gemm_ablk_doubles(int tn);
+// packs A (element (m, k) at src[m * stride_m + k * stride_k], M x K) into the blocked layout of N tile width tn; dst
+// holds ceil(M / tile_m) * ceil(K / 16) * gemm_ablk_doubles(tn) doubles, padding zero-filled
+int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, long long M, long long K, int tn, double* dst,
                      cudaStream_t st);
 extern const int kGemmTileN[];     // instantiated N tile widths, ascending
 extern const int kGemmTileNCount;
