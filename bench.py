@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-ref", action="store_true", help="skip the extra dense-basis measurement")
     ap.add_argument("--chains", type=int, default=0, help="c4: total number of chains x folds (default 320)")
+    ap.add_argument("--no-getk-host", action="store_true", help="skip the host-buffer getK calls (8 GB + 12.8 GB of host memory at C5)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (320 chains x folds) sub-record of the default line")
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass proj/back kernels (no fused sweep)")
     ap.add_argument("--shard-chain", action="store_true",
@@ -517,6 +518,35 @@ def main():
             del S
         else:
             K0 = S
+        # ------------------------------------------------------------- getK through HOST buffers (what an R / ctypes
+        # caller pays): bgge_getk_base with the L x p marker matrix in ordinary (pageable) host memory -- upload,
+        # contraction, epilogue, download of the L x L base kernel -- and one n x n expansion written back to the host
+        getk_host = None
+        if rank == 0 and world == 1 and not args.no_getk_host:
+            X_host = Xp[:p, :L].cpu().numpy()             # (p, L) C-order == column-major L x p, leading dimension L
+            K0_host = np.empty((1, L, L))
+            bw1 = np.ones(1)
+            th0 = time.perf_counter()
+            lib.call("bgge_getk_base", lib.ptr(X_host), L, p, lib.GK if kernel == "GK" else lib.GB, lib.ptr(bw1), 1, 0.5,
+                     lib.ptr(K0_host), None)
+            t_base = time.perf_counter() - th0
+            kerr = float(np.max(np.abs(K0_host[0] - K0.cpu().numpy())))
+            del X_host
+            gid_np = np.tile(np.arange(L, dtype=np.int32), E)
+            env_np = np.repeat(np.arange(E, dtype=np.int32), L)
+            t_expand = None
+            if n <= 46000:
+                G_host = np.empty((n, n), order="F")
+                th0 = time.perf_counter()
+                lib.call("bgge_getk_expand", lib.ptr(K0_host[0]), L, lib.ptr(gid_np), lib.ptr(env_np), n, 0, 0, lib.ptr(G_host))
+                t_expand = time.perf_counter() - th0
+                del G_host
+            getk_host = {"base_call_s": t_base, "h2d_bytes": 8 * L * p, "d2h_bytes": 8 * L * L,
+                         "max_abs_diff_vs_device_pipeline": kerr, "expand_one_kernel_call_s": t_expand,
+                         "expand_d2h_bytes": 8 * n * n if t_expand is not None else 0,
+                         "note": "pageable host buffers, cudaMemcpy inside the call; the factored route (getK(factored=TRUE) / "
+                                 "bgge_fit_kernels) never needs the n x n expansion"}
+            del K0_host
         del Xp
         gid = torch.arange(L, dtype=torch.int32, device=device).repeat(E)
         env = torch.arange(E, dtype=torch.int32, device=device).repeat_interleave(L)
@@ -544,6 +574,12 @@ def main():
         elif model == "MDe":
             kspec += [(1, 2, k) for k in range(E)]
         nk = len(kspec)
+        # cuSOLVER handle creation / module load is a per-process cost, not part of setDEC: absorb it with a tiny problem
+        t_solver_init = time.perf_counter()
+        wtmp = np.eye(64) + 0.01
+        ws, wnr = np.empty(64), C.c_int64()
+        lib.call("bgge_eig", lib.ptr(wtmp), 64, 64, 1e-10, 1, lib.ptr(ws), None, C.byref(wnr))
+        t_solver_init = time.perf_counter() - t_solver_init
         h0 = C.c_void_p()
         lib.call("bgge_gibbs_create", n, nk, 0, stream, C.byref(h0))
         torch.cuda.synchronize()
@@ -848,10 +884,13 @@ def main():
                             "bound by grid-barrier latency (2 per kernel step), not by HBM"}
     jtop = int(top["name"].split("[")[1].rstrip("]")) if "[" in top["name"] else -1
     if jtop >= 0 and kinfo[jtop]["factored_blocks"] > 1:
+        kt = kinfo[jtop]
         roofline["note"] = ("identical diagonal blocks share one W and are swept as a multi-right-hand-side panel "
-                            "(sweep_mrhs_kernel, 4-CTA clusters, 33 clusters = 132 of 148 SMs co-resident): 4x fewer bytes "
-                            "than the dense basis, 4x the FP64 work per byte; ncu (profiles/r02_ncu_mrhs_summary.csv): "
-                            "800.5 MB read per launch, FP64 pipe 36 % of active cycles, issue slots 60 %")
+                            f"(sweep_mrhs_kernel, {kt['cluster_size']}-CTA clusters, {kt['clusters']} clusters = "
+                            f"{kt['cluster_size'] * kt['clusters']} of 148 SMs co-resident"
+                            + (", residual slices in tensor memory" if kt["cluster_size"] <= 2 and L >= 8192 else "")
+                            + f"): {kt['factored_blocks']}x fewer bytes than the dense basis, {kt['factored_blocks']}x the FP64 "
+                            "work per byte; ncu: profiles/r02_ncu_mrhs_summary.csv")
 
     # ----------------------------------------------------------------- C4 (chains x folds, strong scaling) sub-record
     c4 = None
@@ -924,9 +963,10 @@ def main():
                      "quantile_exp_s": t_q, "expansion_s": t_exp, "expansion_gbs": 8.0 * n * n * len(modes) / t_exp / 1e9,
                      "n_gpus_in_contraction": world, "marker_gen_s": t_gen,
                      "row_panel_compute_exchange_s": contr_split[-1] if contr_split else None,
+                     "host_buffers": getk_host,
                      "exchange": ("in-place grouped NCCL broadcasts of contiguous column panels inside libbgge_b200 "
                                   "(bgge_dev_gram_panels)" if world > 1 else None)},
-            "eigen": {"setdec_s": t_eig, "blocks": n_eig_problems, "L": L, "kept_per_block": nr,
+            "eigen": {"setdec_s": t_eig, "cusolver_init_s": t_solver_init, "blocks": n_eig_problems, "L": L, "kept_per_block": nr,
                       "route": "bgge_gibbs_add_expanded_kernel: one L x L syevd per block (factorised, SURVEY 8f-1)"},
         }
         print(json.dumps(line))

@@ -770,6 +770,8 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         BGGE_CUDA(cudaMemcpyAsync(d_isq, isq.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
         return OK;
       };
+      bool identity_map = t == m;   // every genotype once, rows in genotype order (then every weight is 1)
+      for (int64_t i = 0; i < m && identity_map; ++i) identity_map = loc[(size_t)i] == (int)i;
       auto make_virtual = [&](double* W, int64_t ldw, int64_t nr, bool owns_w) -> int {
         std::vector<int> rowptr((size_t)t + 1, 0), rowidx((size_t)m);
         for (int64_t i = 0; i < m; ++i) ++rowptr[(size_t)loc[(size_t)i] + 1];
@@ -788,6 +790,7 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
         bl.d_isq = d_isq;
         bl.owns = owns_w;
         bl.owns_map = true;
+        bl.identity = identity_map;
         bl.col_off = (int64_t)hk.s_host.size();   // where this block's eigenvalues start (insertion order)
     hk.blocks.push_back(bl);
         BGGE_CUDA(cudaStreamSynchronize(st));   // host staging vectors die at the end of this scope
@@ -1180,9 +1183,7 @@ int bgge_gibbs_kernel_info(bgge_gibbs* h, int j, int* fused, int* cluster_size, 
   if (cluster_size) *cluster_size = hk.fused ? hk.fused_cs : hk.cs;
   if (clusters) *clusters = hk.fused ? hk.fused_clusters : hk.n_btasks;
   if (launches) {
-    int nv = 0;
-    for (auto& b : hk.blocks) nv += b.vrows > 0 ? 1 : 0;
-    *launches = 2 + (hk.fused && nv > 0 ? 1 : 0);   // [gather] + sweep + finalize
+    *launches = 2 + (hk.fused && hk.n_vdesc > 0 ? 1 : 0);   // [gather] + sweep + finalize (identity row maps need no gather)
     // a merged unit is launched once, accounted to its first kernel
     if (!g.units.empty() && g.unit_of[(size_t)j] >= 0 && g.units[(size_t)g.unit_of[(size_t)j]].members[0] != j) *launches = 0;
   }

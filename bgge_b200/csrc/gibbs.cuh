@@ -62,6 +62,8 @@ struct FPanel {                  // fused path: columns [c0, c1) of one block, h
   int rs;                        // rows per CTA of the cluster (multiple of 16)
   int slot;                      // upart slot (= cluster index)
   int virt;                      // 1: rows live in the kernel's virtual vectors at offset voff
+  int direct;                    // virt only: 1 = identity row map, the residual is read from r / u at pos0s[] instead of
+                                 // the gathered vector (the output still goes through the virtual partial sums)
   long long voff;
   // multi-right-hand-side panels: nb factorised blocks that share this W (identical diagonal blocks of a BD
   // kernel) are swept together; member k reads / writes the virtual vectors at voffs[k] and draws with the
@@ -119,6 +121,8 @@ struct HostBlock {
   int64_t ldu_dense = 0;
   bool owns_dense = false;
   bool owns_map = false;         // loc / isq / CSR arrays (dU may be shared with an identical block)
+  bool identity = false;         // factorised block whose row map is the identity (every genotype once, in order, weight
+                                 // 1): the sweep reads r / u of its rows directly, no gather launch is needed for it
   int kid = -1;                  // merged units only: the kernel this block belongs to
   int fq_lo = 1 << 30, fq_hi = -1;   // fused plan: clusters that sweep columns of this block (lo > hi: none)
   int64_t stream_rows() const { return vrows > 0 ? vrows : rows; }

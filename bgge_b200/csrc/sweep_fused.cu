@@ -207,7 +207,7 @@ sweep_fused_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ c
           const int row = k * F_ROWS_PER_STEP + 2 * tid;
           e[m][k] = make_double2(0.0, 0.0);
           if (m < pn.nb) {
-            if (pn.virt) {   // factorised block: the residual was already gathered to genotype space
+            if (pn.virt && !pn.direct) {   // factorised block: the residual was already gathered to genotype space
               const long long gi = pn.voffs[m] + row0 + row;
               e[m][k].x = row < my_rows ? ve[gi] : 0.0;
               e[m][k].y = row + 1 < my_rows ? ve[gi + 1] : 0.0;
@@ -837,6 +837,9 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
         p.slot = q;
         p.virt = b0.vrows > 0 ? 1 : 0;
         p.voff = b0.voff;
+        p.direct = 1;
+        for (size_t m = 0; m < gr.members.size(); ++m) p.direct = p.direct && hk.blocks[(size_t)gr.members[m]].identity ? 1 : 0;
+        if (getenv("BGGE_NO_DIRECT_RESIDUAL")) p.direct = 0;
         p.nb = (int)gr.members.size();
         for (size_t m = 0; m < gr.members.size(); ++m) {
           const HostBlock& bm = hk.blocks[(size_t)gr.members[m]];
@@ -873,8 +876,17 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
   {
     std::vector<VDesc> vd;
     int cta = 0;
-    for (auto& bl : hk.blocks)
-      if (bl.vrows > 0) {
+    // (blocks whose row map is the identity are read in place by the sweep -- see FPanel::direct -- unless another
+    // member of their panel needs the gathered form)
+    std::vector<char> need_gather(hk.blocks.size(), 0);
+    for (auto& p : panels)
+      if (p.virt && !p.direct)
+        for (size_t bi = 0; bi < hk.blocks.size(); ++bi)
+          for (int m = 0; m < p.nb; ++m)
+            if (hk.blocks[bi].vrows > 0 && hk.blocks[bi].voff == p.voffs[m]) need_gather[bi] = 1;
+    for (size_t bi = 0; bi < hk.blocks.size(); ++bi) {
+      auto& bl = hk.blocks[bi];
+      if (bl.vrows > 0 && need_gather[bi]) {
         VDesc d{};
         d.vrows = (int)bl.vrows;
         d.pos0 = (int)bl.pos0;
@@ -887,6 +899,7 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
         vd.push_back(d);
         cta += (int)((bl.vrows + 255) / 256);
       }
+    }
     hk.n_vdesc = (int)vd.size();
     hk.vgrid = cta;
     if (!vd.empty()) {

@@ -244,7 +244,7 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
           uacc[k][m] = 0.0;
           double v = 0.0;
           if (m < pn.nb && row < my_rows) {
-            if (pn.virt) {
+            if (pn.virt && !pn.direct) {
               v = ve[pn.voffs[m] + row0 + row];
             } else {
               const long long gi = (long long)pn.pos0s[m] + row0 + row;
