@@ -839,7 +839,9 @@ int plan_fused(Gibbs* g, HostKernel& hk, int j, cudaStream_t st) {
         p.voff = b0.voff;
         p.direct = 1;
         for (size_t m = 0; m < gr.members.size(); ++m) p.direct = p.direct && hk.blocks[(size_t)gr.members[m]].identity ? 1 : 0;
-        if (getenv("BGGE_NO_DIRECT_RESIDUAL")) p.direct = 0;
+        // opt-in: reading r and u in place saves the gather launch, but measured no faster (C5 3050 vs 3119 it/s, C3
+        // 9642 vs 9806, profiles/r02_notes.md) -- the gather overlaps the previous finalize under PDL anyway
+        if (!getenv("BGGE_DIRECT_RESIDUAL")) p.direct = 0;
         p.nb = (int)gr.members.size();
         for (size_t m = 0; m < gr.members.size(); ++m) {
           const HostBlock& bm = hk.blocks[(size_t)gr.members[m]];
