@@ -119,6 +119,7 @@ SIGNATURES = {
     "bgge_batch_create": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, c_void_pp]),
     "bgge_batch_destroy": (None, [C.c_void_p]),
     "bgge_batch_set_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgge_batch_set_xf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "bgge_batch_set_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "bgge_batch_add_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_int]),
@@ -127,6 +128,7 @@ SIGNATURES = {
     "bgge_batch_sync": (C.c_int, [C.c_void_p]),
     "bgge_batch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_int64_p, C.POINTER(C.c_int)]),
     "bgge_batch_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgge_batch_chain_bet": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bgge_batch_summary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "bgge_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_void_pp, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

@@ -281,13 +281,15 @@ def BGGE(y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, verbose=False, tol=
     return out
 
 
-def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, seed=0, chain0=0, eig=None, device=None):
+def BGGE_batch(Y, K, XF=None, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, seed=0, chain0=0, eig=None,
+               device=None):
     """B independent BGGE() chains / cross-validation folds sharing one eigen decomposition (config C4).
 
     Y is a (B, n) array: row b is the phenotype vector of chain b (NaN = masked fold / missing).  Chain b
     uses the RNG stream (seed, chain0 + b), i.e. it reproduces BGGE(Y[b], K, ..., seed=seed, chain=chain0 + b).
     The eigen blocks are computed once (setDEC on the device) and the per-kernel U'e / U b passes of all
-    chains run as skinny FP64 tensor-core GEMMs.  Returns a list of BGGEFit objects.
+    chains run as skinny FP64 tensor-core GEMMs.  XF (n x q, q <= 16) is one fixed-effects design shared by all
+    chains, as in BGGE(XF=) (R/BGGE.R:208-212, 284-290).  Returns a list of BGGEFit objects.
     """
     Y = np.ascontiguousarray(np.atleast_2d(np.asarray(Y, dtype=np.float64)))
     B, n = Y.shape
@@ -310,6 +312,9 @@ def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, 
     try:
         _lib.call("bgge_batch_create", n, nk, B, None, C.byref(hb))
         _lib.call("bgge_batch_set_y", hb, _lib.ptr(Y), None)
+        if XF is not None:
+            XFm = _lib.f64(np.asarray(XF, dtype=np.float64).reshape(n, -1))
+            _lib.call("bgge_batch_set_xf", hb, _lib.ptr(XFm), XFm.shape[1])
         for j, k in enumerate(K.values()):
             tcode = _lib.TYPE_D if k["Type"] == "D" else _lib.TYPE_BD
             if eig is not None:
@@ -353,6 +358,10 @@ def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, 
                   _lib.ptr(varu), _lib.ptr(varusd), _lib.ptr(yout))
         cmu, cve, cvu = np.empty((B, ncum)), np.empty((B, ncum)), np.empty((nk, B, ncum))
         _lib.call("bgge_batch_chain", hb, _lib.ptr(cmu), _lib.ptr(cve), _lib.ptr(cvu))
+        cbet = None
+        if XF is not None:
+            cbet = np.empty((B, ncum, XFm.shape[1]))
+            _lib.call("bgge_batch_chain_bet", hb, _lib.ptr(cbet))
     finally:
         if hb:
             _lib.load().bgge_batch_destroy(hb)
@@ -367,6 +376,8 @@ def BGGE_batch(Y, K, ne=None, ite=1000, burn=200, thin=3, tol=1e-10, R2=0.5, *, 
                                      "varu.sd": float(varusd[j, b])}) for j, nm in enumerate(names))
         out["chain"] = {"mu": cmu[b].copy(), "varE": cve[b].copy(),
                         "K": OrderedDict((nm, {"varU": cvu[j, b].copy()}) for j, nm in enumerate(names))}
+        if cbet is not None:
+            out["chain"]["Bet"] = cbet[b].copy()      # extra (the reference keeps B.mcmc internally)
         out["ite"], out["burn"], out["thin"] = ite, burn, thin
         out["y"] = yout[b].copy()
         fits.append(out)

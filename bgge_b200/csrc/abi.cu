@@ -1431,6 +1431,18 @@ int bgge_batch_set_y(bgge_batch* h, const double* Y, const uint8_t* na_mask) {
   return OK;
 }
 
+// XF: n x q column-major, one design matrix for all chains (R/BGGE.R:208-212, 284-290); q = 0 removes it
+int bgge_batch_set_xf(bgge_batch* h, const double* XF, int q) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(!g.initialised, "batch_set_xf: handle already initialised");
+  BGGE_REQUIRE(q >= 0 && q <= BATCH_MAXQ, "batch_set_xf: q = %d outside [0, %d]", q, BATCH_MAXQ);
+  BGGE_REQUIRE(q == 0 || XF != nullptr, "batch_set_xf: NULL XF");
+  g.q = q;
+  if (q > 0) g.xf_host.assign(XF, XF + g.n * (int64_t)q); else g.xf_host.clear();
+  return OK;
+}
+
 int bgge_batch_set_kernel(bgge_batch* h, int j, int type, double mean_diag) {
   BGGE_HANDLE(h);
   Batch& g = h->g;
@@ -1514,7 +1526,8 @@ int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_i
   for (auto& k : g.kernels)
     for (auto& b : k.blocks) fl += 4 * b.rows * b.nr * (int64_t)g.B;
   if (gemm_flops_per_iter) *gemm_flops_per_iter = fl;
-  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 3;   // per kernel: e', GEMM, draw, GEMM, update; tail: variances, imputation, intercept
+  // per kernel: e', GEMM, draw, GEMM, update; tail: variances, imputation, intercept; fixed effects: reduce, draw, apply
+  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 3 + (g.q > 0 ? 3 : 0);
   return OK;
 }
 
@@ -1537,6 +1550,23 @@ int bgge_batch_chain(bgge_batch* h, double* mu, double* varE, double* varU) {
   if (varE) BGGE_TRY(pull(g.chain_varE.p, varE));
   if (varU)
     for (int j = 0; j < g.nk; ++j) BGGE_TRY(pull(g.chain_varU.p + (size_t)j * nc * Bp, varU + (size_t)j * B * nc));
+  return OK;
+}
+
+// thinned chain of the fixed effects: bet[B x ncum x q] (chain-major, then recorded draw, then coefficient)
+int bgge_batch_chain_bet(bgge_batch* h, double* bet) {
+  BGGE_HANDLE(h);
+  Batch& g = h->g;
+  BGGE_REQUIRE(g.initialised, "batch_chain_bet: handle not initialised");
+  BGGE_REQUIRE(bet != nullptr, "batch_chain_bet: NULL output");
+  BGGE_CUDA(cudaStreamSynchronize(g.stream));
+  const size_t nc = (size_t)g.ncum, Bp = (size_t)g.Bp, B = (size_t)g.B, q = (size_t)g.q;
+  if (nc == 0 || q == 0) return OK;
+  std::vector<double> t(nc * q * Bp);
+  BGGE_CUDA(cudaMemcpy(t.data(), g.chain_bet.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b < B; ++b)
+    for (size_t k = 0; k < nc; ++k)
+      for (size_t c = 0; c < q; ++c) bet[(b * nc + k) * q + c] = t[(k * q + c) * Bp + b];
   return OK;
 }
 
@@ -1579,9 +1609,28 @@ int bgge_batch_summary(bgge_batch* h, double* yHat, double* varE, double* varE_s
     }
   }
   std::vector<double> t(n * Bp);
-  if (yHat)
+  if (yHat) {
     for (size_t b = 0; b < B; ++b)
       for (size_t i = 0; i < n; ++i) yHat[b * n + i] = mu_est[b];
+    if (g.q > 0) {                                                   // + XF colMeans(B_mcmc[draw, ])   (R/BGGE.R:414-415)
+      const size_t q = (size_t)g.q;
+      std::vector<double> cb(B * nc * q);
+      BGGE_TRY(bgge_batch_chain_bet(h, cb.data()));
+      std::vector<double> bmean(q);
+      for (size_t b = 0; b < B; ++b) {
+        for (size_t c = 0; c < q; ++c) {
+          long double a = 0.0L;
+          for (size_t sl : kept) a += cb[(b * nc + sl) * q + c];
+          bmean[c] = k ? (double)(a / (long double)k) : NAN;
+        }
+        for (size_t i = 0; i < n; ++i) {
+          double xb = 0.0;
+          for (size_t c = 0; c < q; ++c) xb += g.xf_host[i + c * n] * bmean[c];
+          yHat[b * n + i] += xb;
+        }
+      }
+    }
+  }
   for (int j = 0; j < g.nk; ++j) {
     if (yHat || u) {
       BGGE_CUDA(cudaMemcpy(t.data(), g.Um.p + (size_t)j * n * Bp, n * Bp * sizeof(double), cudaMemcpyDeviceToHost));

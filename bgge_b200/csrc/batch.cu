@@ -14,6 +14,8 @@ namespace bgge {
 namespace {
 
 constexpr int BT = 256;
+constexpr int TXY = 256;                                       // threads of the (chains x lanes) tiled kernels, see b_draw_kernel
+inline int tile_x(int Bp) { return Bp <= 48 ? 16 : 32; }
 
 __device__ __forceinline__ DrawCfg chain_cfg(const DrawCfg& dc, int b) {
   DrawCfg c = dc;
@@ -21,9 +23,17 @@ __device__ __forceinline__ DrawCfg chain_cfg(const DrawCfg& dc, int b) {
   return c;
 }
 
-// u_j = z/(2n), R = (y - mu0) - sum_j u_j          (R/BGGE.R:254, 260-267)
+// sum of count values p[k * stride] by one warp in a fixed order: lane-strided partial sums, then a xor tree
+__device__ __forceinline__ double warp_sum_strided(const double* __restrict__ p, int count, long long stride, int lane) {
+  double a = 0.0;
+  for (int k = lane; k < count; k += 32) a += p[(long long)k * stride];
+  return warp_sum(a);
+}
+
+// u_j = z/(2n), R = ((y - mu0) - XF Bet) - sum_j u_j          (R/BGGE.R:254, 260-267)
 __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* __restrict__ Y,
-                              const double* __restrict__ mu0, double* __restrict__ U, double* __restrict__ R, DrawCfg dc) {
+                              const double* __restrict__ mu0, double* __restrict__ U, double* __restrict__ R, DrawCfg dc,
+                              int q, const double* __restrict__ xf, const double* __restrict__ Bet) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n * Bp) return;
   const long long i = idx / Bp;
@@ -42,7 +52,111 @@ __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* 
     U[(long long)j * n * Bp + idx] = uj;
     usum = (j == 0) ? uj : usum + uj;
   }
-  R[idx] = (Y[idx] - mu0[b]) - usum;
+  double rv = Y[idx] - mu0[b];
+  if (q > 0) {                                                      // R/BGGE.R:264
+    double xb = 0.0;
+    for (int k = 0; k < q; ++k) xb += xf[i + (long long)k * n] * Bet[(long long)k * Bp + b];
+    rv -= xb;
+  }
+  R[idx] = rv - usum;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fixed effects shared by all chains (R/BGGE.R:284-290, 106-109): three small kernels at the head of an iteration.
+// XF is n x q column-major (every chain of a tile reads the same x: broadcast loads), Bet / BetOld are [q][Bp].
+// ---------------------------------------------------------------------------------------------------------------------
+// partial sums over a row chunk of XF'(temp + XF Bet), temp = R - shift     -> part[chunk][k][Bp]
+__global__ void __launch_bounds__(TXY)
+b_xf_reduce_kernel(long long n, int q, int Bp, int rows_per_chunk, const double* __restrict__ xf,
+                   const double* __restrict__ R, const double* __restrict__ Bet, const double* __restrict__ shift,
+                   double* __restrict__ part, long long* __restrict__ advance_it) {
+  __shared__ double zs[TXY];
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
+  if (advance_it != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && ry == 0) *advance_it += 1;
+  const long long i0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long i1 = min(n, i0 + rows_per_chunk);
+  double acc[BATCH_MAXQ], bet[BATCH_MAXQ];
+#pragma unroll
+  for (int k = 0; k < BATCH_MAXQ; ++k) {
+    acc[k] = 0.0;
+    bet[k] = (k < q && b < Bp) ? Bet[(long long)k * Bp + b] : 0.0;
+  }
+  if (b < Bp) {
+    const double sh = shift[b];
+    for (long long i = i0 + ry; i < i1; i += ty) {
+      double x[BATCH_MAXQ];
+      double xb = 0.0;
+#pragma unroll
+      for (int k = 0; k < BATCH_MAXQ; ++k) {
+        x[k] = k < q ? xf[i + (long long)k * n] : 0.0;
+        if (k < q) xb += x[k] * bet[k];
+      }
+      const double t = (R[i * Bp + b] - sh) + xb;                   // temp + XF Bet   (R/BGGE.R:285)
+#pragma unroll
+      for (int k = 0; k < BATCH_MAXQ; ++k)
+        if (k < q) acc[k] = fma(x[k], t, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < BATCH_MAXQ; ++k) {
+    if (k >= q) break;
+    zs[ry * tx + threadIdx.x] = acc[k];
+    __syncthreads();
+    if (ry == 0 && b < Bp) {
+      double t = 0.0;
+      for (int l = 0; l < ty; ++l) t += zs[l * tx + threadIdx.x];   // fixed order
+      part[((long long)blockIdx.x * q + k) * Bp + b] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per chain: media = tXX XF'temp; Bet = media + chol(sigsq tXX)' z; lane k owns coefficient k
+__global__ void __launch_bounds__(128)
+b_xf_draw_kernel(int q, int B, int Bp, int nchunks, const double* __restrict__ part, const double* __restrict__ txx,
+                 const double* __restrict__ lchol, const double* __restrict__ sigsq, double* __restrict__ Bet,
+                 double* __restrict__ BetOld, const long long* __restrict__ itp, DrawCfg dc) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const long long it = *itp;
+  const DrawCfg c = chain_cfg(dc, b);
+  double v[BATCH_MAXQ];
+#pragma unroll
+  for (int k = 0; k < BATCH_MAXQ; ++k)
+    v[k] = k < q ? warp_sum_strided(part + (long long)k * Bp + b, nchunks, (long long)q * Bp, lane) : 0.0;
+  const double z = lane < q ? draw_normal(c, it, STREAM_XF, (unsigned long long)lane, 0) : 0.0;
+  double media = 0.0, lz = 0.0;
+#pragma unroll
+  for (int k2 = 0; k2 < BATCH_MAXQ; ++k2) {
+    const double zk = __shfl_sync(0xffffffffu, z, k2);
+    if (k2 < q && lane < q) {
+      media += txx[lane + (long long)k2 * q] * v[k2];
+      if (k2 <= lane) lz += lchol[lane + (long long)k2 * q] * zk;
+    }
+  }
+  if (lane < q) {
+    const long long o = (long long)lane * Bp + b;
+    BetOld[o] = Bet[o];
+    Bet[o] = media + sqrt(sigsq[b]) * lz;
+  }
+}
+
+// R = (R + XF BetOld) - XF Bet                                                  (R/BGGE.R:285, 289)
+__global__ void b_xf_apply_kernel(long long n, int q, int B, int Bp, const double* __restrict__ xf,
+                                  const double* __restrict__ Bet, const double* __restrict__ BetOld, double* __restrict__ R) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n * Bp) return;
+  const long long i = idx / Bp;
+  const int b = (int)(idx % Bp);
+  if (b >= B) return;
+  double xo = 0.0, xn = 0.0;
+  for (int k = 0; k < q; ++k) {
+    const double x = xf[i + (long long)k * n];
+    xo += x * BetOld[(long long)k * Bp + b];
+    xn += x * Bet[(long long)k * Bp + b];
+  }
+  R[idx] = (R[idx] + xo) - xn;
 }
 
 // E' = (R - shift_b) + U_j
@@ -61,8 +175,6 @@ __global__ void b_eprime_kernel(long long total, int Bp, const double* __restric
 // (40 at 8 GPUs) a thread-per-chain layout leaves the chip idle behind long serial loops (r02: b_draw 79 us at B = 40).
 // Block = tx chains x ty lanes with tx * ty = 256; tx = 16 for <= 48 chain columns (44 columns = 16 + 16 + 12 lanes
 // busy instead of 32 + 12), else 32.
-constexpr int TXY = 256;
-inline int tile_x(int Bp) { return Bp <= 48 ? 16 : 32; }
 
 // Blocks [0, n_ctiles): one coefficient draw per thread (ty columns x tx chains per block), partial sums of b^2/s per
 // block.  Blocks >= n_ctiles prepare, off the critical path, the draws later kernels of the iteration would otherwise
@@ -179,13 +291,6 @@ b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const doubl
   }
 }
 
-// sum of count values p[k * stride] by one warp in a fixed order: lane-strided partial sums, then a xor tree
-__device__ __forceinline__ double warp_sum_strided(const double* __restrict__ p, int count, long long stride, int lane) {
-  double a = 0.0;
-  for (int k = lane; k < count; k += 32) a += p[(long long)k * stride];
-  return warp_sum(a);
-}
-
 struct ChainArgs {
   long long n;
   int nk, B, Bp, nchunks;
@@ -206,6 +311,9 @@ struct ChainArgs {
   double* chain_mu;
   double* chain_varE;
   double* chain_varU;
+  int q;
+  const double* Bet;    // [q][Bp]
+  double* chain_bet;    // [ncum][q][Bp]
   const double* chiK;   // prepared draws (b_draw_kernel's extra blocks); zmu == nullptr: draw the intercept normal here
   const double* chiE;
   const double* zmu;
@@ -248,7 +356,8 @@ __global__ void __launch_bounds__(TXY)
 b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double* __restrict__ R,
                  const double* __restrict__ U, double* __restrict__ Y, const int* __restrict__ narank,
                  const double* __restrict__ mu, const double* __restrict__ shift, const double* __restrict__ sigsq,
-                 const long long* __restrict__ itp, int do_na, double* __restrict__ part, const double* __restrict__ zna) {
+                 const long long* __restrict__ itp, int do_na, double* __restrict__ part, const double* __restrict__ zna,
+                 int q, const double* __restrict__ xf, const double* __restrict__ Bet) {
   __shared__ double zs[TXY];
   const int tx = blockDim.x, ty = blockDim.y;
   const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
@@ -267,9 +376,11 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
           double uhat = 0.0;
           for (int j = 0; j < nk; ++j) uhat = (j == 0) ? U[idx] : uhat + U[(long long)j * n * Bp + idx];
           const double z = zna[(long long)k * Bp + b];   // drawn by the extra blocks of the last b_draw launch
-          const double yv = ((0.0 + mub) + uhat) + sd * z;
+          double aux = 0.0;                              // XF[yNA, ] Bet (R/BGGE.R:375)
+          for (int c = 0; c < q; ++c) aux += xf[i + (long long)c * n] * Bet[(long long)c * Bp + b];
+          const double yv = ((aux + mub) + uhat) + sd * z;
           Y[idx] = yv;
-          rv = (((yv - uhat) - 0.0) - mub) + shb;
+          rv = (((yv - uhat) - aux) - mub) + shb;
           R[idx] = rv;
         }
       }
@@ -299,6 +410,7 @@ __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, Draw
       a.chain_mu[slot * a.Bp + b] = a.mu[b];
       a.chain_varE[slot * a.Bp + b] = a.sigsq[b];
       for (int j = 0; j < a.nk; ++j) a.chain_varU[((long long)j * a.ncum + slot) * a.Bp + b] = a.sigb[(long long)j * a.Bp + b];
+      for (int k = 0; k < a.q; ++k) a.chain_bet[(slot * a.q + k) * a.Bp + b] = a.Bet[(long long)k * a.Bp + b];
     }
   }
   const double z = a.zmu ? a.zmu[b] : draw_normal(c, it + 1, STREAM_MU, 0ull, 0);
@@ -341,6 +453,9 @@ ChainArgs chain_args(Batch* g, const double* part) {
   a.chain_mu = g->chain_mu.p;
   a.chain_varE = g->chain_varE.p;
   a.chain_varU = g->chain_varU.p;
+  a.q = g->q;
+  a.Bet = g->Bet.p;
+  a.chain_bet = g->chain_bet.p;
   a.chiK = g->chiK.p;
   a.chiE = g->chiE.p;
   a.zmu = g->zmu.p;
@@ -357,7 +472,7 @@ int launch_tail(Batch* g, bool init) {
     b_chain_var_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part.p), g->draw);
   b_na_sumr_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p, g->narank.p,
                                         g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p,
-                                        g->zna.p);
+                                        g->zna.p, g->q, g->xf.p, g->Bet.p);
   ChainArgs ca = chain_args(g, g->part2.p);
   if (init) ca.zmu = nullptr;   // no b_draw launch has run yet: the first intercept's normal is drawn in place
   b_chain_mu_kernel<<<cb, 128, 0, st>>>(ca, g->draw);
@@ -370,10 +485,17 @@ int launch_iteration(Batch* g) {
   const long long total = g->n * g->Bp;
   const unsigned eg = (unsigned)((total + BT - 1) / BT);
   const int tx = tile_x(g->Bp), ty = TXY / tx;
+  if (g->q > 0) {   // fixed effects, between the intercept (drawn by the previous tail) and the kernels; advances `it`
+    b_xf_reduce_kernel<<<dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
+        g->n, g->q, g->Bp, g->rows_per_chunk, g->xf.p, g->R.p, g->Bet.p, g->shift.p, g->xf_part.p, g->it.p);
+    b_xf_draw_kernel<<<(unsigned)((g->B + 3) / 4), 128, 0, st>>>(g->q, g->B, g->Bp, g->nchunks, g->xf_part.p, g->txx.p,
+                                                               g->lchol.p, g->sigsq.p, g->Bet.p, g->BetOld.p, g->it.p, g->draw);
+    b_xf_apply_kernel<<<eg, BT, 0, st>>>(g->n, g->q, g->B, g->Bp, g->xf.p, g->Bet.p, g->BetOld.p, g->R.p);
+  }
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     double* Uj = g->U.p + (size_t)j * total;
-    b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p, j == 0 ? g->it.p : nullptr);
+    b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p, (j == 0 && g->q == 0) ? g->it.p : nullptr);
     BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj));
     const bool last = j == g->nk - 1;
     PreDraws pd{g->chiK.p, g->chiE.p, g->zmu.p, g->zna.p, g->max_na, last ? 1 : 0, g->n_na.p, (long long)g->n,
@@ -490,8 +612,51 @@ int batch_init(Batch* g) {
     for (int j = 0; j < g->nk; ++j) Sc[(size_t)j * Bp + b] = (NU + 2.0) * g->R2 * vy[(size_t)b] / g->kernels[j].mean_diag;
   }
 
+  // ---- fixed effects (R/BGGE.R:208-212): one XF for all chains, Bet_b = solve(crossprod(XF), crossprod(XF, y_b))
+  const int q = g->q;
+  BGGE_REQUIRE(q >= 0 && q <= BATCH_MAXQ, "batch: at most %d fixed effects in the batched sampler (q = %d)", BATCH_MAXQ, q);
+  std::vector<double> bet0((size_t)std::max(1, q) * Bp, 0.0), txx, lch;
+  if (q > 0) {
+    BGGE_REQUIRE((int64_t)g->xf_host.size() == n * q, "batch: XF not set");
+    std::vector<double> xtx((size_t)q * q, 0.0);
+    for (int a = 0; a < q; ++a)
+      for (int c = a; c < q; ++c) {
+        long double v = 0.0L;
+        for (int64_t i = 0; i < n; ++i) v += (long double)g->xf_host[(size_t)(i + a * n)] * g->xf_host[(size_t)(i + c * n)];
+        xtx[(size_t)a + (size_t)c * q] = xtx[(size_t)c + (size_t)a * q] = (double)v;
+      }
+    if (!solve_spd_inverse(q, xtx, txx)) {
+      set_error("batch: crossprod(XF) is singular");
+      return ERR_INVALID;
+    }
+    if (!chol_lower(q, txx, lch)) {
+      set_error("batch: solve(crossprod(XF)) is not positive definite");
+      return ERR_INVALID;
+    }
+    std::vector<double> xty((size_t)q);
+    for (int b = 0; b < B; ++b) {
+      for (int a = 0; a < q; ++a) {
+        long double v = 0.0L;
+        for (int64_t i = 0; i < n; ++i) v += (long double)g->xf_host[(size_t)(i + a * n)] * Y[(size_t)i * Bp + b];
+        xty[(size_t)a] = (double)v;
+      }
+      for (int a = 0; a < q; ++a) {
+        double v = 0.0;
+        for (int c = 0; c < q; ++c) v += txx[(size_t)a + (size_t)c * q] * xty[(size_t)c];
+        bet0[(size_t)a * Bp + b] = v;
+      }
+    }
+  }
+
   // ---- state
   const size_t total = (size_t)n * Bp;
+  BGGE_TRY(up(g->Bet, bet0, st));
+  BGGE_TRY(up(g->BetOld, bet0, st));
+  if (q > 0) {
+    BGGE_TRY(up(g->xf, g->xf_host, st));
+    BGGE_TRY(up(g->txx, txx, st));
+    BGGE_TRY(up(g->lchol, lch, st));
+  }
   BGGE_TRY(up(g->Y, Y, st));
   BGGE_TRY(up(g->narank, narank, st));
   BGGE_TRY(up(g->n_na, nna_host, st));
@@ -526,6 +691,8 @@ int batch_init(Batch* g) {
   BGGE_CUDA(g->chain_mu.alloc(nc * Bp));
   BGGE_CUDA(g->chain_varE.alloc(nc * Bp));
   BGGE_CUDA(g->chain_varU.alloc(nc * Bp * g->nk));
+  BGGE_CUDA(g->chain_bet.alloc(nc * Bp * (size_t)std::max(1, q)));
+  BGGE_CUDA(g->xf_part.alloc((size_t)g->nchunks * (size_t)std::max(1, q) * Bp));
 
   // ---- per kernel: transposed copies, GEMM work items (split-K so that every launch fills the machine)
   for (int j = 0; j < g->nk; ++j) {
@@ -685,7 +852,7 @@ int batch_init(Batch* g) {
     BGGE_TRY(up(bk.back_items, bi, st));
   }
   const unsigned ig = (unsigned)((total + BT - 1) / BT);
-  b_init_kernel<<<ig, BT, 0, st>>>(n, g->nk, B, Bp, g->Y.p, g->mu0.p, g->U.p, g->R.p, g->draw);
+  b_init_kernel<<<ig, BT, 0, st>>>(n, g->nk, B, Bp, g->Y.p, g->mu0.p, g->U.p, g->R.p, g->draw, q, g->xf.p, g->Bet.p);
   BGGE_CUDA(cudaGetLastError());
   BGGE_TRY(launch_tail(g, true));
   BGGE_CUDA(cudaStreamSynchronize(st));

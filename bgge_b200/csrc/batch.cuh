@@ -5,6 +5,8 @@
 
 namespace bgge {
 
+constexpr int BATCH_MAXQ = 16;   // fixed effects the batched sampler keeps in registers per thread
+
 struct BatchBlock {
   int64_t pos0 = 0, rows = 0, nr = 0, ldu = 0, col_off = 0;
   double* dU = nullptr;   // rows x nr, column-major (borrowed from the handle that decomposed, or owned)
@@ -34,6 +36,12 @@ struct Batch {
   cudaStream_t stream = nullptr;
   bool own_stream = false, initialised = false, any_na = false;
   std::vector<BatchKernel> kernels;
+  int q = 0;                             // fixed effects shared by all chains (0: none), q <= BATCH_MAXQ
+  std::vector<double> xf_host;           // n x q, column-major
+  DevBuf<double> xf, txx, lchol;         // XF, solve(crossprod(XF)), its lower Cholesky factor
+  DevBuf<double> Bet, BetOld;            // [q][Bp]
+  DevBuf<double> xf_part;                // [nchunks][q][Bp] partial sums of XF'(temp + XF Bet)
+  DevBuf<double> chain_bet;              // [ncum][q][Bp]
   std::vector<double> y_host;            // chain-major: y of chain b at [b*n, (b+1)*n)
   std::vector<unsigned char> na_host;
   int64_t ite = 0, burn = 0, thin = 1, ncum = 0, done = 0;

@@ -397,7 +397,9 @@ scalar_kernel(const ScalarArgs a, DrawCfg dc) {
   }
 }
 
-// ------------------------------------------------------------------ small host linear algebra (q x q)
+}  // namespace
+
+// ------------------------------------------------------------------ small host linear algebra (q x q; shared with batch.cu)
 bool solve_spd_inverse(int q, std::vector<double> A /*col-major*/, std::vector<double>& inv) {
   // Gauss-Jordan with partial pivoting (same family as LAPACK dgesv behind R's solve())
   inv.assign((size_t)q * q, 0.0);
@@ -446,6 +448,8 @@ bool chol_lower(int q, const std::vector<double>& A, std::vector<double>& Lw) {
   }
   return true;
 }
+
+namespace {
 
 template <typename T>
 int upload(DevBuf<T>& buf, const std::vector<T>& v, cudaStream_t st) {

@@ -292,4 +292,9 @@ int plan_resident(Gibbs* g);
 int launch_resident(Gibbs* g, int64_t iters);
 int ensure_dense(HostBlock& bl, cudaStream_t st);   // materialise U = Z C^{-1/2} W of a factorised block
 
+// q x q host linear algebra of the fixed-effects step (gibbs.cu): inverse of a symmetric positive definite matrix
+// (column-major) and the lower Cholesky factor; false when singular / not positive definite.
+bool solve_spd_inverse(int q, std::vector<double> A, std::vector<double>& inv);
+bool chol_lower(int q, const std::vector<double>& A, std::vector<double>& Lw);
+
 }  // namespace bgge

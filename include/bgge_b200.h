@@ -253,6 +253,8 @@ typedef struct bgge_batch bgge_batch;
 int bgge_batch_create(int64_t n, int nk, int n_chains, void* stream, bgge_batch** out);
 void bgge_batch_destroy(bgge_batch* h);
 int bgge_batch_set_y(bgge_batch* h, const double* Y, const uint8_t* na_mask);              /* B x n */
+/* fixed effects shared by all chains: XF n x q column-major, q <= 16 (R/BGGE.R:208-212, 284-290); before init */
+int bgge_batch_set_xf(bgge_batch* h, const double* XF, int q);
 int bgge_batch_set_kernel(bgge_batch* h, int j, int type, double mean_diag);
 int bgge_batch_add_block(bgge_batch* h, int j, int64_t pos0, int64_t rows, int64_t nr, const double* s, const double* U,
                          int64_t ldu, int on_device);
@@ -263,6 +265,8 @@ int bgge_batch_sync(bgge_batch* h);
 int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_iter, int* launches_per_iter);
 /* mu[B x n_cum], varE[B x n_cum], varU[nk x B x n_cum] */
 int bgge_batch_chain(bgge_batch* h, double* mu, double* varE, double* varU);
+/* thinned chain of the fixed effects, bet[B x n_cum x q] (the reference keeps B.mcmc internally, R/BGGE.R:392) */
+int bgge_batch_chain_bet(bgge_batch* h, double* bet);
 /* yHat[B x n], varE[B], varE_sd[B], u[nk x B x n], u_sd[nk x B x n], varu[nk x B], varu_sd[nk x B], y[B x n] */
 int bgge_batch_summary(bgge_batch* h, double* yHat, double* varE, double* varE_sd, double* u, double* u_sd, double* varu,
                        double* varu_sd, double* y);

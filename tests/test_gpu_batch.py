@@ -138,3 +138,88 @@ def test_single_chain_device_rng_matches_the_oracle_draw_for_draw():
         assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, mode
         assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, mode
         assert relmax(np.asarray(got["yHat"]).ravel(), np.asarray(ref["yHat"]).ravel()) <= 1e-9, mode
+
+
+def _env_design(L, E):
+    XF = np.zeros((L * E, E))
+    for e in range(E):
+        XF[e * L:(e + 1) * L, e] = 1.0
+    return XF
+
+
+@pytest.mark.parametrize("model,B,q_extra", [("MM", 4, 0), ("MDs", 9, 1), ("MDe", 41, 0)])
+def test_batched_chains_with_fixed_effects_match_the_oracle_draw_for_draw(model, B, q_extra):
+    """XF in the batched sampler (R/BGGE.R:208-212, 284-290, 375, 414-415): environment indicators (+ one continuous
+    covariate) shared by all chains, folds with different NA masks, every chain against the oracle fed the chain's own
+    Philox stream.  B = 41 uses the 16-chain thread tiles with a ragged last tile."""
+    import bgge_b200
+    from helpers import PhiloxDraws
+    L, E, p = 36, 3, 50
+    X = markers(L, p, 21)
+    Y, names = design(L, E)
+    n = L * E
+    ne = [L] * E
+    Kf = bgge_b200.getK(Y, X, kernel="GB", model=model, rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel="GB", model=model, rownames=names)
+    rng = np.random.default_rng(22)
+    XF = _env_design(L, E)
+    if q_extra:
+        XF = np.hstack([XF, rng.standard_normal((n, q_extra))])
+    q = XF.shape[1]
+    y = rng.standard_normal(n) + XF @ rng.standard_normal(q)
+    perm = rng.permutation(L)
+    Yb = np.tile(y, (B, 1))
+    for b in range(1, B):
+        Yb[b, np.tile(perm % 6 == b % 6, E)] = np.nan
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(bk["s"].shape[0] for bk in bl) for bl in Ei]
+    ite, burn, thin, seed, chain0 = 10, 2, 2, 5, 1
+    fits = bgge_b200.BGGE_batch(Yb, Kf, XF=XF, ne=ne, ite=ite, burn=burn, thin=thin, seed=seed, chain0=chain0, eig=Ei)
+    for b in (range(B) if B <= 9 else [0, 1, 15, 16, 31, 32, B - 1]):
+        draws = PhiloxDraws(seed, chain0 + b, n, nrs, q=q, n_na=int(np.isnan(Yb[b]).sum()))
+        ref = oracle.BGGE(Yb[b], Kd, XF=XF, ne=ne, ite=ite, burn=burn, thin=thin, draws=draws, eig=Ei)
+        got = fits[b]
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, b
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, b
+        assert relmax(got["chain"]["Bet"], ref["_Bet_chain"]) <= 1e-9, b
+        for nm in ref["K"]:
+            assert relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]) <= 1e-9, (b, nm)
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (b, nm)
+        assert relmax(got["yHat"], ref["yHat"]) <= 1e-9, b
+        assert relmax(got["y"], ref["y"]) <= 1e-9, b
+
+
+def test_batch_with_fixed_effects_reproduces_single_chains():
+    import bgge_b200
+    L, E, p, B = 33, 4, 60, 6
+    X = markers(L, p, 6)
+    Y0, names = design(L, E)
+    K = bgge_b200.getK(Y0, X, kernel="GK", model="MDs", rownames=names)
+    y = phenotype(oracle.gb_kernel(X), L, E, 7)
+    Y = _folds(y, B, 1)
+    XF = _env_design(L, E)
+    kw = dict(XF=XF, ne=[L] * E, ite=30, burn=6, thin=3, seed=4)
+    fits = bgge_b200.BGGE_batch(Y, K, chain0=2, **kw)
+    for b in range(B):
+        ref = bgge_b200.BGGE(Y[b], K, chain=2 + b, mode=1, **kw)
+        got = fits[b]
+        assert relmax(got["chain"]["mu"], ref["chain"]["mu"]) <= 1e-9, b
+        assert relmax(got["chain"]["varE"], ref["chain"]["varE"]) <= 1e-9, b
+        for nm in ref["K"]:
+            assert relmax(got["K"][nm]["u"], ref["K"][nm]["u"]) <= 1e-9, (b, nm)
+        assert relmax(got["yHat"], np.asarray(ref["yHat"]).ravel()) <= 1e-9, b
+        assert relmax(got["y"], ref["y"]) <= 1e-9, b
+
+
+def test_batch_rejects_too_many_or_singular_fixed_effects():
+    import bgge_b200
+    L, E = 20, 2
+    X = markers(L, 30, 1)
+    Y0, names = design(L, E)
+    K = bgge_b200.getK(Y0, X, kernel="GB", model="MM", rownames=names)
+    Y = np.random.default_rng(0).standard_normal((2, L * E))
+    with pytest.raises(Exception, match="outside"):
+        bgge_b200.BGGE_batch(Y, K, XF=np.random.default_rng(1).standard_normal((L * E, 17)), ne=[L] * E, ite=2, burn=0, thin=1)
+    XF = np.ones((L * E, 2))
+    with pytest.raises(Exception, match="singular|positive definite"):
+        bgge_b200.BGGE_batch(Y, K, XF=XF, ne=[L] * E, ite=2, burn=0, thin=1)

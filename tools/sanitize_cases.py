@@ -91,6 +91,15 @@ def main():
     err = relmax(fits[3]["chain"]["varE"], one["chain"]["varE"])
     print(f"batched chains B={B}                   err={err:.2e}", flush=True)
     assert err <= 1e-9
+    XF = np.zeros((L * E, E))
+    for e in range(E):
+        XF[e * L:(e + 1) * L, e] = 1.0
+    Yb[2, 5:9] = np.nan
+    fits = bgge_b200.BGGE_batch(Yb, Kf, XF=XF, ne=[L] * E, ite=6, burn=0, thin=1, seed=5)
+    one = bgge_b200.BGGE(Yb[2], Kf, XF=XF, ne=[L] * E, ite=6, burn=0, thin=1, seed=5, chain=2, mode=2)
+    err = relmax(fits[2]["chain"]["varE"], one["chain"]["varE"])
+    print(f"batched chains B={B} with XF, NA        err={err:.2e}", flush=True)
+    assert err <= 1e-9
     print("sanitize cases ok")
 
 
