@@ -558,6 +558,11 @@ def main():
             for mode, k in modes:
                 lib.call("bgge_dev_expand", vp(K0), L, L, vp(gid), vp(env), n, mode, k, vp(Kbuf), n, stream)
         t_exp = timed(torch, expand_all)
+        # write-only roofline of this box: the expansion stores n^2 doubles and reads almost nothing (K0 stays in L2),
+        # so the denominator is the fill rate of the same buffer, not the copy rate
+        Kbuf.zero_()
+        t_fill = min(timed(torch, Kbuf.zero_) for _ in range(3))
+        fill_gbs = 8.0 * n * n / t_fill / 1e9
         mean_diag0 = float(torch.diagonal(K0).mean().item())
 
         # ------------------------------------------------------------- eigen (setup, timed separately)
@@ -961,6 +966,7 @@ def main():
                      "frac_of_dgemm_burst": flops / t_contr / 1e12 / dg_burst,
                      "frac_of_dgemm_sustained": flops / t_contr / 1e12 / dg_sust,
                      "quantile_exp_s": t_q, "expansion_s": t_exp, "expansion_gbs": 8.0 * n * n * len(modes) / t_exp / 1e9,
+                     "write_only_fill_gbs": fill_gbs, "expansion_frac_of_fill": 8.0 * n * n * len(modes) / t_exp / 1e9 / fill_gbs,
                      "n_gpus_in_contraction": world, "marker_gen_s": t_gen,
                      "row_panel_compute_exchange_s": contr_split[-1] if contr_split else None,
                      "host_buffers": getk_host,

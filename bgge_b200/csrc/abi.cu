@@ -338,8 +338,7 @@ int bgge_dev_gk_exp(const double* dD, int64_t ldd, int64_t L, double bw, const d
 int bgge_dev_expand(const double* dK0, int64_t ldk, int64_t L, const int32_t* d_gid, const int32_t* d_env, int64_t n,
                     int mode, int env_k, double* dOut, int64_t ldo, void* stream) {
   BGGE_TRY(ensure_device());
-  (void)L;
-  return expand_launch(dK0, ldk, d_gid, d_env, n, mode, env_k, dOut, ldo, as_stream(stream));
+  return expand_launch(dK0, ldk, L, d_gid, d_env, n, mode, env_k, dOut, ldo, as_stream(stream));
 }
 
 int bgge_getk_base(const double* X, int64_t L, int64_t p, int kind, const double* bandwidth, int nb, double quantil,
@@ -382,7 +381,7 @@ int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int3
     BGGE_CUDA(cudaMemcpy(denv.p, env, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
   }
   BGGE_CUDA(dOut.alloc((size_t)n * n));
-  BGGE_TRY(expand_launch(dK0.p, L, dgid.p, denv.p, n, mode, env_k, dOut.p, n, nullptr));
+  BGGE_TRY(expand_launch(dK0.p, L, L, dgid.p, denv.p, n, mode, env_k, dOut.p, n, nullptr));
   BGGE_CUDA(cudaMemcpy(out, dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
   return OK;
 }
@@ -418,7 +417,7 @@ int bgge_getk(const double* X, int64_t L, int64_t p, int kind, const double* ban
   BGGE_CUDA(dOut.alloc((size_t)n * n));
   int o = 0;
   auto emit = [&](const double* k0, int mode, int k) -> int {
-    BGGE_TRY(expand_launch(k0, L, dgid.p, denv.p, n, mode, k, dOut.p, n, nullptr));
+    BGGE_TRY(expand_launch(k0, L, L, dgid.p, denv.p, n, mode, k, dOut.p, n, nullptr));
     BGGE_CUDA(cudaMemcpy(out[o++], dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
     return OK;
   };
@@ -938,7 +937,7 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       DevBuf<double> dA, dW, dS;
       BGGE_CUDA(dA.alloc((size_t)m * m));
       BGGE_CUDA(dW.alloc((size_t)m));
-      BGGE_TRY(expand_launch(dK0, ld0, dgid_all.p + pos, denv_all.p + pos, m, mode, env_k, dA.p, m, st));
+      BGGE_TRY(expand_launch(dK0, ld0, L, dgid_all.p + pos, denv_all.p + pos, m, mode, env_k, dA.p, m, st));
       int64_t nr = 0;
       BGGE_TRY(eig_decompose(dA.p, m, m, tol, dW.p, &nr, st));
       if (nr == 0) continue;

@@ -161,6 +161,92 @@ __global__ void expand_kernel(const double* __restrict__ K0, int64_t ldk, const 
   }
 }
 
+// Two rows per thread, one 16-byte streaming store per element pair (ldo even, 16-byte aligned output): the pass is
+// write-only -- K0 and the row codes stay in L2 -- so it is bound by the store path; evict-first stores keep the
+// 12.8 GB output of a C5 kernel from flushing K0 out of L2.  Same values as expand_kernel (a gather and a mask).
+// jord (optional): the columns in genotype order (expand_order_*): the CTAs that run together then need the same few
+// columns of K0 -- K0 (0.8 GB at C5) is read from HBM once instead of once per environment -- and write E distant
+// regions of the output at a time: 4285 -> 6105 GB/s at n = 40000 (memset of the same buffer: 7325 GB/s,
+// profiles/r02_expand_probe.log).  The order only decides WHEN an element is written, never its value.
+template <int MODE>
+__global__ void expand2_kernel(const double* __restrict__ K0, int64_t ldk, const int* __restrict__ gid,
+                               const int* __restrict__ env, int64_t n, int kenv, double* __restrict__ out,
+                               int64_t ldo, const int* __restrict__ jord) {
+  const int64_t i = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const bool two = i + 1 < n;
+  const int ga = gid[i], gb = two ? gid[i + 1] : ga;
+  const int ea = (MODE == 1 || MODE == 2) ? env[i] : 0;
+  const int eb = (MODE == 1 || MODE == 2) ? (two ? env[i + 1] : ea) : 0;
+  const int64_t j0 = (int64_t)blockIdx.y * 16;
+#pragma unroll 4
+  for (int jj = 0; jj < 16; ++jj) {
+    if (j0 + jj >= n) break;
+    const int64_t j = jord ? (int64_t)jord[j0 + jj] : j0 + jj;
+    const int gj = gid[j];
+    const double* col = K0 + (int64_t)gj * ldk;
+    double2 v;
+    if (MODE == 0) {
+      v.x = __ldg(col + ga);
+      v.y = __ldg(col + gb);
+    } else if (MODE == 1) {
+      const int ej = env[j];
+      v.x = (ea == ej) ? __ldg(col + ga) : 0.0;
+      v.y = (eb == ej) ? __ldg(col + gb) : 0.0;
+    } else if (MODE == 2) {
+      const bool cj = env[j] == kenv;
+      v.x = (cj && ea == kenv) ? __ldg(col + ga) : 0.0;
+      v.y = (cj && eb == kenv) ? __ldg(col + gb) : 0.0;
+    } else {
+      v.x = (ga == gj) ? 1.0 : 0.0;
+      v.y = (gb == gj) ? 1.0 : 0.0;
+    }
+    double* dst = out + i + j * ldo;
+    if (two) __stcs(reinterpret_cast<double2*>(dst), v);
+    else __stcs(dst, v.x);
+  }
+}
+
+// Counting sort of the columns by genotype code (codes in [0, L); anything else goes to bucket L): count -> exclusive
+// scan -> scatter.  The order inside a bucket depends on the atomics and is irrelevant (see expand2_kernel).
+__global__ void expand_order_count_kernel(const int* __restrict__ gid, int64_t n, int L, int* __restrict__ cnt) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int g = gid[j];
+  atomicAdd(&cnt[(unsigned)g < (unsigned)L ? g : L], 1);
+}
+
+__global__ void __launch_bounds__(1024) expand_order_scan_kernel(int* __restrict__ cnt, int nb) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int per = (nb + 1023) / 1024;
+  const int lo = min(nb, t * per), hi = min(nb, lo + per);
+  int s = 0;
+  for (int k = lo; k < hi; ++k) s += cnt[k];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {   // inclusive scan of the per-thread sums
+    const int v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = t > 0 ? part[t - 1] : 0;
+  for (int k = lo; k < hi; ++k) {
+    const int c = cnt[k];
+    cnt[k] = run;
+    run += c;
+  }
+}
+
+__global__ void expand_order_fill_kernel(const int* __restrict__ gid, int64_t n, int L, int* __restrict__ cursor,
+                                         int* __restrict__ jord) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int g = gid[j];
+  jord[atomicAdd(&cursor[(unsigned)g < (unsigned)L ? g : L], 1)] = (int)j;
+}
+
 }  // namespace
 
 // ====================================================================== launchers
@@ -220,12 +306,53 @@ int gk_exp_launch(const double* dD, int64_t ldd, int64_t L, double bw, const dou
   return OK;
 }
 
-int expand_launch(const double* dK0, int64_t ldk, const int* d_gid, const int* d_env, int64_t n, int mode, int kenv,
-                  double* dOut, int64_t ldo, cudaStream_t st) {
+int expand_launch(const double* dK0, int64_t ldk, int64_t L, const int* d_gid, const int* d_env, int64_t n, int mode,
+                  int kenv, double* dOut, int64_t ldo, cudaStream_t st) {
   if (n <= 0) return OK;
   BGGE_REQUIRE(mode >= 0 && mode <= 3, "expand: unknown mode %d", mode);
   const unsigned gy = (unsigned)((n + 15) / 16);
   BGGE_REQUIRE(gy <= 65535, "expand: n=%lld exceeds grid limit", (long long)n);
+  if (ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(dOut) & 15u) == 0 && !getenv("BGGE_EXPAND_SCALAR")) {
+    dim3 grid2((unsigned)((n + 511) / 512), gy);
+    // large outputs: columns in genotype order (stream-ordered scratch: L + 1 bucket cursors, n column indices)
+    int64_t sort_min = 2048;
+    if (const char* ev = getenv("BGGE_EXPAND_SORT_MIN")) sort_min = atoll(ev);   // test / tuning hook
+    int* scratch = nullptr;
+    int* jord = nullptr;
+    if (L > 0 && L < (1ll << 30) && n >= sort_min && n < (1ll << 31)) {
+      {   // keep the stream-ordered pool's memory across synchronisations (default: released at every sync)
+        static bool tuned[64] = {};
+        int dev = 0;
+        BGGE_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !tuned[dev]) {
+          cudaMemPool_t mp;
+          if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+            unsigned long long keep = 64ull << 20;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+          }
+          cudaGetLastError();
+          tuned[dev] = true;
+        }
+      }
+      BGGE_CUDA(cudaMallocAsync((void**)&scratch, (size_t)(L + 1 + n) * sizeof(int), st));
+      jord = scratch + (L + 1);
+      const unsigned gb = (unsigned)((n + 255) / 256);
+      BGGE_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(L + 1) * sizeof(int), st));
+      expand_order_count_kernel<<<gb, 256, 0, st>>>(d_gid, n, (int)L, scratch);
+      expand_order_scan_kernel<<<1, 1024, 0, st>>>(scratch, (int)L + 1);
+      expand_order_fill_kernel<<<gb, 256, 0, st>>>(d_gid, n, (int)L, scratch, jord);
+    }
+    switch (mode) {
+      case 0: expand2_kernel<0><<<grid2, 256, 0, st>>>(dK0, ldk, d_gid, d_env, n, kenv, dOut, ldo, jord); break;
+      case 1: expand2_kernel<1><<<grid2, 256, 0, st>>>(dK0, ldk, d_gid, d_env, n, kenv, dOut, ldo, jord); break;
+      case 2: expand2_kernel<2><<<grid2, 256, 0, st>>>(dK0, ldk, d_gid, d_env, n, kenv, dOut, ldo, jord); break;
+      default: expand2_kernel<3><<<grid2, 256, 0, st>>>(dK0, ldk, d_gid, d_env, n, kenv, dOut, ldo, jord); break;
+    }
+    const cudaError_t le = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, st);
+    BGGE_CUDA(le);
+    return OK;
+  }
   dim3 grid((unsigned)((n + 255) / 256), gy);
   switch (mode) {
     case 0: expand_kernel<0><<<grid, 256, 0, st>>>(dK0, ldk, d_gid, d_env, n, kenv, dOut, ldo); break;

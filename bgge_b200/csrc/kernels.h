@@ -21,8 +21,9 @@ int quantile7_launch(const double* dD, int64_t ldd, int64_t L, double prob, void
                      cudaStream_t st);
 int gk_exp_launch(const double* dD, int64_t ldd, int64_t L, double bw, const double* d_q, double* dK0, int64_t ldk,
                   cudaStream_t st);
-int expand_launch(const double* dK0, int64_t ldk, const int* d_gid, const int* d_env, int64_t n, int mode, int kenv,
-                  double* dOut, int64_t ldo, cudaStream_t st);
+// L = order of K0 (genotype codes lie in [0, L)); L <= 0: unknown, columns are expanded in their natural order
+int expand_launch(const double* dK0, int64_t ldk, int64_t L, const int* d_gid, const int* d_env, int64_t n, int mode,
+                  int kenv, double* dOut, int64_t ldo, cudaStream_t st);
 
 // eig.cu
 int eig_decompose(double* dA, int64_t m, int64_t lda, double tol, double* d_W, int64_t* nr_out, cudaStream_t st);

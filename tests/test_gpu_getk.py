@@ -101,6 +101,30 @@ def test_expansion_is_bit_exact_gather(lib):
         assert np.array_equal(out, G)
 
 
+@pytest.mark.parametrize("n,sort_min", [(2500, None), (2501, None), (101, "1"), (2500, "1000000")])
+def test_expansion_in_genotype_order_is_bit_exact(lib, monkeypatch, n, sort_min):
+    """Large outputs are written column by column in genotype order (counting sort of the row codes on the device,
+    16-byte streaming stores); odd n takes the 8-byte kernel.  Shuffled, unbalanced codes, some genotypes absent."""
+    if sort_min is not None:
+        monkeypatch.setenv("BGGE_EXPAND_SORT_MIN", sort_min)
+    rng = np.random.default_rng(n)
+    L, E = 300, 5
+    K0 = rng.standard_normal((L, L))
+    gid = rng.integers(0, L - 7, size=n).astype(np.int32)
+    env = rng.integers(0, E, size=n).astype(np.int32)
+    for mode, k in [(lib.EXPAND_G, 0), (lib.EXPAND_GE, 0), (lib.EXPAND_ENV, 3), (lib.EXPAND_GI, 0)]:
+        out = np.full((n, n), np.nan, order="F")
+        lib.call("bgge_getk_expand", lib.ptr(lib.f64(K0)), L, lib.ptr(gid), lib.ptr(env), n, mode, k, lib.ptr(out))
+        G = K0[np.ix_(gid, gid)]
+        if mode == lib.EXPAND_GE:
+            G = G * (env[:, None] == env[None, :])
+        elif mode == lib.EXPAND_ENV:
+            G = G * ((env == k)[:, None] & (env == k)[None, :])
+        elif mode == lib.EXPAND_GI:
+            G = (gid[:, None] == gid[None, :]).astype(np.float64)
+        assert np.array_equal(out, G), mode
+
+
 def test_setkernel_path_and_errors():
     import bgge_b200
     L, E = 12, 2
