@@ -781,7 +781,8 @@ def main():
         if sharded:
             e2e_val, call_s = e2e_sweep_val, []
         else:
-            fit_call()                                   # warm-up: cuSOLVER handle / workspace, module load
+            for _ in range(max(3, min(args.warmup, 3))):   # W >= 3 warm-up calls: cuSOLVER handle / workspace, pool growth
+                fit_call()
             call_s.clear()
             if world > 1:
                 dist.barrier()

@@ -596,6 +596,9 @@ int mrhs_configure(int64_t max_rows, int nb, bool merged, MrhsCfg* cfg) {
     for (int cs = std::max(cs_min, cd.cs_lo); cs <= cd.cs_hi; cs *= 2) {
       const int64_t rs = round_up((max_rows + cs - 1) / cs, 16);
       const int kr_need = (int)((rs + M_T - 1) / M_T);
+      // more than 7 row steps per column on one CTA: two CTAs with half the steps each measured faster
+      // (C3 unit of two members, 3000 rows: 9730 -> 10060 it/s), so leave cs = 1 to the shorter blocks
+      if (!cd.tm && cs == 1 && kr_need > 7 && cd.cs_hi >= 2 && !getenv("BGGE_MRHS_CS")) continue;
       const Inst* inst = find_inst(nb, kr_need, cd.tm);
       if (!inst) continue;
       const size_t slot_bytes = (size_t)inst->g * rs * sizeof(double);
