@@ -18,6 +18,7 @@
 #include <nccl.h>
 #include <dlfcn.h>
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -60,7 +61,8 @@ void nccl_bind() {
       if (n.so) break;
     }
   if (!n.so) {
-    n.why = std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "?");
+    const char* de = dlerror();   // (a second dlerror() call would return NULL)
+    n.why = std::string("libnccl.so.2 could not be loaded: ") + (de ? de : "?");
     return;
   }
   bool ok = true;
@@ -274,26 +276,56 @@ int bgge_getk_base_multi(bgge_comm* const* comms, int ndev, const double* X, int
   const int64_t p_pad = pc * ndev;
   std::vector<int> status((size_t)ndev, OK);
   std::vector<std::string> msg((size_t)ndev);
+  // Host rendezvous in front of the first collective: a device that failed to allocate or upload must not leave the
+  // others waiting inside NCCL, so everybody learns about a failure before anybody enters the all-gather.
+  std::mutex rv_mu;
+  std::condition_variable rv_cv;
+  int rv_arrived = 0;
+  bool rv_failed = false;
+  auto rendezvous = [&](bool ok) -> bool {   // returns true when every device got here without an error
+    std::unique_lock<std::mutex> lk(rv_mu);
+    if (!ok) rv_failed = true;
+    if (++rv_arrived == ndev) rv_cv.notify_all();
+    else rv_cv.wait(lk, [&] { return rv_arrived == ndev; });
+    return !rv_failed;
+  };
   auto worker = [&](int d) -> int {
     bgge_comm* c = comms[d];
-    BGGE_CUDA(cudaSetDevice(c->device));
-    BGGE_TRY(ensure_device());
-    cudaStream_t st;
-    BGGE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = nullptr;
+    auto open_device = [&]() -> int {
+      BGGE_CUDA(cudaSetDevice(c->device));
+      BGGE_TRY(ensure_device());
+      BGGE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      return OK;
+    };
+    const int os = open_device();
+    if (os != OK) {
+      rendezvous(false);
+      return os;
+    }
     struct StreamGuard {
       cudaStream_t s;
       ~StreamGuard() { cudaStreamDestroy(s); }
     } sg{st};
     DevBuf<double> dX, S;
-    BGGE_CUDA(dX.alloc((size_t)ldx * (size_t)p_pad));
-    BGGE_CUDA(S.alloc((size_t)L * L));
+    double* mine = nullptr;
     // my marker columns [d pc, (d + 1) pc): zero the slice (row / column padding), then a strided copy of what exists
-    double* mine = dX.p + (size_t)d * pc * ldx;
-    BGGE_CUDA(cudaMemsetAsync(mine, 0, (size_t)pc * ldx * sizeof(double), st));
-    const int64_t cfirst = (int64_t)d * pc, ccount = std::max<int64_t>(0, std::min<int64_t>(p, cfirst + pc) - cfirst);
-    if (ccount > 0)
-      BGGE_CUDA(cudaMemcpy2DAsync(mine, (size_t)ldx * sizeof(double), X + (size_t)cfirst * L, (size_t)L * sizeof(double),
-                                  (size_t)L * sizeof(double), (size_t)ccount, cudaMemcpyHostToDevice, st));
+    auto prepare = [&]() -> int {
+      BGGE_CUDA(dX.alloc((size_t)ldx * (size_t)p_pad));
+      BGGE_CUDA(S.alloc((size_t)L * L));
+      mine = dX.p + (size_t)d * pc * ldx;
+      BGGE_CUDA(cudaMemsetAsync(mine, 0, (size_t)pc * ldx * sizeof(double), st));
+      const int64_t cfirst = (int64_t)d * pc, ccount = std::max<int64_t>(0, std::min<int64_t>(p, cfirst + pc) - cfirst);
+      if (ccount > 0)
+        BGGE_CUDA(cudaMemcpy2DAsync(mine, (size_t)ldx * sizeof(double), X + (size_t)cfirst * L, (size_t)L * sizeof(double),
+                                    (size_t)L * sizeof(double), (size_t)ccount, cudaMemcpyHostToDevice, st));
+      return OK;
+    };
+    const int ps = prepare();
+    if (!rendezvous(ps == OK)) {
+      if (ps == OK) set_error("another device failed before the exchange");
+      return ps == OK ? ERR_STATE : ps;
+    }
     if (ndev > 1)
       BGGE_NCCL(g_nccl.AllGather(mine, dX.p, (size_t)pc * ldx, ncclDouble, (ncclComm_t)c->comm, st));
     const double divisor = kind == BGGE_KERNEL_GB ? (double)p : 1.0;
