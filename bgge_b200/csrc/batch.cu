@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(TXY)
 b_xf_reduce_kernel(long long n, int q, int Bp, int rows_per_chunk, const double* __restrict__ xf,
                    const double* __restrict__ R, const double* __restrict__ Bet, const double* __restrict__ shift,
                    double* __restrict__ part, long long* __restrict__ advance_it) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   __shared__ double zs[TXY];
   const int tx = blockDim.x, ty = blockDim.y;
   const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(128)
 b_xf_draw_kernel(int q, int B, int Bp, int nchunks, const double* __restrict__ part, const double* __restrict__ txx,
                  const double* __restrict__ lchol, const double* __restrict__ sigsq, double* __restrict__ Bet,
                  double* __restrict__ BetOld, const long long* __restrict__ itp, DrawCfg dc) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const long long it = *itp;
@@ -145,6 +149,8 @@ b_xf_draw_kernel(int q, int B, int Bp, int nchunks, const double* __restrict__ p
 // R = (R + XF BetOld) - XF Bet                                                  (R/BGGE.R:285, 289)
 __global__ void b_xf_apply_kernel(long long n, int q, int B, int Bp, const double* __restrict__ xf,
                                   const double* __restrict__ Bet, const double* __restrict__ BetOld, double* __restrict__ R) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n * Bp) return;
   const long long i = idx / Bp;
@@ -164,6 +170,8 @@ __global__ void b_xf_apply_kernel(long long n, int q, int B, int Bp, const doubl
 // after it in the stream sees the new value -- one launch less per iteration than a separate increment)
 __global__ void b_eprime_kernel(long long total, int Bp, const double* __restrict__ R, const double* __restrict__ Uj,
                                 const double* __restrict__ shift, double* __restrict__ Ep, long long* __restrict__ advance_it) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (advance_it != nullptr && idx == 0) *advance_it += 1;
   if (idx >= total) return;
@@ -196,6 +204,8 @@ b_draw_kernel(int nr, int n_ctiles, int B, int Bp, int nsplit, const double* __r
               const double* __restrict__ s, const double* __restrict__ sigb, const double* __restrict__ tau,
               double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp, int j, DrawCfg dc,
               PreDraws pd) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   __shared__ double zs[TXY];
   const int tx = blockDim.x, ty = blockDim.y;
   const int b = blockIdx.y * tx + threadIdx.x, cy = threadIdx.y;
@@ -250,6 +260,8 @@ b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const doubl
                 const unsigned char* __restrict__ cover, double* __restrict__ R, double* __restrict__ Uj,
                 double* __restrict__ Um, double* __restrict__ Um2, const long long* __restrict__ itp, long long thin,
                 long long burn, const double* __restrict__ shift, double* __restrict__ part, int want_sse) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   __shared__ double zs[TXY];
   const int tx = blockDim.x, ty = blockDim.y;
   const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
@@ -323,6 +335,8 @@ struct ChainArgs {
 // the sums are formed by the whole warp; then lane j draws the chi-square of kernel j and lane nk the residual one, so
 // the Marsaglia-Tsang rejection loops run side by side instead of one after the other
 __global__ void __launch_bounds__(128) b_chain_var_kernel(const ChainArgs a, DrawCfg dc) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   __shared__ double ss[4][MAXK + 1];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + w;
@@ -358,6 +372,8 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
                  const double* __restrict__ mu, const double* __restrict__ shift, const double* __restrict__ sigsq,
                  const long long* __restrict__ itp, int do_na, double* __restrict__ part, const double* __restrict__ zna,
                  int q, const double* __restrict__ xf, const double* __restrict__ Bet) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   __shared__ double zs[TXY];
   const int tx = blockDim.x, ty = blockDim.y;
   const int b = blockIdx.y * tx + threadIdx.x, ry = threadIdx.y;
@@ -398,6 +414,8 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
 
 // per chain: record the thinned chain (R/BGGE.R:384-395), draw the next intercept (R/BGGE.R:278-281)
 __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, DrawCfg dc) {
+  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
+  pdl_trigger();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= a.B) return;
   const long long it = *a.it;
@@ -417,6 +435,28 @@ __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, Draw
   const double nmu = (sr / (double)a.n + a.mu0[b]) + sqrt(a.sigsq[b] / (double)a.n) * z;
   a.mu[b] = nmu;
   a.shift[b] = nmu - a.mu0[b];
+}
+
+// Launch with the programmatic-serialization attribute (captured into the iteration graph as a programmatic edge):
+// the kernels of an iteration are short and strictly dependent, so the launch latency between them is a visible
+// share of the iteration at few chains per GPU.  Every kernel starts with pdl_wait(); pdl_trigger().
+bool batch_pdl() {
+  static const bool on = pdl_enabled() && !(getenv("BGGE_BATCH_PDL") && atoi(getenv("BGGE_BATCH_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = batch_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 template <typename T>
@@ -469,13 +509,13 @@ int launch_tail(Batch* g, bool init) {
   const dim3 cblock(tx, ty);
   const unsigned cb = (unsigned)((g->B + 3) / 4);   // one warp per chain
   if (!init)   // the per-chunk sums of (R - shift)^2 were left in `part` by the last kernel's update pass
-    b_chain_var_kernel<<<cb, 128, 0, st>>>(chain_args(g, g->part.p), g->draw);
-  b_na_sumr_kernel<<<cgrid, cblock, 0, st>>>(g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p, g->narank.p,
-                                        g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p,
-                                        g->zna.p, g->q, g->xf.p, g->Bet.p);
+    BGGE_CUDA(launch_dep(b_chain_var_kernel, dim3(cb), dim3(128), st, chain_args(g, g->part.p), g->draw));
+  BGGE_CUDA(launch_dep(b_na_sumr_kernel, cgrid, cblock, st, g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p,
+                       g->narank.p, g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p, g->zna.p,
+                       g->q, g->xf.p, g->Bet.p));
   ChainArgs ca = chain_args(g, g->part2.p);
   if (init) ca.zmu = nullptr;   // no b_draw launch has run yet: the first intercept's normal is drawn in place
-  b_chain_mu_kernel<<<cb, 128, 0, st>>>(ca, g->draw);
+  BGGE_CUDA(launch_dep(b_chain_mu_kernel, dim3(cb), dim3(128), st, ca, g->draw));
   BGGE_CUDA(cudaGetLastError());
   return OK;
 }
@@ -486,29 +526,30 @@ int launch_iteration(Batch* g) {
   const unsigned eg = (unsigned)((total + BT - 1) / BT);
   const int tx = tile_x(g->Bp), ty = TXY / tx;
   if (g->q > 0) {   // fixed effects, between the intercept (drawn by the previous tail) and the kernels; advances `it`
-    b_xf_reduce_kernel<<<dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
-        g->n, g->q, g->Bp, g->rows_per_chunk, g->xf.p, g->R.p, g->Bet.p, g->shift.p, g->xf_part.p, g->it.p);
-    b_xf_draw_kernel<<<(unsigned)((g->B + 3) / 4), 128, 0, st>>>(g->q, g->B, g->Bp, g->nchunks, g->xf_part.p, g->txx.p,
-                                                               g->lchol.p, g->sigsq.p, g->Bet.p, g->BetOld.p, g->it.p, g->draw);
-    b_xf_apply_kernel<<<eg, BT, 0, st>>>(g->n, g->q, g->B, g->Bp, g->xf.p, g->Bet.p, g->BetOld.p, g->R.p);
+    BGGE_CUDA(launch_dep(b_xf_reduce_kernel, dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), st, g->n,
+                         g->q, g->Bp, g->rows_per_chunk, g->xf.p, g->R.p, g->Bet.p, g->shift.p, g->xf_part.p, g->it.p));
+    BGGE_CUDA(launch_dep(b_xf_draw_kernel, dim3((unsigned)((g->B + 3) / 4)), dim3(128), st, g->q, g->B, g->Bp, g->nchunks,
+                         g->xf_part.p, g->txx.p, g->lchol.p, g->sigsq.p, g->Bet.p, g->BetOld.p, g->it.p, g->draw));
+    BGGE_CUDA(launch_dep(b_xf_apply_kernel, dim3(eg), dim3(BT), st, g->n, g->q, g->B, g->Bp, g->xf.p, g->Bet.p, g->BetOld.p, g->R.p));
   }
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     double* Uj = g->U.p + (size_t)j * total;
-    b_eprime_kernel<<<eg, BT, 0, st>>>(total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p, (j == 0 && g->q == 0) ? g->it.p : nullptr);
-    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj));
+    BGGE_CUDA(launch_dep(b_eprime_kernel, dim3(eg), dim3(BT), st, total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p,
+                         (j == 0 && g->q == 0) ? g->it.p : nullptr));
+    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj, batch_pdl()));
     const bool last = j == g->nk - 1;
     PreDraws pd{g->chiK.p, g->chiE.p, g->zmu.p, g->zna.p, g->max_na, last ? 1 : 0, g->n_na.p, (long long)g->n,
                 (long long)bk.nr_total};
     const int extra = 1 + (last && g->any_na ? (g->max_na + ty - 1) / ty : 0);   // prepared draws, see b_draw_kernel
-    b_draw_kernel<<<dim3((unsigned)(bk.n_ctiles + extra), (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
-        (int)bk.nr_total, bk.n_ctiles, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
-        g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw, pd);
-    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st, bk.grid_back));
-    b_update_kernel<<<dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), 0, st>>>(
-        g->n, g->Bp, g->rows_per_chunk, bk.ksplit_back, bk.Upart.p, total, bk.cover.p, g->R.p, Uj, g->Um.p + (size_t)j * total,
-        g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn, g->shift.p, g->part.p, j == g->nk - 1 ? 1 : 0);
-    BGGE_CUDA(cudaGetLastError());
+    BGGE_CUDA(launch_dep(b_draw_kernel, dim3((unsigned)(bk.n_ctiles + extra), (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), st,
+                         (int)bk.nr_total, bk.n_ctiles, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
+                         g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw, pd));
+    BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st, bk.grid_back, batch_pdl()));
+    BGGE_CUDA(launch_dep(b_update_kernel, dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), st, g->n,
+                         g->Bp, g->rows_per_chunk, bk.ksplit_back, bk.Upart.p, total, bk.cover.p, g->R.p, Uj,
+                         g->Um.p + (size_t)j * total, g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn, g->shift.p,
+                         g->part.p, j == g->nk - 1 ? 1 : 0));
   }
   return launch_tail(g, false);
 }

@@ -52,6 +52,10 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
     mbar_fence_init();
   }
   __syncthreads();
+  // programmatic dependent launch: everything above (shared-memory clearing, barrier set-up) overlaps the tail of the
+  // previous kernel; the operands are only touched from here on
+  pdl_wait();
+  pdl_trigger();
 
   if (warp >= GCONS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -186,7 +190,7 @@ gemm_pack_kernel(const double* __restrict__ src, long long sm_, long long sk_, l
 }
 
 template <int TN, int MI>
-int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint) {
+int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint, bool pdl) {
   static bool attr[64] = {false};   // function attributes are per device
   int dev = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
@@ -196,8 +200,17 @@ int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int gri
     attr[dev] = true;
   }
   const int grid = grid_hint > 0 ? std::min(grid_hint, nitems) : (nitems < sm_count() ? nitems : sm_count());
-  dgemm_dmma_kernel<TN, MI><<<grid, GTHREADS, GemmSmem<TN, MI>::BYTES, st>>>(d_items, nitems);
-  BGGE_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GTHREADS);
+  cfg.dynamicSmemBytes = GemmSmem<TN, MI>::BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = la;
+  cfg.numAttrs = pdl ? 1 : 0;
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, dgemm_dmma_kernel<TN, MI>, d_items, nitems));
   return OK;
 }
 }  // namespace
@@ -221,17 +234,17 @@ int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, 
   return OK;
 }
 
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid) {
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid, bool pdl) {
   if (nitems <= 0) return OK;
   switch (tn) {
-    case 16: return dgemm_launch_t<16, 4>(d_items, nitems, st, grid);
-    case 32: return dgemm_launch_t<32, 4>(d_items, nitems, st, grid);
-    case 40: return dgemm_launch_t<40, 4>(d_items, nitems, st, grid);
-    case 48: return dgemm_launch_t<48, 4>(d_items, nitems, st, grid);
-    case 64: return dgemm_launch_t<64, 2>(d_items, nitems, st, grid);
-    case 80: return dgemm_launch_t<80, 2>(d_items, nitems, st, grid);
-    case 96: return dgemm_launch_t<96, 2>(d_items, nitems, st, grid);
-    case 128: return dgemm_launch_t<128, 2>(d_items, nitems, st, grid);
+    case 16: return dgemm_launch_t<16, 4>(d_items, nitems, st, grid, pdl);
+    case 32: return dgemm_launch_t<32, 4>(d_items, nitems, st, grid, pdl);
+    case 40: return dgemm_launch_t<40, 4>(d_items, nitems, st, grid, pdl);
+    case 48: return dgemm_launch_t<48, 4>(d_items, nitems, st, grid, pdl);
+    case 64: return dgemm_launch_t<64, 2>(d_items, nitems, st, grid, pdl);
+    case 80: return dgemm_launch_t<80, 2>(d_items, nitems, st, grid, pdl);
+    case 96: return dgemm_launch_t<96, 2>(d_items, nitems, st, grid, pdl);
+    case 128: return dgemm_launch_t<128, 2>(d_items, nitems, st, grid, pdl);
     default: break;
   }
   set_error("dgemm: unsupported N tile %d", tn);
