@@ -182,7 +182,8 @@ sweep_mrhs_kernel(const FPanel* __restrict__ panels, const int2* __restrict__ cl
   BGGE_DEVASSERT(reinterpret_cast<unsigned char*>(s.tmem + 4) <= msm + dynamic_smem_bytes());
   BGGE_DEVASSERT(ns >= 3 && ns <= M_MAXNS && lag >= 1 && lag + 1 <= M_NP && ns + lag + 1 <= M_NPX && cs <= M_MAXCS);
   // unpredicated row steps: the furthest read of the last ring slot stays in front of the mbarriers
-  BGGE_DEVASSERT(s.ring + (size_t)(ns - 1) * slot_doubles + max_rs + (size_t)(KR - 1) * M_T + M_T <= reinterpret_cast<double*>(s.full) ||
+  // (last slot, last of its G columns, row step KR - 1, thread M_T - 1)
+  BGGE_DEVASSERT(s.ring + (size_t)(ns - 1) * slot_doubles + (size_t)(G - 1) * max_rs + (size_t)KR * M_T <= reinterpret_cast<double*>(s.full) ||
                  cp.y == 0);
 
   // rows of a slot beyond the CTA's slice are never written by the bulk copies: zero everything once so they are

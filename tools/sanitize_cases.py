@@ -16,7 +16,7 @@ import bgge_b200                                # noqa: E402
 from helpers import design, markers, relmax     # noqa: E402
 
 
-def fit_case(label, L, E, p, kernel, model, mode, env, ite=3, with_xf=False, n_na=3):
+def fit_case(label, L, E, p, kernel, model, mode, env, ite=3, with_xf=False, n_na=3, want_path=None):
     X = markers(L, p, 1)
     Y, names = design(L, E)
     n = L * E
@@ -50,6 +50,9 @@ def fit_case(label, L, E, p, kernel, model, mode, env, ite=3, with_xf=False, n_n
     paths = [(k["path"], k["cluster_size"]) for k in info["kernels"]]
     print(f"{label:34s} resident={info['resident']} units={info['merged_units']} paths={paths} err={err:.2e}", flush=True)
     assert err <= 1e-9, label
+    assert np.all(np.isfinite(got["chain"]["varE"])) and np.ptp(got["chain"]["varE"]) > 0, label
+    if want_path is not None:          # the case must run on the engine its label names
+        assert paths[-1][0] == want_path, (label, paths)
 
 
 def main():
@@ -59,9 +62,14 @@ def main():
     fit_case("fused nb=4 cs=8 (old engine)", 96, 4, 60, "GK", "MDs", 2, {"BGGE_MRHS": "0", "BGGE_FUSED_CS": "8"})
     fit_case("fused nb=2 cs=2 (old engine)", 96, 2, 60, "GK", "MDs", 2, {"BGGE_MRHS": "0", "BGGE_FUSED_CS": "2"})
     # multi-RHS engine forced on small blocks: NB = 4 / 2, cs = 1 / 2 / 4, few clusters -> long pipelines
-    fit_case("mrhs nb=4 cs=1", 200, 4, 260, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_FUSED_MAX_CLUSTERS": "2"})
-    fit_case("mrhs nb=4 cs=4", 200, 4, 260, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_MRHS_CS": "4", "BGGE_FUSED_MAX_CLUSTERS": "1"})
-    fit_case("mrhs nb=2 cs=2", 200, 2, 260, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_MRHS_CS": "2", "BGGE_FUSED_MAX_CLUSTERS": "2"})
+    fit_case("mrhs nb=4 cs=1", 200, 4, 260, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_FUSED_MAX_CLUSTERS": "2"}, want_path=2)
+    fit_case("mrhs nb=4 cs=4", 200, 4, 260, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_MRHS_CS": "4", "BGGE_FUSED_MAX_CLUSTERS": "1"},
+             want_path=2)
+    fit_case("mrhs nb=2 cs=2", 2900, 2, 300, "GK", "MDs", 2, {"BGGE_MRHS": "2", "BGGE_MRHS_CS": "2", "BGGE_FUSED_MAX_CLUSTERS": "4"},
+             want_path=2)
+    # residual slices in tensor memory (tcgen05.alloc / st / ld / dealloc), 1- and 2-CTA clusters
+    fit_case("mrhs nb=4 tmem cs=1", 2500, 4, 300, "GK", "MDs", 2, {"BGGE_MRHS_TMEM": "2", "BGGE_FUSED_MAX_CLUSTERS": "3"}, want_path=2)
+    fit_case("mrhs nb=4 tmem cs=2", 2500, 4, 300, "GK", "MDs", 2, {"BGGE_MRHS_TMEM": "2", "BGGE_MRHS_CS": "2"}, want_path=2)
     fit_case("mrhs merged units 4+2 (MDe)", 120, 6, 150, "GK", "MDe", 2, {"BGGE_MRHS": "2"}, ite=4)
     # resident kernel: XF + NA, merged steps
     fit_case("resident MDs + XF + NA", 64, 3, 80, "GK", "MDs", 1, {}, ite=4, with_xf=True)
