@@ -163,8 +163,8 @@ int upload_markers(const double* X, int64_t L, int64_t p, DevBuf<double>& dX, in
   *p_pad = round_up(p, 16);
   BGGE_CUDA(dX.alloc((size_t)(*ldx) * (size_t)(*p_pad)));
   BGGE_CUDA(cudaMemset(dX.p, 0, (size_t)(*ldx) * (size_t)(*p_pad) * sizeof(double)));
-  BGGE_CUDA(cudaMemcpy2D(dX.p, (size_t)(*ldx) * sizeof(double), X, (size_t)L * sizeof(double),
-                         (size_t)L * sizeof(double), (size_t)p, cudaMemcpyHostToDevice));
+  BGGE_TRY(host_copy_2d(dX.p, (size_t)(*ldx) * sizeof(double), X, (size_t)L * sizeof(double), (size_t)L * sizeof(double),
+                        (size_t)p, cudaMemcpyHostToDevice));
   return OK;
 }
 
@@ -351,7 +351,7 @@ int bgge_getk_base(const double* X, int64_t L, int64_t p, int kind, const double
   std::vector<DevBuf<double>> K0;
   BGGE_TRY(base_kernels_device(dX.p, ldx, L, p, p_pad, kind, bandwidth, nb, quantil, K0, out_q, nullptr));
   for (size_t b = 0; b < K0.size(); ++b)
-    BGGE_CUDA(cudaMemcpy(out_K0 + b * (size_t)L * L, K0[b].p, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost));
+    BGGE_TRY(host_copy(out_K0 + b * (size_t)L * L, K0[b].p, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost));
   return OK;
 }
 
@@ -372,7 +372,7 @@ int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int3
   DevBuf<int> dgid, denv;
   if (K0) {
     BGGE_CUDA(dK0.alloc((size_t)L * L));
-    BGGE_CUDA(cudaMemcpy(dK0.p, K0, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice));
+    BGGE_TRY(host_copy(dK0.p, K0, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice));
   }
   BGGE_CUDA(dgid.alloc((size_t)n));
   BGGE_CUDA(cudaMemcpy(dgid.p, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
@@ -382,7 +382,7 @@ int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int3
   }
   BGGE_CUDA(dOut.alloc((size_t)n * n));
   BGGE_TRY(expand_launch(dK0.p, L, L, dgid.p, denv.p, n, mode, env_k, dOut.p, n, nullptr));
-  BGGE_CUDA(cudaMemcpy(out, dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+  BGGE_TRY(host_copy(out, dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
   return OK;
 }
 
@@ -418,7 +418,7 @@ int bgge_getk(const double* X, int64_t L, int64_t p, int kind, const double* ban
   int o = 0;
   auto emit = [&](const double* k0, int mode, int k) -> int {
     BGGE_TRY(expand_launch(k0, L, L, dgid.p, denv.p, n, mode, k, dOut.p, n, nullptr));
-    BGGE_CUDA(cudaMemcpy(out[o++], dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    BGGE_TRY(host_copy(out[o++], dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
     return OK;
   };
   for (int b = 0; b < nbase; ++b) BGGE_TRY(emit(K0[(size_t)b].p, BGGE_EXPAND_G, 0));
@@ -464,8 +464,8 @@ int bgge_eig(const double* K, int64_t m, int64_t ldk, double tol, int canonical_
   DevBuf<double> dA, dS, dU;
   BGGE_CUDA(dA.alloc((size_t)m * m));
   BGGE_CUDA(dS.alloc((size_t)m));
-  BGGE_CUDA(cudaMemcpy2D(dA.p, (size_t)m * sizeof(double), K, (size_t)ldk * sizeof(double), (size_t)m * sizeof(double),
-                         (size_t)m, cudaMemcpyHostToDevice));
+  BGGE_TRY(host_copy_2d(dA.p, (size_t)m * sizeof(double), K, (size_t)ldk * sizeof(double), (size_t)m * sizeof(double), (size_t)m,
+                        cudaMemcpyHostToDevice));
   if (out_U) BGGE_CUDA(dU.alloc((size_t)m * m));
   int64_t nr = 0;
   BGGE_TRY(bgge_dev_eig(dA.p, m, m, tol, canonical_sign, dS.p, dU.p, m, m, &nr, nullptr));
@@ -606,8 +606,8 @@ int bgge_gibbs_add_kernel_matrix(bgge_gibbs* h, int j, int type, const double* K
     DevBuf<double> dA, dW, dS;
     BGGE_CUDA(dA.alloc((size_t)m * m));
     BGGE_CUDA(dW.alloc((size_t)m));
-    BGGE_CUDA(cudaMemcpy2D(dA.p, (size_t)m * sizeof(double), K + sp.first + sp.first * ldk, (size_t)ldk * sizeof(double),
-                           (size_t)m * sizeof(double), (size_t)m, kind));
+    BGGE_TRY(host_copy_2d(dA.p, (size_t)m * sizeof(double), K + sp.first + sp.first * ldk, (size_t)ldk * sizeof(double),
+                          (size_t)m * sizeof(double), (size_t)m, kind));   // (device-to-device goes straight to cudaMemcpy2D)
     int64_t nr = 0;
     BGGE_TRY(eig_decompose(dA.p, m, m, tol, dW.p, &nr, g.stream));
     if (nr == 0) continue;                                          // R/BGGE.R:162
@@ -664,8 +664,8 @@ int bgge_gibbs_add_expanded_kernel(bgge_gibbs* h, int j, int type, const double*
       ld0 = ldk;
     } else {
       BGGE_CUDA(k0buf.alloc((size_t)L * L));
-      BGGE_CUDA(cudaMemcpy2D(k0buf.p, (size_t)L * sizeof(double), K0, (size_t)ldk * sizeof(double), (size_t)L * sizeof(double),
-                             (size_t)L, cudaMemcpyHostToDevice));
+      BGGE_TRY(host_copy_2d(k0buf.p, (size_t)L * sizeof(double), K0, (size_t)ldk * sizeof(double), (size_t)L * sizeof(double),
+                            (size_t)L, cudaMemcpyHostToDevice));
       dK0 = k0buf.p;
     }
     BGGE_CUDA(cudaMemcpy2D(diag.data(), sizeof(double), dK0, (size_t)(ld0 + 1) * sizeof(double), sizeof(double), (size_t)L,
@@ -1733,7 +1733,7 @@ int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const b
         if (!dK0) {
           std::unique_ptr<DevBuf<double>> b(new DevBuf<double>());
           BGGE_CUDA(b->alloc((size_t)kd.L * kd.L));
-          BGGE_CUDA(cudaMemcpy(b->p, kd.K0, (size_t)kd.L * kd.L * sizeof(double), cudaMemcpyHostToDevice));
+          BGGE_TRY(host_copy(b->p, kd.K0, (size_t)kd.L * kd.L * sizeof(double), cudaMemcpyHostToDevice));
           dK0 = b->p;
           up.emplace_back(kd.K0, std::move(b));
         }

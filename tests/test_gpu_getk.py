@@ -125,6 +125,36 @@ def test_expansion_in_genotype_order_is_bit_exact(lib, monkeypatch, n, sort_min)
         assert np.array_equal(out, G), mode
 
 
+def test_staged_host_copies_are_exact(lib, monkeypatch):
+    """Large pageable host buffers travel through the threaded pinned-staging pipeline (csrc/staging.cu): marker upload
+    (pitched destination), base-kernel download, n x n expansion download.  Same bits as the plain cudaMemcpy path."""
+    rng = np.random.default_rng(5)
+    L, p, E = 700, 3000, 3
+    X = np.asfortranarray(rng.standard_normal((L, p)))
+    n = L * E
+    gid = np.tile(np.arange(L, dtype=np.int32), E)
+    env = np.repeat(np.arange(E, dtype=np.int32), L)
+
+    def run():
+        K0 = np.empty((1, L, L))
+        lib.call("bgge_getk_base", lib.ptr(X), L, p, lib.GB, None, 0, 0.5, lib.ptr(K0), None)
+        out = np.full((n, n), np.nan, order="F")
+        lib.call("bgge_getk_expand", lib.ptr(np.asfortranarray(K0[0].T)), L, lib.ptr(gid), lib.ptr(env), n, lib.EXPAND_GE, 0,
+                 lib.ptr(out))
+        return K0[0].copy(), out
+
+    monkeypatch.setenv("BGGE_NO_STAGED_COPY", "1")
+    K_plain, G_plain = run()
+    monkeypatch.delenv("BGGE_NO_STAGED_COPY")
+    monkeypatch.setenv("BGGE_STAGED_MIN_BYTES", str(1 << 20))
+    for threads in ("2", "5", "8"):
+        monkeypatch.setenv("BGGE_COPY_THREADS", threads)
+        K_st, G_st = run()
+        assert np.array_equal(K_st, K_plain), threads
+        assert np.array_equal(G_st, G_plain), threads
+    assert relmax(K_plain, oracle.gb_kernel(X)) <= 1e-12
+
+
 def test_setkernel_path_and_errors():
     import bgge_b200
     L, E = 12, 2
