@@ -40,8 +40,13 @@ std::mutex g_pool_mu;
 std::map<void*, PoolBlock> g_pool_live;                          // blocks handed out
 std::multimap<std::pair<int, size_t>, void*> g_pool_free;        // (device, bytes) -> cached block
 size_t g_pool_cached = 0;
-constexpr size_t POOL_MAX_BLOCK = 2048ull << 20;                 // larger blocks go straight back to the driver
-constexpr size_t POOL_MAX_CACHED = 4096ull << 20;                // (syevd and K-split workspaces of the C5 shapes are 1-2 GB)
+// Blocks above POOL_MAX_BLOCK go straight back to the driver; at most POOL_MAX_CACHED bytes stay cached (per
+// process; bgge_release_cache() hands them back).  Sized for the C5 setDEC: one BGGE() call allocates the base kernel,
+// the scaled L x L problem, the eigenvectors (0.8 GB each) and cuSOLVER's 3.2 GB syevd workspace -- with smaller limits
+// every call went through cudaMalloc / cudaFree of those blocks, which r02 measured at 1.5 ms usually but 50-450 ms
+// every few calls (BGGE_TIMING=1), i.e. the difference between 1.11 and 1.56 s per call.
+constexpr size_t POOL_MAX_BLOCK = 4096ull << 20;
+constexpr size_t POOL_MAX_CACHED = 10240ull << 20;
 
 size_t pool_round(size_t b) {
   if (b <= (1u << 20)) {
@@ -1709,11 +1714,22 @@ int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const b
   BGGE_REQUIRE(!any_bd || ne != nullptr, "For type BD, number of subjects in each sub matrices should be provided");  // R/BGGE.R:129
   BGGE_REQUIRE(!(any_bd && n_ne <= 1), "Type BD should be used only for block diagonal matrices");              // R/BGGE.R:223
   BGGE_REQUIRE(!any_fact || gid != nullptr, "fit_kernels: genotype codes missing");
+  // BGGE_TIMING=1: wall-clock of the stages of this call on stderr (device drained at every mark)
+  const bool timing = getenv("BGGE_TIMING") != nullptr;
+  auto tlast = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto tn = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bgge timing] fit_kernels %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(tn - tlast).count());
+    tlast = tn;
+  };
   bgge_gibbs* h = nullptr;
   BGGE_TRY(bgge_gibbs_create(n, nk, q, nullptr, &h));
   std::unique_ptr<bgge_gibbs, void (*)(bgge_gibbs*)> guard(h, bgge_gibbs_destroy);
   BGGE_TRY(bgge_gibbs_set_y(h, y, na_mask));
   if (q > 0) BGGE_TRY(bgge_gibbs_set_xf(h, XF));
+  mark("create + y");
   {
     // every distinct base kernel is uploaded once and shared by the kernels that expand it (G and GE of MDs, G and
     // the E environment kernels of MDe)
@@ -1736,17 +1752,21 @@ int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const b
           BGGE_TRY(host_copy(b->p, kd.K0, (size_t)kd.L * kd.L * sizeof(double), cudaMemcpyHostToDevice));
           dK0 = b->p;
           up.emplace_back(kd.K0, std::move(b));
+          mark("base kernel upload");
         }
       }
       BGGE_TRY(bgge_gibbs_add_expanded_kernel(h, j, kd.type, dK0, kd.L, kd.L, 1, gid, env, n, kd.mode, kd.env_k, ne, n_ne, tol,
                                               1));
       ++nfact;
+      mark("setDEC of one kernel");
     }
     if (factored_kernels) *factored_kernels = nfact;
     BGGE_CUDA(cudaStreamSynchronize(h->g.stream));   // the base kernels die here; the eigen blocks are what the chain keeps
   }
   if (rng_mode == BGGE_RNG_TAPE) BGGE_TRY(bgge_gibbs_set_tape(h, normals, n_normals, chisq, n_chisq));
+  mark("release base kernels");
   BGGE_TRY(bgge_gibbs_init(h, ite, burn, thin, R2, rng_mode, seed, 0));
+  mark("init (plans, state)");
   const int64_t piece = (chunk > 0 && progress) ? chunk : ite;
   for (int64_t done = 0; done < ite;) {                                                                          // R/BGGE.R:274
     const int64_t k = std::min(piece, ite - done);
@@ -1762,8 +1782,14 @@ int bgge_fit_kernels(const double* y, const uint8_t* na_mask, int64_t n, const b
       }
     }
   }
+  mark("sweeps");
   BGGE_TRY(bgge_gibbs_summary(h, yHat, varE, varE_sd, u, u_sd, varu, varu_sd, y_out));
   BGGE_TRY(bgge_gibbs_chain(h, chain_mu, chain_varE, chain_varU, chain_bet));
+  mark("summaries + chains");
+  if (timing) {
+    guard.reset();
+    mark("destroy");
+  }
   return OK;
 }
 

@@ -5,7 +5,11 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cusolverDn.h>
+#include <memory>
+#include <new>
 #include <vector>
 #include <mutex>
 
@@ -222,10 +226,31 @@ int eig_decompose(double* dA, int64_t m, int64_t lda, double tol, double* d_W, i
     set_error("cusolverDnXsyevd_bufferSize failed: %d", (int)cs);
     return ERR_SOLVER;
   }
+  const bool timing = getenv("BGGE_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bgge timing]   eig m=%lld %-22s %8.3f ms (host workspace %zu B, device %zu B)\n", (long long)m, what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), whost, wdev);
+    t0 = t1;
+  };
   BGGE_CUDA(work.alloc(wdev));
-  std::vector<unsigned char> hwork(whost);
+  lap("device workspace");
+  // host workspace: one buffer per thread, kept across calls and never value-initialised (a fresh, zero-filled
+  // std::vector of this size is page-faulted in on every call)
+  static thread_local std::unique_ptr<unsigned char[]> hbuf;
+  static thread_local size_t hcap = 0;
+  if (whost > hcap) {
+    hbuf.reset(new (std::nothrow) unsigned char[whost]);
+    BGGE_REQUIRE(hbuf != nullptr, "eig: out of host memory (%zu bytes of cuSOLVER workspace)", whost);
+    hcap = whost;
+  }
+  lap("host workspace");
   cs = cusolverDnXsyevd(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, CUDA_R_64F, dA, lda,
-                        CUDA_R_64F, d_W, CUDA_R_64F, work.p, wdev, hwork.data(), whost, info.p);
+                        CUDA_R_64F, d_W, CUDA_R_64F, work.p, wdev, hbuf.get(), whost, info.p);
+  lap("Xsyevd");
   cusolverDnDestroyParams(params);
   if (cs != CUSOLVER_STATUS_SUCCESS) {
     set_error("cusolverDnXsyevd failed: %d", (int)cs);
