@@ -544,7 +544,7 @@ def main():
             getk_host = {"base_call_s": t_base, "h2d_bytes": 8 * L * p, "d2h_bytes": 8 * L * L,
                          "max_abs_diff_vs_device_pipeline": kerr, "expand_one_kernel_call_s": t_expand,
                          "expand_d2h_bytes": 8 * n * n if t_expand is not None else 0,
-                         "note": "pageable host buffers, cudaMemcpy inside the call; the factored route (getK(factored=TRUE) / "
+                         "note": "pageable host buffers, copies inside the call (threaded pinned staging, csrc/staging.cu); the factored route (getK(factored=TRUE) / "
                                  "bgge_fit_kernels) never needs the n x n expansion"}
             del K0_host
         del Xp
