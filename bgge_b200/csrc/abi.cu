@@ -8,6 +8,8 @@
 #include "multi.cuh"
 #include "rng.cuh"
 #include <chrono>
+#include <string>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -173,18 +175,112 @@ int upload_markers(const double* X, int64_t L, int64_t p, DevBuf<double>& dX, in
   return OK;
 }
 
-// device base kernels: K0[b] (L x L, ld L) for each bandwidth
+// S[i] = (P_0[i] + P_1[i] + ... + P_{k-1}[i]) / divisor, planes `stride` doubles apart, fixed order
+__global__ void sum_planes_kernel(const double* __restrict__ P, long long stride, int k, long long count, double divisor,
+                                  double* __restrict__ S) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    double a = P[i];
+    for (int c = 1; c < k; ++c) a += P[(long long)c * stride + i];
+    S[i] = a / divisor;
+  }
+}
+
+// S = X X' / divisor for a HOST marker matrix (L x p, column-major, leading dimension L).  Small matrices: one upload,
+// one contraction.  Large ones (>= 1 GB): the marker columns are cut into chunks that travel through two device
+// buffers -- chunk c + 1 is uploaded (staging.cu) while the tensor cores contract chunk c into its own L x L plane --
+// and the planes are added in chunk order at the end (deterministic; equal to the one-shot result to rounding).
+// C5 (8 GB of markers, 4 chunks): bgge_getk_base 0.69 s (upload, then contraction) -> 0.39-0.43 s.
+int gram_from_host(const double* X, int64_t L, int64_t p, double divisor, double* dS, cudaStream_t st) {
+  const int64_t ldx = round_up(L, 128);
+  const int64_t T = (L + 127) / 128;
+  const size_t bytes = (size_t)L * (size_t)p * sizeof(double);
+  int nch = 1;
+  if (bytes >= (1ull << 30) && !getenv("BGGE_NO_CHUNKED_GRAM")) nch = (int)std::min<size_t>(8, std::max<size_t>(2, (bytes + (1ull << 30)) >> 31));   // ~2 GB per chunk
+  if (const char* ev = getenv("BGGE_GRAM_HOST_CHUNKS")) nch = std::max(1, std::min(16, atoi(ev)));   // test / tuning hook
+  nch = (int)std::min<int64_t>(nch, (p + 1023) / 1024);
+  if (nch <= 1) {
+    DevBuf<double> dX;
+    int64_t l2, p_pad;
+    BGGE_TRY(upload_markers(X, L, p, dX, &l2, &p_pad));
+    BGGE_TRY(gram_launch(dX.p, l2, L, p_pad, 0, T, dS, L, 0, divisor, 1, st));
+    BGGE_CUDA(cudaStreamSynchronize(st));
+    return OK;
+  }
+  const int64_t pc = round_up((p + nch - 1) / nch, 16);   // marker columns per chunk
+  int dev = 0;
+  BGGE_CUDA(cudaGetDevice(&dev));
+  DevBuf<double> buf[2], planes;
+  cudaStream_t aux = nullptr, gst = nullptr;
+  struct Cleanup {
+    cudaStream_t *a, *b;
+    ~Cleanup() {
+      if (*a) cudaStreamDestroy(*a);
+      if (*b) cudaStreamDestroy(*b);
+    }
+  } cleanup{&aux, &gst};
+  for (int k = 0; k < 2; ++k) BGGE_CUDA(buf[k].alloc((size_t)ldx * (size_t)pc));
+  BGGE_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+  BGGE_CUDA(cudaStreamCreateWithFlags(&gst, cudaStreamNonBlocking));
+  BGGE_CUDA(planes.alloc((size_t)nch * (size_t)L * (size_t)L));
+  BGGE_CUDA(cudaStreamSynchronize(st));
+  // zero the buffer (row and column padding), then bring the chunk's columns in; nothing else touches the buffer
+  auto upload = [&](int c) -> int {
+    const int b = c & 1;
+    const int64_t c0 = (int64_t)c * pc, cols = std::max<int64_t>(0, std::min<int64_t>(p, c0 + pc) - c0);
+    BGGE_CUDA(cudaMemsetAsync(buf[b].p, 0, (size_t)ldx * (size_t)pc * sizeof(double), aux));
+    BGGE_CUDA(cudaStreamSynchronize(aux));
+    if (cols > 0)
+      BGGE_TRY(host_copy_2d(buf[b].p, (size_t)ldx * sizeof(double), X + (size_t)c0 * (size_t)L, (size_t)L * sizeof(double),
+                            (size_t)L * sizeof(double), (size_t)cols, cudaMemcpyHostToDevice, false));
+    return OK;
+  };
+  BGGE_TRY(upload(0));
+  for (int c = 0; c < nch; ++c) {
+    // gram_launch returns when its kernels have finished (its work lists die with it): it runs on a helper thread
+    // while this thread uploads the next chunk into the other buffer
+    int gstatus = OK;
+    std::string gmsg;
+    std::thread worker([&, c]() {
+      if (cudaSetDevice(dev) != cudaSuccess) {
+        gstatus = ERR_CUDA;
+        gmsg = "cudaSetDevice failed on the contraction thread";
+        return;
+      }
+      gstatus = gram_launch(buf[c & 1].p, ldx, L, pc, 0, T, planes.p + (size_t)c * (size_t)L * (size_t)L, L, 0, 1.0, 1, gst);
+      if (gstatus != OK) gmsg = last_error();
+    });
+    const int ustatus = c + 1 < nch ? upload(c + 1) : OK;
+    worker.join();
+    if (gstatus != OK) {
+      set_error("%s", gmsg.c_str());
+      return gstatus;
+    }
+    BGGE_TRY(ustatus);
+  }
+  const long long count = (long long)L * L;
+  sum_planes_kernel<<<(unsigned)std::min<long long>(4096, (count + 255) / 256), 256, 0, st>>>(planes.p, count, nch, count, divisor, dS);
+  BGGE_CUDA(cudaGetLastError());
+  BGGE_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+// device base kernels: K0[b] (L x L, ld L) for each bandwidth.  dX == nullptr: hostX (L x p, ld L) is contracted through
+// gram_from_host instead.
 int base_kernels_device(const double* dX, int64_t ldx, int64_t L, int64_t p, int64_t p_pad, int kind,
                         const double* bandwidth, int nb, double quantil, std::vector<DevBuf<double>>& K0,
-                        double* out_q, cudaStream_t st) {
+                        double* out_q, cudaStream_t st, const double* hostX = nullptr) {
   BGGE_REQUIRE(kind == BGGE_KERNEL_GB || kind == BGGE_KERNEL_GK,
                "kernel selected is not available. Please choose one method available or make available other "
                "kernel through argument K");
   const int64_t T = (L + 127) / 128;
+  auto gram = [&](double* dS, double divisor) -> int {
+    if (dX) return gram_launch(dX, ldx, L, p_pad, 0, T, dS, L, 0, divisor, 1, st);
+    return gram_from_host(hostX, L, p, divisor, dS, st);
+  };
   if (kind == BGGE_KERNEL_GB) {
     K0.resize(1);
     BGGE_CUDA(K0[0].alloc((size_t)L * L));
-    BGGE_TRY(gram_launch(dX, ldx, L, p_pad, 0, T, K0[0].p, L, 0, (double)p, 1, st));
+    BGGE_TRY(gram(K0[0].p, (double)p));
     BGGE_CUDA(cudaStreamSynchronize(st));
     return OK;
   }
@@ -195,7 +291,7 @@ int base_kernels_device(const double* dX, int64_t ldx, int64_t L, int64_t p, int
   BGGE_CUDA(diag.alloc((size_t)L));
   BGGE_CUDA(q.alloc(1));
   BGGE_CUDA(scratch.alloc(quantile_scratch_bytes()));
-  BGGE_TRY(gram_launch(dX, ldx, L, p_pad, 0, T, D.p, L, 0, 1.0, 1, st));
+  BGGE_TRY(gram(D.p, 1.0));
   BGGE_TRY(gk_distance_launch(D.p, L, L, diag.p, st));
   BGGE_TRY(quantile7_launch(D.p, L, L, quantil, scratch.p, q.p, st));
   K0.resize((size_t)nb);
@@ -350,11 +446,8 @@ int bgge_getk_base(const double* X, int64_t L, int64_t p, int kind, const double
                    double* out_K0, double* out_q) {
   BGGE_TRY(ensure_device());
   BGGE_REQUIRE(X && out_K0 && L > 0 && p > 0, "getk_base: NULL pointer or empty matrix");
-  DevBuf<double> dX;
-  int64_t ldx, p_pad;
-  BGGE_TRY(upload_markers(X, L, p, dX, &ldx, &p_pad));
   std::vector<DevBuf<double>> K0;
-  BGGE_TRY(base_kernels_device(dX.p, ldx, L, p, p_pad, kind, bandwidth, nb, quantil, K0, out_q, nullptr));
+  BGGE_TRY(base_kernels_device(nullptr, 0, L, p, 0, kind, bandwidth, nb, quantil, K0, out_q, nullptr, X));
   for (size_t b = 0; b < K0.size(); ++b)
     BGGE_TRY(host_copy(out_K0 + b * (size_t)L * L, K0[b].p, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost));
   return OK;
@@ -406,10 +499,7 @@ int bgge_getk(const double* X, int64_t L, int64_t p, int kind, const double* ban
 
   std::vector<DevBuf<double>> K0;
   {
-    DevBuf<double> dX;
-    int64_t ldx, p_pad;
-    BGGE_TRY(upload_markers(X, L, p, dX, &ldx, &p_pad));
-    BGGE_TRY(base_kernels_device(dX.p, ldx, L, p, p_pad, kind, bandwidth, nb, quantil, K0, out_q, nullptr));
+    BGGE_TRY(base_kernels_device(nullptr, 0, L, p, 0, kind, bandwidth, nb, quantil, K0, out_q, nullptr, X));
   }   // markers released before the n x n expansions are allocated
   DevBuf<int> dgid, denv;
   DevBuf<double> dOut;

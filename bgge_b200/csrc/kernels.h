@@ -71,7 +71,8 @@ extern const int kGemmTileN[];     // instantiated N tile widths, ascending
 extern const int kGemmTileNCount;
 
 // staging.cu: synchronous host <-> device copies; large pageable buffers go through a threaded pinned-staging pipeline
-int host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind);
+int host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
+                 bool sync_device = true);
 int host_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 
 }  // namespace bgge

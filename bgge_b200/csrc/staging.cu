@@ -110,7 +110,10 @@ int lane_copy(Lane& ln, int dev, unsigned char* dst, size_t dpitch, const unsign
 
 // Synchronous 2-D copy between a host buffer and device memory (kind: cudaMemcpyHostToDevice / DeviceToHost).
 // Large pageable buffers go through the threaded staging pipeline, everything else through cudaMemcpy2D.
-int host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind) {
+// sync_device = false: the caller guarantees that no work in flight touches the device range (the copy may then
+// overlap kernels that are still running on other buffers).
+int host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
+                 bool sync_device) {
   if (width == 0 || height == 0) return OK;
   const bool to_device = kind == cudaMemcpyHostToDevice;
   const void* host_ptr = to_device ? src : dst;
@@ -131,7 +134,7 @@ int host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_
   std::lock_guard<std::mutex> lk(g_copy_mu);
   // the lanes use their own streams: everything the caller enqueued before (on any stream) must be complete first,
   // as it would be for a cudaMemcpy that follows kernels on the default stream
-  BGGE_CUDA(cudaDeviceSynchronize());
+  if (sync_device) BGGE_CUDA(cudaDeviceSynchronize());
   const int lanes = (int)std::min<size_t>((size_t)T, height);
   for (int t = 0; t < lanes; ++t) BGGE_TRY(lane_init(g_lanes[dev][t]));
   std::vector<int> status((size_t)lanes, OK);
@@ -159,7 +162,7 @@ int host_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
   // a flat buffer as rows of 1 MB (+ a tail) so that the lanes get contiguous ranges
   const size_t w = 1u << 20;
   const size_t rows = bytes / w, tail = bytes - rows * w;
-  if (rows > 0) BGGE_TRY(host_copy_2d(dst, w, src, w, w, rows, kind));
+  if (rows > 0) BGGE_TRY(host_copy_2d(dst, w, src, w, w, rows, kind, true));
   if (tail > 0)
     BGGE_CUDA(cudaMemcpy(static_cast<unsigned char*>(dst) + rows * w, static_cast<const unsigned char*>(src) + rows * w, tail, kind));
   return OK;

@@ -1,6 +1,6 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
-( timeout 900 python -m pytest tests/test_gpu_getk.py tests/test_gpu_abi.py -x -q 2>&1 | tail -6 )
-for th in 0 2 4 8; do
+( timeout 900 python -m pytest tests/test_gpu_getk.py tests/test_gpu_abi.py -x -q 2>&1 | tail -12 )
+for th in 8; do
   if [ $th = 0 ]; then export BGGE_NO_STAGED_COPY=1; else unset BGGE_NO_STAGED_COPY; export BGGE_COPY_THREADS=$th; fi
   timeout 600 python bench.py --no-c4 --no-cpu-baseline --no-dense-ref --steps 2 --warmup 3 > gpurun_out/r02_v13_t$th.json 2>gpurun_out/r02_v13_t$th.err; echo "threads $th rc=$?"
   python - <<PY
