@@ -54,6 +54,8 @@ SIGNATURES = {
     "bgge_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "bgge_set_device": (C.c_int, [C.c_int]),
     "bgge_release_cache": (C.c_int, []),
+    "bgge_factor_matches": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_void_p]),
     "bgge_device_memory": (C.c_int, [c_uint64_p, c_uint64_p]),
     "bgge_getk_base": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                  C.c_void_p, c_double_p]),

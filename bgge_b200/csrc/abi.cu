@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "multi.cuh"
 #include "rng.cuh"
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -481,6 +482,47 @@ int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int3
   BGGE_CUDA(dOut.alloc((size_t)n * n));
   BGGE_TRY(expand_launch(dK0.p, L, L, dgid.p, denv.p, n, mode, env_k, dOut.p, n, nullptr));
   BGGE_TRY(host_copy(out, dOut.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+  return OK;
+}
+
+int bgge_factor_matches(const double* K, int64_t n, int64_t ldk, const double* K0, int64_t L, const int32_t* gid,
+                        const int32_t* env, int mode, int env_k, int* matches) {
+  BGGE_REQUIRE(K && gid && matches && n > 0 && ldk >= n && L > 0, "factor_matches: NULL pointer or empty input");
+  BGGE_REQUIRE(mode >= BGGE_EXPAND_G && mode <= BGGE_EXPAND_GI, "factor_matches: unknown expansion mode %d", mode);
+  BGGE_REQUIRE(mode == BGGE_EXPAND_GI || K0 != nullptr, "factor_matches: K0 is NULL");
+  BGGE_REQUIRE(mode == BGGE_EXPAND_G || mode == BGGE_EXPAND_GI || env != nullptr, "factor_matches: env codes missing");
+  BGGE_TRY(check_codes(gid, n, L, "gid"));
+  std::atomic<bool> differs{false};
+  int T = (int)std::thread::hardware_concurrency();
+  if (const char* ev = getenv("BGGE_HOST_THREADS")) T = atoi(ev);
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(T, 32), n * n / (1 << 20) + 1));
+  auto work = [&](int t) {
+    for (int64_t j = t; j < n && !differs.load(std::memory_order_relaxed); j += T) {   // interleaved columns: early exit
+      const double* col = K + j * ldk;
+      const int gj = gid[j];
+      bool bad = false;
+      if (mode == BGGE_EXPAND_GI) {
+        for (int64_t i = 0; i < n; ++i) bad |= !(col[i] == (gid[i] == gj ? 1.0 : 0.0));
+      } else {
+        const double* kc = K0 + (int64_t)gj * L;
+        if (mode == BGGE_EXPAND_G) {
+          for (int64_t i = 0; i < n; ++i) bad |= !(col[i] == kc[gid[i]]);
+        } else if (mode == BGGE_EXPAND_GE) {
+          const int ej = env[j];
+          for (int64_t i = 0; i < n; ++i) bad |= !(col[i] == (env[i] == ej ? kc[gid[i]] : 0.0));
+        } else {
+          const bool cj = env[j] == env_k;
+          for (int64_t i = 0; i < n; ++i) bad |= !(col[i] == (cj && env[i] == env_k ? kc[gid[i]] : 0.0));
+        }
+      }
+      if (bad) differs.store(true, std::memory_order_relaxed);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  *matches = differs.load() ? 0 : 1;
   return OK;
 }
 

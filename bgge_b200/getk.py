@@ -65,6 +65,21 @@ def factor_matches(entry, chunk=1 << 24):
     K = np.asarray(K)
     if K.shape != (n, n):
         return False
+    if K.dtype == np.float64 and (K.flags.f_contiguous or K.flags.c_contiguous) and chunk == 1 << 24:
+        # the library's threaded host pass (a 40000^2 kernel: a fraction of a second instead of ~10 s of numpy).  A
+        # C-ordered K is read as its transpose, so K0 is handed over in the same order: (K')[i,j] vs (K0')[g_i,g_j]
+        # is K[j,i] vs K0[g_j,g_i], the same set of comparisons
+        K0 = f["K0"]
+        if K0 is not None:
+            K0 = np.asfortranarray(K0, dtype=np.float64) if K.flags.f_contiguous else np.ascontiguousarray(K0, dtype=np.float64)
+        gid32 = np.ascontiguousarray(gid, dtype=np.int32)
+        env32 = np.ascontiguousarray(env, dtype=np.int32)
+        if gid32.size and (gid32.min() < 0 or gid32.max() >= f["L"]):
+            return False
+        ok = C.c_int(0)
+        _lib.call("bgge_factor_matches", _lib.ptr(K), n, n, None if K0 is None else _lib.ptr(K0), int(f["L"]), _lib.ptr(gid32),
+                  _lib.ptr(env32), int(mode), int(k), C.byref(ok))
+        return bool(ok.value)
     cols = max(1, min(n, chunk // max(1, n)))
     for c0 in range(0, n, cols):
         c1 = min(n, c0 + cols)

@@ -77,6 +77,16 @@ int bgge_getk_expand(const double* K0, int64_t L, const int32_t* gid, const int3
                      int mode, int env_k, double* out);
 
 /*
+ * Does the host matrix K (n x n, leading dimension ldk) still equal the expansion of K0 (L x L, leading dimension L;
+ * NULL for the intercept mode) that bgge_getk_expand would produce?  Every entry is compared (==, so -0 equals +0 and
+ * a NaN never matches); *matches = 1 / 0.  Host-only (no device needed), multi-threaded.  BGGE() uses it to decide
+ * whether a kernel entry may take the factorised route or must be decomposed as the dense matrix it was given
+ * (the reference always decomposes the matrix it is given, R/BGGE.R:144,160).
+ */
+int bgge_factor_matches(const double* K, int64_t n, int64_t ldk, const double* K0, int64_t L, const int32_t* gid,
+                        const int32_t* env, int mode, int env_k, int* matches);
+
+/*
  * Whole getK numeric body in one call: one upload of X, every requested kernel built on the
  * device and copied to out[k] (n x n each), in the order getK() returns them:
  *   G_1..G_nb, then for MDs GE_1..GE_nb, for MDe env_0..env_{E-1} per base kernel, then Gi.

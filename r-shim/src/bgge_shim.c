@@ -50,23 +50,15 @@ SEXP bgge_R_expand(SEXP K0, SEXP L_, SEXP gid, SEXP env, SEXP mode, SEXP env_k) 
 }
 
 /* Does `Kernel` (n x n) still equal the expansion its factor describes?  Exact comparison of every entry (a user may
- * have edited the matrix after getK(); the reference always decomposes the matrix it is given, R/BGGE.R:144,160). */
+ * have edited the matrix after getK(); the reference always decomposes the matrix it is given, R/BGGE.R:144,160);
+ * the library runs the pass on all host cores. */
 SEXP bgge_R_factor_matches(SEXP Kernel, SEXP K0, SEXP L_, SEXP gid, SEXP env, SEXP mode, SEXP env_k) {
   const int64_t n = XLENGTH(gid), L = (int64_t)Rf_asInteger(L_);
   const int md = Rf_asInteger(mode), ek = Rf_asInteger(env_k);
   if (!Rf_isReal(Kernel) || Rf_nrows(Kernel) != n || Rf_ncols(Kernel) != n) return Rf_ScalarLogical(0);
-  const double* K = REAL(Kernel);
-  const double* B = Rf_isNull(K0) ? NULL : REAL(K0);
-  const int* g = INTEGER(gid);
-  const int* e = INTEGER(env);
-  for (int64_t j = 0; j < n; ++j)
-    for (int64_t i = 0; i < n; ++i) {
-      double want = B ? B[g[i] + (int64_t)g[j] * L] : (g[i] == g[j] ? 1.0 : 0.0);
-      if (md == BGGE_EXPAND_GE && e[i] != e[j]) want = 0.0;
-      if (md == BGGE_EXPAND_ENV && !(e[i] == ek && e[j] == ek)) want = 0.0;
-      if (memcmp(&want, &K[i + j * n], sizeof(double)) != 0 && !(want == 0.0 && K[i + j * n] == 0.0)) return Rf_ScalarLogical(0);
-    }
-  return Rf_ScalarLogical(1);
+  int ok = 0;
+  check(bgge_factor_matches(REAL(Kernel), n, n, Rf_isNull(K0) ? NULL : REAL(K0), L, INTEGER(gid), INTEGER(env), md, ek, &ok));
+  return Rf_ScalarLogical(ok);
 }
 
 /* ---- BGGE ----------------------------------------------------------------------------------------------------------- */

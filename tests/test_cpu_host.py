@@ -243,6 +243,19 @@ def test_factor_matches_compares_every_entry():
             assert not factor_matches(ent, chunk=97), (mode, i, j)
             ent["Kernel"][i, j] = old
         assert factor_matches(ent)
+        # row-major storage goes through the library as the transpose (K0 handed over in the same order)
+        entc = {"Type": "D", "Kernel": np.ascontiguousarray(base).copy(), "factor": ent["factor"]}
+        assert factor_matches(entc)
+        entc["Kernel"][7, 1] += 1e-12
+        assert not factor_matches(entc)
+        # a NaN never matches, -0.0 equals 0.0
+        entn = {"Type": "D", "Kernel": np.asfortranarray(base.copy()), "factor": ent["factor"]}
+        zi = np.argwhere(entn["Kernel"] == 0.0)
+        if len(zi):
+            entn["Kernel"][tuple(zi[0])] = -0.0
+            assert factor_matches(entn)
+        entn["Kernel"][3, 3] = np.nan
+        assert not factor_matches(entn)
     assert factor_matches({"Type": "D", "factor": ent["factor"]})          # factored-only entry
     assert not factor_matches({"Type": "D", "Kernel": base})               # no description to match
 
