@@ -334,31 +334,40 @@ struct ChainArgs {
 // per chain (one warp each): sigb_j, sigsq, tau        (R/BGGE.R:95-103, 360-367)
 // the sums are formed by the whole warp; then lane j draws the chi-square of kernel j and lane nk the residual one, so
 // the Marsaglia-Tsang rejection loops run side by side instead of one after the other
+// sum of count values p[k * stride] by a block of 128 threads in a fixed order (thread-strided partial sums, xor tree
+// per warp, the four warp sums added in warp order); every thread gets the total.  One block per chain: with one WARP
+// per chain each lane walked ~10 dependent-latency loads of the 300+ per-chunk partials (r02: 7.9 us for 40 chains).
+__device__ __forceinline__ double block_sum_strided(const double* __restrict__ p, int count, long long stride, double* red) {
+  double a = 0.0;
+  for (int k = threadIdx.x; k < count; k += 128) a += p[(long long)k * stride];
+  a = warp_sum(a);
+  __syncthreads();                       // red may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  return ((red[0] + red[1]) + red[2]) + red[3];
+}
+
 __global__ void __launch_bounds__(128) b_chain_var_kernel(const ChainArgs a, DrawCfg dc) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
-  __shared__ double ss[4][MAXK + 1];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + w;
-  if (b >= a.B) return;
-  const long long it = *a.it;
-  const DrawCfg c = chain_cfg(dc, b);
+  __shared__ double red[4];
+  __shared__ double ss[MAXK + 1];
+  const int b = blockIdx.x;              // one block per chain
+  (void)dc;
   for (int j = 0; j < a.nk; ++j) {
-    const double zq = warp_sum_strided(a.zqpart[j] + b, a.n_zq[j], a.Bp, lane);   // sum b^2/s
-    if (lane == 0) ss[w][j] = zq;
+    const double zq = block_sum_strided(a.zqpart[j] + b, a.n_zq[j], a.Bp, red);   // sum b^2/s
+    if (threadIdx.x == 0) ss[j] = zq;
   }
-  const double sse = warp_sum_strided(a.part + b, a.nchunks, a.Bp, lane);         // e'e
-  if (lane == 0) ss[w][a.nk] = sse;
-  __syncwarp();
-  (void)c;
-  (void)it;
-  for (int j = lane; j <= a.nk; j += 32) {
+  const double sse = block_sum_strided(a.part + b, a.nchunks, a.Bp, red);         // e'e
+  if (threadIdx.x == 0) ss[a.nk] = sse;
+  __syncthreads();
+  for (int j = threadIdx.x; j <= a.nk; j += 128) {
     if (j < a.nk) {
       const double chi = a.chiK[(long long)j * a.Bp + b];    // drawn by the extra block of kernel j's b_draw launch
-      a.sigb[(long long)j * a.Bp + b] = (ss[w][j] + NU * a.Sc[(long long)j * a.Bp + b]) / chi;
+      a.sigb[(long long)j * a.Bp + b] = (ss[j] + NU * a.Sc[(long long)j * a.Bp + b]) / chi;
     } else {
       const double chi = a.chiE[b];
-      const double s2 = (ss[w][j] + a.Sce[b]) / chi;
+      const double s2 = (ss[j] + a.Sce[b]) / chi;
       a.sigsq[b] = s2;
       a.tau[b] = 1.0 / s2;
     }
@@ -416,11 +425,11 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
 __global__ void __launch_bounds__(128) b_chain_mu_kernel(const ChainArgs a, DrawCfg dc) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (b >= a.B) return;
+  __shared__ double red[4];
+  const int b = blockIdx.x;              // one block per chain
   const long long it = *a.it;
-  const double sr = warp_sum_strided(a.part + b, a.nchunks, a.Bp, lane);
-  if (lane != 0) return;
+  const double sr = block_sum_strided(a.part + b, a.nchunks, a.Bp, red);
+  if (threadIdx.x != 0) return;
   const DrawCfg c = chain_cfg(dc, b);
   if (it > 0 && it % a.thin == 0) {
     const long long slot = it / a.thin - 1;
@@ -507,7 +516,7 @@ int launch_tail(Batch* g, bool init) {
   const int tx = tile_x(g->Bp), ty = TXY / tx;
   const dim3 cgrid((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx));
   const dim3 cblock(tx, ty);
-  const unsigned cb = (unsigned)((g->B + 3) / 4);   // one warp per chain
+  const unsigned cb = (unsigned)g->B;               // one block per chain
   if (!init)   // the per-chunk sums of (R - shift)^2 were left in `part` by the last kernel's update pass
     BGGE_CUDA(launch_dep(b_chain_var_kernel, dim3(cb), dim3(128), st, chain_args(g, g->part.p), g->draw));
   BGGE_CUDA(launch_dep(b_na_sumr_kernel, cgrid, cblock, st, g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p,
