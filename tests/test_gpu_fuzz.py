@@ -22,3 +22,10 @@ def test_random_models_match_the_oracle(seed):
         msg = fuzz_parity.one_case(rng, i)
         ran += "skipped" not in msg
     assert ran >= 15
+
+
+def test_random_batched_models_match_the_oracle():
+    import fuzz_parity
+    rng = np.random.default_rng(21)
+    for i in range(12):
+        fuzz_parity.batch_case(rng, i)

@@ -108,13 +108,66 @@ def one_case(rng, idx):
     return f"{desc} resident={info['resident']} units={info['merged_units']} paths={paths} err={worst:.1e}"
 
 
+def batch_case(rng, idx):
+    """The batched sampler (skinny DMMA GEMMs, every N-tile width and both thread-tile shapes): random chain counts,
+    folds, shared fixed effects; a few chains of each batch against the oracle fed the chain's own Philox stream."""
+    from helpers import PhiloxDraws
+    L = int(rng.choice([12, 33, 64, 130, 300]))
+    E = int(rng.integers(2, 5))
+    p = int(rng.choice([20, 80, 400]))
+    B = int(rng.choice([1, 2, 7, 8, 9, 16, 23, 40, 41, 48, 49, 64, 77, 80, 96, 100, 128, 130]))
+    model = str(rng.choice(["MM", "MDs", "MDe"]))
+    kernel = str(rng.choice(["GB", "GK"]))
+    X = markers(L, p, int(rng.integers(1 << 30)))
+    Y, names = design(L, E)
+    n = L * E
+    ne = [L] * E
+    q = int(rng.choice([0, 0, 1, E]))
+    XF = None
+    if q == E:
+        XF = np.zeros((n, E))
+        for e in range(E):
+            XF[e * L:(e + 1) * L, e] = 1.0
+    elif q == 1:
+        XF = rng.standard_normal((n, 1))
+    y = rng.standard_normal(n)
+    Yb = np.tile(y, (B, 1))
+    for b in range(1, B):
+        k = int(rng.integers(0, max(1, n // 5)))
+        if k:
+            Yb[b, rng.choice(n, k, replace=False)] = np.nan
+    ite, burn, thin = int(rng.integers(3, 8)), int(rng.integers(0, 2)), int(rng.integers(1, 3))
+    seed, chain0 = int(rng.integers(1 << 40)), int(rng.integers(0, 50))
+    desc = f"#{idx} batch B={B} L={L} E={E} p={p} {kernel} {model} q={q} ite={ite} thin={thin}"
+    Kf = bgge_b200.getK(Y, X, kernel=kernel, model=model, rownames=names, factored=True)
+    Kd = oracle.getK(Y, X, kernel=kernel, model=model, rownames=names)
+    Ei = bgge_b200.setDEC(Kf, ne, 1e-10)
+    nrs = [sum(bk["s"].shape[0] for bk in bl) for bl in Ei]
+    fits = bgge_b200.BGGE_batch(Yb, Kf, XF=XF, ne=ne, ite=ite, burn=burn, thin=thin, seed=seed, chain0=chain0, eig=Ei)
+    worst = 0.0
+    for b in sorted(set([0, B - 1, int(rng.integers(0, B)), int(rng.integers(0, B))])):
+        draws = PhiloxDraws(seed, chain0 + b, n, nrs, q=q, n_na=int(np.isnan(Yb[b]).sum()))
+        ref = oracle.BGGE(Yb[b], Kd, XF=XF, ne=ne, ite=ite, burn=burn, thin=thin, draws=draws, eig=Ei)
+        got = fits[b]
+        errs = [relmax(got["chain"]["mu"], ref["chain"]["mu"]), relmax(got["chain"]["varE"], ref["chain"]["varE"]),
+                relmax(got["yHat"], np.asarray(ref["yHat"]).ravel()), relmax(got["y"], ref["y"])]
+        for nm in ref["K"]:
+            errs.append(relmax(got["chain"]["K"][nm]["varU"], ref["chain"]["K"][nm]["varU"]))
+            errs.append(relmax(got["K"][nm]["u"], ref["K"][nm]["u"]))
+        if ref["chain"]["mu"].size:
+            worst = max(worst, max(errs))
+    assert worst <= 1e-9, (desc, worst)
+    return f"{desc} err={worst:.1e}"
+
+
 def main():
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2026
+    kind = sys.argv[3] if len(sys.argv) > 3 else "single"
     rng = np.random.default_rng(seed)
     for i in range(ncases):
-        print(one_case(rng, i), flush=True)
-    print(f"fuzz parity ok: {ncases} cases, seed {seed}")
+        print((batch_case if kind == "batch" else one_case)(rng, i), flush=True)
+    print(f"fuzz parity ok: {ncases} {kind} cases, seed {seed}")
 
 
 if __name__ == "__main__":
