@@ -1662,8 +1662,8 @@ int bgge_batch_info(bgge_batch* h, int* padded_chains, int64_t* gemm_flops_per_i
   for (auto& k : g.kernels)
     for (auto& b : k.blocks) fl += 4 * b.rows * b.nr * (int64_t)g.B;
   if (gemm_flops_per_iter) *gemm_flops_per_iter = fl;
-  // per kernel: e', GEMM, draw, GEMM, update; tail: variances, imputation, intercept; fixed effects: reduce, draw, apply
-  if (launches_per_iter) *launches_per_iter = 5 * g.nk + 3 + (g.q > 0 ? 3 : 0);
+  // per kernel: GEMM, draw, GEMM, update; tail: variances, imputation, intercept; fixed effects: reduce, draw, apply
+  if (launches_per_iter) *launches_per_iter = 4 * g.nk + 3 + (g.q > 0 ? 3 : 0);
   return OK;
 }
 

@@ -31,26 +31,30 @@ __device__ __forceinline__ double warp_sum_strided(const double* __restrict__ p,
 }
 
 // u_j = z/(2n), R = ((y - mu0) - XF Bet) - sum_j u_j          (R/BGGE.R:254, 260-267)
+// (E0 = R + U_0 is the B operand of the first GEMM of an iteration -- see the note at b_draw_kernel -- and is kept up
+// to date by whichever kernel changes R or the next U: here, b_update_kernel, b_na_sumr_kernel, b_xf_apply_kernel)
 __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* __restrict__ Y,
                               const double* __restrict__ mu0, double* __restrict__ U, double* __restrict__ R, DrawCfg dc,
-                              int q, const double* __restrict__ xf, const double* __restrict__ Bet) {
+                              int q, const double* __restrict__ xf, const double* __restrict__ Bet, double* __restrict__ Ep) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n * Bp) return;
   const long long i = idx / Bp;
   const int b = (int)(idx % Bp);
   if (b >= B) {
     R[idx] = 0.0;
+    Ep[idx] = 0.0;
     for (int j = 0; j < nk; ++j) U[(long long)j * n * Bp + idx] = 0.0;
     return;
   }
   const DrawCfg c = chain_cfg(dc, b);
   const double sd = 1.0 / (2.0 * (double)n);
-  double usum = 0.0;
+  double usum = 0.0, u0 = 0.0;
   for (int j = 0; j < nk; ++j) {
     const long long k = (long long)j * n + i;
     const double uj = draw_normal(c, 0, STREAM_INIT_U, (unsigned long long)k, 0) * sd;
     U[(long long)j * n * Bp + idx] = uj;
     usum = (j == 0) ? uj : usum + uj;
+    if (j == 0) u0 = uj;
   }
   double rv = Y[idx] - mu0[b];
   if (q > 0) {                                                      // R/BGGE.R:264
@@ -59,6 +63,7 @@ __global__ void b_init_kernel(long long n, int nk, int B, int Bp, const double* 
     rv -= xb;
   }
   R[idx] = rv - usum;
+  Ep[idx] = (rv - usum) + u0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -148,7 +153,8 @@ b_xf_draw_kernel(int q, int B, int Bp, int nchunks, const double* __restrict__ p
 
 // R = (R + XF BetOld) - XF Bet                                                  (R/BGGE.R:285, 289)
 __global__ void b_xf_apply_kernel(long long n, int q, int B, int Bp, const double* __restrict__ xf,
-                                  const double* __restrict__ Bet, const double* __restrict__ BetOld, double* __restrict__ R) {
+                                  const double* __restrict__ Bet, const double* __restrict__ BetOld, double* __restrict__ R,
+                                  const double* __restrict__ U0, double* __restrict__ Ep) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -162,22 +168,15 @@ __global__ void b_xf_apply_kernel(long long n, int q, int B, int Bp, const doubl
     xo += x * BetOld[(long long)k * Bp + b];
     xn += x * Bet[(long long)k * Bp + b];
   }
-  R[idx] = (R[idx] + xo) - xn;
+  const double rn = (R[idx] + xo) - xn;
+  R[idx] = rn;
+  Ep[idx] = rn + U0[idx];
 }
 
-// E' = (R - shift_b) + U_j
-// (the first launch of an iteration also advances the iteration counter: nothing in this kernel reads it, everything
-// after it in the stream sees the new value -- one launch less per iteration than a separate increment)
-__global__ void b_eprime_kernel(long long total, int Bp, const double* __restrict__ R, const double* __restrict__ Uj,
-                                const double* __restrict__ shift, double* __restrict__ Ep, long long* __restrict__ advance_it) {
-  pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
-  pdl_trigger();
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (advance_it != nullptr && idx == 0) *advance_it += 1;
-  if (idx >= total) return;
-  Ep[idx] = (R[idx] - shift[idx % Bp]) + Uj[idx];
-}
-
+// The projection d = U'((R - shift_b) + U_j) is computed as U'E0 - shift_b U'1 with E0 = R + U_j: E0 does not depend on
+// the intercept, so the pass that last changes R (the previous kernel's update, the imputation, the fixed-effects
+// apply) writes it on the side and no separate E' pass over the n x B matrices is needed; U'1 (column sums of U over the
+// block's rows) is computed once at init.  The first GEMM of an iteration advances the iteration counter.
 // d = sum of K-split partials; b = tau v d + sqrt(v) z; partial sums of b^2/s        (R/BGGE.R:302-305, 96)
 // Small kernels of the batched sampler are tiled as (32 chains) x (8 row / column lanes): with few chains per GPU
 // (40 at 8 GPUs) a thread-per-chain layout leaves the chip idle behind long serial loops (r02: b_draw 79 us at B = 40).
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(TXY)
 b_draw_kernel(int nr, int n_ctiles, int B, int Bp, int nsplit, const double* __restrict__ Dpart, long long dstride,
               const double* __restrict__ s, const double* __restrict__ sigb, const double* __restrict__ tau,
               double* __restrict__ Bm, double* __restrict__ zqpart, const long long* __restrict__ itp, int j, DrawCfg dc,
-              PreDraws pd) {
+              PreDraws pd, const double* __restrict__ shift, const double* __restrict__ ut1) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
   __shared__ double zs[TXY];
@@ -232,6 +231,7 @@ b_draw_kernel(int nr, int n_ctiles, int B, int Bp, int nsplit, const double* __r
       const double lam = sigb[b], tb = tau[b];
       double d = 0.0;
       for (int sp = 0; sp < nsplit; ++sp) d += Dpart[(long long)sp * dstride + (long long)cc * Bp + b];
+      d -= shift[b] * ut1[cc];              // U'(E0 - shift 1)
       const double sv = s[cc];
       const double vari = sv * lam / (1.0 + sv * lam * tb);
       const double media = tb * vari * d;
@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(TXY)
 b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const double* __restrict__ Upart, long long ustride,
                 const unsigned char* __restrict__ cover, double* __restrict__ R, double* __restrict__ Uj,
                 double* __restrict__ Um, double* __restrict__ Um2, const long long* __restrict__ itp, long long thin,
-                long long burn, const double* __restrict__ shift, double* __restrict__ part, int want_sse) {
+                long long burn, const double* __restrict__ shift, double* __restrict__ part, int want_sse,
+                const double* Unext, int next_is_self, double* __restrict__ Ep) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
   __shared__ double zs[TXY];
@@ -281,6 +282,7 @@ b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const doubl
       const double rn = (R[idx] + Uj[idx]) - un;
       R[idx] = rn;
       Uj[idx] = un;
+      Ep[idx] = rn + (next_is_self ? un : Unext[idx]);   // E0 of the next kernel step (single-kernel models: this kernel)
       if (keep) {
         const double m = Um[idx];
         const double dlt = un - m;
@@ -301,6 +303,19 @@ b_update_kernel(long long n, int Bp, int rows_per_chunk, int nsplit, const doubl
       part[(long long)blockIdx.x * Bp + b] = t;
     }
   }
+}
+
+// ut1[c] = sum over the block's rows of U[row, c]  (one block per eigen-column, fixed order)
+__global__ void __launch_bounds__(128) b_colsum_kernel(const double* __restrict__ U, long long ldu, long long rows,
+                                                        double* __restrict__ out) {
+  __shared__ double red[4];
+  const double* col = U + (long long)blockIdx.x * ldu;
+  double a = 0.0;
+  for (long long i = threadIdx.x; i < rows; i += 128) a += col[i];
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = ((red[0] + red[1]) + red[2]) + red[3];
 }
 
 struct ChainArgs {
@@ -380,7 +395,7 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
                  const double* __restrict__ U, double* __restrict__ Y, const int* __restrict__ narank,
                  const double* __restrict__ mu, const double* __restrict__ shift, const double* __restrict__ sigsq,
                  const long long* __restrict__ itp, int do_na, double* __restrict__ part, const double* __restrict__ zna,
-                 int q, const double* __restrict__ xf, const double* __restrict__ Bet) {
+                 int q, const double* __restrict__ xf, const double* __restrict__ Bet, double* __restrict__ Ep) {
   pdl_wait();   // programmatic dependent launch: resident early, runs once the predecessor has completed
   pdl_trigger();
   __shared__ double zs[TXY];
@@ -407,6 +422,7 @@ b_na_sumr_kernel(long long n, int nk, int B, int Bp, int rows_per_chunk, double*
           Y[idx] = yv;
           rv = (((yv - uhat) - aux) - mub) + shb;
           R[idx] = rv;
+          Ep[idx] = rv + U[idx];                  // E0 of the next iteration's first kernel step
         }
       }
       a += rv;
@@ -521,7 +537,7 @@ int launch_tail(Batch* g, bool init) {
     BGGE_CUDA(launch_dep(b_chain_var_kernel, dim3(cb), dim3(128), st, chain_args(g, g->part.p), g->draw));
   BGGE_CUDA(launch_dep(b_na_sumr_kernel, cgrid, cblock, st, g->n, g->nk, g->B, g->Bp, g->rows_per_chunk, g->R.p, g->U.p, g->Y.p,
                        g->narank.p, g->mu.p, g->shift.p, g->sigsq.p, g->it.p, (!init && g->any_na) ? 1 : 0, g->part2.p, g->zna.p,
-                       g->q, g->xf.p, g->Bet.p));
+                       g->q, g->xf.p, g->Bet.p, g->Ep.p));
   ChainArgs ca = chain_args(g, g->part2.p);
   if (init) ca.zmu = nullptr;   // no b_draw launch has run yet: the first intercept's normal is drawn in place
   BGGE_CUDA(launch_dep(b_chain_mu_kernel, dim3(cb), dim3(128), st, ca, g->draw));
@@ -539,26 +555,28 @@ int launch_iteration(Batch* g) {
                          g->q, g->Bp, g->rows_per_chunk, g->xf.p, g->R.p, g->Bet.p, g->shift.p, g->xf_part.p, g->it.p));
     BGGE_CUDA(launch_dep(b_xf_draw_kernel, dim3((unsigned)((g->B + 3) / 4)), dim3(128), st, g->q, g->B, g->Bp, g->nchunks,
                          g->xf_part.p, g->txx.p, g->lchol.p, g->sigsq.p, g->Bet.p, g->BetOld.p, g->it.p, g->draw));
-    BGGE_CUDA(launch_dep(b_xf_apply_kernel, dim3(eg), dim3(BT), st, g->n, g->q, g->B, g->Bp, g->xf.p, g->Bet.p, g->BetOld.p, g->R.p));
+    BGGE_CUDA(launch_dep(b_xf_apply_kernel, dim3(eg), dim3(BT), st, g->n, g->q, g->B, g->Bp, g->xf.p, g->Bet.p, g->BetOld.p, g->R.p,
+                         g->U.p, g->Ep.p));
   }
   for (int j = 0; j < g->nk; ++j) {
     BatchKernel& bk = g->kernels[j];
     double* Uj = g->U.p + (size_t)j * total;
-    BGGE_CUDA(launch_dep(b_eprime_kernel, dim3(eg), dim3(BT), st, total, g->Bp, g->R.p, Uj, g->shift.p, g->Ep.p,
-                         (j == 0 && g->q == 0) ? g->it.p : nullptr));
-    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj, batch_pdl()));
+    // (E0 = R + U_j is already in place; the first launch of the iteration advances the iteration counter)
+    BGGE_TRY(dgemm_launch(bk.proj_items.p, bk.n_proj, g->tn, st, bk.grid_proj, batch_pdl(), (j == 0 && g->q == 0) ? g->it.p : nullptr));
     const bool last = j == g->nk - 1;
     PreDraws pd{g->chiK.p, g->chiE.p, g->zmu.p, g->zna.p, g->max_na, last ? 1 : 0, g->n_na.p, (long long)g->n,
                 (long long)bk.nr_total};
     const int extra = 1 + (last && g->any_na ? (g->max_na + ty - 1) / ty : 0);   // prepared draws, see b_draw_kernel
     BGGE_CUDA(launch_dep(b_draw_kernel, dim3((unsigned)(bk.n_ctiles + extra), (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), st,
                          (int)bk.nr_total, bk.n_ctiles, g->B, g->Bp, bk.ksplit_proj, bk.Dpart.p, bk.nr_pad * g->Bp, bk.s.p,
-                         g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw, pd));
+                         g->sigb.p + (size_t)j * g->Bp, g->tau.p, bk.Bm.p, bk.zqpart.p, g->it.p, j, g->draw, pd, g->shift.p,
+                         bk.ut1.p));
     BGGE_TRY(dgemm_launch(bk.back_items.p, bk.n_back, g->tn, st, bk.grid_back, batch_pdl()));
     BGGE_CUDA(launch_dep(b_update_kernel, dim3((unsigned)g->nchunks, (unsigned)((g->Bp + tx - 1) / tx)), dim3(tx, ty), st, g->n,
                          g->Bp, g->rows_per_chunk, bk.ksplit_back, bk.Upart.p, total, bk.cover.p, g->R.p, Uj,
                          g->Um.p + (size_t)j * total, g->Um2.p + (size_t)j * total, g->it.p, g->thin, g->burn, g->shift.p,
-                         g->part.p, j == g->nk - 1 ? 1 : 0));
+                         g->part.p, j == g->nk - 1 ? 1 : 0, g->U.p + (size_t)((j + 1) % g->nk) * total, g->nk == 1 ? 1 : 0,
+                         g->Ep.p));
   }
   return launch_tail(g, false);
 }
@@ -788,6 +806,11 @@ int batch_init(Batch* g) {
     BGGE_CUDA(cudaMemsetAsync(bk.Bm.p, 0, (size_t)bk.nr_pad * Bp * sizeof(double), st));
     BGGE_CUDA(bk.zqpart.alloc((size_t)bk.n_ctiles * Bp));
     BGGE_TRY(up(bk.s, bk.s_host, st));
+    BGGE_CUDA(bk.ut1.alloc((size_t)bk.nr_pad));
+    BGGE_CUDA(cudaMemsetAsync(bk.ut1.p, 0, (size_t)bk.nr_pad * sizeof(double), st));
+    for (auto& bl : bk.blocks)
+      b_colsum_kernel<<<(unsigned)bl.nr, 128, 0, st>>>(bl.dU, bl.ldu, bl.rows, bk.ut1.p + bl.col_off);
+    BGGE_CUDA(cudaGetLastError());
   }
   // ---- GEMM work items, stream-K style: the (tile, k-block) space of a GEMM is cut into one contiguous range per
   // persistent CTA (equal k-block counts), a range that crosses a tile boundary becomes two items.  Every item writes
@@ -902,7 +925,7 @@ int batch_init(Batch* g) {
     BGGE_TRY(up(bk.back_items, bi, st));
   }
   const unsigned ig = (unsigned)((total + BT - 1) / BT);
-  b_init_kernel<<<ig, BT, 0, st>>>(n, g->nk, B, Bp, g->Y.p, g->mu0.p, g->U.p, g->R.p, g->draw, q, g->xf.p, g->Bet.p);
+  b_init_kernel<<<ig, BT, 0, st>>>(n, g->nk, B, Bp, g->Y.p, g->mu0.p, g->U.p, g->R.p, g->draw, q, g->xf.p, g->Bet.p, g->Ep.p);
   BGGE_CUDA(cudaGetLastError());
   BGGE_TRY(launch_tail(g, true));
   BGGE_CUDA(cudaStreamSynchronize(st));

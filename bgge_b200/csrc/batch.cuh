@@ -24,6 +24,8 @@ struct BatchKernel {
   int ksplit_proj = 1, ksplit_back = 1, n_proj = 0, n_back = 0, n_ctiles = 0;   // ksplit_* = planes of partial outputs
   int grid_proj = 0, grid_back = 0;      // persistent CTAs the stream-K item lists were laid out for
   DevBuf<double> s, Dpart, Upart, Bm, zqpart;
+  DevBuf<double> ut1;                    // U'1 per eigen-column (column sums over the block's rows): the GEMM runs on
+                                         // E0 = R + U_j, the draw subtracts shift * U'1 (see b_draw_kernel)
   DevBuf<GemmItem> proj_items, back_items;
   DevBuf<unsigned char> cover;           // 1 for rows some block of this kernel covers
 };

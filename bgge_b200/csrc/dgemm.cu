@@ -32,7 +32,7 @@ struct GemmSmem {
 
 template <int TN, int MI>
 __global__ void __launch_bounds__(GTHREADS, 1)
-dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
+dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems, long long* __restrict__ advance) {
   using SM = GemmSmem<TN, MI>;
   constexpr int GM = SM::GM, GSLD_A = SM::SLD_A;
   constexpr long long ABLK = (long long)GK * GSLD_A;   // doubles of one blocked A chunk == one A ring stage
@@ -56,6 +56,9 @@ dgemm_dmma_kernel(const GemmItem* __restrict__ items, int nitems) {
   // previous kernel; the operands are only touched from here on
   pdl_wait();
   pdl_trigger();
+  // (the batched sampler lets the first launch of an iteration advance its iteration counter: nothing in this kernel
+  // reads it, everything launched after it sees the new value)
+  if (advance != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *advance += 1;
 
   if (warp >= GCONS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -190,7 +193,7 @@ gemm_pack_kernel(const double* __restrict__ src, long long sm_, long long sk_, l
 }
 
 template <int TN, int MI>
-int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint, bool pdl) {
+int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int grid_hint, bool pdl, long long* advance) {
   static bool attr[64] = {false};   // function attributes are per device
   int dev = 0;
   BGGE_CUDA(cudaGetDevice(&dev));
@@ -210,7 +213,7 @@ int dgemm_launch_t(const GemmItem* d_items, int nitems, cudaStream_t st, int gri
   la[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = la;
   cfg.numAttrs = pdl ? 1 : 0;
-  BGGE_CUDA(cudaLaunchKernelEx(&cfg, dgemm_dmma_kernel<TN, MI>, d_items, nitems));
+  BGGE_CUDA(cudaLaunchKernelEx(&cfg, dgemm_dmma_kernel<TN, MI>, d_items, nitems, advance));
   return OK;
 }
 }  // namespace
@@ -234,17 +237,17 @@ int gemm_pack_launch(const double* src, long long stride_m, long long stride_k, 
   return OK;
 }
 
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid, bool pdl) {
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid, bool pdl, long long* advance) {
   if (nitems <= 0) return OK;
   switch (tn) {
-    case 16: return dgemm_launch_t<16, 4>(d_items, nitems, st, grid, pdl);
-    case 32: return dgemm_launch_t<32, 4>(d_items, nitems, st, grid, pdl);
-    case 40: return dgemm_launch_t<40, 4>(d_items, nitems, st, grid, pdl);
-    case 48: return dgemm_launch_t<48, 4>(d_items, nitems, st, grid, pdl);
-    case 64: return dgemm_launch_t<64, 2>(d_items, nitems, st, grid, pdl);
-    case 80: return dgemm_launch_t<80, 2>(d_items, nitems, st, grid, pdl);
-    case 96: return dgemm_launch_t<96, 2>(d_items, nitems, st, grid, pdl);
-    case 128: return dgemm_launch_t<128, 2>(d_items, nitems, st, grid, pdl);
+    case 16: return dgemm_launch_t<16, 4>(d_items, nitems, st, grid, pdl, advance);
+    case 32: return dgemm_launch_t<32, 4>(d_items, nitems, st, grid, pdl, advance);
+    case 40: return dgemm_launch_t<40, 4>(d_items, nitems, st, grid, pdl, advance);
+    case 48: return dgemm_launch_t<48, 4>(d_items, nitems, st, grid, pdl, advance);
+    case 64: return dgemm_launch_t<64, 2>(d_items, nitems, st, grid, pdl, advance);
+    case 80: return dgemm_launch_t<80, 2>(d_items, nitems, st, grid, pdl, advance);
+    case 96: return dgemm_launch_t<96, 2>(d_items, nitems, st, grid, pdl, advance);
+    case 128: return dgemm_launch_t<128, 2>(d_items, nitems, st, grid, pdl, advance);
     default: break;
   }
   set_error("dgemm: unsupported N tile %d", tn);

@@ -58,7 +58,9 @@ struct GemmItem {
 };
 // grid > 0: number of persistent CTAs the item list was laid out for (item w runs on CTA w % grid)
 // pdl: launch with the programmatic-serialization attribute (the kernel waits for its predecessor itself)
-int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid = 0, bool pdl = false);
+// advance: optional device counter incremented once by the launch (the kernel itself never reads it)
+int dgemm_launch(const GemmItem* d_items, int nitems, int tn, cudaStream_t st, int grid = 0, bool pdl = false,
+                 long long* advance = nullptr);
 // M tile of the GEMM instantiation for N tile width tn (256 rows for tn <= 48, else 128) and the size of one blocked
 // A chunk ([16][tile_m + 4] doubles)
 int gemm_tile_m(int tn);
