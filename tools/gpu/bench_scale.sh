@@ -1,4 +1,4 @@
-# usage: bash tools/gpu/r02_scale.sh N   (under gpurun --gpus N)
+# usage: bash tools/gpu/bench_scale.sh N   (under gpurun --gpus N)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
 N=${1:-8}
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/bench_r02_c5_${N}gpu.json 2> gpurun_out/bench_r02_c5_${N}gpu.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r02_c5_${N}gpu.err | cut -c1-300

@@ -1,6 +1,6 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
 CMD="python bench.py --workload c4 --chains 40 --steps 1 --warmup 3 --iters 20 --no-cpu-baseline"
-timeout 600 $CMD > gpurun_out/r02_v17_plain.json 2>gpurun_out/r02_v17_plain.err || { echo plain failed; tail -5 gpurun_out/r02_v17_plain.err; exit 1; }
+timeout 600 $CMD > gpurun_out/launches_c4_40_plain.json 2>gpurun_out/launches_c4_40_plain.err || { echo plain failed; tail -5 gpurun_out/launches_c4_40_plain.err; exit 1; }
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"b_|dgemm" -c 400 --csv --log-file gpurun_out/r02_launches_c4_40.csv $CMD > /dev/null 2>&1; echo "ncu rc=$?"
 python - <<'PY'
 import csv, collections
