@@ -302,3 +302,27 @@ def test_r_shim_type_checks_against_the_header():
     r = subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Werror", "-x", "c", os.path.join(ROOT, "include", "bgge_b200.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_factor_matches_entry_point_with_pitch_and_bad_codes():
+    """bgge_factor_matches through ctypes (host-only, no device needed): a pitched K (ldk > n), a mismatch in the last
+    column, out-of-range genotype codes rejected with the library's error."""
+    import ctypes as C
+    from bgge_b200 import _lib
+    rng = np.random.default_rng(3)
+    L, n, ldk = 9, 31, 40
+    K0 = np.asfortranarray(rng.standard_normal((L, L)))
+    gid = rng.integers(0, L, size=n).astype(np.int32)
+    env = rng.integers(0, 3, size=n).astype(np.int32)
+    Kp = np.full((ldk, n), np.nan, order="F")
+    Kp[:n, :] = K0[np.ix_(gid, gid)] * (env[:, None] == env[None, :])
+    ok = C.c_int(-1)
+    _lib.call("bgge_factor_matches", _lib.ptr(Kp), n, ldk, _lib.ptr(K0), L, _lib.ptr(gid), _lib.ptr(env), _lib.EXPAND_GE, 0, C.byref(ok))
+    assert ok.value == 1
+    Kp[n - 1, n - 1] += 1.0
+    _lib.call("bgge_factor_matches", _lib.ptr(Kp), n, ldk, _lib.ptr(K0), L, _lib.ptr(gid), _lib.ptr(env), _lib.EXPAND_GE, 0, C.byref(ok))
+    assert ok.value == 0
+    bad = gid.copy()
+    bad[4] = L
+    with pytest.raises(_lib.BGGEError, match="outside"):
+        _lib.call("bgge_factor_matches", _lib.ptr(Kp), n, ldk, _lib.ptr(K0), L, _lib.ptr(bad), _lib.ptr(env), _lib.EXPAND_GE, 0, C.byref(ok))
